@@ -1,0 +1,400 @@
+"""CPU oracle: float64 NumPy restatement of scMerge's RUV-III fit-and-adjust path.
+
+TEST INFRASTRUCTURE ONLY.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline`
+/ `--impl reference` legs may import this module; the product path (`scmerge_b200/`) never does.
+
+PARITY UNPINNED: the reference is a pure-R package (no golden vectors in its tests, R is not
+installable here), so the absolute values produced by this restatement cannot be checked against a
+run of the reference itself.  What *is* pinned (tests/test_oracle.py) are the relations the
+reference's own tests/docs assert: exact ~= randomized to 2 % (`tests/testthat/test-fastRUVIII.R:11-16`),
+equality with classic `ruv::RUVIII` (`R/fastRUVIII.R:30-38`), cell-permutation equivariance at
+1.5e-8 (`tests/testthat/test-resampling-columns.R:26`), and agreement of the literal form with the
+algebraically reduced (Gram) form.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+Third-party arithmetic that the reference calls but does not vendor (DESCRIPTION:22-41, unpinned):
+  ruv::replicate.matrix, ruv::RUV1, ruv::RUVIII  (CRAN `ruv`)      -> restated from the published algorithm
+  BiocSingular::runSVD(ExactParam) = base::svd (LAPACK dgesdd)     -> numpy.linalg.svd
+  BiocSingular::runSVD(RandomParam) = rsvd::rsvd(p=10, q=2)        -> `rsvd` below
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------------
+# helpers restating un-vendored `ruv` functions
+# --------------------------------------------------------------------------------------------------
+
+
+def replicate_matrix(a) -> np.ndarray:
+    """ruv::replicate.matrix (call sites R/fastRUVIII.R:48, R/scMerge2_utilis.R:41, R/ruvSimulate.R:73).
+
+    numeric 0/1 matrix -> returned unchanged; label vector -> one-hot `model.matrix(~a-1)` with
+    columns in sorted level order; 2-D array of labels (data.frame) -> rows pasted with "_" first.
+    """
+    a = np.asarray(a)
+    if a.ndim == 2 and np.issubdtype(a.dtype, np.number):
+        return a.astype(np.float64)
+    if a.ndim == 2:
+        a = np.array(["_".join(str(x) for x in row) for row in a])
+    levels, inv = np.unique(a, return_inverse=True)
+    M = np.zeros((a.shape[0], levels.shape[0]))
+    M[np.arange(a.shape[0]), inv] = 1.0
+    return M
+
+
+def tological(ctl, n: int) -> np.ndarray:
+    """R/fastRUVIII.R:113-117. Accepts a logical mask or 0-based integer indices."""
+    ctl = np.asarray(ctl)
+    if ctl.dtype == bool:
+        out = np.zeros(n, dtype=bool)
+        out[: ctl.shape[0]] = ctl
+        return out
+    out = np.zeros(n, dtype=bool)
+    out[ctl] = True
+    return out
+
+
+def my_residop(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """R/fastRUVIII.R:121-129, literal: A - B (B'B)^-1 B' A (dense projector, left to right)."""
+    tBB = B.T @ B
+    tBB_inv = np.linalg.inv(tBB)  # Matrix::solve(tBB)
+    BtBB_inv = B @ tBB_inv
+    tBA = B.T @ A
+    return A - BtBB_inv @ tBA
+
+
+def rsvd(A: np.ndarray, k: int, p: int = 10, q: int = 2, rng=None):
+    """rsvd::rsvd defaults as dispatched by BiocSingular::RandomParam (un-vendored; published algorithm:
+    Erichson et al., 'Randomized matrix decompositions using R').  Returns (u, d, v) truncated to k."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    flipped = A.shape[0] < A.shape[1]
+    if flipped:
+        A = A.T
+    m, n = A.shape
+    l = min(int(round(k)) + int(round(p)), n)
+    O = rng.standard_normal((n, l))
+    Y = A @ O
+    for _ in range(q):
+        Y, _r = np.linalg.qr(Y)
+        Z, _r = np.linalg.qr(A.T @ Y)
+        Y = A @ Z
+    Q, _r = np.linalg.qr(Y)
+    B = Q.T @ A
+    ub, d, vt = np.linalg.svd(B, full_matrices=False)
+    u, v = Q @ ub, vt.T
+    u, d, v = u[:, :k], d[:k], v[:, :k]
+    return (v, d, u) if flipped else (u, d, v)
+
+
+def svd_k_bound(m: int, n_groups: int, n_ctl: int, exact: bool, cap) -> int:
+    """R/fastRUVIII.R:66-70 (cap = svd_k, default 50) and R/scMerge2_utilis.R:60-65 (cap = k).
+    The non-exact branch ignores the user's svd_k (reference quirk)."""
+    if exact:
+        return int(min(m - n_groups, n_ctl, cap))
+    return int(min(m - n_groups, n_ctl))
+
+
+# --------------------------------------------------------------------------------------------------
+# fastRUVIII
+# --------------------------------------------------------------------------------------------------
+
+
+def fastRUVIII(Y, M, ctl, k, svd_k=50, exact=True, fullalpha=None, return_info=False,
+               inputcheck=True, rng=None):
+    """R/fastRUVIII.R:41-111, literal.  Y is m x n (cells x genes).  `exact` <=> inherits(BSPARAM,
+    "ExactParam").  eta is always NULL at every call site, so ruv::RUV1 is the identity (:64)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    m, n = Y.shape
+    M = replicate_matrix(M)
+    ctl = tological(ctl, n)
+    if inputcheck:  # :52-60
+        if np.isnan(Y).sum() > 0:
+            raise ValueError("Y contains missing values.  This is not supported.")
+        if np.isinf(Y).sum() > 0:
+            raise ValueError("Y contains infinities.  This is not supported.")
+    s = svd_k_bound(m, M.shape[1], int(ctl.sum()), exact, svd_k)
+    if M.shape[1] >= m or k == 0:  # :78-80
+        newY, fullalpha = Y, None
+    else:
+        if fullalpha is None:
+            Y0 = my_residop(Y, M)  # :89
+            if exact:
+                u, _d, _vt = np.linalg.svd(Y0, full_matrices=False)  # :91 base::svd via ExactParam
+                u = u[:, :s]
+            else:
+                u, _d, _v = rsvd(Y0, s, rng=rng)
+            fullalpha = u.T @ Y  # :93  (Y, not Y0)
+        alpha = fullalpha[: min(k, fullalpha.shape[0])]  # :97
+        ac = alpha[:, ctl]  # :98
+        W = Y[:, ctl] @ ac.T @ np.linalg.inv(ac @ ac.T)  # :99 explicit solve(), left to right
+        newY = Y - W @ alpha  # :100-101
+    if not return_info:
+        return newY
+    return {"newY": newY, "M": M, "fullalpha": fullalpha}
+
+
+def group_ids(M: np.ndarray) -> np.ndarray:
+    """int32 group id per row of a one-hot replicate matrix (what the device path consumes)."""
+    M = np.asarray(M)
+    if not np.all((M == 0) | (M == 1)) or not np.all(M.sum(axis=1) == 1):
+        raise ValueError("M is not a one-hot partition matrix")
+    return np.argmax(M, axis=1).astype(np.int32)
+
+
+def fastRUVIII_reduced(Y, M, ctl, k, svd_k=50):
+    """Algebraically reduced exact form (SURVEY.md section 0.3 / Appendix A 'device-side reduced form'):
+    group-mean residual -> n x n Gram -> top-s eigenpairs -> fullalpha = sqrt(lambda) v' ->
+    newY = Y - (Y_c V_c (V_c'V_c)^-1) V_k'.  Must agree with `fastRUVIII` to ~1e-12."""
+    Y = np.asarray(Y, dtype=np.float64)
+    m, n = Y.shape
+    g = group_ids(replicate_matrix(M))
+    ctl = tological(ctl, n)
+    G = int(g.max()) + 1
+    s = svd_k_bound(m, G, int(ctl.sum()), True, svd_k)
+    counts = np.bincount(g, minlength=G).astype(np.float64)
+    sums = np.zeros((G, n))
+    np.add.at(sums, g, Y)
+    Y0 = Y - (sums / counts[:, None])[g]
+    lam, V = np.linalg.eigh(Y0.T @ Y0)
+    order = np.argsort(lam)[::-1][:s]
+    lam, V = lam[order], V[:, order]
+    fullalpha = np.sqrt(np.maximum(lam, 0))[:, None] * V.T
+    kk = min(k, s)
+    Vk = V[:, :kk]
+    Vc = Vk[ctl]
+    Bm = Vc @ np.linalg.inv(Vc.T @ Vc)
+    newY = Y - (Y[:, ctl] @ Bm) @ Vk.T
+    return {"newY": newY, "fullalpha": fullalpha}
+
+
+def ruvIII_classic(Y, M, ctl, k):
+    """ruv::RUVIII (CRAN `ruv`, un-vendored), restated from the published algorithm (Molania et al. 2019):
+    Y0 = residop(Y, M); fullalpha = t(eigen(Y0 Y0')$vectors[, 1:(m - ncol(M))]) %*% Y; then alpha/ac/W as
+    in fastRUVIII.  The reference documents fastRUVIII == ruv::RUVIII (R/fastRUVIII.R:30-38)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    m, n = Y.shape
+    M = replicate_matrix(M)
+    ctl = tological(ctl, n)
+    Y0 = my_residop(Y, M)
+    lam, U = np.linalg.eigh(Y0 @ Y0.T)
+    U = U[:, np.argsort(lam)[::-1][: m - M.shape[1]]]
+    fullalpha = U.T @ Y
+    alpha = fullalpha[: min(k, fullalpha.shape[0])]
+    ac = alpha[:, ctl]
+    W = Y[:, ctl] @ ac.T @ np.linalg.inv(ac @ ac.T)
+    return Y - W @ alpha
+
+
+# --------------------------------------------------------------------------------------------------
+# scRUVIII (standardise -> fastRUVIII -> de-standardise)
+# --------------------------------------------------------------------------------------------------
+
+
+def standardize2(Y, batch):
+    """R/scRUVIII.R:158-175.  Y is genes x cells here (as in the reference)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    num_cell = Y.shape[1]
+    levels, b = np.unique(np.asarray(batch), return_inverse=True)
+    num_batch = levels.shape[0]
+    stand_mean = Y.mean(axis=1)
+    design = np.zeros((num_cell, num_batch))
+    design[np.arange(num_cell), b] = 1.0
+    a = design.T @ design
+    bmat = (Y @ design).T
+    B_hat = np.linalg.inv(a.T @ a) @ a.T @ bmat  # solve_axb, :153-156
+    B_designed = B_hat.T @ design.T
+    stand_var = ((Y - B_designed) ** 2).sum(axis=1) / (num_cell - num_batch)
+    stand_Y = (Y - stand_mean[:, None]) / np.sqrt(stand_var)[:, None]
+    return {"stand_Y": stand_Y, "stand_mean": stand_mean, "stand_var": stand_var}
+
+
+def scRUVIII(Y, M, ctl, k, batch, fullalpha=None, exact=True, svd_k=50, rng=None):
+    """R/scRUVIII.R:41-137 without the silhouette-based k selection (:80-114, out of scope).
+    Y is genes x cells.  `k` may be an int or a sequence; returns {k: {newY (cells x genes), fullalpha}}
+    plus 'optimal_ruvK' = k[0] for a single k (f_score = 1, :80-82)."""
+    ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
+    sc = standardize2(Y, batch)
+    stand_tY = sc["stand_Y"].T
+    stand_sd = np.sqrt(sc["stand_var"])
+    stand_mean = sc["stand_mean"]
+    first = fastRUVIII(stand_tY, M, ctl, ks[0], svd_k=svd_k, exact=exact, fullalpha=fullalpha,
+                       return_info=True, rng=rng)
+    out = {ks[0]: first}
+    for kk in ks[1:]:  # :70-74 re-use fullalpha
+        out[kk] = fastRUVIII(stand_tY, M, ctl, kk, fullalpha=first["fullalpha"], return_info=True)
+    for kk in ks:  # :117-119
+        r = dict(out[kk])
+        r["newY"] = (r["newY"].T * stand_sd[:, None] + stand_mean[:, None]).T
+        out[kk] = r
+    out["optimal_ruvK"] = ks[0] if len(ks) == 1 else None
+    out["stand_mean"], out["stand_sd"] = stand_mean, stand_sd
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# scMerge2: pseudobulk aggregation, pseudoRUVIII, getAdjustedMat
+# --------------------------------------------------------------------------------------------------
+
+
+def create_chunk(n: int, chunk_size: int = 1000):
+    """R/scMerge2_utilis.R:153-170.  Returns 1-based inclusive (start, end) pairs like the reference."""
+    starts = list(range(1, n + 1, chunk_size))
+    ends = [s + chunk_size - 1 for s in starts]
+    ends[-1] = n
+    if len(ends) > 1 and ends[-1] - ends[-2] < chunk_size / 2:
+        starts, ends = starts[:-1], ends[:-1]
+        ends[-1] = n
+    return list(zip(starts, ends))
+
+
+def create_pseudobulk(exprs, cell_info, which, k_fold=None):
+    """Arithmetic of create_pseudoBulk + aggregate.Matrix, R/scMerge2_utilis.R:461-486,325-346.
+
+    exprs: genes x cells of ONE batch; cell_info: label per cell; `which`: fold id (1..K) per cell, i.e.
+    cvTools::cvFolds' `which` re-ordered to cell order (the R RNG draw is an input, not restated).
+    Returns (bulk: P x genes, names: 'type_fold'), rows fold-major, types in sorted level order."""
+    exprs = np.asarray(exprs, dtype=np.float64)
+    cell_info = np.asarray(cell_info)
+    which = np.asarray(which)
+    K = int(which.max()) if k_fold is None else int(k_fold)
+    rows, names = [], []
+    for i in range(1, K + 1):
+        idx = np.nonzero(which == i)[0]
+        types = np.unique(cell_info[idx])
+        for t in types:
+            sel = idx[cell_info[idx] == t]
+            rows.append(exprs[:, sel].sum(axis=1) / sel.shape[0])
+            names.append(f"{t}_{i}")
+    return np.array(rows), names
+
+
+def pseudoRUVIII(Y, Y_pseudo, M, ctl, k, exact=True, fullalpha=None, subset=None, normalised=True,
+                 by_chunk=True, chunk_size=50000, rng=None):
+    """R/scMerge2_utilis.R:17-150.  Y: cells x genes, Y_pseudo: pseudobulks x genes, M over pseudobulks."""
+    Y = np.asarray(Y, dtype=np.float64)
+    Y_pseudo = np.asarray(Y_pseudo, dtype=np.float64)
+    n = Y.shape[1]
+    m_pseudo = Y_pseudo.shape[0]
+    M = replicate_matrix(M)
+    ctl = tological(ctl, n)
+    s = svd_k_bound(m_pseudo, M.shape[1], int(ctl.sum()), exact, k)  # :60-65 (cap = k)
+    if M.shape[1] >= m_pseudo or k == 0:  # :72-76 returns the pseudobulk matrix itself
+        return Y_pseudo
+    if fullalpha is None:  # :83-85
+        Y0 = my_residop(Y_pseudo, M)
+        if exact:
+            u, _d, _vt = np.linalg.svd(Y0, full_matrices=False)
+            u = u[:, :s]
+        else:
+            u, _d, _v = rsvd(Y0, s, rng=rng)
+        fullalpha = u.T @ Y_pseudo
+    alpha = fullalpha[: min(k, fullalpha.shape[0])]
+    if not normalised:
+        return {"M": M, "fullalpha": fullalpha}
+    ac = alpha[:, ctl]
+    adjusted_means = Y.mean(axis=0)  # :97 over ALL cells
+    inv = np.linalg.inv(ac @ ac.T)
+    cols = slice(None) if subset is None else np.asarray(subset)
+
+    def adjust(rows):
+        Y_stand = Y[rows] - adjusted_means
+        W = Y_stand[:, ctl] @ ac.T @ inv
+        return Y[rows][:, cols] - W @ alpha[:, cols]  # subtraction from the UNcentred Y (:117-121)
+
+    if Y.shape[0] >= 1.5 * chunk_size and by_chunk:  # :104-124
+        parts = [adjust(slice(a - 1, b)) for a, b in create_chunk(Y.shape[0], chunk_size)]
+        newY = np.concatenate(parts, axis=0)
+    else:
+        newY = adjust(slice(None))
+    return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": adjusted_means}
+
+
+def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, return_subset_genes=None):
+    """R/scMerge2.R:368-410.  exprsMat: genes x cells; ctl / return_subset_genes: boolean masks or 0-based
+    indices over genes (the reference resolves names with intersect(colnames, .), keeping matrix order)."""
+    Y = np.asarray(exprsMat, dtype=np.float64).T
+    n = Y.shape[1]
+    ctl = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
+    means = Y.mean(axis=0) if adjusted_means is None else np.asarray(adjusted_means)
+    Y_stand = Y - means
+    alpha = fullalpha[: min(ruvK, fullalpha.shape[0])]
+    ac = alpha[:, ctl]
+    W = Y_stand[:, ctl] @ ac.T @ np.linalg.inv(ac @ ac.T)
+    if return_subset_genes is not None:
+        sub = np.nonzero(tological(return_subset_genes, n))[0]
+        newY = Y[:, sub] - W @ alpha[:, sub]
+    else:
+        newY = Y - W @ alpha
+    return newY.T
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic data + comparison metrics
+# --------------------------------------------------------------------------------------------------
+
+
+def ruv_simulate(m=100, n=5000, nc=None, n_celltypes=3, n_batch=2, k=20, lam=0.1, rng=None):
+    """Distribution of R/ruvSimulate.R:41-84 with NumPy's RNG (R's RNG stream is not reproducible here)."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    nc = n // 2 if nc is None else nc
+    ctl = np.zeros(n, dtype=bool)
+    ctl[:nc] = True
+    celltypes = (np.arange(m) % n_celltypes) + 1
+    X = celltypes[:, None].astype(np.float64)
+    beta = rng.poisson(2 * lam, size=(1, n)).astype(np.float64)
+    beta[:, ctl] = 0
+    W = rng.poisson(lam, size=(m, k)).astype(np.float64)
+    W[:, 0] = np.arange(m) % n_batch
+    alpha = rng.poisson(lam, size=(k, n)).astype(np.float64)
+    eps = rng.poisson(lam, size=(m, n)).astype(np.float64)
+    Y = X @ beta + W @ alpha + eps
+    cell_types = np.array([f"cellTypes{c}" for c in celltypes])
+    batch = np.array([f"batch{(i % n_batch) + 1}" for i in range(m)])
+    M = replicate_matrix(np.stack([cell_types, batch], axis=1))
+    return {"Y": Y, "ctl": ctl, "M": M, "cellTypes": cell_types, "batch": batch, "X": X}
+
+
+def planted_factors(m, n, c, k, n_types=20, n_batch=4, seed=20240, noise=0.5, dtype=np.float64):
+    """Generator G1 of SURVEY.md section 8(d): gene offsets + cell-type means (zero on ctl) + k unwanted
+    factors (one-hot batch + Gaussian columns, scaled to leave a spectral gap after factor k) + noise."""
+    rng = np.random.default_rng(seed)
+    ctl = np.zeros(n, dtype=bool)
+    ctl[:c] = True
+    types = rng.integers(0, n_types, size=m)
+    batch = rng.integers(0, n_batch, size=m)
+    theta = rng.standard_normal((n_types, n))
+    theta[:, ctl] = 0
+    Wb = np.zeros((m, k))
+    nb = min(n_batch, k)
+    Wb[np.arange(m), batch % nb] = 1.0
+    if k > nb:
+        Wb[:, nb:] = rng.standard_normal((m, k - nb))
+    scale = np.linspace(3.0, 1.5, k)
+    A = rng.standard_normal((k, n)) * scale[:, None]
+    Y = rng.standard_normal(n) * 2.0 + theta[types] + Wb @ A + noise * rng.standard_normal((m, n))
+    return {"Y": Y.astype(dtype), "ctl": ctl, "types": types.astype(np.int32), "batch": batch.astype(np.int32)}
+
+
+def rel_frobenius(a, b) -> float:
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def principal_angles(A_rows, B_rows) -> np.ndarray:
+    """Principal angles (radians) between the row spaces of two k x n matrices."""
+    Qa, _ = np.linalg.qr(np.asarray(A_rows).T)
+    Qb, _ = np.linalg.qr(np.asarray(B_rows).T)
+    sv = np.clip(np.linalg.svd(Qa.T @ Qb, compute_uv=False), -1.0, 1.0)
+    # use sin for small angles: || (I - Qb Qb') Qa ||
+    resid = Qa - Qb @ (Qb.T @ Qa)
+    sin = np.linalg.svd(resid, compute_uv=False)
+    return np.where(sv > 0.9, np.arcsin(np.clip(sin[::-1], 0, 1)), np.arccos(sv))
+
+
+def sign_align(rows, ref_rows) -> np.ndarray:
+    """Flip the sign of each row to match the reference rows (singular vectors are sign-ambiguous)."""
+    rows = np.array(rows, copy=True)
+    sg = np.sign(np.einsum("ij,ij->i", rows, np.asarray(ref_rows)))
+    sg[sg == 0] = 1
+    return rows * sg[:, None]

@@ -1,0 +1,157 @@
+"""CPU tests: pin the oracle on the relations the reference's own tests/docs assert
+and on the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ruv_oracle as orc
+
+
+def mean_rel_diff(a, b):
+    """R's all.equal() numeric criterion: mean relative difference."""
+    return np.abs(a - b).sum() / np.abs(a).sum()
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return orc.ruv_simulate(m=400, n=500, nc=400, n_celltypes=3, n_batch=2, lam=0.1,
+                            rng=np.random.default_rng(12345))
+
+
+def test_literal_equals_reduced(sim):
+    a = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, return_info=True)
+    b = orc.fastRUVIII_reduced(sim["Y"], sim["M"], sim["ctl"], 20)
+    assert orc.rel_frobenius(b["newY"], a["newY"]) < 1e-10
+    assert np.max(orc.principal_angles(b["fullalpha"][:20], a["fullalpha"][:20])) < 1e-8
+    fa = orc.sign_align(b["fullalpha"][:20], a["fullalpha"][:20])
+    assert orc.rel_frobenius(fa, a["fullalpha"][:20]) < 1e-8
+
+
+def test_equals_classic_ruvIII(sim):
+    # documented equality, R/fastRUVIII.R:30-38 (all.equal(improved1, old))
+    a = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20)
+    b = orc.ruvIII_classic(sim["Y"], sim["M"], sim["ctl"], 20)
+    assert mean_rel_diff(a, b) < 1.5e-8
+
+
+def test_exact_vs_randomized(sim):
+    # tests/testthat/test-fastRUVIII.R:11-16: expect_equal(improved1, improved2, tol = 0.02)
+    a = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, exact=True)
+    b = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, exact=False, svd_k=100,
+                       rng=np.random.default_rng(1))
+    assert mean_rel_diff(a, b) < 0.02
+
+
+def test_cell_permutation_equivariance(sim):
+    # tests/testthat/test-resampling-columns.R:26 (default tolerance 1.5e-8)
+    perm = np.random.default_rng(3).permutation(sim["Y"].shape[0])
+    a = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20)
+    b = orc.fastRUVIII(sim["Y"][perm], sim["M"][perm], sim["ctl"], 20)
+    assert mean_rel_diff(a[perm], b) < 1.5e-8
+
+
+def test_early_out_and_truncation(sim):
+    Y, ctl = sim["Y"][:6], sim["ctl"]
+    out = orc.fastRUVIII(Y, np.arange(6), ctl, 3, return_info=True)  # ncol(M) >= m
+    assert out["fullalpha"] is None and np.array_equal(out["newY"], Y)
+    out = orc.fastRUVIII(sim["Y"], sim["M"], ctl, 0, return_info=True)  # k == 0
+    assert out["fullalpha"] is None
+    out = orc.fastRUVIII(sim["Y"], sim["M"], ctl, 80, return_info=True)  # k > s silently truncates
+    assert out["fullalpha"].shape[0] == 50
+
+
+def test_input_checks(sim):
+    Y = sim["Y"].copy()
+    Y[3, 4] = np.nan
+    with pytest.raises(ValueError, match="missing"):
+        orc.fastRUVIII(Y, sim["M"], sim["ctl"], 5)
+    Y[3, 4] = np.inf
+    with pytest.raises(ValueError, match="infinities"):
+        orc.fastRUVIII(Y, sim["M"], sim["ctl"], 5)
+
+
+def test_residop_is_group_mean_subtraction(sim):
+    g = orc.group_ids(sim["M"])
+    Y0 = orc.my_residop(sim["Y"], sim["M"])
+    for j in range(int(g.max()) + 1):
+        assert np.allclose(Y0[g == j], sim["Y"][g == j] - sim["Y"][g == j].mean(axis=0), atol=1e-12)
+
+
+def test_standardize2_plain_formulas():
+    rng = np.random.default_rng(0)
+    Y = rng.normal(size=(30, 50)) + 3
+    batch = np.array(["b%d" % (i % 3) for i in range(50)])
+    sc = orc.standardize2(Y, batch)
+    _lv, b = np.unique(batch, return_inverse=True)
+    bm = np.stack([Y[:, b == j].mean(axis=1) for j in range(3)], axis=1)
+    var = ((Y - bm[:, b]) ** 2).sum(axis=1) / (50 - 3)
+    assert np.allclose(sc["stand_var"], var, rtol=1e-12)
+    assert np.allclose(sc["stand_Y"], (Y - Y.mean(axis=1)[:, None]) / np.sqrt(var)[:, None], rtol=1e-12)
+
+
+def test_scruviii_multik_reuses_fullalpha():
+    L = orc.ruv_simulate(m=200, n=300, nc=100, rng=np.random.default_rng(1234))
+    Y = np.log2(L["Y"] + 1).T
+    Y = Y[Y.var(axis=1) > 0]
+    ctl = L["ctl"][: Y.shape[0]]
+    res = orc.scRUVIII(Y, L["M"], ctl, [5, 10], L["batch"])
+    single = orc.scRUVIII(Y, L["M"], ctl, 10, L["batch"])
+    assert orc.rel_frobenius(res[10]["newY"], single[10]["newY"]) < 1e-12
+
+
+def test_create_chunk():
+    assert orc.create_chunk(9, 4) == [(1, 4), (5, 9)]  # short tail (< chunk/2) merged
+    assert orc.create_chunk(10, 4) == [(1, 4), (5, 8), (9, 10)]  # tail == chunk/2 is kept
+    assert orc.create_chunk(11, 4) == [(1, 4), (5, 8), (9, 11)]
+    assert orc.create_chunk(3, 4) == [(1, 3)]
+    assert orc.create_chunk(8, 4) == [(1, 4), (5, 8)]
+
+
+def test_pseudoruviii_chunked_equals_whole_and_getadjusted():
+    P = orc.planted_factors(900, 120, 60, 5, n_types=3, n_batch=2, seed=11)
+    which = (np.random.default_rng(5).permutation(900) % 4) + 1
+    bulks, keys = [], []
+    for b in range(2):
+        sel = P["batch"] == b
+        bulk, nm = orc.create_pseudobulk(P["Y"][sel].T, P["types"][sel], which[sel], k_fold=4)
+        bulks.append(bulk)
+        keys += [int(x.split("_")[0]) for x in nm]
+    Yp = np.concatenate(bulks)
+    whole = orc.pseudoRUVIII(P["Y"], Yp, np.array(keys), P["ctl"], 5, by_chunk=False)
+    chunk = orc.pseudoRUVIII(P["Y"], Yp, np.array(keys), P["ctl"], 5, chunk_size=200)
+    assert orc.rel_frobenius(chunk["newY"], whole["newY"]) < 1e-13
+    adj = orc.getAdjustedMat(P["Y"].T, whole["fullalpha"], ctl=P["ctl"], ruvK=5)
+    assert orc.rel_frobenius(adj.T, whole["newY"]) < 1e-13
+    sub = np.arange(10, 40)
+    adj = orc.getAdjustedMat(P["Y"].T, whole["fullalpha"], ctl=P["ctl"], ruvK=5, return_subset_genes=sub)
+    assert orc.rel_frobenius(adj.T, whole["newY"][:, sub]) < 1e-13
+
+
+def test_pseudobulk_means():
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(7, 40))
+    types = np.array(["a", "b"])[rng.integers(0, 2, 40)]
+    which = (np.arange(40) % 3) + 1
+    bulk, names = orc.create_pseudobulk(X, types, which)
+    assert names[0] == "a_1" and len(names) == 6
+    sel = (which == 2) & (types == "b")
+    assert np.allclose(bulk[names.index("b_2")], X[:, sel].mean(axis=1))
+
+
+def test_golden_example(golden_dir):
+    d = np.load(os.path.join(golden_dir, "example_sce.npz"))
+    g = np.load(os.path.join(golden_dir, "golden_example.npz"))
+    assert d["logcounts"].shape == (1047, 200) and int(d["ctl"].sum()) == 752
+    res = orc.scRUVIII(d["logcounts"], d["cellTypes"], d["ctl"], 20, d["batch"])
+    assert orc.rel_frobenius(res[20]["newY"][:16], g["newY_rows"]) < 1e-10
+    assert abs(np.linalg.norm(res[20]["newY"]) / g["newY_fro"] - 1) < 1e-12
+    fa = orc.sign_align(res[20]["fullalpha"][:20], g["fullalpha"][:20])
+    assert orc.rel_frobenius(fa, g["fullalpha"][:20]) < 1e-8
+
+
+def test_golden_sim(golden_dir):
+    g = np.load(os.path.join(golden_dir, "golden_sim.npz"))
+    out = orc.fastRUVIII(g["sim_Y"].astype(np.float64), g["sim_M"].astype(np.float64), g["sim_ctl"], 20)
+    assert orc.rel_frobenius(out[:16], g["sim_newY_rows"]) < 1e-10
+    assert abs(np.linalg.norm(out) / g["sim_newY_fro"] - 1) < 1e-12
