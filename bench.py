@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- RUV-III fit-and-adjust throughput (cells/s) on B200, the metric of BASELINE.json.
+
+One "step" = one full fastRUVIII pass (replicate sums -> Gram -> top-k eigenpairs -> coefficients -> fused
+adjust) over one synthetic cells x genes matrix.  Workload at every N: `fastRUVIII 1M cells x 2000 genes per GPU,
+500 control genes, k = 20, 20 replicate groups` (BASELINE.json metric config; weak scaling: each rank owns
+1M cells, the group sums and the 2000 x 2000 Gram are all-reduced over NCCL).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells M] ...
+    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1)
+
+Prints ONE JSON line (rank 0).  `value` = device-resident cells/s (inputs in HBM), `e2e` = the same call with
+pinned HOST buffers (H2D of Y and D2H of newY inside the timed region), `roofline` = the dominant kernel
+(gram_syrk_kernel, FP64 tensor pipe) timed with CUDA events inside the timed steps, `cpu_baseline` = the NumPy
+oracle (port of the reference's R path) on a bounded sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--cells", type=int, default=1_000_000, help="cells per GPU")
+    p.add_argument("--genes", type=int, default=2000)
+    p.add_argument("--ctl", type=int, default=500)
+    p.add_argument("--k", type=int, default=20)
+    p.add_argument("--types", type=int, default=20)
+    p.add_argument("--batches", type=int, default=4)
+    p.add_argument("--cpu-cells", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return (f"fastRUVIII synthetic {a.cells} cells/GPU x {a.genes} genes, {a.ctl} ctl genes, k={a.k}, "
+            f"{a.types} replicate groups, exact mode")
+
+
+# ---- clocks sampler (B200_PROFILING.md recipe) ------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+# ---- synthetic data: generator G1 (planted unwanted factors), generated on the device ----------------------
+def make_data(a, ctx, rank, torch):
+    import scmerge_b200 as sm
+    m, n, c, k, T, Bt = a.cells, a.genes, a.ctl, a.k, a.types, a.batches
+    dev = torch.device("cuda", ctx.device)
+    gs = torch.Generator(device=dev)
+    gs.manual_seed(20241)  # shared across ranks: gene-level parameters
+    theta = torch.randn(T, n, generator=gs, device=dev, dtype=torch.float64)
+    theta[:, :c] = 0
+    scale = torch.linspace(3.0, 1.5, k, device=dev, dtype=torch.float64)
+    A = torch.randn(k, n, generator=gs, device=dev, dtype=torch.float64) * scale[:, None]
+    offs = torch.randn(n, generator=gs, device=dev, dtype=torch.float64) * 2.0
+    gc = torch.Generator(device=dev)
+    gc.manual_seed(777 + rank)  # per-rank: cell-level draws
+    types = torch.randint(0, T, (m,), generator=gc, device=dev)
+    batch = torch.randint(0, Bt, (m,), generator=gc, device=dev)
+    dY = sm.DeviceMatrix(ctx, m, n)
+    Yt = torch.as_tensor(dY.buf, device=dev).view(m, dY.ld)
+    nb = min(Bt - 1, k)  # one-hot columns for all batches but the last (full column rank after centring)
+    for r0 in range(0, m, 100_000):
+        r1 = min(m, r0 + 100_000)
+        Wb = torch.zeros(r1 - r0, k, device=dev, dtype=torch.float64)
+        b = batch[r0:r1]
+        hit = torch.nonzero(b < nb).squeeze(1)
+        Wb[hit, b[hit]] = 1.0
+        if k > nb:
+            Wb[:, nb:] = torch.randn(r1 - r0, k - nb, generator=gc, device=dev, dtype=torch.float64)
+        Yt[r0:r1, :n] = offs + theta[types[r0:r1]] + Wb @ A + 0.5 * torch.randn(r1 - r0, n, generator=gc, device=dev,
+                                                                               dtype=torch.float64)
+    torch.cuda.synchronize()
+    ctl = np.zeros(n, dtype=bool)
+    ctl[:c] = True
+    return dY, types.to(torch.int32).cpu().numpy(), ctl
+
+
+def fp64_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3 best of 5 (MEASURED_PEAKS.json has no fp64 entry; same method as its bf16 one)."""
+    N = 8192
+    x = torch.randn(N, N, dtype=torch.float64, device=dev)
+    y = torch.randn(N, N, dtype=torch.float64, device=dev)
+    z = torch.empty_like(x)
+    torch.matmul(x, y, out=z)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(x, y, out=z); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del x, y, z
+    torch.cuda.empty_cache()
+    return 2 * N ** 3 / (best * 1e-3) * 1e-12
+
+
+# ---- CPU arms ---------------------------------------------------------------------------------------------
+def cpu_sample(a):
+    from oracle import ruv_oracle as orc
+    P = orc.planted_factors(a.cpu_cells, a.genes, a.ctl, a.k, n_types=a.types, n_batch=a.batches, seed=20241)
+    return orc, P
+
+
+def cpu_time_once(a, orc, P):
+    t0 = time.perf_counter()
+    orc.fastRUVIII(P["Y"], P["types"], P["ctl"], a.k)
+    return time.perf_counter() - t0
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, P = cpu_sample(a)
+    for _ in range(min(a.warmup, 1)):
+        cpu_time_once(a, orc, P)
+    times = [cpu_time_once(a, orc, P) for _ in range(max(1, a.steps))]
+    t = float(np.mean(times))
+    v = a.cpu_cells / t
+    cores = os.cpu_count()
+    sample = f"{a.cpu_cells} cells x {a.genes} genes per step (same generator/config; exact path is linear in cells)"
+    out = {"impl": "reference", "metric": "RUV-III cells/sec", "value": v, "unit": "cells/s", "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a)},
+           "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
+                            "what": "NumPy/LAPACK literal restatement of R/fastRUVIII.R:41-129 (R is not installable here)"},
+           "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import scmerge_b200 as sm
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = sm.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        from scmerge_b200.dist import torch_allreduce_hook
+        ctx.set_allreduce(torch_allreduce_hook(local), world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dY, keys, ctl = make_data(a, ctx, rank, torch)
+    dOut = sm.DeviceMatrix(ctx, a.cells, a.genes)
+    peak64 = fp64_peak(torch, dev) if rank == 0 else 0.0
+
+    def step():
+        return sm.fastRUVIII(dY, keys, ctl, k=a.k, out=dOut)
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    time.sleep(0.3)
+    l0 = ctx.launch_count()
+    stage_acc = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+        for kname, v in ctx.timers().items():
+            stage_acc[kname] = stage_acc.get(kname, 0.0) + v
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clk = clocks.summary(tw0, tw1) if clocks else None
+    stages = {k2: v / a.steps for k2, v in stage_acc.items()}
+
+    # ---- end to end: pinned host Y in, pinned host newY out, through the same public call
+    e2e = None
+    if not a.no_e2e:
+        Yh = sm.pinned_empty((a.cells, a.genes))
+        Oh = sm.pinned_empty((a.cells, a.genes))
+        dY.to_host(Yh)
+        dOut.free()
+        n_e2e = max(1, min(a.steps, 3))
+        sm.fastRUVIII(Yh, keys, ctl, k=a.k, out=Oh, ctx=ctx)  # warm-up
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(n_e2e):
+            sm.fastRUVIII(Yh, keys, ctl, k=a.k, out=Oh, ctx=ctx)
+        f1.record()
+        barrier()
+        t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        nbytes = a.cells * a.genes * 8
+        e2e = {"value": a.cells * world * n_e2e / (float(t2.item()) * 1e-3), "unit": "cells/s", "steps": n_e2e,
+               "h2d_bytes_per_step": nbytes + 4 * a.cells, "d2h_bytes_per_step": nbytes + 8 * 50 * a.genes,
+               "api": "scmerge_b200.fastRUVIII(numpy pinned Y, keys, ctl, k, out=numpy pinned)"}
+
+    if rank == 0:
+        m, n = a.cells, a.genes
+        syrk_ms = stages.get("gram_syrk_kernel", 0.0)
+        flops = m * n * (n + 1.0)
+        ach = flops / (syrk_ms * 1e-3) * 1e-12 if syrk_ms > 0 else 0.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6.65 TB/s"
+        sec = {}
+        if stages.get("seg_colsum", 0) > 0:
+            gb = 8.0 * m * n / (stages["seg_colsum"] * 1e-3) * 1e-9
+            sec["seg_colsum"] = {"bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "ms": stages["seg_colsum"]}
+        if stages.get("adjust", 0) > 0:
+            gb = 16.0 * m * n / (stages["adjust"] * 1e-3) * 1e-9
+            sec["adjust_rank_k"] = {"bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "ms": stages["adjust"]}
+        out = {"metric": "RUV-III cells/sec", "value": a.cells * world * a.steps / (ms_max * 1e-3), "unit": "cells/s",
+               "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (planted-factor generator G1, on device)",
+               "config": {"workload": workload_name(a), "global_cells": a.cells * world, "l2": "inputs (16 GB/GPU) larger than L2",
+                          "parallelism": f"cells sharded over {world} GPU(s); all-reduce of group sums + {n}x{n} Gram"},
+               "clocks": clk, "gpu_launches": launches, "e2e": e2e,
+               "roofline": {"kernel": "gram_syrk_kernel (FP64 DMMA SYRK)", "bound": "tensor", "achieved": ach, "peak": peak64,
+                            "unit": "TFLOP/s", "frac": ach / peak64 if peak64 else None, "traffic": None,
+                            "algorithmic": "m*n*(n+1) flop per launch", "ms_per_launch": syrk_ms,
+                            "peak_source": "cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry)"},
+               "hbm_kernels": sec, "hbm_peak_source": hbm_src, "stages_ms": stages}
+        if not a.no_cpu and world == 1:
+            orc, P = cpu_sample(a)
+            tcpu = cpu_time_once(a, orc, P)
+            out["cpu_baseline"] = {"value": a.cpu_cells / tcpu, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{a.cpu_cells} cells x {a.genes} genes, one pass of the NumPy oracle (dense residop + thin dgesdd + adjust)",
+                                   "seconds": tcpu}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

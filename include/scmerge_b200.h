@@ -1,0 +1,166 @@
+/*
+ * scmerge_b200 -- C ABI of the B200-native RUV-III fit-and-adjust path.
+ *
+ * The reference (SydneyBioX/scMerge v1.19.0) is pure R and has NO FFI: the boundary it exposes is a
+ * set of R closures.  This header is the C-ABI a `.Call` shim (r-package/src/rshim.c)
+ * binds to replace the arithmetic inside those closures.  Each entry point cites the reference lines
+ * whose work it takes over (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; `scm_last_error()` returns a thread-local message.
+ *   - no exceptions, no C++/torch types cross the ABI: plain pointers and sizes only.
+ *   - "d_" arguments are DEVICE pointers (owned by the caller, e.g. from scm_dev_alloc); "h_" are HOST pointers.
+ *   - the canonical device layout of an expression matrix is ROW-MAJOR cells x genes (`Y[cell*ld + gene]`),
+ *     which is byte-identical to R's column-major genes x cells (what scMerge()/scMerge2() hold,
+ *     R/scMerge.R:91, R/scMerge2.R:298).  R's cells x genes column-major (a direct fastRUVIII(Y) call)
+ *     is converted on the device by scm_transpose().
+ *   - all arithmetic is IEEE float64; replicate / batch / pseudobulk keys are int32, 0-based, -1 = "skip row".
+ *   - all work is enqueued on the context's stream; functions with host outputs synchronise that stream.
+ *   - there is no CPU fallback: every entry point fails with SCM_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef SCMERGE_B200_H
+#define SCMERGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCM_OK 0
+#define SCM_ERR_INVALID (-1)     /* bad argument */
+#define SCM_ERR_CUDA (-2)        /* CUDA runtime / launch failure */
+#define SCM_ERR_NONFINITE (-3)   /* NA / Inf in the input (R/fastRUVIII.R:52-60 stop()) */
+#define SCM_ERR_SINGULAR (-4)    /* ac %*% t(ac) not invertible (R `solve()` error, R/fastRUVIII.R:99) */
+#define SCM_ERR_UNSUPPORTED (-5) /* shape outside what the device path implements */
+#define SCM_ERR_NOCONV (-6)      /* eigensolver did not reach the requested tolerance */
+#define SCM_ERR_COMM (-7)        /* the host-supplied all-reduce hook failed */
+
+#define SCM_MODE_EXACT 0      /* BSPARAM = ExactParam(): subspace iteration converged to `tol` */
+#define SCM_MODE_RANDOMIZED 1 /* BSPARAM = RandomParam(): rsvd-style, oversampling p, q power iterations */
+
+#define SCM_MAX_K 64     /* largest ruvK the fused adjust kernel is instantiated for */
+#define SCM_MAX_BLOCK 112 /* largest subspace block (s + oversampling) of the single-CTA Rayleigh-Ritz solver */
+
+typedef struct scm_ctx scm_ctx;
+typedef struct scm_coef scm_coef;
+
+/* Host-supplied in-place sum all-reduce over the ranks that share the cells (one process per GPU).
+ * `dtype`: 0 = float64, 1 = int64.  Must be enqueued on (or ordered after) `stream`.  Return 0 on success. */
+typedef int (*scm_allreduce_fn)(void* d_buf, int64_t count, int dtype, void* stream, void* user);
+
+const char* scm_last_error(void);
+int scm_version(void);
+
+/* ---- context, memory, layout ------------------------------------------------------------------------ */
+int scm_ctx_create(int device, void* cuda_stream /* NULL = own stream */, scm_ctx** out);
+int scm_ctx_destroy(scm_ctx* ctx);
+int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size);
+int scm_ctx_sync(scm_ctx* ctx);
+int scm_ctx_launch_count(scm_ctx* ctx, int64_t* n_launches); /* kernels launched by this library so far */
+
+int scm_dev_alloc(scm_ctx* ctx, int64_t bytes, void** d_ptr);
+int scm_dev_free(scm_ctx* ctx, void* d_ptr);
+int scm_host_alloc_pinned(int64_t bytes, void** h_ptr);
+int scm_host_free_pinned(void* h_ptr);
+int scm_h2d(scm_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes);
+int scm_d2h(scm_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes);
+/* Strided host<->device matrix copy (cudaMemcpy2DAsync): `rows` rows of `row_bytes`, pitches in bytes.
+ * kind: 0 = host->device, 1 = device->host (synchronises), 2 = device->device. */
+int scm_copy2d(scm_ctx* ctx, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+               int64_t rows, int kind);
+/* out[c*ldo + r] = in[r*ldi + c]; converts R cells x genes column-major into the canonical layout
+ * (the free `t()` of R/scRUVIII.R:48, R/scMerge2.R:298-299,313). */
+int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, int64_t ldi, double* d_out, int64_t ldo);
+
+/* ---- K1: segmented column sums ---------------------------------------------------------------------
+ * sums[g, j] = sum over rows i with key[i] == g of f(Y[i, j]),  counts[g] = #rows,
+ *   f(y) = y                       (d_center == NULL)
+ *   f(y) = (y - center[g, j])^2    (d_center != NULL)
+ * Replaces the dense-indicator products of my_residop (R/fastRUVIII.R:121-129), the batch means and
+ * pooled variance of standardize2 (R/scRUVIII.R:158-175), aggregate.Matrix / create_pseudoBulk
+ * (R/scMerge2_utilis.R:325-346,461-486) and colMeans (R/scMerge2_utilis.R:97) with G = 1.
+ * `d_nonfinite` (optional int32[1]) is set to 1 if any visited element is NA/NaN/Inf (R/fastRUVIII.R:52-60).
+ * Deterministic: the result is bit-identical run to run for the same inputs.  LOCAL to this rank. */
+int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld,
+                   const int32_t* d_key, int32_t G, const double* d_center,
+                   double* d_sums, int64_t* d_counts, int32_t* d_nonfinite);
+
+/* Same pass, followed by the division by the group sizes on the device: means[g, :] = sums[g, :] / counts[g]
+ * (rows of empty groups are 0).  This is `res / cellTypes_n_mat` of create_pseudoBulk (R/scMerge2_utilis.R:474-477)
+ * and colMeans (R/scMerge2_utilis.R:97, R/scMerge2.R:393). */
+int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld,
+                    const int32_t* d_key, int32_t G, double* d_means, int64_t* d_counts, int32_t* d_nonfinite);
+
+/* ---- K3: Gram of the shifted matrix -----------------------------------------------------------------
+ * gram[n x n] = sum_i (y_i - shift)(y_i - shift)'   (shift may be NULL), full symmetric output.
+ * FP64 tensor-core (DMMA) SYRK over lower-triangular 128x128 tiles, split over cells, deterministic.
+ * Together with scm_gram_residual() this replaces Y0 <- my_residop(Y, M) + the Gram that
+ * BiocSingular::runSVD's dgesdd implicitly works on (R/fastRUVIII.R:89-91).  LOCAL to this rank. */
+int scm_gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift, double* d_gram);
+
+/* gram <- diag(scale) * ( gram - sum_g cnt_g (mu_g - shift)(mu_g - shift)' ) * diag(scale), mu_g = sums_g / cnt_g.
+ * Turns the shifted Gram of Y into the Gram of the replicate residual Y0 (optionally of the standardised
+ * matrix, scale = 1/sd, R/scRUVIII.R:171).  d_shift / d_scale may be NULL. */
+int scm_gram_residual(scm_ctx* ctx, double* d_gram, int64_t n, const double* d_sums, const int64_t* d_counts,
+                      int32_t G, const double* d_shift, const double* d_scale);
+
+/* ---- K4: top-s eigenpairs of a symmetric PSD matrix -------------------------------------------------
+ * Block subspace iteration (DMMA GEMMs, CholeskyQR2, single-CTA Jacobi Rayleigh-Ritz).
+ *   mode EXACT      : iterate until the Davis-Kahan estimate of the angle between the computed and the true
+ *                     top-`kconv` invariant subspace, ||R_kconv||_F / (theta_kconv - theta_kconv+1), is <= tol
+ *                     (default 1e-10), at most maxit iterations; SCM_ERR_NOCONV (results still written) otherwise
+ *   mode RANDOMIZED : rsvd semantics in gene space: oversampling p = 10, q = 2 power iterations, no test
+ * d_vecs: s x n row-major (row r = eigenvector r, unit norm, largest |entry| positive), d_vals: s (descending).
+ * Replaces BiocSingular::runSVD (R/fastRUVIII.R:91, R/scMerge2_utilis.R:84): with u the left singular
+ * vectors of Y0, t(u) %*% Y == diag(sqrt(vals)) %*% vecs  (R/fastRUVIII.R:93). */
+int scm_eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, int32_t kconv, int mode,
+                 double tol, int32_t maxit, uint64_t seed, double* d_vals, double* d_vecs,
+                 int32_t* iters_out, double* resid_out);
+
+/* fullalpha[r, :] = sqrt(max(vals[r], 0)) * vecs[r, :] * colscale   (s x n; R/fastRUVIII.R:93) */
+int scm_fullalpha(scm_ctx* ctx, const double* d_vals, const double* d_vecs, int32_t s, int64_t n, double* d_fullalpha);
+
+/* ---- K5: adjustment coefficients --------------------------------------------------------------------
+ * From alpha = first k rows of d_alpha (k x n, row-major, any row scaling/rotation of the factor basis:
+ * fullalpha or unit eigenvectors), the control mask and the optional column vectors builds
+ *   B = diag(pre) * 1[ctl] * ac' (ac ac')^-1   (n x k),   A = alpha * diag(post)   (k x n)
+ * so that  newY = Y - ((Y - center) B) A.  fastRUVIII: center/pre/post NULL (R/fastRUVIII.R:97-101);
+ * pseudoRUVIII/getAdjustedMat: center = colMeans (R/scMerge2_utilis.R:97-137, R/scMerge2.R:392-406);
+ * scRUVIII: center = stand_mean, pre = 1/sd, post = sd (standardise + de-standardise fused, R/scRUVIII.R:47-55,117-119).
+ * Fails with SCM_ERR_SINGULAR when ac ac' is not positive definite. */
+int scm_coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, const uint8_t* d_ctl,
+                    const double* d_center, const double* d_pre, const double* d_post, scm_coef** out);
+int scm_coef_destroy(scm_ctx* ctx, scm_coef* coef);
+
+/* ---- K6: fused rank-k adjustment --------------------------------------------------------------------
+ * out[i, :] = Y[i, :] - ((Y[i, :] - center) B) A      (in place allowed: d_out == d_Y)
+ * d_subset (int32[nsub], optional): only these gene columns are produced, out is m x nsub
+ * (return_subset_genes, R/scMerge2_utilis.R:117-121, R/scMerge2.R:402-406).
+ * d_W (optional, m x k row-major): emits W = (Y - center) B (R/fastRUVIII.R:99).  Rank-local. */
+int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef,
+               const int32_t* d_subset, int32_t nsub, double* d_out, int64_t ldo, double* d_W);
+
+/* ---- drivers (what the R closures call) -------------------------------------------------------------
+ * scm_ruv3_fit: the fit half of fastRUVIII (R/fastRUVIII.R:46-93) on a device-resident, cell-sharded Y.
+ *   group : replicate id per local cell (from ruv::replicate.matrix(M), one-hot rows), G groups in total
+ *   batch : NULL for fastRUVIII / pseudoRUVIII; batch id per cell (Bt batches) for scRUVIII, which adds
+ *           standardize2 (R/scRUVIII.R:158-175): stand_mean / stand_sd are returned in d_mean / d_sd (n each)
+ *   s     : rows of fullalpha to return (host applies the svd_k rule R/fastRUVIII.R:66-70), kconv = min(k, s)
+ * Cross-rank state (group sums, batch sums, the n x n Gram) is summed through the all-reduce hook.
+ * Outputs: d_fullalpha (s x n), d_sigma (s singular values of Y0). */
+int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld,
+                 const int32_t* d_group, int32_t G, const int32_t* d_batch, int32_t Bt,
+                 int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                 double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd,
+                 int32_t* iters_out, double* resid_out);
+
+/* Stage timers (ms, CUDA events on the context stream) of the last scm_ruv3_fit / scm_adjust:
+ * 0 seg_colsum, 1 gram (SYRK + split reduce), 2 allreduce, 3 eig, 4 coef, 5 adjust, 6 standardise,
+ * 7 the gram_syrk kernel alone. */
+int scm_timers(scm_ctx* ctx, double* ms, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -366,8 +366,9 @@ def planted_factors(m, n, c, k, n_types=20, n_batch=4, seed=20240, noise=0.5, dt
     theta = rng.standard_normal((n_types, n))
     theta[:, ctl] = 0
     Wb = np.zeros((m, k))
-    nb = min(n_batch, k)
-    Wb[np.arange(m), batch % nb] = 1.0
+    nb = min(n_batch - 1, k)  # one-hot columns for all batches but the last: full column rank after centring
+    hit = batch < nb
+    Wb[np.nonzero(hit)[0], batch[hit]] = 1.0
     if k > nb:
         Wb[:, nb:] = rng.standard_normal((m, k - nb))
     scale = np.linspace(3.0, 1.5, k)

@@ -1,0 +1,12 @@
+"""scmerge_b200: B200-native RUV-III fit-and-adjust path of scMerge behind the reference's interface.
+
+The arithmetic lives in `libscmerge_b200.so` (hand-written sm_100a CUDA, C ABI in include/scmerge_b200.h);
+this package is the host-side mirror of the R closures.  There is no CPU fallback.
+"""
+from ._lib import LIB_PATH, NonFiniteError, NotConvergedWarning, ScmError, SingularError, lib  # noqa: F401
+from .device import Context, DeviceArray, DeviceMatrix, default_context, pinned_empty  # noqa: F401
+from .ruv import (ExactParam, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
+                  create_pseudoBulk, fastRUVIII, getAdjustedMat, pseudoRUVIII, replicate_keys, replicate_matrix,
+                  scRUVIII, tological)
+
+__version__ = "0.1.0"

@@ -1,0 +1,146 @@
+// Shared infrastructure of libscmerge_b200: error handling, context, scratch memory, PTX helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/scmerge_b200.h"
+
+namespace scm {
+
+static thread_local char g_err[512] = "";
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SCM_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return scm::fail(SCM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define SCM_TRY(expr)           \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+#define SCM_LAUNCH_CHECK(ctx)   \
+    do {                        \
+        (ctx)->launches++;      \
+        SCM_CUDA(cudaGetLastError()); \
+    } while (0)
+
+enum Stage { ST_SEG = 0, ST_GRAM = 1, ST_COMM = 2, ST_EIG = 3, ST_COEF = 4, ST_ADJUST = 5, ST_STD = 6, ST_SYRK = 7, ST_COUNT = 8 };
+
+}  // namespace scm
+
+struct scm_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    scm_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    int world = 1;
+    cudaEvent_t ev0[scm::ST_COUNT], ev1[scm::ST_COUNT];
+    bool ev_used[scm::ST_COUNT];
+    double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
+};
+
+namespace scm {
+
+// Stream-ordered scratch allocation that frees itself on scope exit.
+struct Scratch {
+    scm_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit Scratch(scm_ctx* c) : ctx(c) {}
+    template <typename T>
+    int alloc(T** out, int64_t count) {
+        void* p = nullptr;
+        int64_t bytes = count * (int64_t)sizeof(T);
+        if (bytes <= 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, (size_t)bytes, ctx->stream);
+        if (e != cudaSuccess) return fail(SCM_ERR_CUDA, "scratch alloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        ptrs.push_back(p);
+        *out = (T*)p;
+        return 0;
+    }
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+    }
+};
+
+struct StageTimer {
+    scm_ctx* ctx;
+    int st;
+    StageTimer(scm_ctx* c, int s) : ctx(c), st(s) {
+        cudaEventRecord(ctx->ev0[st], ctx->stream);
+    }
+    ~StageTimer() {
+        cudaEventRecord(ctx->ev1[st], ctx->stream);
+        ctx->ev_used[st] = true;
+    }
+};
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------------
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4).
+// lane = 4*gid + tig: a = A[gid][tig], b = B[tig][gid], c0/c1 = C[gid][2*tig], C[gid][2*tig+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// streaming 16-byte global load / store (read-once / write-once data: keep it out of L1)
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream2(double* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};\n" ::"l"(p), "d"(v.x), "d"(v.y));
+}
+
+__device__ __forceinline__ bool nonfinite(double v) {
+    return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace scm

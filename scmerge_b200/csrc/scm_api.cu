@@ -1,0 +1,355 @@
+// C ABI of libscmerge_b200 (see include/scmerge_b200.h).  Single translation unit: all kernels are header-only.
+#include "adjust.cuh"
+#include "common.cuh"
+#include "eig_topk.cuh"
+#include "gemm_f64.cuh"
+#include "gram_syrk.cuh"
+#include "seg_colsum.cuh"
+
+namespace scm {
+
+__global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
+                                 double* __restrict__ out, int64_t ldo) {
+    __shared__ double tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * ldi + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * ldo + r] = tile[threadIdx.x][j];
+    }
+}
+
+// meta[0] = nonfinite flag, meta[1] = local rows (summed across ranks by the hook)
+__global__ void meta_kernel(const int32_t* __restrict__ flag, int64_t m_local, int64_t* __restrict__ meta) {
+    meta[0] = flag[0] ? 1 : 0;
+    meta[1] = m_local;
+}
+
+// mean[j] = sum_g sums[g, j] / total
+__global__ void colmean_kernel(const double* __restrict__ sums, int32_t G, int64_t n, const int64_t* __restrict__ meta,
+                               double* __restrict__ mean) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int g = 0; g < G; g++) s += sums[(int64_t)g * n + j];
+    mean[j] = s / (double)meta[1];
+}
+
+// sums[g, :] /= counts[g]  (empty groups -> 0)
+__global__ void groupmean_kernel(double* __restrict__ sums, const int64_t* __restrict__ counts, int32_t G, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int g = 0; g < G; g++) {
+        const int64_t c = counts[g];
+        sums[(int64_t)g * n + j] = c > 0 ? sums[(int64_t)g * n + j] / (double)c : 0.0;
+    }
+}
+
+// pooled within-batch sd (R/scRUVIII.R:170): sd[j] = sqrt( sum_b ssq[b, j] / (m - #non-empty batches) )
+__global__ void pooled_sd_kernel(const double* __restrict__ ssq, const int64_t* __restrict__ counts, int32_t Bt, int64_t n,
+                                 const int64_t* __restrict__ meta, double* __restrict__ sd, double* __restrict__ inv_sd) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int nb = 0;
+    double s = 0.0;
+    for (int b = 0; b < Bt; b++) { nb += counts[b] > 0; s += ssq[(int64_t)b * n + j]; }
+    const double v = s / (double)(meta[1] - nb);
+    sd[j] = sqrt(v);
+    inv_sd[j] = 1.0 / sqrt(v);  // var == 0 -> Inf, like the reference (no zero-variance guard, R/scRUVIII.R:171)
+}
+
+__global__ void fullalpha_kernel(const double* __restrict__ vals, const double* __restrict__ vecs, int32_t s, int64_t n,
+                                 double* __restrict__ fa, double* __restrict__ sigma) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const double sg = sqrt(fmax(vals[r], 0.0));
+    if (j < n && fa) fa[(int64_t)r * n + j] = sg * vecs[(int64_t)r * n + j];
+    if (j == 0 && sigma) sigma[r] = sg;
+}
+
+inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
+    if (ctx->world <= 1 || !ctx->allreduce) return 0;
+    StageTimer t(ctx, ST_COMM);
+    const int rc = ctx->allreduce(d_buf, count, dtype, (void*)ctx->stream, ctx->allreduce_user);
+    if (rc != 0) return fail(SCM_ERR_COMM, "all-reduce hook returned %d", rc);
+    return 0;
+}
+
+}  // namespace scm
+
+using namespace scm;
+
+#define SCM_REQUIRE_CTX(ctx)                                             \
+    do {                                                                 \
+        if (!(ctx)) return scm::fail(SCM_ERR_INVALID, "null context");   \
+        SCM_CUDA(cudaSetDevice((ctx)->device));                          \
+    } while (0)
+
+extern "C" {
+
+const char* scm_last_error(void) { return scm::g_err; }
+int scm_version(void) { return 100; }
+
+int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
+    if (!out) return fail(SCM_ERR_INVALID, "scm_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(SCM_ERR_CUDA, "no CUDA device available (%s): libscmerge_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SCM_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    SCM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SCM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SCM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    scm_ctx* c = new scm_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (int i = 0; i < ST_COUNT; i++) {
+        SCM_CUDA(cudaEventCreate(&c->ev0[i]));
+        SCM_CUDA(cudaEventCreate(&c->ev1[i]));
+        c->ev_used[i] = false;
+    }
+    SCM_CUDA(cudaMallocHost((void**)&c->h_pinned, sizeof(double) * 4096));
+    // keep freed scratch in the pool: the fit re-allocates the same sizes every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    *out = c;
+    return 0;
+}
+
+int scm_ctx_destroy(scm_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev0[i]); cudaEventDestroy(ctx->ev1[i]); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return 0;
+}
+
+int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size) {
+    if (!ctx) return fail(SCM_ERR_INVALID, "null context");
+    ctx->allreduce = fn; ctx->allreduce_user = user; ctx->world = world_size;
+    return 0;
+}
+
+int scm_ctx_sync(scm_ctx* ctx) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scm_ctx_launch_count(scm_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return fail(SCM_ERR_INVALID, "null argument");
+    *n = ctx->launches;
+    return 0;
+}
+
+int scm_dev_alloc(scm_ctx* ctx, int64_t bytes, void** d_ptr) {
+    SCM_REQUIRE_CTX(ctx);
+    if (bytes < 0 || !d_ptr) return fail(SCM_ERR_INVALID, "scm_dev_alloc: bad arguments");
+    SCM_CUDA(cudaMalloc(d_ptr, (size_t)(bytes > 0 ? bytes : 16)));
+    return 0;
+}
+int scm_dev_free(scm_ctx* ctx, void* d_ptr) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    SCM_CUDA(cudaFree(d_ptr));
+    return 0;
+}
+int scm_host_alloc_pinned(int64_t bytes, void** h_ptr) {
+    if (bytes < 0 || !h_ptr) return fail(SCM_ERR_INVALID, "scm_host_alloc_pinned: bad arguments");
+    SCM_CUDA(cudaMallocHost(h_ptr, (size_t)(bytes > 0 ? bytes : 16)));
+    return 0;
+}
+int scm_host_free_pinned(void* h_ptr) {
+    SCM_CUDA(cudaFreeHost(h_ptr));
+    return 0;
+}
+int scm_h2d(scm_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int scm_d2h(scm_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scm_copy2d(scm_ctx* ctx, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+               int64_t rows, int kind) {
+    SCM_REQUIRE_CTX(ctx);
+    if (rows <= 0 || row_bytes <= 0) return 0;
+    const cudaMemcpyKind kk = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    SCM_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)rows, kk, ctx->stream));
+    if (kind == 1) SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, int64_t ldi, double* d_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    if (rows <= 0 || cols <= 0) return 0;
+    if (ceil_div(rows, 32) > 65535) return fail(SCM_ERR_UNSUPPORTED, "scm_transpose: more than 2M rows; transpose by column blocks");
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(d_in, rows, cols, ldi, d_out, ldo);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,
+                   const double* d_center, double* d_sums, int64_t* d_counts, int32_t* d_nonfinite) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_SEG);
+    return seg_colsum(ctx, d_Y, m, n, ld, d_key, G, d_center, d_sums, d_counts, d_nonfinite);
+}
+
+int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,
+                    double* d_means, int64_t* d_counts, int32_t* d_nonfinite) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!d_counts) return fail(SCM_ERR_INVALID, "scm_seg_colmean: d_counts is required");
+    StageTimer t(ctx, ST_SEG);
+    SCM_TRY(seg_colsum(ctx, d_Y, m, n, ld, d_key, G, nullptr, d_means, d_counts, d_nonfinite));
+    groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, n);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift, double* d_gram) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_GRAM);
+    return gram(ctx, d_Y, m, n, ld, d_shift, d_gram, true);
+}
+
+int scm_gram_residual(scm_ctx* ctx, double* d_gram, int64_t n, const double* d_sums, const int64_t* d_counts, int32_t G,
+                      const double* d_shift, const double* d_scale) {
+    SCM_REQUIRE_CTX(ctx);
+    return gram_residual(ctx, d_gram, n, d_sums, d_counts, G, d_shift, d_scale);
+}
+
+int scm_eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit,
+                 uint64_t seed, double* d_vals, double* d_vecs, int32_t* iters_out, double* resid_out) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_EIG);
+    return eig_topk(ctx, d_gram, n, s, kconv, mode, tol, maxit, seed, d_vals, d_vecs, iters_out, resid_out);
+}
+
+int scm_fullalpha(scm_ctx* ctx, const double* d_vals, const double* d_vecs, int32_t s, int64_t n, double* d_fullalpha) {
+    SCM_REQUIRE_CTX(ctx);
+    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)s);
+    fullalpha_kernel<<<grid, 256, 0, ctx->stream>>>(d_vals, d_vecs, s, n, d_fullalpha, nullptr);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, const uint8_t* d_ctl, const double* d_center,
+                    const double* d_pre, const double* d_post, scm_coef** out) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!out) return fail(SCM_ERR_INVALID, "scm_coef_create: out is NULL");
+    StageTimer t(ctx, ST_COEF);
+    return coef_create(ctx, d_alpha, n, k, d_ctl, d_center, d_pre, d_post, out);
+}
+int scm_coef_destroy(scm_ctx* ctx, scm_coef* coef) {
+    SCM_REQUIRE_CTX(ctx);
+    return coef_destroy(ctx, coef);
+}
+
+int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, const int32_t* d_subset,
+               int32_t nsub, double* d_out, int64_t ldo, double* d_W) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_ADJUST);
+    return adjust(ctx, d_Y, m, n, ld, coef, d_subset, nsub, d_out, ldo, d_W);
+}
+
+int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const int32_t* d_group, int32_t G,
+                 const int32_t* d_batch, int32_t Bt, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                 double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd, int32_t* iters_out, double* resid_out) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!d_Y || !d_group || G <= 0 || n <= 0 || s <= 0 || !d_fullalpha)
+        return fail(SCM_ERR_INVALID, "scm_ruv3_fit: bad arguments");
+    if (d_batch && (Bt <= 0 || !d_mean || !d_sd)) return fail(SCM_ERR_INVALID, "scm_ruv3_fit: batch given without Bt / d_mean / d_sd");
+    cudaStream_t st = ctx->stream;
+    Scratch ws(ctx);
+    double *gsums, *shift, *Gm, *vals, *vecs, *inv_sd = nullptr;
+    int64_t *gcounts, *meta;
+    int32_t* flag;
+    SCM_TRY(ws.alloc(&gsums, (int64_t)G * n)); SCM_TRY(ws.alloc(&gcounts, G)); SCM_TRY(ws.alloc(&meta, 2));
+    SCM_TRY(ws.alloc(&flag, 1)); SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&Gm, n * n));
+    SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n));
+    SCM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    {   // residual operator, part 1: replicate-group sums (my_residop, R/fastRUVIII.R:121-129) + NA/Inf scan (:52-60)
+        StageTimer t(ctx, ST_SEG);
+        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_group, G, nullptr, gsums, gcounts, flag));
+        meta_kernel<<<1, 1, 0, st>>>(flag, m_local, meta);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    SCM_TRY(allreduce(ctx, gsums, (int64_t)G * n, 0));
+    SCM_TRY(allreduce(ctx, gcounts, G, 1));
+    SCM_TRY(allreduce(ctx, meta, 2, 1));
+    colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, G, n, meta, shift);
+    SCM_LAUNCH_CHECK(ctx);
+    if (d_batch) {  // standardize2 (R/scRUVIII.R:158-175): global mean, pooled within-batch variance
+        StageTimer t(ctx, ST_STD);
+        double *bsums, *ssq;
+        int64_t* bcounts;
+        SCM_TRY(ws.alloc(&bsums, (int64_t)Bt * n)); SCM_TRY(ws.alloc(&ssq, (int64_t)Bt * n)); SCM_TRY(ws.alloc(&bcounts, Bt));
+        SCM_TRY(ws.alloc(&inv_sd, n));
+        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_batch, Bt, nullptr, bsums, bcounts, nullptr));
+        SCM_TRY(allreduce(ctx, bsums, (int64_t)Bt * n, 0));
+        SCM_TRY(allreduce(ctx, bcounts, Bt, 1));
+        groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, Bt, n);
+        SCM_LAUNCH_CHECK(ctx);
+        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_batch, Bt, bsums, ssq, nullptr, nullptr));
+        SCM_TRY(allreduce(ctx, ssq, (int64_t)Bt * n, 0));
+        pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bcounts, Bt, n, meta, d_sd, inv_sd);
+        SCM_LAUNCH_CHECK(ctx);
+        SCM_CUDA(cudaMemcpyAsync(d_mean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    }
+    {   // Gram of the shifted cells (local), summed over ranks, then corrected to the Gram of the residual Y0
+        StageTimer t(ctx, ST_GRAM);
+        SCM_TRY(gram(ctx, d_Y, m_local, n, ld, shift, Gm, true));
+    }
+    SCM_TRY(allreduce(ctx, Gm, n * n, 0));
+    SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, G, shift, inv_sd));
+    int64_t hmeta[2];
+    SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+    int rc;
+    {   // runSVD (R/fastRUVIII.R:91) + t(u) %*% Y (:93) == sqrt(lambda) v'
+        StageTimer t(ctx, ST_EIG);
+        rc = eig_topk(ctx, Gm, n, s, kconv, mode, tol, maxit, seed, vals, vecs, iters_out, resid_out);
+        if (rc != 0 && rc != SCM_ERR_NOCONV) return rc;
+        dim3 grid((unsigned)ceil_div(n, 256), (unsigned)s);
+        fullalpha_kernel<<<grid, 256, 0, st>>>(vals, vecs, s, n, d_fullalpha, d_sigma);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    SCM_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int scm_timers(scm_ctx* ctx, double* ms, int n) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        ms[i] = 0.0;
+        if (i < ST_COUNT && ctx->ev_used[i]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->ev0[i], ctx->ev1[i]) == cudaSuccess) ms[i] = t;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+"""Device-side plumbing above the C ABI: context, device buffers, cell x gene matrices, pinned host arrays.
+
+No arithmetic happens here; every numeric result comes out of libscmerge_b200's kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+_DT = {np.dtype(np.float64): 8, np.dtype(np.int32): 4, np.dtype(np.int64): 8, np.dtype(np.uint8): 1}
+
+
+class Context:
+    """Owns a `scm_ctx` (one GPU, one stream).  `stream` may be a raw cudaStream_t (int), e.g.
+    `torch.cuda.current_stream().cuda_stream`, so that torch events and NCCL order with our kernels."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(self._h)))
+        self.device = int(device)
+        self.stream = stream
+        self._cb = None  # keep the ctypes callback alive
+        self._fin = weakref.finalize(self, L.lib().scm_ctx_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        L.check(L.lib().scm_ctx_sync(self._h))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        L.check(L.lib().scm_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def timers(self) -> dict:
+        ms = (C.c_double * 8)()
+        L.check(L.lib().scm_timers(self._h, ms, 8))
+        names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel"]
+        return dict(zip(names, list(ms)))
+
+    def set_allreduce(self, fn, world_size: int):
+        """fn(dev_ptr:int, count:int, dtype:int(0 f64, 1 i64), stream:int) -> None; sums in place across ranks."""
+        def _cb(ptr, count, dtype, stream, _user):
+            try:
+                fn(ptr, count, dtype, stream)
+                return 0
+            except Exception as exc:  # the error text travels through scm_last_error's generic message
+                import traceback
+                traceback.print_exc()
+                del exc
+                return 1
+        self._cb = L.ALLREDUCE_FN(_cb)
+        L.check(L.lib().scm_ctx_set_allreduce(self._h, self._cb, None, int(world_size)))
+
+    # ---- memory -------------------------------------------------------------------------------
+    def empty(self, shape, dtype=np.float64) -> "DeviceArray":
+        return DeviceArray(self, shape, dtype)
+
+    def to_device(self, host: np.ndarray) -> "DeviceArray":
+        host = np.ascontiguousarray(host)
+        d = DeviceArray(self, host.shape, host.dtype)
+        if host.nbytes:
+            L.check(L.lib().scm_h2d(self._h, d.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
+            self.sync()  # `host` may be a temporary
+        return d
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceArray:
+    """A dense C-contiguous device buffer owned by the library (scm_dev_alloc / scm_dev_free)."""
+
+    def __init__(self, ctx: Context, shape, dtype=np.float64):
+        self.ctx = ctx
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in _DT:
+            raise TypeError(f"unsupported dtype {self.dtype}")
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        L.check(L.lib().scm_dev_alloc(ctx.handle, self.nbytes, C.byref(p)))
+        self._p = p
+        self._fin = weakref.finalize(self, _free, ctx, p)
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return self._p
+
+    @property
+    def address(self) -> int:
+        return int(self._p.value or 0)
+
+    def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+        assert out.flags.c_contiguous and out.nbytes == self.nbytes
+        if self.nbytes:
+            L.check(L.lib().scm_d2h(self.ctx.handle, out.ctypes.data_as(C.c_void_p), self._p, self.nbytes))
+        return out
+
+    def free(self):
+        self._fin()
+
+    @property
+    def __cuda_array_interface__(self):  # lets torch / cupy wrap the buffer without a copy
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.address, False), "version": 3,
+                "strides": None}
+
+
+def _free(ctx: Context, p):
+    try:
+        L.lib().scm_dev_free(ctx.handle, p)
+    except Exception:
+        pass
+
+
+class DeviceMatrix:
+    """cells x genes expression matrix in the canonical device layout (row-major, leading dimension `ld` even
+    so that every row is 16-byte aligned for the vector loads)."""
+
+    def __init__(self, ctx: Context, m: int, n: int, ld: int | None = None, buf: DeviceArray | None = None):
+        self.ctx, self.m, self.n = ctx, int(m), int(n)
+        self.ld = int(ld) if ld is not None else (self.n + 1) // 2 * 2
+        self.buf = buf if buf is not None else DeviceArray(ctx, (self.m * self.ld,), np.float64)
+
+    @property
+    def ptr(self):
+        return self.buf.ptr
+
+    @classmethod
+    def from_host(cls, ctx: Context, Y: np.ndarray) -> "DeviceMatrix":
+        """Y: 2-D float64, cells x genes.  C-order is copied as is; Fortran order (what R hands to a direct
+        fastRUVIII(Y) call: cells x genes column-major) is uploaded and transposed on the device."""
+        Y = np.asarray(Y)
+        if Y.ndim != 2:
+            raise ValueError("Y must be a 2-D matrix")
+        if Y.dtype != np.float64:
+            Y = Y.astype(np.float64)
+        m, n = Y.shape
+        out = cls(ctx, m, n)
+        lib = L.lib()
+        if m == 0 or n == 0:
+            return out
+        if Y.flags.c_contiguous:
+            L.check(lib.scm_copy2d(ctx.handle, out.ptr, out.ld * 8, Y.ctypes.data_as(C.c_void_p), n * 8, n * 8, m, 0))
+            ctx.sync()
+        elif Y.flags.f_contiguous:
+            tmp = ctx.to_device(Y.T)  # genes x cells row-major == the column-major bytes
+            L.check(lib.scm_transpose(ctx.handle, tmp.ptr, n, m, m, out.ptr, out.ld))
+            ctx.sync()
+            tmp.free()
+        else:
+            return cls.from_host(ctx, np.ascontiguousarray(Y))
+        return out
+
+    def to_host(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.m, self.n), dtype=np.float64)
+        assert out.shape == (self.m, self.n) and out.flags.c_contiguous and out.dtype == np.float64
+        if self.m and self.n:
+            L.check(L.lib().scm_copy2d(self.ctx.handle, out.ctypes.data_as(C.c_void_p), self.n * 8, self.ptr, self.ld * 8,
+                                       self.n * 8, self.m, 1))
+        return out
+
+    def free(self):
+        self.buf.free()
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (cudaMallocHost): full-speed async H2D / D2H."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = C.c_void_p()
+    L.check(L.lib().scm_host_alloc_pinned(nbytes, C.byref(p)))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    weakref.finalize(buf, L.lib().scm_host_free_pinned, p)
+    return arr

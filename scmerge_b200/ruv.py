@@ -1,0 +1,440 @@
+"""Host-side mirror of scMerge's RUV-III interface (same names, argument meaning and error behaviour as the
+R closures), driving the B200 kernels through the C ABI.  No numerics are done in Python: this module only
+resolves arguments (replicate matrix -> int32 keys, ctl -> mask, the svd_k rule), moves buffers and calls
+libscmerge_b200.
+
+    fastRUVIII      R/fastRUVIII.R:41-111        scRUVIII        R/scRUVIII.R:41-137
+    pseudoRUVIII    R/scMerge2_utilis.R:17-150   getAdjustedMat  R/scMerge2.R:368-410
+    create_pseudoBulk / aggregate_matrix   R/scMerge2_utilis.R:325-346,461-486 (arithmetic only)
+
+Matrices are numpy float64 arrays (host; copied to the GPU inside the call) or `DeviceMatrix` objects
+(already resident; results are returned as `DeviceMatrix` too).  Orientation follows the reference:
+`fastRUVIII`/`pseudoRUVIII` take cells x genes, `scRUVIII`/`getAdjustedMat` take genes x cells.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib as L
+from .device import Context, DeviceArray, DeviceMatrix, default_context
+
+__all__ = ["fastRUVIII", "scRUVIII", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
+           "replicate_matrix", "replicate_keys", "tological", "createChunk", "RUVFit", "ExactParam", "RandomParam",
+           "IrlbaParam"]
+
+
+# ---- BiocSingular parameter objects (only their class matters to the reference, R/fastRUVIII.R:66) --------
+class ExactParam:
+    exact = True
+
+
+class RandomParam:
+    exact = False
+
+
+class IrlbaParam:
+    exact = False
+
+
+def _is_exact(BSPARAM) -> bool:
+    if BSPARAM is None:
+        return True
+    if isinstance(BSPARAM, str):
+        return BSPARAM.lower().startswith("exact")
+    return bool(getattr(BSPARAM, "exact", False))
+
+
+# ---- argument resolution (host logic, no arithmetic) ---------------------------------------------------
+def replicate_matrix(a) -> np.ndarray:
+    """ruv::replicate.matrix (call site R/fastRUVIII.R:48): numeric matrix -> unchanged; label vector ->
+    one-hot with columns in sorted level order; 2-D labels (data.frame) -> rows pasted with '_'."""
+    keys, G = replicate_keys(a)
+    M = np.zeros((keys.shape[0], G))
+    M[np.arange(keys.shape[0]), keys] = 1.0
+    return M
+
+
+def replicate_keys(M):
+    """Replicate structure -> (int32 group id per cell, number of groups).  A numeric matrix must be a one-hot
+    partition (every row exactly one 1): the device path implements the residual operator as a segmented
+    mean, which is what my_residop (R/fastRUVIII.R:121-129) computes for such M; a general M is rejected."""
+    if isinstance(M, DeviceArray):
+        raise TypeError("pass replicate keys as a host array")
+    a = np.asarray(M)
+    if a.ndim == 2 and np.issubdtype(a.dtype, np.number):
+        if a.shape[1] == 0:
+            raise ValueError("replicate matrix has no columns")
+        ok = np.all((a == 0) | (a == 1)) and np.all(a.sum(axis=1) == 1)
+        if not ok:
+            raise ValueError("M is not a one-hot replicate matrix (each row must contain exactly one 1); "
+                             "the device path does not support a general projector")
+        return np.argmax(a, axis=1).astype(np.int32), int(a.shape[1])
+    if a.ndim == 2:
+        a = np.array(["_".join(str(x) for x in row) for row in a])
+    if a.ndim != 1:
+        raise ValueError("M must be a replicate matrix or a label vector")
+    levels, inv = np.unique(a, return_inverse=True)
+    return inv.astype(np.int32), int(levels.shape[0])
+
+
+def tological(ctl, n: int) -> np.ndarray:
+    """R/fastRUVIII.R:113-117 (0-based integer indices or a logical mask)."""
+    ctl = np.asarray(ctl)
+    out = np.zeros(n, dtype=bool)
+    if ctl.dtype == bool:
+        out[: ctl.shape[0]] = ctl[:n]
+    else:
+        out[ctl.astype(np.int64)] = True
+    return out
+
+
+def createChunk(n: int, chunkSize: int = 1000):
+    """R/scMerge2_utilis.R:153-170 (1-based inclusive ranges).  Kept for interface parity: the fused adjust
+    kernel makes chunking invisible, so pseudoRUVIII accepts byChunk/chunkSize but does not need them."""
+    starts = list(range(1, n + 1, chunkSize))
+    ends = [s + chunkSize - 1 for s in starts]
+    ends[-1] = n
+    if len(ends) > 1 and ends[-1] - ends[-2] < chunkSize / 2:
+        starts, ends = starts[:-1], ends[:-1]
+        ends[-1] = n
+    return list(zip(starts, ends))
+
+
+def _svd_k(m, G, n_ctl, exact, cap):
+    """R/fastRUVIII.R:66-70 / R/scMerge2_utilis.R:60-65 (the non-exact branch ignores the user's svd_k)."""
+    return int(min(m - G, n_ctl, cap)) if exact else int(min(m - G, n_ctl))
+
+
+def _device_rows_cap(s: int, k: int, exact: bool):
+    """The device eigensolver's Rayleigh-Ritz block is limited to MAX_BLOCK columns.  In randomized mode the
+    reference's quirk asks for min(m - G, n_ctl) rows of fullalpha (often hundreds, i.e. rsvd at nearly full rank,
+    which is as accurate as the exact SVD).  The device path then returns max(k, 50) rows and, because three
+    products with a truncated block cannot reproduce that accuracy, runs the converged iteration instead.
+    Returns (rows, exact)."""
+    cap = L.MAX_BLOCK - (10 if not exact else 16)
+    cap = cap // 8 * 8 - 8
+    if s > cap:
+        want = min(s, max(int(k), 50), cap)
+        warnings.warn(f"fullalpha truncated to {want} rows (reference rule gives {s}); the device eigensolver "
+                      f"block is limited to {L.MAX_BLOCK} columns", stacklevel=3)
+        return want, True
+    return s, exact
+
+
+def _as_device(ctx: Context, Y):
+    if isinstance(Y, DeviceMatrix):
+        return Y, False
+    return DeviceMatrix.from_host(ctx, Y), True
+
+
+def _dptr(a):
+    return a.ptr if a is not None else None
+
+
+class RUVFit:
+    """Result of the fit half of RUV-III: the small, host-side 'checkpoint' (fullalpha and, for scRUVIII, the
+    standardisation vectors).  `fullalpha` is s x n like the reference's (R/fastRUVIII.R:93)."""
+
+    def __init__(self, fullalpha, sigma=None, stand_mean=None, stand_sd=None, iters=0, resid=0.0):
+        self.fullalpha, self.sigma = fullalpha, sigma
+        self.stand_mean, self.stand_sd = stand_mean, stand_sd
+        self.iters, self.resid = iters, resid
+
+
+# ---- device drivers -----------------------------------------------------------------------------------
+def _fit(ctx: Context, dY: DeviceMatrix, keys: np.ndarray, G: int, s: int, k: int, exact: bool, batch_keys=None, Bt=0,
+         tol=1e-10, maxit=500, seed=1) -> RUVFit:
+    lib = L.lib()
+    n = dY.n
+    d_keys = ctx.to_device(np.ascontiguousarray(keys, dtype=np.int32))
+    d_batch = ctx.to_device(np.ascontiguousarray(batch_keys, dtype=np.int32)) if batch_keys is not None else None
+    d_fa = ctx.empty((s, n))
+    d_sig = ctx.empty((s,))
+    d_mean = ctx.empty((n,)) if d_batch is not None else None
+    d_sd = ctx.empty((n,)) if d_batch is not None else None
+    iters, resid = C.c_int32(0), C.c_double(0.0)
+    rc = lib.scm_ruv3_fit(ctx.handle, dY.ptr, dY.m, n, dY.ld, d_keys.ptr, G, _dptr(d_batch), Bt, s, min(k, s),
+                          L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, d_fa.ptr, d_sig.ptr,
+                          _dptr(d_mean), _dptr(d_sd), C.byref(iters), C.byref(resid))
+    if rc == L.ERR_NOCONV:
+        warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
+    else:
+        L.check(rc)
+    fit = RUVFit(d_fa.to_host(), d_sig.to_host(), d_mean.to_host() if d_mean is not None else None,
+                 d_sd.to_host() if d_sd is not None else None, iters.value, resid.value)
+    for a in (d_keys, d_batch, d_fa, d_sig, d_mean, d_sd):
+        if a is not None:
+            a.free()
+    return fit
+
+
+def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: np.ndarray, center=None, pre=None,
+            post=None, subset=None, out: DeviceMatrix | None = None, want_W=False):
+    """newY = Y - ((Y - center) B) A on the device (scm_coef_create + scm_adjust)."""
+    lib = L.lib()
+    n = dY.n
+    kk = int(min(k, fullalpha.shape[0]))
+    if kk > L.MAX_K:
+        raise L.ScmError(L.ERR_UNSUPPORTED, f"ruvK = {kk} > {L.MAX_K} is not supported by the fused adjust kernel")
+    d_alpha = ctx.to_device(np.ascontiguousarray(fullalpha[:kk], dtype=np.float64))
+    d_ctl = ctx.to_device(np.ascontiguousarray(ctl, dtype=np.uint8))
+    vecs = [ctx.to_device(np.ascontiguousarray(v, dtype=np.float64)) if v is not None else None for v in (center, pre, post)]
+    coef = C.c_void_p()
+    try:
+        L.check(lib.scm_coef_create(ctx.handle, d_alpha.ptr, n, kk, d_ctl.ptr, _dptr(vecs[0]), _dptr(vecs[1]), _dptr(vecs[2]),
+                                    C.byref(coef)))
+        d_sub, nsub = None, 0
+        if subset is not None:
+            sub = np.ascontiguousarray(subset, dtype=np.int32)
+            d_sub, nsub = ctx.to_device(sub), int(sub.shape[0])
+        n_out = nsub if d_sub is not None else n
+        if out is None:
+            out = DeviceMatrix(ctx, dY.m, n_out)
+        d_W = ctx.empty((dY.m, kk)) if want_W else None
+        L.check(lib.scm_adjust(ctx.handle, dY.ptr, dY.m, n, dY.ld, coef, _dptr(d_sub), nsub, out.ptr, out.ld, _dptr(d_W)))
+        ctx.sync()
+        W = d_W.to_host() if d_W is not None else None
+    finally:
+        if coef:
+            lib.scm_coef_destroy(ctx.handle, coef)
+        for a in [d_alpha, d_ctl] + vecs:
+            if a is not None:
+                a.free()
+    return out, W
+
+
+def _finish(out: DeviceMatrix, made_copy_in: bool, host_out=None):
+    """Return numpy when the caller gave numpy, else the DeviceMatrix."""
+    if not made_copy_in:
+        return out
+    res = out.to_host(host_out)
+    out.free()
+    return res
+
+
+# ---- the reference's closures ---------------------------------------------------------------------------
+def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, average=False, BPPARAM=None,
+               BSPARAM=None, fullalpha=None, return_info=False, inputcheck=True, ctx: Context | None = None, out=None):
+    """R/fastRUVIII.R:41-111.  Y: m x n (cells x genes); M: replicate matrix or labels; ctl: mask / indices.
+    Returns newY (m x n), or {'newY','M','fullalpha'} with return_info.  `BPPARAM`, `average`,
+    `include_intercept` are accepted and unused like in the reference (eta must be None: every caller passes NULL)."""
+    del BPPARAM, average, include_intercept
+    if eta is not None:
+        raise NotImplementedError("eta (gene-wise covariates, ruv::RUV1) is not supported; all scMerge callers pass NULL")
+    if k is None:
+        raise TypeError("k must be given (the reference fails on k = NULL, R/fastRUVIII.R:78)")
+    ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
+    m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
+    keys, G = replicate_keys(M)
+    if keys.shape[0] != m:
+        raise ValueError("M must have one row per row of Y")
+    ctl = tological(ctl, n)
+    exact = _is_exact(BSPARAM)
+    s = _svd_k(m, G, int(ctl.sum()), exact, svd_k)
+    if G >= m or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input
+        newY, fa = Y, None
+        return {"newY": newY, "M": M, "fullalpha": fa} if return_info else newY
+    dY, copied = _as_device(ctx, Y)
+    if fullalpha is None:
+        # NA/Inf check (R/fastRUVIII.R:52-60) is fused into the first pass over Y; inputcheck=False only skips the raise
+        del inputcheck
+        s_dev, exact_dev = _device_rows_cap(s, k, exact)
+        fit = _fit(ctx, dY, keys, G, s_dev, int(k), exact_dev)
+        fullalpha = fit.fullalpha
+    fullalpha = np.asarray(fullalpha, dtype=np.float64)
+    dout, _ = _adjust(ctx, dY, fullalpha, int(k), ctl, out=out if isinstance(out, DeviceMatrix) else None)
+    newY = _finish(dout, copied, out if isinstance(out, np.ndarray) else None)
+    if copied:
+        dY.free()
+    if not return_info:
+        return newY
+    return {"newY": newY, "M": M, "fullalpha": fullalpha}
+
+
+def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, return_all_RUV=True, BPPARAM=None,
+             BSPARAM=None, svd_k=50, ctx: Context | None = None):
+    """R/scRUVIII.R:41-137.  Y: genes x cells (numpy) -- byte-identical to the device layout cells x genes.
+    Standardisation and de-standardisation (R/scRUVIII.R:47-50,117-119) are fused into the Gram scaling and the
+    adjust coefficients, so Y is read but never rewritten.  The silhouette-based choice among several k
+    (R/scRUVIII.R:80-114) is out of scope: with several k every result is returned and optimal_ruvK is None."""
+    del BPPARAM, cell_type
+    if batch is None:
+        raise ValueError("batch is required")
+    ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
+    ctx = ctx or default_context()
+    if isinstance(Y, DeviceMatrix):
+        dY, copied = Y, False
+    else:
+        Y = np.asarray(Y, dtype=np.float64)
+        # genes x cells: C-order needs a transpose on the device, Fortran order is already cells x genes row-major
+        dY, copied = DeviceMatrix.from_host(ctx, Y.T), True
+    m, n = dY.m, dY.n
+    keys, G = replicate_keys(M)
+    bkeys, Bt = replicate_keys(np.asarray(batch))
+    ctl = tological(ctl, n)
+    exact = _is_exact(BSPARAM)
+    s = _svd_k(m, G, int(ctl.sum()), exact, svd_k)
+    results = {}
+    if G >= m or ks[0] == 0:
+        raise NotImplementedError("degenerate replicate structure (ncol(M) >= m): nothing to adjust")
+    s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
+    if fullalpha is None:
+        fit = _fit(ctx, dY, keys, G, s_dev, ks[0], exact_dev, batch_keys=bkeys, Bt=Bt)
+    else:  # still need stand_mean / stand_sd: run the standardisation passes only via a fit with s = 1
+        fit0 = _fit(ctx, dY, keys, G, 1, 1, True, batch_keys=bkeys, Bt=Bt, maxit=2, tol=1.0)
+        fit = RUVFit(np.asarray(fullalpha, dtype=np.float64), None, fit0.stand_mean, fit0.stand_sd)
+    for kk in ks:
+        dout, _ = _adjust(ctx, dY, fit.fullalpha, kk, ctl, center=fit.stand_mean, pre=1.0 / fit.stand_sd, post=fit.stand_sd)
+        newY = _finish(dout, copied)
+        results[kk] = {"newY": newY, "M": M, "fullalpha": fit.fullalpha}
+    if copied:
+        dY.free()
+    optimal = ks[0] if len(ks) == 1 else None
+    if return_all_RUV:
+        results["optimal_ruvK"] = optimal
+        results["stand_mean"], results["stand_sd"] = fit.stand_mean, fit.stand_sd
+        return results
+    res = dict(results[ks[0]])
+    res["optimal_ruvK"] = optimal
+    return res
+
+
+def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, inputcheck=True, fullalpha=None,
+                 return_info=False, subset=None, BPPARAM=None, BSPARAM=None, normalised=True, verbose=True, byChunk=True,
+                 chunkSize=50000, ctx: Context | None = None):
+    """R/scMerge2_utilis.R:17-150.  Fit on the pseudobulk matrix (P x n), adjust every cell of Y (m x n).
+    byChunk / chunkSize / BPPARAM are accepted for parity; the fused kernel streams all cells in one launch."""
+    del BPPARAM, include_intercept, verbose, byChunk, chunkSize, inputcheck
+    if eta is not None:
+        raise NotImplementedError("eta is not supported")
+    ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
+    n = Y.n if isinstance(Y, DeviceMatrix) else np.shape(Y)[1]
+    P = Y_pseudo.m if isinstance(Y_pseudo, DeviceMatrix) else np.shape(Y_pseudo)[0]
+    keys, G = replicate_keys(M)
+    ctl = tological(ctl, n)
+    exact = _is_exact(BSPARAM)
+    s = _svd_k(P, G, int(ctl.sum()), exact, k)  # Exact branch caps at k here (R/scMerge2_utilis.R:60-61)
+    if G >= P or k == 0:  # R/scMerge2_utilis.R:72-76 returns the pseudobulk matrix itself
+        return Y_pseudo
+    if fullalpha is None:
+        dP, pcopied = _as_device(ctx, Y_pseudo)
+        s_dev, exact_dev = _device_rows_cap(s, k, exact)
+        try:
+            fit = _fit(ctx, dP, keys, G, s_dev, int(k), exact_dev)
+        except L.NonFiniteError as e:  # the reference only warns here (R/scMerge2_utilis.R:49-52) and then fails in svd
+            warnings.warn(str(e))
+            raise
+        if pcopied:
+            dP.free()
+        fullalpha = fit.fullalpha
+    fullalpha = np.asarray(fullalpha, dtype=np.float64)
+    if not normalised:
+        return {"M": M, "fullalpha": fullalpha}
+    dY, copied = _as_device(ctx, Y)
+    means = column_means(dY)  # adjusted_means <- colMeans(Y) over ALL cells (R/scMerge2_utilis.R:97)
+    sub = None if subset is None else np.nonzero(tological(subset, n))[0] if np.asarray(subset).dtype == bool else np.asarray(subset)
+    dout, _ = _adjust(ctx, dY, fullalpha, int(k), ctl, center=means, subset=sub)
+    newY = _finish(dout, copied)
+    if copied:
+        dY.free()
+    if not return_info:
+        return newY
+    return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": means}
+
+
+def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, return_subset_genes=None,
+                   ctx: Context | None = None):
+    """R/scMerge2.R:368-410.  exprsMat: genes x cells; returns genes x cells (numpy) or a DeviceMatrix (cells x genes
+    device layout, which *is* genes x cells column-major) when given one."""
+    ctx = ctx or (exprsMat.ctx if isinstance(exprsMat, DeviceMatrix) else default_context())
+    if isinstance(exprsMat, DeviceMatrix):
+        dY, copied = exprsMat, False
+    else:
+        dY, copied = DeviceMatrix.from_host(ctx, np.asarray(exprsMat, dtype=np.float64).T), True
+    n = dY.n
+    ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
+    if ctl_mask.sum() == 0:
+        raise ValueError("No provided ctl genes in the data")
+    sub = None
+    if return_subset_genes is not None:
+        sub = np.nonzero(tological(return_subset_genes, n))[0]
+        if sub.shape[0] == 0:
+            raise ValueError("No provided return_subset_genes genes in the data")
+    means = column_means(dY) if adjusted_means is None else np.asarray(adjusted_means, dtype=np.float64)
+    dout, _ = _adjust(ctx, dY, np.asarray(fullalpha, dtype=np.float64), int(ruvK), ctl_mask, center=means, subset=sub)
+    if copied:
+        dY.free()
+        res = dout.to_host().T
+        dout.free()
+        return res
+    return dout
+
+
+# ---- K1 front-ends ----------------------------------------------------------------------------------------
+def segmented_sums(dY: DeviceMatrix, keys: np.ndarray, G: int, center: np.ndarray | None = None, check_finite=False,
+                   mean=False):
+    """(sums | means G x n, counts G[, nonfinite flag]) of the rows of a device matrix grouped by int32 key (-1 = skip)."""
+    ctx = dY.ctx
+    d_keys = ctx.to_device(np.ascontiguousarray(keys, dtype=np.int32))
+    d_sums, d_cnt = ctx.empty((G, dY.n)), ctx.empty((G,), np.int64)
+    d_center = ctx.to_device(np.ascontiguousarray(center, dtype=np.float64)) if center is not None else None
+    d_flag = ctx.to_device(np.zeros(1, dtype=np.int32)) if check_finite else None
+    if mean:
+        L.check(L.lib().scm_seg_colmean(ctx.handle, dY.ptr, dY.m, dY.n, dY.ld, d_keys.ptr, G, d_sums.ptr, d_cnt.ptr,
+                                        _dptr(d_flag)))
+    else:
+        L.check(L.lib().scm_seg_colsum(ctx.handle, dY.ptr, dY.m, dY.n, dY.ld, d_keys.ptr, G, _dptr(d_center), d_sums.ptr,
+                                       d_cnt.ptr, _dptr(d_flag)))
+    sums, cnt = d_sums.to_host(), d_cnt.to_host()
+    flag = int(d_flag.to_host()[0]) if d_flag is not None else None
+    for a in (d_keys, d_sums, d_cnt, d_center, d_flag):
+        if a is not None:
+            a.free()
+    return (sums, cnt, flag) if check_finite else (sums, cnt)
+
+
+def column_means(dY: DeviceMatrix) -> np.ndarray:
+    means, _cnt = segmented_sums(dY, np.zeros(dY.m, dtype=np.int32), 1, mean=True)
+    return means[0]
+
+
+def aggregate_matrix(x, groupings, ctx: Context | None = None):
+    """aggregate.Matrix (R/scMerge2_utilis.R:325-346): rows of x (cells x genes) summed by group label;
+    result rows in sorted level order.  Returns (sums, levels, counts)."""
+    ctx = ctx or default_context()
+    levels, inv = np.unique(np.asarray(groupings), return_inverse=True)
+    dX, copied = _as_device(ctx, x)
+    sums, cnt = segmented_sums(dX, inv.astype(np.int32), int(levels.shape[0]))
+    if copied:
+        dX.free()
+    return sums, levels, cnt
+
+
+def create_pseudoBulk(exprsMat, cell_info, k_fold=30, which=None, ctx: Context | None = None, seed=None):
+    """create_pseudoBulk (R/scMerge2_utilis.R:461-486) for ONE batch.  exprsMat: genes x cells.  `which` is the fold
+    id (1..K) per cell -- cvTools::cvFolds' random assignment; pass the R draw for bit-identical groups, otherwise a
+    seeded NumPy permutation with the same structure (`rep(1:K, length.out = n)` over a random order) is used.
+    One segmented-mean launch over the composite key (fold, type) replaces the per-fold sparse products.
+    Returns (bulk P x genes, names 'type_fold') with rows fold-major and types in sorted level order."""
+    ctx = ctx or default_context()
+    X = np.asarray(exprsMat, dtype=np.float64)
+    ncell = X.shape[1]
+    K = min(ncell, int(k_fold))
+    if which is None:
+        order = np.random.default_rng(seed).permutation(ncell)
+        which = np.empty(ncell, dtype=np.int64)
+        which[order] = (np.arange(ncell) % K) + 1
+    which = np.asarray(which)
+    levels, t = np.unique(np.asarray(cell_info), return_inverse=True)
+    T = levels.shape[0]
+    key = ((which - 1) * T + t).astype(np.int32)
+    dX = DeviceMatrix.from_host(ctx, X.T)
+    means, cnt = segmented_sums(dX, key, K * T, mean=True)
+    dX.free()
+    keep = cnt > 0  # droplevels(): (fold, type) combinations without cells give no row
+    bulk = means[keep]
+    names = [f"{levels[i % T]}_{i // T + 1}" for i in np.nonzero(keep)[0]]
+    return bulk, names

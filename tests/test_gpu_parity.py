@@ -1,0 +1,283 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every device result comes through the C ABI
+(ctypes -> libscmerge_b200.so) and is compared with the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): adjusted matrix relative Frobenius error <= 1e-8 (sign-invariant by
+construction), principal angles of the alpha / W subspaces ~ 0, group / pseudobulk indices and counts bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ruv_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_NEWY = 1e-8
+
+
+@pytest.fixture(scope="module")
+def sm():
+    import scmerge_b200 as s
+    return s
+
+
+@pytest.fixture(scope="module")
+def ctx(sm):
+    return sm.default_context()
+
+
+def mean_rel_diff(a, b):
+    return np.abs(a - b).sum() / np.abs(a).sum()
+
+
+# ---- stage level ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,G", [(1000, 257, 7), (5000, 512, 1), (3000, 130, 700), (64, 33, 64), (20000, 96, 3)])
+def test_seg_colsum(sm, ctx, m, n, G):
+    from scmerge_b200.ruv import segmented_sums
+    rng = np.random.default_rng(m + n)
+    Y = rng.normal(size=(m, n)) * 3 + 1
+    keys = rng.integers(0, G, size=m).astype(np.int32)
+    keys[rng.random(m) < 0.05] = -1  # skipped rows
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    sums, cnt, flag = segmented_sums(dY, keys, G, check_finite=True)
+    ref = np.zeros((G, n))
+    valid = keys >= 0
+    np.add.at(ref, keys[valid], Y[valid])
+    assert np.array_equal(cnt, np.bincount(keys[valid], minlength=G))  # bit-exact counts
+    assert flag == 0
+    assert np.allclose(sums, ref, rtol=1e-12, atol=1e-11)
+    # squared deviations about per-group centres + determinism
+    centre = ref / np.maximum(cnt, 1)[:, None]
+    ssq, _ = segmented_sums(dY, keys, G, center=centre)
+    ref2 = np.zeros((G, n))
+    np.add.at(ref2, keys[valid], (Y[valid] - centre[keys[valid]]) ** 2)
+    assert np.allclose(ssq, ref2, rtol=1e-11, atol=1e-11)
+    sums2, _ = segmented_sums(dY, keys, G)
+    assert np.array_equal(sums, sums2)  # bit-identical run to run
+    dY.free()
+
+
+def test_seg_colsum_nonfinite_flag(sm, ctx):
+    from scmerge_b200.ruv import segmented_sums
+    Y = np.ones((300, 40))
+    Y[17, 5] = np.nan
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    assert segmented_sums(dY, np.zeros(300, dtype=np.int32), 1, check_finite=True)[2] == 1
+    Y[17, 5] = -np.inf
+    dY2 = sm.DeviceMatrix.from_host(ctx, Y)
+    assert segmented_sums(dY2, np.zeros(300, dtype=np.int32), 1, check_finite=True)[2] == 1
+
+
+@pytest.mark.parametrize("m,n,shift", [(1000, 128, False), (777, 300, True), (5000, 257, True), (40, 513, False),
+                                       (70000, 260, True)])
+def test_gram(sm, ctx, m, n, shift):
+    from scmerge_b200 import _lib as L
+    rng = np.random.default_rng(m * 7 + n)
+    Y = rng.normal(size=(m, n)) + 2.0
+    a = Y.mean(axis=0) if shift else None
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    dG = ctx.empty((n, n))
+    da = ctx.to_device(a) if shift else None
+    L.check(L.lib().scm_gram(ctx.handle, dY.ptr, m, n, dY.ld, da.ptr if da else None, dG.ptr))
+    G = dG.to_host()
+    Z = Y - a if shift else Y
+    ref = Z.T @ Z
+    assert np.allclose(G, G.T, rtol=0, atol=0)  # exactly symmetric (mirrored tiles)
+    assert np.linalg.norm(G - ref) / np.linalg.norm(ref) < 1e-13
+
+
+def test_gram_residual_matches_centred_gram(sm, ctx):
+    from scmerge_b200 import _lib as L
+    from scmerge_b200.ruv import segmented_sums
+    rng = np.random.default_rng(5)
+    m, n, G = 4000, 200, 9
+    Y = rng.normal(size=(m, n)) + rng.normal(size=n) * 4
+    g = rng.integers(0, G, size=m).astype(np.int32)
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    sums, cnt = segmented_sums(dY, g, G)
+    a = Y.mean(axis=0)
+    scale = 1.0 / (1.0 + rng.random(n))
+    dG, da, ds = ctx.empty((n, n)), ctx.to_device(a), ctx.to_device(scale)
+    dsums, dcnt = ctx.to_device(sums), ctx.to_device(cnt)
+    lib = L.lib()
+    L.check(lib.scm_gram(ctx.handle, dY.ptr, m, n, dY.ld, da.ptr, dG.ptr))
+    L.check(lib.scm_gram_residual(ctx.handle, dG.ptr, n, dsums.ptr, dcnt.ptr, G, da.ptr, ds.ptr))
+    Y0 = (Y - (sums / cnt[:, None])[g]) * scale
+    ref = Y0.T @ Y0
+    assert np.linalg.norm(dG.to_host() - ref) / np.linalg.norm(ref) < 1e-12
+
+
+@pytest.mark.parametrize("n,s,mode", [(300, 20, 0), (1047, 50, 0), (500, 30, 1)])
+def test_eig_topk(sm, ctx, n, s, mode):
+    from scmerge_b200 import _lib as L
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    lam = np.concatenate([np.linspace(100, 20, s), np.linspace(5, 0.01, n - s)])
+    Gm = (Q * lam) @ Q.T
+    Gm = 0.5 * (Gm + Gm.T)
+    dG = ctx.to_device(Gm)
+    dvals, dvecs = ctx.empty((s,)), ctx.empty((s, n))
+    it, res = C.c_int32(), C.c_double()
+    rc = L.lib().scm_eig_topk(ctx.handle, dG.ptr, n, s, s, mode, 1e-11, 500, 7, dvals.ptr, dvecs.ptr, C.byref(it), C.byref(res))
+    L.check(rc)
+    vals, vecs = dvals.to_host(), dvecs.to_host()
+    if mode == 0:
+        assert np.allclose(vals, lam[:s], rtol=1e-10)
+        ang = orc.principal_angles(vecs, Q[:, :s].T)
+        assert ang.max() < 1e-7
+        assert np.allclose(vecs @ vecs.T, np.eye(s), atol=1e-10)
+    else:  # randomized: 3 products, loose
+        assert np.allclose(vals[:5], lam[:5], rtol=1e-2)
+
+
+# ---- end to end through the reference-facing functions ---------------------------------------------------
+@pytest.fixture(scope="module")
+def sim():
+    return orc.ruv_simulate(m=400, n=500, nc=400, n_celltypes=3, n_batch=2, lam=0.1, rng=np.random.default_rng(12345))
+
+
+def test_fastruviii_exact_vs_oracle(sm, sim):
+    ref = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, return_info=True)
+    out = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20, return_info=True)
+    assert out["fullalpha"].shape == ref["fullalpha"].shape == (50, 500)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(out["fullalpha"][:20], ref["fullalpha"][:20]).max() < 1e-6
+    # singular values (row norms of fullalpha) of the well separated part of the spectrum
+    rn, rr = np.linalg.norm(out["fullalpha"], axis=1), np.linalg.norm(ref["fullalpha"], axis=1)
+    assert np.allclose(rn[:20], rr[:20], rtol=1e-8)
+
+
+def test_fastruviii_label_vector_and_fortran_input(sm, sim):
+    keys = orc.group_ids(sim["M"])
+    a = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=10)
+    b = sm.fastRUVIII(np.asfortranarray(sim["Y"]), keys, np.nonzero(sim["ctl"])[0], k=10)  # R layout, labels, int ctl
+    assert orc.rel_frobenius(b, a) < 1e-12
+
+
+def test_fastruviii_randomized_close_to_exact(sm, sim):
+    # tests/testthat/test-fastRUVIII.R:11-16, tol = 0.02 (mean relative difference)
+    a = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20)
+    with pytest.warns(UserWarning):  # fullalpha rows capped on the device path (documented deviation)
+        b = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20, BSPARAM=sm.RandomParam(), svd_k=100)
+    assert mean_rel_diff(a, b) < 0.02
+
+
+def test_cell_permutation_equivariance(sm, sim):
+    # tests/testthat/test-resampling-columns.R:26 (tolerance 1.5e-8)
+    perm = np.random.default_rng(3).permutation(sim["Y"].shape[0])
+    a = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20)
+    b = sm.fastRUVIII(sim["Y"][perm], sim["M"][perm], sim["ctl"], k=20)
+    assert mean_rel_diff(a[perm], b) < 1.5e-8
+
+
+def test_fastruviii_reuses_fullalpha_and_truncates_k(sm, sim):
+    first = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20, return_info=True)
+    again = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=5, fullalpha=first["fullalpha"])
+    ref = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 5)
+    assert orc.rel_frobenius(again, ref) < TOL_NEWY
+    big = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=60, fullalpha=first["fullalpha"])  # k > s -> s rows
+    ref60 = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 60)
+    assert mean_rel_diff(ref60, big) < 0.05  # rows 21..50 live in the noise bulk: only loosely pinned
+
+
+def test_early_out_and_errors(sm, sim):
+    Y = sim["Y"][:6]
+    out = sm.fastRUVIII(Y, np.arange(6), sim["ctl"], k=3, return_info=True)  # ncol(M) >= m
+    assert out["fullalpha"] is None and out["newY"] is Y
+    assert sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=0) is sim["Y"]
+    bad = sim["Y"].copy()
+    bad[3, 4] = np.nan
+    with pytest.raises(ValueError, match="missing values or infinities"):
+        sm.fastRUVIII(bad, sim["M"], sim["ctl"], k=5)
+    with pytest.raises(ValueError, match="one-hot"):
+        sm.fastRUVIII(sim["Y"], np.ones((400, 2)), sim["ctl"], k=5)
+    with pytest.raises(TypeError):
+        sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"])
+
+
+def test_golden_example_scruviii(sm, golden_dir):
+    """BASELINE.json configs[0]: bundled example data, mouse scSEG controls, ruvK = 20, via scRUVIII."""
+    d = np.load(os.path.join(golden_dir, "example_sce.npz"))
+    g = np.load(os.path.join(golden_dir, "golden_example.npz"))
+    res = sm.scRUVIII(d["logcounts"], d["cellTypes"], d["ctl"], k=20, batch=d["batch"])
+    ref = orc.scRUVIII(d["logcounts"], d["cellTypes"], d["ctl"], 20, d["batch"])
+    assert orc.rel_frobenius(res[20]["newY"], ref[20]["newY"]) < TOL_NEWY
+    assert orc.rel_frobenius(res[20]["newY"][:16], g["newY_rows"]) < TOL_NEWY
+    assert np.allclose(res["stand_mean"], g["stand_mean"], rtol=1e-12)
+    assert np.allclose(res["stand_sd"], g["stand_sd"], rtol=1e-11)
+    assert orc.principal_angles(res[20]["fullalpha"][:20], g["fullalpha"][:20]).max() < 1e-6
+
+
+def test_scruviii_multi_k(sm):
+    L_ = orc.ruv_simulate(m=200, n=300, nc=100, rng=np.random.default_rng(1234))
+    Y = np.log2(L_["Y"] + 1).T
+    keep = Y.var(axis=1) > 0
+    Y, ctl = Y[keep], L_["ctl"][keep]
+    res = sm.scRUVIII(Y, L_["M"], ctl, k=[5, 10], batch=L_["batch"])
+    ref = orc.scRUVIII(Y, L_["M"], ctl, [5, 10], L_["batch"])
+    for kk in (5, 10):
+        assert orc.rel_frobenius(res[kk]["newY"], ref[kk]["newY"]) < TOL_NEWY
+    assert res["optimal_ruvK"] is None
+
+
+def _pseudo_case(seed=777, m=1200, n=300, c=120, k=8):
+    P = orc.planted_factors(m, n, c, k, n_types=4, n_batch=3, seed=seed)
+    which = (np.random.default_rng(5).permutation(m) % 6) + 1
+    return P, which
+
+
+def test_pseudobulk_and_pseudoruviii(sm, golden_dir):
+    P, which = _pseudo_case()
+    bulks, keys, bulks_ref = [], [], []
+    for b in range(3):
+        sel = P["batch"] == b
+        bulk, names = sm.create_pseudoBulk(P["Y"][sel].T, P["types"][sel], k_fold=6, which=which[sel])
+        ref, names_ref = orc.create_pseudobulk(P["Y"][sel].T, P["types"][sel], which[sel], k_fold=6)
+        assert names == names_ref  # pseudobulk indices bit-exact
+        assert np.allclose(bulk, ref, rtol=1e-13, atol=1e-13)
+        bulks.append(bulk)
+        bulks_ref.append(ref)
+        keys += [int(x.split("_")[0]) for x in names]
+    Yp = np.concatenate(bulks)
+    out = sm.pseudoRUVIII(P["Y"], Yp, np.array(keys), P["ctl"], k=8, return_info=True)
+    ref = orc.pseudoRUVIII(P["Y"], np.concatenate(bulks_ref), np.array(keys), P["ctl"], 8)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert np.allclose(out["adjusted_means"], ref["adjusted_means"], rtol=1e-13)
+    g = np.load(os.path.join(golden_dir, "golden_sim.npz"))
+    assert orc.rel_frobenius(out["newY"][:16], g["ps_newY_rows"]) < TOL_NEWY
+    # subset of genes + getAdjustedMat from the stored fullalpha
+    sub = np.arange(10, 90, 3)
+    o2 = sm.pseudoRUVIII(P["Y"], Yp, np.array(keys), P["ctl"], k=8, subset=sub, fullalpha=out["fullalpha"])
+    assert orc.rel_frobenius(o2, ref["newY"][:, sub]) < TOL_NEWY
+    adj = sm.getAdjustedMat(P["Y"].T, out["fullalpha"], ctl=P["ctl"], ruvK=8)
+    assert orc.rel_frobenius(adj.T, ref["newY"]) < TOL_NEWY
+    adj = sm.getAdjustedMat(P["Y"].T, out["fullalpha"], ctl=P["ctl"], ruvK=8, return_subset_genes=sub)
+    assert orc.rel_frobenius(adj.T, ref["newY"][:, sub]) < TOL_NEWY
+
+
+@pytest.mark.parametrize("k", [5, 20, 33, 50])
+def test_k_sweep_planted(sm, k):
+    """ruvK sweep (BASELINE.json configs[4] shape family) on planted factors with a spectral gap after k."""
+    P = orc.planted_factors(6000, 400, 150, k, n_types=5, n_batch=3, seed=100 + k)
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], k, return_info=True)
+    out = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=k, return_info=True)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(out["fullalpha"][:k], ref["fullalpha"][:k]).max() < 1e-6
+
+
+def test_w_output_and_device_resident(sm, ctx, sim):
+    from scmerge_b200.ruv import _adjust
+    ref = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, return_info=True)
+    alpha = ref["fullalpha"][:20]
+    ac = alpha[:, sim["ctl"]]
+    W_ref = sim["Y"][:, sim["ctl"]] @ ac.T @ np.linalg.inv(ac @ ac.T)
+    dY = sm.DeviceMatrix.from_host(ctx, sim["Y"])
+    dout, W = _adjust(ctx, dY, ref["fullalpha"], 20, sim["ctl"], want_W=True)
+    # W is defined up to the basis of alpha: compare W alpha (basis-free) and the column spaces
+    assert orc.rel_frobenius(dout.to_host(), ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(W.T, W_ref.T).max() < 1e-6
+    res = sm.fastRUVIII(dY, sim["M"], sim["ctl"], k=20)  # device in -> device out
+    assert isinstance(res, sm.DeviceMatrix)
+    assert orc.rel_frobenius(res.to_host(), ref["newY"]) < TOL_NEWY
