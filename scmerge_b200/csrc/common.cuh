@@ -57,6 +57,7 @@ struct scm_ctx {
     int world = 1;
     cudaEvent_t ev0[scm::ST_COUNT], ev1[scm::ST_COUNT];
     bool ev_used[scm::ST_COUNT];
+    bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
 };
 

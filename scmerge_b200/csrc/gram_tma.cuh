@@ -1,0 +1,226 @@
+// K3 (primary path): Gram SYRK with TMA-staged operand tiles and an mbarrier full/empty pipeline.
+//
+// Same decomposition as gram_syrk.cuh (lower-triangular 128x128 tiles x S splits over cells, 8 warps x 64x32 warp
+// tiles of DMMA.8x8x4, partial buffer + ordered reduce) but:
+//   * operand tiles arrive by `cp.async.bulk.tensor.2d` (TMA): one elected thread issues 16 bulk copies per stage
+//     ([16 cells x 16 genes] boxes, SWIZZLE_128B), so the compute warps execute no copy / address code at all;
+//     out-of-range genes and cells are zero-filled by the TMA unit,
+//   * stages are handed over with mbarriers (full: TMA transaction bytes, empty: one arrival per warp), there is
+//     no __syncthreads in the main loop and warps may drift up to GT_STAGES-1 chunks apart, which keeps the
+//     tensor pipe fed while another warp waits,
+//   * fragment loads read the 128B-swizzled layout conflict-free by permuting the k index of each 8-cell
+//     group (k-steps use cells {0,2,4,6} then {1,3,5,7}; any permutation of the summation index is legal),
+//   * the column shift is subtracted in registers when fragments are loaded (12 DADD per 32 DMMA).
+// Requires ld % 2 == 0 and a 16-byte aligned base (TMA global stride rule); otherwise gram_syrk.cuh is used.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gram_syrk.cuh"
+
+namespace scm {
+
+constexpr int GT_KC = 16;
+constexpr int GT_STAGES = 6;
+constexpr int GT_SLAB_BYTES = 16 * GT_KC * 8;      // one TMA box: 16 cells x 16 genes
+constexpr int GT_TILE_BYTES = 8 * GT_SLAB_BYTES;   // 128 genes
+constexpr int GT_STAGE_BYTES = 2 * GT_TILE_BYTES;  // A + B
+constexpr int GT_SMEM_BYTES = GT_STAGES * GT_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+// One 16-cell chunk: 4 k-steps x (8 + 4 fragment loads, 32 DMMA).  off[p][q] are the thread's swizzled byte offsets.
+template <bool TAIL>
+__device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const uint8_t* __restrict__ sb, const int (&off)[2][2],
+                                           int wm, int wn, int tig, const double (&sA)[8], const double (&sB)[4], int rows_valid,
+                                           double (&acc)[8][4][2]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        const int p = ks & 1;
+        const int half = (ks >> 1) * 1024;  // second 8-cell swizzle atom of the box
+        double af[8], bf[4];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            af[a] = *reinterpret_cast<const double*>(sa + (wm * 4 + (a >> 1)) * GT_SLAB_BYTES + half + off[p][a & 1]);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            bf[b] = *reinterpret_cast<const double*>(sb + (wn * 2 + (b >> 1)) * GT_SLAB_BYTES + half + off[p][b & 1]);
+        if (TAIL) {
+            const double msk = (8 * (ks >> 1) + 2 * tig + p) < rows_valid ? 1.0 : 0.0;  // zero-filled cells stay zero
+#pragma unroll
+            for (int a = 0; a < 8; a++) af[a] -= msk * sA[a];
+#pragma unroll
+            for (int b = 0; b < 4; b++) bf[b] -= msk * sB[b];
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; a++) af[a] -= sA[a];
+#pragma unroll
+            for (int b = 0; b < 4; b++) bf[b] -= sB[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, const double* __restrict__ shift, int T, int S,
+                int64_t rows_per_split, double* __restrict__ partial) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_BYTES);
+    uint64_t* empty = full + GT_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    if (tid == 0) {
+        for (int s = 0; s < GT_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    int off[2][2];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            off[p][q] = (2 * tig + p) * 128 + ((((gid >> 1) ^ (2 * tig + p)) ^ (q << 2)) << 4) + (gid & 1) * 8;
+
+    uint32_t gl = 0, gu = 0;  // chunks loaded (meaningful in thread 0) / consumed so far by this CTA
+    const int64_t units = (int64_t)T * S;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = (int)(u / T);
+        int ti, tj;
+        tri_decode((int)(u % T), ti, tj);
+        const bool diag = (ti == tj);
+        const int64_t row_begin = (int64_t)split * rows_per_split;
+        const int64_t row_end = min(m, row_begin + rows_per_split);
+        const int nchunk = row_end > row_begin ? (int)ceil_div(row_end - row_begin, GT_KC) : 0;
+        const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
+        double sA[8], sB[4];
+#pragma unroll
+        for (int a = 0; a < 8; a++) { const int64_t g = colA0 + wm * 64 + a * 8 + gid; sA[a] = (shift && g < n) ? shift[g] : 0.0; }
+#pragma unroll
+        for (int b = 0; b < 4; b++) { const int64_t g = colB0 + wn * 32 + b * 8 + gid; sB[b] = (shift && g < n) ? shift[g] : 0.0; }
+        double acc[8][4][2];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+        int issued = 0;
+        auto produce = [&](int upto) {  // thread 0 only: keep the ring filled up to chunk index `upto` (exclusive)
+            while (issued < upto) {
+                const int slot = gl % GT_STAGES;
+                if (gl >= GT_STAGES) mbar_wait(&empty[slot], ((gl / GT_STAGES) - 1) & 1);
+                uint8_t* sa = smem + slot * GT_STAGE_BYTES;
+                mbar_expect_tx(&full[slot], diag ? GT_TILE_BYTES : GT_STAGE_BYTES);
+                const int row = (int)(row_begin + (int64_t)issued * GT_KC);
+#pragma unroll
+                for (int sl = 0; sl < 8; sl++) tma_load_2d(sa + sl * GT_SLAB_BYTES, &tmap, colA0 + 16 * sl, row, &full[slot]);
+                if (!diag) {
+#pragma unroll
+                    for (int sl = 0; sl < 8; sl++)
+                        tma_load_2d(sa + GT_TILE_BYTES + sl * GT_SLAB_BYTES, &tmap, colB0 + 16 * sl, row, &full[slot]);
+                }
+                gl++;
+                issued++;
+            }
+        };
+        for (int c = 0; c < nchunk; c++) {
+            if (tid == 0) produce(min(nchunk, c + GT_STAGES - 1));
+            __syncwarp();
+            const int slot = gu % GT_STAGES;
+            mbar_wait(&full[slot], (gu / GT_STAGES) & 1);
+            const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
+            const uint8_t* sb = diag ? sa : sa + GT_TILE_BYTES;
+            const int64_t r0 = row_begin + (int64_t)c * GT_KC;
+            if (r0 + GT_KC <= row_end) gram_chunk<false>(sa, sb, off, wm, wn, tig, sA, sB, GT_KC, acc);
+            else gram_chunk<true>(sa, sb, off, wm, wn, tig, sA, sB, (int)(row_end - r0), acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            gu++;
+        }
+        double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int i = wm * 64 + a * 8 + gid, j = wn * 32 + b * 8 + 2 * tig;
+                *reinterpret_cast<double2*>(out + i * GR_BT + j) = make_double2(acc[a][b][0], acc[a][b][1]);
+            }
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// Returns 1 when the TMA path is not applicable (caller falls back to the cp.async kernel), 0 on success, <0 on error.
+inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift,
+                           const GramPlan& p, double* partial) {
+    if (ld % 2 != 0 || ((uintptr_t)d_Y) % 16 != 0 || m >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31)) return 1;
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return 1;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)m};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {16, (cuuint32_t)GT_KC};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)d_Y, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        attr_set = true;
+    }
+    gram_tma_kernel<<<p.grid, 256, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial);
+    return 0;
+}
+
+}  // namespace scm

@@ -4,6 +4,7 @@
 #include "eig_topk.cuh"
 #include "gemm_f64.cuh"
 #include "gram_syrk.cuh"
+#include "gram_tma.cuh"
 #include "seg_colsum.cuh"
 
 namespace scm {
@@ -108,6 +109,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     scm_ctx* c = new scm_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < ST_COUNT; i++) {

@@ -76,6 +76,14 @@ def replicate_keys(M):
         a = np.array(["_".join(str(x) for x in row) for row in a])
     if a.ndim != 1:
         raise ValueError("M must be a replicate matrix or a label vector")
+    if np.issubdtype(a.dtype, np.integer) and a.shape[0] > 0:
+        lo, hi = int(a.min()), int(a.max())
+        if lo >= 0 and hi < 4 * a.shape[0] + 1024:  # O(m) path for integer labels (sorted level order = numeric order)
+            present = np.bincount(a, minlength=hi + 1) > 0
+            if present.all():
+                return a.astype(np.int32, copy=False), hi + 1
+            remap = np.cumsum(present) - 1
+            return remap[a].astype(np.int32), int(present.sum())
     levels, inv = np.unique(a, return_inverse=True)
     return inv.astype(np.int32), int(levels.shape[0])
 

@@ -1,0 +1,110 @@
+"""CPU tests (no GPU needed): the C-ABI library loads and exports every symbol declared in include/scmerge_b200.h,
+the product path fails loudly without a device, and the host-side argument logic mirrors the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "scmerge_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(scm_[a-z0-9_]+)\s*\(", text)) - {"scm_allreduce_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    from scmerge_b200 import _lib
+    handle = _lib.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert handle.scm_version() >= 100
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_no_cpu_fallback_without_device():
+    import scmerge_b200 as sm
+    h = C.c_void_p()
+    rc = sm.lib().scm_ctx_create(0, None, C.byref(h))
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert rc == 0
+        sm.lib().scm_ctx_destroy(h)
+    else:
+        assert rc == sm._lib.ERR_CUDA
+        assert b"no CPU fallback" in sm.lib().scm_last_error()
+        with pytest.raises(sm.ScmError):
+            sm.fastRUVIII(np.zeros((8, 4)), np.arange(8) % 2, np.arange(4), k=1)
+
+
+def test_product_path_never_imports_the_oracle():
+    for dirpath, _d, files in os.walk(os.path.join(ROOT, "scmerge_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src
+
+
+def test_replicate_keys_and_matrix():
+    from scmerge_b200 import replicate_keys, replicate_matrix
+    keys, G = replicate_keys(np.array(["b", "a", "b", "c"]))
+    assert G == 3 and keys.tolist() == [1, 0, 1, 2] and keys.dtype == np.int32  # sorted level order
+    M = replicate_matrix(np.array(["b", "a", "b", "c"]))
+    assert M.tolist() == [[0, 1, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    keys2, G2 = replicate_keys(M)
+    assert G2 == 3 and np.array_equal(keys2, keys)
+    keys3, G3 = replicate_keys(np.array([["t1", "b1"], ["t1", "b2"], ["t1", "b1"]]))  # data.frame -> pasted
+    assert G3 == 2 and keys3.tolist() == [0, 1, 0]
+    keys4, G4 = replicate_keys(np.array([3, 3, 7, 5], dtype=np.int64))  # integer labels
+    assert G4 == 3 and keys4.tolist() == [0, 0, 2, 1]
+    with pytest.raises(ValueError, match="one-hot"):
+        replicate_keys(np.array([[1.0, 1.0], [0.0, 1.0]]))
+    with pytest.raises(ValueError, match="one-hot"):
+        replicate_keys(np.array([[0.5, 0.5], [0.0, 1.0]]))
+
+
+def test_tological_chunks_and_svd_k_rule():
+    from scmerge_b200 import createChunk, tological
+    from scmerge_b200.ruv import _device_rows_cap, _svd_k
+    assert tological([0, 2], 4).tolist() == [True, False, True, False]
+    assert tological(np.array([True, False]), 3).tolist() == [True, False, False]
+    assert createChunk(9, 4) == [(1, 4), (5, 9)] and createChunk(10, 4) == [(1, 4), (5, 8), (9, 10)]
+    assert createChunk(120000, 50000) == [(1, 50000), (50001, 120000)]
+    # R/fastRUVIII.R:66-70: exact caps at svd_k, non-exact ignores it (quirk)
+    assert _svd_k(400, 6, 400, True, 50) == 50 and _svd_k(400, 6, 400, False, 50) == 394
+    assert _svd_k(40, 6, 400, True, 50) == 34
+    assert _device_rows_cap(50, 20, True) == (50, True)
+    with pytest.warns(UserWarning, match="truncated"):
+        assert _device_rows_cap(394, 20, False) == (50, True)  # truncated block -> converged iteration
+    assert _device_rows_cap(40, 20, False) == (40, False)
+
+
+def test_early_out_needs_no_device():
+    import scmerge_b200 as sm
+    Y = np.arange(12.0).reshape(6, 2)
+    out = sm.fastRUVIII(Y, np.arange(6), [0], k=3, return_info=True)  # ncol(M) >= m (R/fastRUVIII.R:78-80)
+    assert out["newY"] is Y and out["fullalpha"] is None
+    assert sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=0) is Y
+    with pytest.raises(TypeError):
+        sm.fastRUVIII(Y, np.arange(6) % 2, [0])
+    with pytest.raises(NotImplementedError):
+        sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=1, eta=np.ones((1, 2)))
+
+
+def test_shard_rows_partition():
+    from scmerge_b200.dist import shard_rows
+    for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
+        parts = [shard_rows(m, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == m
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))

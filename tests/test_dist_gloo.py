@@ -1,0 +1,85 @@
+"""world_size-2 `gloo` tests on CPU for the N>1 host logic.
+
+What is rank-local and what crosses ranks in scm_ruv3_fit is mirrored here with NumPy stand-ins for the
+device stages (the oracle's arithmetic), driven through the SAME all-reduce hook and row sharding the GPU
+path uses.  The test proves the decomposition
+
+    group sums / counts  -> all-reduce -> shift a = global column mean
+    local Gram of (Y - a) -> all-reduce -> minus sum_g n_g (mu_g - a)(mu_g - a)'  == Gram of the residual Y0
+
+gives every rank the single-process result, and that the hook sums raw buffers in place.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    from oracle import ruv_oracle as orc
+    from scmerge_b200.dist import shard_rows, torch_allreduce_hook
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hook = torch_allreduce_hook(None)
+
+        def allreduce(arr):  # exactly what the C library does: hand the hook a raw pointer
+            assert arr.flags.c_contiguous
+            hook(arr.ctypes.data, arr.size, 0 if arr.dtype == np.float64 else 1, 0)
+
+        P = orc.planted_factors(1500, 60, 24, 4, n_types=5, n_batch=3, seed=9)
+        Y, g, G = P["Y"], P["types"], 5
+        lo, hi = shard_rows(Y.shape[0], world, rank)
+        Yl, gl = Y[lo:hi], g[lo:hi]
+        sums = np.zeros((G, Y.shape[1]))
+        np.add.at(sums, gl, Yl)
+        counts = np.bincount(gl, minlength=G).astype(np.int64)
+        meta = np.array([0, hi - lo], dtype=np.int64)
+        allreduce(sums); allreduce(counts); allreduce(meta)
+        a = sums.sum(axis=0) / meta[1]
+        gram = (Yl - a).T @ (Yl - a)
+        allreduce(gram)
+        mu = sums / counts[:, None]
+        C = np.sqrt(counts)[:, None] * (mu - a)
+        G0 = gram - C.T @ C
+        # single-process truth
+        full_sums = np.zeros((G, Y.shape[1]))
+        np.add.at(full_sums, g, Y)
+        Y0 = Y - (full_sums / np.bincount(g, minlength=G)[:, None])[g]
+        ref = Y0.T @ Y0
+        q.put((rank, int(meta[1]), float(np.linalg.norm(G0 - ref) / np.linalg.norm(ref)), float(np.abs(G0).sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_fit_decomposition_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [1500, 1500]           # the row counts were summed across ranks
+    assert all(r[2] < 1e-12 for r in res)                  # sharded Gram of the residual == single process
+    assert res[0][3] == res[1][3]                          # bit-identical on both ranks (no broadcast needed)
