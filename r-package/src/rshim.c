@@ -1,0 +1,123 @@
+/* .Call shim between R and libscmerge_b200 (include/scmerge_b200.h).  Logic-free by design: it unpacks
+ * SEXPs, forwards to the C ABI and turns non-zero status codes into R errors.  NOT compiled in this
+ * repository's environment (no R headers here); see INTEGRATION.md for the build line.
+ *
+ * Replaces, inside scMerge's own closures, the arithmetic of
+ *   fastRUVIII  (R/fastRUVIII.R:41-111)      -> scm_fit(), scm_adjust_()
+ *   scRUVIII    (R/scRUVIII.R:41-137)        -> scm_fit() with batch keys, scm_adjust_() with center/pre/post
+ *   pseudoRUVIII (R/scMerge2_utilis.R:17-150), getAdjustedMat (R/scMerge2.R:368-410) -> same two calls
+ *   create_pseudoBulk / aggregate.Matrix (R/scMerge2_utilis.R:325-346,461-486)       -> scm_segmean()
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include "scmerge_b200.h"
+
+#define CHECK(call) do { int rc_ = (call); if (rc_ != 0 && rc_ != SCM_ERR_NOCONV) Rf_error("%s", scm_last_error()); \
+                         if (rc_ == SCM_ERR_NOCONV) Rf_warning("%s", scm_last_error()); } while (0)
+
+static scm_ctx* g_ctx = NULL;
+static scm_ctx* ctx(void) { if (!g_ctx) CHECK(scm_ctx_create(0, NULL, &g_ctx)); return g_ctx; }
+
+/* device matrix held by R as an external pointer {ptr, m, n, ld}; freed by the finalizer */
+typedef struct { double* p; int64_t m, n, ld; } dmat;
+static void dmat_fin(SEXP x) { dmat* d = (dmat*)R_ExternalPtrAddr(x); if (d) { scm_dev_free(ctx(), d->p); R_Free(d); R_ClearExternalPtr(x); } }
+
+/* Y: R numeric matrix.  layout 0: genes x cells (column-major == our row-major cells x genes), 1: cells x genes */
+SEXP scm_upload(SEXP Y, SEXP layout) {
+    SEXP dim = Rf_getAttrib(Y, R_DimSymbol);
+    int64_t r = INTEGER(dim)[0], c = INTEGER(dim)[1];
+    dmat* d = R_Calloc(1, dmat);
+    int lay = Rf_asInteger(layout);
+    d->m = lay == 0 ? c : r; d->n = lay == 0 ? r : c; d->ld = (d->n + 1) / 2 * 2;
+    CHECK(scm_dev_alloc(ctx(), d->m * d->ld * 8, (void**)&d->p));
+    if (lay == 0) CHECK(scm_copy2d(ctx(), d->p, d->ld * 8, REAL(Y), d->n * 8, d->n * 8, d->m, 0));
+    else {
+        double* tmp; CHECK(scm_dev_alloc(ctx(), r * c * 8, (void**)&tmp));
+        CHECK(scm_h2d(ctx(), tmp, REAL(Y), r * c * 8));
+        CHECK(scm_transpose(ctx(), tmp, c, r, r, d->p, d->ld));   /* [gene][cell] -> [cell][gene] */
+        CHECK(scm_dev_free(ctx(), tmp));
+    }
+    CHECK(scm_ctx_sync(ctx()));
+    SEXP out = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(out, dmat_fin, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+
+static void* to_dev(const void* h, int64_t bytes) { void* d; CHECK(scm_dev_alloc(ctx(), bytes, &d)); CHECK(scm_h2d(ctx(), d, h, bytes)); return d; }
+
+/* fit: group (int, 0-based), G, batch (int or NULL), Bt, s, kconv, mode -> list(fullalpha s x n [row-major], sigma, mean, sd) */
+SEXP scm_fit(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kconv, SEXP mode) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int s = Rf_asInteger(s_), has_b = !Rf_isNull(batch);
+    int32_t* dg = (int32_t*)to_dev(INTEGER(group), d->m * 4);
+    int32_t* db = has_b ? (int32_t*)to_dev(INTEGER(batch), d->m * 4) : NULL;
+    double *dfa, *dsig, *dmean = NULL, *dsd = NULL;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)s * d->n * 8, (void**)&dfa)); CHECK(scm_dev_alloc(ctx(), s * 8, (void**)&dsig));
+    if (has_b) { CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dmean)); CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dsd)); }
+    int32_t iters; double resid;
+    CHECK(scm_ruv3_fit(ctx(), d->p, d->m, d->n, d->ld, dg, Rf_asInteger(G), db, has_b ? Rf_asInteger(Bt) : 0, s, Rf_asInteger(kconv),
+                       Rf_asInteger(mode), 1e-10, 300, 1, dfa, dsig, dmean, dsd, &iters, &resid));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SEXP fa = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, s));          /* n x s column-major == s x n row-major; R side t()s it */
+    CHECK(scm_d2h(ctx(), REAL(fa), dfa, (int64_t)s * d->n * 8)); SET_VECTOR_ELT(out, 0, fa);
+    SEXP sg = PROTECT(Rf_allocVector(REALSXP, s)); CHECK(scm_d2h(ctx(), REAL(sg), dsig, s * 8)); SET_VECTOR_ELT(out, 1, sg);
+    if (has_b) {
+        SEXP mu = PROTECT(Rf_allocVector(REALSXP, d->n)); CHECK(scm_d2h(ctx(), REAL(mu), dmean, d->n * 8)); SET_VECTOR_ELT(out, 2, mu);
+        SEXP sd = PROTECT(Rf_allocVector(REALSXP, d->n)); CHECK(scm_d2h(ctx(), REAL(sd), dsd, d->n * 8)); SET_VECTOR_ELT(out, 3, sd);
+        UNPROTECT(2);
+    }
+    scm_dev_free(ctx(), dg); scm_dev_free(ctx(), db); scm_dev_free(ctx(), dfa); scm_dev_free(ctx(), dsig);
+    scm_dev_free(ctx(), dmean); scm_dev_free(ctx(), dsd);
+    UNPROTECT(3);
+    return out;
+}
+
+/* adjust: alpha (n x k column-major == k x n row-major), ctl (logical n), center/pre/post (numeric n or NULL), subset (int 0-based or NULL)
+ * returns an R matrix genes(or subset) x cells, i.e. the byte image of the device result */
+SEXP scm_adjust_(SEXP Yp, SEXP alpha, SEXP k_, SEXP ctl, SEXP center, SEXP pre, SEXP post, SEXP subset) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int k = Rf_asInteger(k_), nsub = Rf_isNull(subset) ? 0 : Rf_length(subset);
+    double* da = (double*)to_dev(REAL(alpha), (int64_t)k * d->n * 8);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    double* dce = Rf_isNull(center) ? NULL : (double*)to_dev(REAL(center), d->n * 8);
+    double* dpr = Rf_isNull(pre) ? NULL : (double*)to_dev(REAL(pre), d->n * 8);
+    double* dpo = Rf_isNull(post) ? NULL : (double*)to_dev(REAL(post), d->n * 8);
+    int32_t* dsub = nsub ? (int32_t*)to_dev(INTEGER(subset), nsub * 4) : NULL;
+    scm_coef* coef; CHECK(scm_coef_create(ctx(), da, d->n, k, dc, dce, dpr, dpo, &coef));
+    int64_t nout = nsub ? nsub : d->n, ldo = (nout + 1) / 2 * 2;
+    double* dout; CHECK(scm_dev_alloc(ctx(), d->m * ldo * 8, (void**)&dout));
+    CHECK(scm_adjust(ctx(), d->p, d->m, d->n, d->ld, coef, dsub, nsub, dout, ldo, NULL));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)nout, (int)d->m));
+    CHECK(scm_copy2d(ctx(), REAL(out), nout * 8, dout, ldo * 8, nout * 8, d->m, 1));
+    scm_coef_destroy(ctx(), coef);
+    scm_dev_free(ctx(), da); scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dce); scm_dev_free(ctx(), dpr); scm_dev_free(ctx(), dpo);
+    scm_dev_free(ctx(), dsub); scm_dev_free(ctx(), dout);
+    UNPROTECT(1);
+    return out;
+}
+
+/* segmented means by key: returns G x n (as n x G column-major) and counts */
+SEXP scm_segmean(SEXP Yp, SEXP key, SEXP G_) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int G = Rf_asInteger(G_);
+    int32_t* dk = (int32_t*)to_dev(INTEGER(key), d->m * 4);
+    double* dm; int64_t* dc;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)G * d->n * 8, (void**)&dm)); CHECK(scm_dev_alloc(ctx(), G * 8, (void**)&dc));
+    CHECK(scm_seg_colmean(ctx(), d->p, d->m, d->n, d->ld, dk, G, dm, dc, NULL));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP mm = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, G)); CHECK(scm_d2h(ctx(), REAL(mm), dm, (int64_t)G * d->n * 8));
+    int64_t* hc = (int64_t*)R_alloc(G, 8); CHECK(scm_d2h(ctx(), hc, dc, G * 8));
+    SEXP cc = PROTECT(Rf_allocVector(REALSXP, G)); for (int g = 0; g < G; g++) REAL(cc)[g] = (double)hc[g];
+    SET_VECTOR_ELT(out, 0, mm); SET_VECTOR_ELT(out, 1, cc);
+    scm_dev_free(ctx(), dk); scm_dev_free(ctx(), dm); scm_dev_free(ctx(), dc);
+    UNPROTECT(3);
+    return out;
+}
+
+static const R_CallMethodDef calls[] = {
+    {"scm_upload", (DL_FUNC)&scm_upload, 2}, {"scm_fit", (DL_FUNC)&scm_fit, 8},
+    {"scm_adjust_", (DL_FUNC)&scm_adjust_, 8}, {"scm_segmean", (DL_FUNC)&scm_segmean, 3}, {NULL, NULL, 0}};
+void R_init_scMergeB200(DllInfo* dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

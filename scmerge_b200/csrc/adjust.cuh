@@ -217,15 +217,19 @@ __device__ __forceinline__ void store4(double* __restrict__ rowp, int64_t g0, in
 
 constexpr int ADJ_WARPS = 4;
 
+// One CTA = 8*MT cells.  Its 4 warps split the GENE blocks round-robin (warp w takes blocks w, w+4, ...), so the
+// four warps touch adjacent 128-byte lines of the same rows, the part of the rows pass A has read is at most
+// 8*MT rows x c genes per CTA (it is still in L2 when pass B re-reads it), and every warp keeps one block of
+// loads in flight while it computes on the previous one (explicit double buffering: ya / yb).
 template <int KT, int MT, bool PASS_B>
-__global__ void __launch_bounds__(ADJ_WARPS * 32)
+__global__ void __launch_bounds__(ADJ_WARPS * 32, (KT <= 3) ? 3 : 2)
 adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, const double* __restrict__ Bfrag,
               const double* __restrict__ Afrag, const double* __restrict__ w0, const int32_t* __restrict__ ctl_blocks,
               int nblk_ctl, int nblk, int k, double* __restrict__ out, int64_t ldo, double* __restrict__ Wout, int vec_in, int vec_out) {
+    __shared__ double s_part[ADJ_WARPS][MT * KT * 2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int64_t row0 = ((int64_t)blockIdx.x * ADJ_WARPS + warp) * (8 * MT);
-    if (row0 >= m) return;
+    const int64_t row0 = (int64_t)blockIdx.x * (8 * MT);
     const double* rowp[MT];
     bool rowok[MT];
 #pragma unroll
@@ -234,18 +238,18 @@ adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, co
         rowok[mt] = r < m;
         rowp[mt] = Y + (rowok[mt] ? r : 0) * ld;
     }
-    // ---- pass A: W = Y B - w0 over the control-gene blocks
+    auto load_block = [&](double (&y)[MT][4], int gb) {
+        const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) load4(rowp[mt], g0, n, vec_in, rowok[mt], y[mt]);
+    };
+    // ---- pass A: partial W over this warp's control-gene blocks
     double w[MT][KT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) w[mt][nt][0] = w[mt][nt][1] = 0.0;
-    for (int bi = 0; bi < nblk_ctl; bi++) {
-        const int gb = ctl_blocks[bi];
-        const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
-        double y[MT][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) load4(rowp[mt], g0, n, vec_in, rowok[mt], y[mt]);
+    auto pass_a_block = [&](const double (&y)[MT][4], int gb) {
         const double2* bf = reinterpret_cast<const double2*>(Bfrag + ((int64_t)gb * 32 + lane) * KT * 4);
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) {
@@ -256,47 +260,89 @@ adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, co
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) dmma884(w[mt][nt][0], w[mt][nt][1], y[mt][j], b[j]);
         }
+    };
+    {
+        double ya[MT][4], yb[MT][4];
+        int bi = warp;
+        if (bi < nblk_ctl) load_block(ya, ctl_blocks[bi]);
+        while (bi < nblk_ctl) {
+            int nb = bi + ADJ_WARPS;
+            if (nb < nblk_ctl) load_block(yb, ctl_blocks[nb]);
+            pass_a_block(ya, ctl_blocks[bi]);
+            bi = nb;
+            if (bi >= nblk_ctl) break;
+            nb = bi + ADJ_WARPS;
+            if (nb < nblk_ctl) load_block(ya, ctl_blocks[nb]);
+            pass_a_block(yb, ctl_blocks[bi]);
+            bi = nb;
+        }
     }
+    // ---- combine the four partial W tiles (fixed order => deterministic), subtract center' B
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < KT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) s_part[warp][(mt * KT + nt) * 2 + e][lane] = w[mt][nt][e];
+    __syncthreads();
 #pragma unroll
     for (int nt = 0; nt < KT; nt++) {
         const int kk = 8 * nt + 2 * tig;
         const double c0 = kk < k ? w0[kk] : 0.0, c1 = kk + 1 < k ? w0[kk + 1] : 0.0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
-            w[mt][nt][0] -= c0; w[mt][nt][1] -= c1;
-            if (Wout && rowok[mt]) {
-                double* wr = Wout + (row0 + mt * 8 + gid) * k;
-                if (kk < k) wr[kk] = w[mt][nt][0];
-                if (kk + 1 < k) wr[kk + 1] = w[mt][nt][1];
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < ADJ_WARPS; ww++) {
+                t0 += s_part[ww][(mt * KT + nt) * 2 + 0][lane];
+                t1 += s_part[ww][(mt * KT + nt) * 2 + 1][lane];
             }
-            w[mt][nt][0] = -w[mt][nt][0]; w[mt][nt][1] = -w[mt][nt][1];  // pass B adds (-W) A
+            t0 -= c0; t1 -= c1;
+            if (Wout && warp == 0 && rowok[mt]) {
+                double* wr = Wout + (row0 + mt * 8 + gid) * k;
+                if (kk < k) wr[kk] = t0;
+                if (kk + 1 < k) wr[kk + 1] = t1;
+            }
+            w[mt][nt][0] = -t0; w[mt][nt][1] = -t1;  // pass B adds (-W) A
         }
     }
     if constexpr (PASS_B) {
-    // ---- pass B: out = Y + (-W) A, 16 genes (two n-tiles) per step
-    double* outp[MT];
+        // ---- pass B: out = Y + (-W) A over this warp's gene blocks, 16 genes (two n-tiles) per block
+        double* outp[MT];
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++) outp[mt] = out + (rowok[mt] ? row0 + mt * 8 + gid : 0) * ldo;
-    for (int gb = 0; gb < nblk; gb++) {
-        const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
-        double y[MT][4];
+        for (int mt = 0; mt < MT; mt++) outp[mt] = out + (rowok[mt] ? row0 + mt * 8 + gid : 0) * ldo;
+        auto pass_b_block = [&](double (&y)[MT][4], int gb) {
+            const double2* af = reinterpret_cast<const double2*>(Afrag + ((int64_t)gb * 32 + lane) * KT * 4);
+            double2 a[2 * KT];
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) load4(rowp[mt], g0, n, vec_in, rowok[mt], y[mt]);
-        const double2* af = reinterpret_cast<const double2*>(Afrag + ((int64_t)gb * 32 + lane) * KT * 4);
+            for (int i = 0; i < 2 * KT; i++) a[i] = __ldg(af + i);
 #pragma unroll
-        for (int tau = 0; tau < 2; tau++)
+            for (int tau = 0; tau < 2; tau++)
 #pragma unroll
-            for (int nt = 0; nt < KT; nt++) {
-                const double2 a = __ldg(af + tau * KT + nt);
+                for (int nt = 0; nt < KT; nt++)
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a.x);
-                    dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a.y);
-                }
-            }
+                    for (int mt = 0; mt < MT; mt++) {
+                        dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
+                        dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
+                    }
+            const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) store4(outp[mt], g0, n, vec_out, rowok[mt], y[mt]);
-    }
+            for (int mt = 0; mt < MT; mt++) store4(outp[mt], g0, n, vec_out, rowok[mt], y[mt]);
+        };
+        double ya[MT][4], yb[MT][4];
+        int gb = warp;
+        if (gb < nblk) load_block(ya, gb);
+        while (gb < nblk) {
+            int nb = gb + ADJ_WARPS;
+            if (nb < nblk) load_block(yb, nb);
+            pass_b_block(ya, gb);
+            gb = nb;
+            if (gb >= nblk) break;
+            nb = gb + ADJ_WARPS;
+            if (nb < nblk) load_block(ya, nb);
+            pass_b_block(yb, gb);
+            gb = nb;
+        }
     }
 }
 
@@ -321,7 +367,7 @@ inline int adjust_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, 
                          double* d_out, int64_t ldo, double* d_W) {
     const int vec_in = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
     const int vec_out = pass_b ? ((ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0)) : 0;
-    const int64_t rows_per_cta = (int64_t)ADJ_WARPS * 8 * MT;
+    const int64_t rows_per_cta = 8 * MT;
     const unsigned grid = (unsigned)ceil_div(m, rows_per_cta);
     if (pass_b)
         adjust_kernel<KT, MT, true><<<grid, ADJ_WARPS * 32, 0, ctx->stream>>>(d_Y, m, n, ld, c->Bfrag, c->Afrag, c->w0, c->ctl_blocks,
