@@ -234,7 +234,6 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
         raise NotImplementedError("eta (gene-wise covariates, ruv::RUV1) is not supported; all scMerge callers pass NULL")
     if k is None:
         raise TypeError("k must be given (the reference fails on k = NULL, R/fastRUVIII.R:78)")
-    ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
     m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
     keys, G = replicate_keys(M)
     if keys.shape[0] != m:
@@ -245,6 +244,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if G >= m or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input
         newY, fa = Y, None
         return {"newY": newY, "M": M, "fullalpha": fa} if return_info else newY
+    ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
     dY, copied = _as_device(ctx, Y)
     if fullalpha is None:
         # NA/Inf check (R/fastRUVIII.R:52-60) is fused into the first pass over Y; inputcheck=False only skips the raise
