@@ -20,7 +20,10 @@ class Context:
 
     def __init__(self, device: int = 0, stream: int | None = None):
         self._h = C.c_void_p()
-        L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(self._h)))
+        # stream=None: the library creates its own non-blocking stream.  stream=0 is torch's default stream, i.e. the
+        # legacy NULL stream, which must be passed as the cudaStreamLegacy handle (1) because NULL means "own stream".
+        handle = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
+        L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(handle), C.byref(self._h)))
         self.device = int(device)
         self.stream = stream
         self._cb = None  # keep the ctypes callback alive
