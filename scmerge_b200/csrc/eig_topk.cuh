@@ -107,34 +107,50 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
         V[idx] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
+    // One half-warp (16 lanes) per column pair: all <= 56 disjoint pairs of a round run concurrently on the 64
+    // half-warps.  Squared column norms are cached (recomputed once per sweep, updated by the Rutishauser formulas
+    // ||a_p'||^2 = alpha - t*gamma, ||a_q'||^2 = beta + t*gamma), so a pair costs one dot product + the rotation.
     const int npair = lp / 2;
+    const int hw = tid >> 4, hl = tid & 15;
+    double* nrm2 = s_norm;  // reused as the squared-norm cache during the sweeps
     int sweep = 0;
     for (; sweep < max_sweeps; sweep++) {
         if (tid == 0) s_rot = 0;
+        for (int j = warp; j < lp; j += nwarp) {
+            double a = 0.0;
+            for (int i = lane; i < lp; i += 32) a += A[j * lp + i] * A[j * lp + i];
+            a = warp_sum(a);
+            if (lane == 0) nrm2[j] = a;
+        }
         __syncthreads();
         for (int r = 0; r < lp - 1; r++) {
-            for (int pi = warp; pi < npair; pi += nwarp) {
-                int p, q;
-                if (pi == 0) { p = lp - 1; q = r; }
-                else { p = (r + pi) % (lp - 1); q = (r - pi + (lp - 1)) % (lp - 1); }
-                double* ap = A + p * lp; double* aq = A + q * lp;
-                double al = 0.0, be = 0.0, ga = 0.0;
-                for (int i = lane; i < lp; i += 32) { const double x = ap[i], y = aq[i]; al += x * x; be += y * y; ga += x * y; }
-                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                // rotate unless the columns are orthogonal to rounding level (l * eps ~ 2e-14: a tighter
-                // threshold is below the rounding noise of the dot product and never lets a sweep come out clean)
+            const bool act = hw < npair;
+            int p = 0, q = 0;
+            if (act) {
+                if (hw == 0) { p = lp - 1; q = r; }
+                else { p = (r + hw) % (lp - 1); q = (r - hw + (lp - 1)) % (lp - 1); }
+            }
+            double* ap = A + p * lp; double* aq = A + q * lp;
+            double ga = 0.0;
+            if (act) for (int i = hl; i < lp; i += 16) ga += ap[i] * aq[i];
+            const double al = nrm2[p], be = nrm2[q];  // read before the shuffles: they order it against lane 0's update
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);  // all lanes: warp stays converged
+            if (act) {
+                // rotate unless the columns are orthogonal to rounding level (l * eps ~ 2e-14: a tighter threshold is
+                // below the rounding noise of the dot product and never lets a sweep come out clean)
                 if (fabs(ga) > 2e-14 * sqrt(al * be) && fabs(ga) > 1e-300) {
                     const double zeta = (be - al) / (2.0 * ga);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    const double c = rsqrt(1.0 + t * t), s = c * t;
                     double* vp = V + p * lp; double* vq = V + q * lp;
-                    for (int i = lane; i < lp; i += 32) {
+                    for (int i = hl; i < lp; i += 16) {
                         const double x = ap[i], y = aq[i];
                         ap[i] = c * x - s * y; aq[i] = s * x + c * y;
                         const double vx = vp[i], vy = vq[i];
                         vp[i] = c * vx - s * vy; vq[i] = s * vx + c * vy;
                     }
-                    if (lane == 0) s_rot = 1;
+                    if (hl == 0) { nrm2[p] = al - t * ga; nrm2[q] = be + t * ga; s_rot = 1; }
                 }
             }
             __syncthreads();

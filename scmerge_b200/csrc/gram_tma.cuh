@@ -93,7 +93,11 @@ __device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+// 3 warpgroups: 8 consumer warps (setmaxnreg.inc -> 232 registers) + one producer warpgroup (setmaxnreg.dec -> 40;
+// only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
+constexpr int GT_THREADS = 384;
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, const double* __restrict__ shift, int T, int S,
                 int64_t rows_per_split, double* __restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
@@ -117,8 +121,41 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
         for (int q = 0; q < 2; q++)
             off[p][q] = (2 * tig + p) * 128 + ((((gid >> 1) ^ (2 * tig + p)) ^ (q << 2)) << 4) + (gid & 1) * 8;
 
-    uint32_t gl = 0, gu = 0;  // chunks loaded (meaningful in thread 0) / consumed so far by this CTA
     const int64_t units = (int64_t)T * S;
+    if (warp >= 8) {
+        // ===== producer warpgroup: one lane walks the same unit / chunk sequence and keeps the ring full =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (tid != 256) return;
+        uint32_t gl = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int split = (int)(u / T);
+            int ti, tj;
+            tri_decode((int)(u % T), ti, tj);
+            const bool diag = (ti == tj);
+            const int64_t row_begin = (int64_t)split * rows_per_split;
+            const int64_t row_end = min(m, row_begin + rows_per_split);
+            const int nchunk = row_end > row_begin ? (int)ceil_div(row_end - row_begin, GT_KC) : 0;
+            const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
+            for (int c = 0; c < nchunk; c++, gl++) {
+                const int slot = gl % GT_STAGES;
+                if (gl >= GT_STAGES) mbar_wait(&empty[slot], ((gl / GT_STAGES) - 1) & 1);
+                uint8_t* sa = smem + slot * GT_STAGE_BYTES;
+                mbar_expect_tx(&full[slot], diag ? GT_TILE_BYTES : GT_STAGE_BYTES);
+                const int row = (int)(row_begin + (int64_t)c * GT_KC);
+#pragma unroll
+                for (int sl = 0; sl < 8; sl++) tma_load_2d(sa + sl * GT_SLAB_BYTES, &tmap, colA0 + 16 * sl, row, &full[slot]);
+                if (!diag) {
+#pragma unroll
+                    for (int sl = 0; sl < 8; sl++)
+                        tma_load_2d(sa + GT_TILE_BYTES + sl * GT_SLAB_BYTES, &tmap, colB0 + 16 * sl, row, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+    // ===== consumer warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    uint32_t gu = 0;  // chunks consumed so far by this CTA
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
         const int split = (int)(u / T);
         int ti, tj;
@@ -139,28 +176,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
 #pragma unroll
             for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-        int issued = 0;
-        auto produce = [&](int upto) {  // thread 0 only: keep the ring filled up to chunk index `upto` (exclusive)
-            while (issued < upto) {
-                const int slot = gl % GT_STAGES;
-                if (gl >= GT_STAGES) mbar_wait(&empty[slot], ((gl / GT_STAGES) - 1) & 1);
-                uint8_t* sa = smem + slot * GT_STAGE_BYTES;
-                mbar_expect_tx(&full[slot], diag ? GT_TILE_BYTES : GT_STAGE_BYTES);
-                const int row = (int)(row_begin + (int64_t)issued * GT_KC);
-#pragma unroll
-                for (int sl = 0; sl < 8; sl++) tma_load_2d(sa + sl * GT_SLAB_BYTES, &tmap, colA0 + 16 * sl, row, &full[slot]);
-                if (!diag) {
-#pragma unroll
-                    for (int sl = 0; sl < 8; sl++)
-                        tma_load_2d(sa + GT_TILE_BYTES + sl * GT_SLAB_BYTES, &tmap, colB0 + 16 * sl, row, &full[slot]);
-                }
-                gl++;
-                issued++;
-            }
-        };
         for (int c = 0; c < nchunk; c++) {
-            if (tid == 0) produce(min(nchunk, c + GT_STAGES - 1));
-            __syncwarp();
             const int slot = gu % GT_STAGES;
             mbar_wait(&full[slot], (gu / GT_STAGES) & 1);
             const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
@@ -219,7 +235,7 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
         SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
         attr_set = true;
     }
-    gram_tma_kernel<<<p.grid, 256, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial);
+    gram_tma_kernel<<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial);
     return 0;
 }
 
