@@ -155,6 +155,22 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
                  double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd,
                  int32_t* iters_out, double* resid_out);
 
+/* scm_ruv3_host: the whole closure on HOST matrices (what `.Call` hands over), with the PCIe copies overlapped with
+ * the kernels: Y is uploaded in row chunks on a copy stream while the replicate sums and the Gram accumulate behind
+ * it, then the adjust kernel runs chunk by chunk in place and every finished chunk is downloaded while the next is
+ * computed.  Use page-locked host buffers (scm_host_alloc_pinned) for full PCIe speed.
+ *   h_Y, h_out        : row-major cells x genes (== R genes x cells column-major), leading dimensions ldh / ldo
+ *   h_batch != NULL   : scRUVIII (standardise + de-standardise fused, R/scRUVIII.R:41-137); else fastRUVIII
+ *   h_fullalpha_in    : non-NULL (s_in x n) = adjust only (fullalpha re-use R/fastRUVIII.R:83, pseudoRUVIII /
+ *                       getAdjustedMat R/scMerge2_utilis.R:97-137, R/scMerge2.R:392-406) with
+ *                       center_mode 0 none, 1 column means of Y (computed during the upload), 2 h_center
+ *   outputs (optional): h_fullalpha s x n, h_sigma s, h_mean n (stand_mean or the column means), h_sd n */
+int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,
+                  const int32_t* h_batch, int32_t Bt, const uint8_t* h_ctl, int32_t k, int32_t s, int mode, double tol,
+                  int32_t maxit, uint64_t seed, const double* h_fullalpha_in, int32_t s_in, int center_mode,
+                  const double* h_center, double* h_out, int64_t ldo, double* h_fullalpha, double* h_sigma, double* h_mean,
+                  double* h_sd, int32_t* iters_out, double* resid_out);
+
 /* Stage timers (ms, CUDA events on the context stream) of the last scm_ruv3_fit / scm_adjust:
  * 0 seg_colsum, 1 gram (SYRK + split reduce), 2 allreduce, 3 eig, 4 coef, 5 adjust, 6 standardise,
  * 7 the gram_syrk kernel alone. */

@@ -48,6 +48,8 @@ SIGNATURES = {
     "scm_adjust": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i64, _vp],
     "scm_ruv3_fit": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _int, _dbl, _i32, _u64,
                      _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
+    "scm_ruv3_host": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _int, _dbl, _i32, _u64, _vp, _i32, _int,
+                      _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
     "scm_timers": [_vp, C.POINTER(_dbl), _int],
 }
 _RESTYPES = {"scm_last_error": C.c_char_p}

@@ -50,6 +50,7 @@ struct scm_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // PCIe transfers of the host-matrix drivers (created on first use)
     bool own_stream = false;
     int64_t launches = 0;
     scm_allreduce_fn allreduce = nullptr;

@@ -200,7 +200,7 @@ gram_syrk_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld,
 // gram[i][j] = sum_s partial[s][tile(i,j)][..] for j-tile <= i-tile, mirrored for the upper triangle.
 // One CTA per lower tile; writes both (ti,tj) and its transpose.
 __global__ void __launch_bounds__(256)
-gram_reduce_kernel(const double* __restrict__ partial, int T, int S, int64_t n, double* __restrict__ gram) {
+gram_reduce_kernel(const double* __restrict__ partial, int T, int S, int64_t n, double* __restrict__ gram, int accumulate) {
     __shared__ double tile[32][33];
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);
@@ -208,10 +208,10 @@ gram_reduce_kernel(const double* __restrict__ partial, int T, int S, int64_t n, 
     const int bi = (blockIdx.y >> 2) * 32, bj = (blockIdx.y & 3) * 32;  // 32x32 sub-block of the tile
     for (int r = ty; r < 32; r += 8) {
         const int i = bi + r, j = bj + tx;
-        double acc = 0.0;
+        const int64_t gi = (int64_t)ti * GR_BT + i, gj = (int64_t)tj * GR_BT + j;
+        double acc = (accumulate && gi < n && gj < n) ? gram[gi * n + gj] : 0.0;  // chunked fits add into the running Gram
         for (int s = 0; s < S; s++) acc += partial[((int64_t)s * T + blockIdx.x) * (GR_BT * GR_BT) + i * GR_BT + j];
         tile[r][tx] = acc;
-        const int64_t gi = (int64_t)ti * GR_BT + i, gj = (int64_t)tj * GR_BT + j;
         if (gi < n && gj < n) gram[gi * n + gj] = acc;
     }
     __syncthreads();
@@ -254,11 +254,11 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
                            const GramPlan& p, double* partial);
 
 inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift, double* d_gram,
-                bool timed = false) {
+                bool timed = false, bool accumulate = false) {
     if (m < 0 || n <= 0 || ld < n) return fail(SCM_ERR_INVALID, "gram: bad shape m=%lld n=%lld ld=%lld", (long long)m, (long long)n, (long long)ld);
     cudaStream_t st = ctx->stream;
     if (m == 0) {
-        SCM_CUDA(cudaMemsetAsync(d_gram, 0, sizeof(double) * n * n, st));
+        if (!accumulate) SCM_CUDA(cudaMemsetAsync(d_gram, 0, sizeof(double) * n * n, st));
         return 0;
     }
     static bool attr_set = false;
@@ -282,7 +282,7 @@ inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t l
         gram_syrk_kernel<1><<<p.grid, GR_THREADS, GR_SMEM_BYTES, st>>>(d_Y, m, n, ld, d_shift, p.T, p.S, p.rows_per_split, partial);
     if (timed) { cudaEventRecord(ctx->ev1[ST_SYRK], st); ctx->ev_used[ST_SYRK] = true; }
     SCM_LAUNCH_CHECK(ctx);
-    gram_reduce_kernel<<<dim3(p.T, 16), 256, 0, st>>>(partial, p.T, p.S, n, d_gram);
+    gram_reduce_kernel<<<dim3(p.T, 16), 256, 0, st>>>(partial, p.T, p.S, n, d_gram, accumulate ? 1 : 0);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }

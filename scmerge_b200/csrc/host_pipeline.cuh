@@ -1,0 +1,224 @@
+// End-to-end driver for HOST matrices: RUV-III with the PCIe transfers overlapped with the kernels.
+//
+//   upload  : Y arrives in row chunks on a copy stream; as soon as a chunk has landed the compute stream adds its
+//             replicate-group sums (K1) and its shifted Gram (K3, accumulate) -- the fit streams behind the H2D copy
+//             (the Gram identity of DESIGN.md section 2 holds for ANY fixed shift, so the shift is the column mean of
+//             the first chunk and no second pass over Y is needed),
+//   solve   : Gram correction, top-s eigenpairs, coefficients (small, latency bound),
+//   download: the fused adjust kernel (K6) runs chunk by chunk IN PLACE and each finished chunk goes back over
+//             PCIe while the next one is being adjusted.
+// Included by scm_api.cu after the small helper kernels (meta_kernel, colmean_kernel, ...).
+#pragma once
+#include "adjust.cuh"
+#include "common.cuh"
+#include "eig_topk.cuh"
+#include "gram_tma.cuh"
+#include "seg_colsum.cuh"
+
+namespace scm {
+
+__global__ void add_f64_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] += src[i];
+}
+__global__ void add_i64_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] += src[i];
+}
+// meta[0] |= flag, meta[1] += rows
+__global__ void meta_acc_kernel(const int32_t* __restrict__ flag, int64_t rows, int64_t* __restrict__ meta) {
+    if (flag[0]) meta[0] = 1;
+    meta[1] += rows;
+}
+__global__ void reciprocal_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 1.0 / x[i];
+}
+
+struct HostArgs {
+    const double* h_Y; int64_t m, n, ldh;
+    const int32_t* h_group; int32_t G;
+    const int32_t* h_batch; int32_t Bt;
+    const uint8_t* h_ctl; int32_t k, s; int mode; double tol; int32_t maxit; uint64_t seed;
+    const double* h_fullalpha_in; int32_t s_in;  // adjust-only when given
+    int center_mode;                             // adjust-only: 0 none, 1 column means of Y, 2 h_center
+    const double* h_center;
+    double* h_out; int64_t ldo;
+    double *h_fullalpha, *h_sigma, *h_mean, *h_sd;
+    int32_t* iters_out; double* resid_out;
+};
+
+inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
+    const int64_t m = a.m, n = a.n;
+    if (!a.h_Y || !a.h_out || m <= 0 || n <= 0 || a.ldh < n || a.ldo < n || !a.h_ctl) return fail(SCM_ERR_INVALID, "scm_ruv3_host: bad arguments");
+    const bool do_fit = a.h_fullalpha_in == nullptr;
+    const bool sc = do_fit && a.h_batch != nullptr;
+    if (do_fit && (!a.h_group || a.G <= 0 || a.s <= 0)) return fail(SCM_ERR_INVALID, "scm_ruv3_host: fit requested without groups / s");
+    cudaStream_t st = ctx->stream;
+    if (!ctx->copy_stream) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream;
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    int64_t rows_per_chunk = ((int64_t)512 << 20) / (ld * 8);
+    rows_per_chunk = rows_per_chunk / 1024 * 1024;
+    if (rows_per_chunk < 4096) rows_per_chunk = 4096;
+    if (const char* e = getenv("SCM_HOST_CHUNK_ROWS")) {  // test hook: force several chunks on small inputs
+        const long v = atol(e);
+        if (v >= 16) rows_per_chunk = v;
+    }
+    const int nchunks = (int)ceil_div(m, rows_per_chunk);
+    std::vector<cudaEvent_t> ev(nchunks);
+    for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t ev_alloc, ev_done;
+    SCM_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    SCM_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    struct EvGuard {
+        std::vector<cudaEvent_t>& v; cudaEvent_t a, b;
+        ~EvGuard() { for (auto e : v) cudaEventDestroy(e); cudaEventDestroy(a); cudaEventDestroy(b); }
+    } guard{ev, ev_alloc, ev_done};
+
+    Scratch ws(ctx);
+    double *dY, *gsums = nullptr, *tsums = nullptr, *shift = nullptr, *Gm = nullptr, *vals = nullptr, *vecs = nullptr, *fa = nullptr;
+    double *bsums = nullptr, *ssq = nullptr, *sd = nullptr, *inv_sd = nullptr, *center = nullptr, *sig = nullptr;
+    int64_t *gcounts = nullptr, *tcounts = nullptr, *bcounts = nullptr, *meta = nullptr;
+    int32_t *dgroup = nullptr, *dbatch = nullptr, *flag = nullptr;
+    uint8_t* dctl;
+    const int32_t s = do_fit ? a.s : a.s_in;
+    SCM_TRY(ws.alloc(&dY, m * ld));
+    SCM_TRY(ws.alloc(&dctl, n));
+    SCM_TRY(ws.alloc(&fa, (int64_t)s * n));
+    SCM_TRY(ws.alloc(&meta, 2)); SCM_TRY(ws.alloc(&flag, 1));
+    SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&center, n));
+    SCM_CUDA(cudaMemsetAsync(meta, 0, 16, st));
+    SCM_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    SCM_CUDA(cudaMemcpyAsync(dctl, a.h_ctl, n, cudaMemcpyHostToDevice, st));
+    const int32_t Gk = do_fit ? a.G : 1;  // adjust-only runs use one group (column means)
+    SCM_TRY(ws.alloc(&gsums, (int64_t)Gk * n)); SCM_TRY(ws.alloc(&tsums, (int64_t)Gk * n));
+    SCM_TRY(ws.alloc(&gcounts, Gk)); SCM_TRY(ws.alloc(&tcounts, Gk));
+    SCM_TRY(ws.alloc(&dgroup, m));
+    SCM_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * Gk * n, st));
+    SCM_CUDA(cudaMemsetAsync(gcounts, 0, sizeof(int64_t) * Gk, st));
+    if (do_fit) {
+        SCM_TRY(ws.alloc(&Gm, n * n)); SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n)); SCM_TRY(ws.alloc(&sig, s));
+        SCM_CUDA(cudaMemcpyAsync(dgroup, a.h_group, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+    } else {
+        SCM_CUDA(cudaMemsetAsync(dgroup, 0, sizeof(int32_t) * m, st));
+        SCM_CUDA(cudaMemcpyAsync(fa, a.h_fullalpha_in, sizeof(double) * s * n, cudaMemcpyHostToDevice, st));
+    }
+    if (sc) {
+        SCM_TRY(ws.alloc(&dbatch, m)); SCM_TRY(ws.alloc(&bsums, (int64_t)a.Bt * n)); SCM_TRY(ws.alloc(&ssq, (int64_t)a.Bt * n));
+        SCM_TRY(ws.alloc(&bcounts, a.Bt)); SCM_TRY(ws.alloc(&sd, n)); SCM_TRY(ws.alloc(&inv_sd, n));
+        SCM_CUDA(cudaMemcpyAsync(dbatch, a.h_batch, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+    }
+    SCM_CUDA(cudaEventRecord(ev_alloc, st));
+    SCM_CUDA(cudaStreamWaitEvent(cs, ev_alloc, 0));  // the copy stream may touch the pool allocations from here on
+
+    // ---- upload, with the fit accumulating behind it
+    const bool need_sums = do_fit || a.center_mode == 1;
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+        SCM_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, a.h_Y + r0 * a.ldh, a.ldh * 8, n * 8, rows, cudaMemcpyHostToDevice, cs));
+        SCM_CUDA(cudaEventRecord(ev[c], cs));
+        SCM_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+        if (!need_sums) continue;
+        {
+            StageTimer t(ctx, ST_SEG);
+            SCM_TRY(seg_colsum(ctx, dY + r0 * ld, rows, n, ld, dgroup + r0, Gk, nullptr, tsums, tcounts, flag));
+            add_f64_kernel<<<(unsigned)ceil_div((int64_t)Gk * n, 256), 256, 0, st>>>(gsums, tsums, (int64_t)Gk * n);
+            SCM_LAUNCH_CHECK(ctx);
+            add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcounts, tcounts, Gk);
+            SCM_LAUNCH_CHECK(ctx);
+            meta_acc_kernel<<<1, 1, 0, st>>>(flag, rows, meta);
+            SCM_LAUNCH_CHECK(ctx);
+        }
+        if (!do_fit) continue;
+        if (c == 0) {
+            // shift = column mean of the first chunk (summed over ranks so that every rank uses the same vector)
+            int64_t* m0;
+            SCM_TRY(ws.alloc(&m0, 2));
+            SCM_CUDA(cudaMemcpyAsync(m0, meta, 16, cudaMemcpyDeviceToDevice, st));
+            SCM_CUDA(cudaMemcpyAsync(tsums, gsums, sizeof(double) * Gk * n, cudaMemcpyDeviceToDevice, st));
+            SCM_TRY(allreduce(ctx, tsums, (int64_t)Gk * n, 0));
+            SCM_TRY(allreduce(ctx, m0, 2, 1));
+            colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, m0, shift);
+            SCM_LAUNCH_CHECK(ctx);
+        }
+        StageTimer t(ctx, ST_GRAM);
+        SCM_TRY(gram(ctx, dY + r0 * ld, rows, n, ld, shift, Gm, c == nchunks - 1, c > 0));
+    }
+    int rc = 0;
+    scm_coef* coef = nullptr;
+    if (do_fit) {
+        SCM_TRY(allreduce(ctx, gsums, (int64_t)Gk * n, 0));
+        SCM_TRY(allreduce(ctx, gcounts, Gk, 1));
+        SCM_TRY(allreduce(ctx, meta, 2, 1));
+        SCM_TRY(allreduce(ctx, Gm, n * n, 0));
+        colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, Gk, n, meta, center);  // global mean (stand_mean)
+        SCM_LAUNCH_CHECK(ctx);
+        if (sc) {  // standardize2: pooled within-batch sd needs the batch means first -> one more pass over the resident Y
+            StageTimer t(ctx, ST_STD);
+            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, a.Bt, nullptr, bsums, bcounts, nullptr));
+            SCM_TRY(allreduce(ctx, bsums, (int64_t)a.Bt * n, 0));
+            SCM_TRY(allreduce(ctx, bcounts, a.Bt, 1));
+            groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, a.Bt, n);
+            SCM_LAUNCH_CHECK(ctx);
+            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, a.Bt, bsums, ssq, nullptr, nullptr));
+            SCM_TRY(allreduce(ctx, ssq, (int64_t)a.Bt * n, 0));
+            pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bcounts, a.Bt, n, meta, sd, inv_sd);
+            SCM_LAUNCH_CHECK(ctx);
+        }
+        SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, a.G, shift, inv_sd));
+        int64_t hmeta[2];
+        SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
+        SCM_CUDA(cudaStreamSynchronize(st));
+        if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+        {
+            StageTimer t(ctx, ST_EIG);
+            const int32_t kconv = a.k < s ? a.k : s;
+            rc = eig_topk(ctx, Gm, n, s, kconv, a.mode, a.tol, a.maxit, a.seed, vals, vecs, a.iters_out, a.resid_out);
+            if (rc != 0 && rc != SCM_ERR_NOCONV) return rc;
+            dim3 grid((unsigned)ceil_div(n, 256), (unsigned)s);
+            fullalpha_kernel<<<grid, 256, 0, st>>>(vals, vecs, s, n, fa, sig);
+            SCM_LAUNCH_CHECK(ctx);
+        }
+        if (a.h_fullalpha) SCM_CUDA(cudaMemcpyAsync(a.h_fullalpha, fa, sizeof(double) * s * n, cudaMemcpyDeviceToHost, st));
+        if (a.h_sigma) SCM_CUDA(cudaMemcpyAsync(a.h_sigma, sig, sizeof(double) * s, cudaMemcpyDeviceToHost, st));
+        if (sc && a.h_mean) SCM_CUDA(cudaMemcpyAsync(a.h_mean, center, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (sc && a.h_sd) SCM_CUDA(cudaMemcpyAsync(a.h_sd, sd, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    } else if (a.center_mode == 1) {
+        SCM_TRY(allreduce(ctx, gsums, n, 0));
+        SCM_TRY(allreduce(ctx, meta, 2, 1));
+        colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, 1, n, meta, center);
+        SCM_LAUNCH_CHECK(ctx);
+        if (a.h_mean) SCM_CUDA(cudaMemcpyAsync(a.h_mean, center, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    } else if (a.center_mode == 2) {
+        if (!a.h_center) return fail(SCM_ERR_INVALID, "scm_ruv3_host: center_mode 2 without h_center");
+        SCM_CUDA(cudaMemcpyAsync(center, a.h_center, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    }
+    {
+        StageTimer t(ctx, ST_COEF);
+        const int32_t kk = a.k < s ? a.k : s;
+        const double* c_center = sc ? center : (do_fit ? nullptr : (a.center_mode ? center : nullptr));
+        int crc = coef_create(ctx, fa, n, kk, dctl, c_center, sc ? inv_sd : nullptr, sc ? sd : nullptr, &coef);
+        if (crc != 0) return crc;
+    }
+    // ---- adjust in place chunk by chunk, each finished chunk goes back to the host while the next is computed
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+        {
+            StageTimer t(ctx, ST_ADJUST);
+            int arc = adjust(ctx, dY + r0 * ld, rows, n, ld, coef, nullptr, 0, dY + r0 * ld, ld, nullptr);
+            if (arc != 0) { coef_destroy(ctx, coef); return arc; }
+        }
+        SCM_CUDA(cudaEventRecord(ev[c], st));
+        SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
+        SCM_CUDA(cudaMemcpy2DAsync(a.h_out + r0 * a.ldo, a.ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+    }
+    SCM_CUDA(cudaEventRecord(ev_done, cs));
+    SCM_CUDA(cudaStreamWaitEvent(st, ev_done, 0));  // scratch is freed in stream order on `st`: wait for the downloads
+    coef_destroy(ctx, coef);
+    SCM_CUDA(cudaStreamSynchronize(cs));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+}  // namespace scm

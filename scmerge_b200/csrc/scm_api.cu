@@ -82,6 +82,8 @@ inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
 
 }  // namespace scm
 
+#include "host_pipeline.cuh"
+
 using namespace scm;
 
 #define SCM_REQUIRE_CTX(ctx)                                             \
@@ -341,6 +343,17 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
     }
     SCM_CUDA(cudaStreamSynchronize(st));
     return rc;
+}
+
+int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,
+                  const int32_t* h_batch, int32_t Bt, const uint8_t* h_ctl, int32_t k, int32_t s, int mode, double tol, int32_t maxit,
+                  uint64_t seed, const double* h_fullalpha_in, int32_t s_in, int center_mode, const double* h_center, double* h_out,
+                  int64_t ldo, double* h_fullalpha, double* h_sigma, double* h_mean, double* h_sd, int32_t* iters_out,
+                  double* resid_out) {
+    SCM_REQUIRE_CTX(ctx);
+    HostArgs a{h_Y, m, n, ldh, h_group, G, h_batch, Bt, h_ctl, k, s, mode, tol, maxit, seed, h_fullalpha_in, s_in, center_mode,
+               h_center, h_out, ldo, h_fullalpha, h_sigma, h_mean, h_sd, iters_out, resid_out};
+    return ruv3_host(ctx, a);
 }
 
 int scm_timers(scm_ctx* ctx, double* ms, int n) {

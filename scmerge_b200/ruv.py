@@ -214,6 +214,45 @@ def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: 
     return out, W
 
 
+def _is_host_matrix(Y) -> bool:
+    return isinstance(Y, np.ndarray) and Y.ndim == 2 and Y.dtype == np.float64 and Y.flags.c_contiguous and Y.size > 0
+
+
+def _host_pipeline(ctx: Context, Y: np.ndarray, ctl: np.ndarray, k: int, keys=None, G=0, s=0, exact=True, batch_keys=None, Bt=0,
+                   fullalpha_in=None, center_mode=0, center=None, out=None, tol=1e-10, maxit=500, seed=1):
+    """scm_ruv3_host: upload / fit / adjust / download of a HOST cells x genes matrix with the PCIe copies overlapped
+    with the kernels.  Returns (newY, RUVFit)."""
+    lib = L.lib()
+    m, n = Y.shape
+    if out is None:
+        out = np.empty((m, n), dtype=np.float64)
+    assert out.shape == (m, n) and out.dtype == np.float64 and out.flags.c_contiguous
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
+    ctl8 = np.ascontiguousarray(ctl, dtype=np.uint8)
+    do_fit = fullalpha_in is None
+    keys32 = np.ascontiguousarray(keys, dtype=np.int32) if do_fit else None
+    b32 = np.ascontiguousarray(batch_keys, dtype=np.int32) if (do_fit and batch_keys is not None) else None
+    fa_in = np.ascontiguousarray(fullalpha_in, dtype=np.float64) if not do_fit else None
+    s_out = s if do_fit else fa_in.shape[0]
+    if min(k, s_out) > L.MAX_K:
+        raise L.ScmError(L.ERR_UNSUPPORTED, f"ruvK = {min(k, s_out)} > {L.MAX_K} is not supported by the fused adjust kernel")
+    fa = np.empty((s_out, n)) if do_fit else fa_in
+    sig = np.empty(s_out) if do_fit else None
+    mean = np.empty(n) if (b32 is not None or center_mode == 1) else None
+    sd = np.empty(n) if b32 is not None else None
+    cen = np.ascontiguousarray(center, dtype=np.float64) if center is not None else None
+    iters, resid = C.c_int32(0), C.c_double(0.0)
+    rc = lib.scm_ruv3_host(ctx.handle, vp(Y), m, n, n, vp(keys32), G, vp(b32), Bt, vp(ctl8), int(k), int(s_out),
+                           L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, vp(fa_in), 0 if do_fit else s_out,
+                           center_mode, vp(cen), vp(out), n, vp(fa) if do_fit else None, vp(sig), vp(mean), vp(sd),
+                           C.byref(iters), C.byref(resid))
+    if rc == L.ERR_NOCONV:
+        warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
+    else:
+        L.check(rc)
+    return out, RUVFit(fa, sig, mean, sd, iters.value, resid.value)
+
+
 def _finish(out: DeviceMatrix, made_copy_in: bool, host_out=None):
     """Return numpy when the caller gave numpy, else the DeviceMatrix."""
     if not made_copy_in:
@@ -245,6 +284,16 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
         newY, fa = Y, None
         return {"newY": newY, "M": M, "fullalpha": fa} if return_info else newY
     ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
+    if _is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray)):
+        # host matrix: one pipelined call (H2D / fit / adjust / D2H overlapped)
+        if fullalpha is None:
+            s_dev, exact_dev = _device_rows_cap(s, k, exact)
+            newY, fit = _host_pipeline(ctx, Y, ctl, int(k), keys=keys, G=G, s=s_dev, exact=exact_dev, out=out)
+            fullalpha = fit.fullalpha
+        else:
+            fullalpha = np.asarray(fullalpha, dtype=np.float64)
+            newY, _ = _host_pipeline(ctx, Y, ctl, int(k), fullalpha_in=fullalpha, center_mode=0, out=out)
+        return {"newY": newY, "M": M, "fullalpha": fullalpha} if return_info else newY
     dY, copied = _as_device(ctx, Y)
     if fullalpha is None:
         # NA/Inf check (R/fastRUVIII.R:52-60) is fused into the first pass over Y; inputcheck=False only skips the raise
@@ -273,6 +322,26 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
         raise ValueError("batch is required")
     ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
     ctx = ctx or default_context()
+    if isinstance(Y, np.ndarray) and _is_host_matrix(Y.T) and len(ks) == 1 and fullalpha is None:
+        # genes x cells in column-major order (R's layout) is cells x genes row-major: pipelined host path
+        Yt = Y.T
+        m, n = Yt.shape
+        keys, G = replicate_keys(M)
+        bkeys, Bt = replicate_keys(np.asarray(batch))
+        ctlm = tological(ctl, n)
+        exact = _is_exact(BSPARAM)
+        s = _svd_k(m, G, int(ctlm.sum()), exact, svd_k)
+        if G >= m or ks[0] == 0:
+            raise NotImplementedError("degenerate replicate structure (ncol(M) >= m): nothing to adjust")
+        s_dev, exact_dev = _device_rows_cap(s, ks[0], exact)
+        newY, fit = _host_pipeline(ctx, Yt, ctlm, ks[0], keys=keys, G=G, s=s_dev, exact=exact_dev, batch_keys=bkeys, Bt=Bt)
+        res = {ks[0]: {"newY": newY, "M": M, "fullalpha": fit.fullalpha}, "optimal_ruvK": ks[0],
+               "stand_mean": fit.stand_mean, "stand_sd": fit.stand_sd}
+        if return_all_RUV:
+            return res
+        one = dict(res[ks[0]])
+        one["optimal_ruvK"] = ks[0]
+        return one
     if isinstance(Y, DeviceMatrix):
         dY, copied = Y, False
     else:
@@ -341,6 +410,12 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
     fullalpha = np.asarray(fullalpha, dtype=np.float64)
     if not normalised:
         return {"M": M, "fullalpha": fullalpha}
+    if _is_host_matrix(Y) and subset is None:
+        # host matrix: column means accumulate during the chunked upload, adjust + download are overlapped
+        newY, st = _host_pipeline(ctx, Y, ctl, int(k), fullalpha_in=fullalpha, center_mode=1)
+        if not return_info:
+            return newY
+        return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": st.stand_mean}
     dY, copied = _as_device(ctx, Y)
     means = column_means(dY)  # adjusted_means <- colMeans(Y) over ALL cells (R/scMerge2_utilis.R:97)
     sub = None if subset is None else np.nonzero(tological(subset, n))[0] if np.asarray(subset).dtype == bool else np.asarray(subset)

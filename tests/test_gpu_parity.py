@@ -267,6 +267,38 @@ def test_k_sweep_planted(sm, k):
     assert orc.principal_angles(out["fullalpha"][:k], ref["fullalpha"][:k]).max() < 1e-6
 
 
+def test_host_pipeline_multichunk(sm, monkeypatch):
+    """scm_ruv3_host with the upload / download cut into several chunks (fit accumulates behind the H2D copies,
+    shift = mean of the first chunk only) must equal the oracle and the single-chunk run."""
+    P = orc.planted_factors(5000, 260, 100, 7, n_types=5, n_batch=3, seed=5)
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 7, return_info=True)
+    one = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=7)
+    monkeypatch.setenv("SCM_HOST_CHUNK_ROWS", "1024")
+    Yp, out = sm.pinned_empty(P["Y"].shape), sm.pinned_empty(P["Y"].shape)
+    Yp[:] = P["Y"]
+    res = sm.fastRUVIII(Yp, P["types"], P["ctl"], k=7, return_info=True, out=out)
+    assert res["newY"] is out
+    assert orc.rel_frobenius(out, ref["newY"]) < TOL_NEWY
+    assert orc.rel_frobenius(out, one) < 1e-11
+    # fullalpha re-use (adjust only) and the scRUVIII / pseudoRUVIII host paths, still chunked
+    again = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=4, fullalpha=res["fullalpha"])
+    assert orc.rel_frobenius(again, orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 4)) < TOL_NEWY
+    batch = np.array([f"b{b}" for b in P["batch"]])
+    Yg = np.asfortranarray(P["Y"].T)  # genes x cells, column-major: R's layout
+    sc = sm.scRUVIII(Yg, P["types"], P["ctl"], k=7, batch=batch)
+    ref_sc = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 7, batch)
+    assert orc.rel_frobenius(sc[7]["newY"], ref_sc[7]["newY"]) < TOL_NEWY
+    assert np.allclose(sc["stand_sd"], ref_sc["stand_sd"], rtol=1e-11)
+    adj = sm.pseudoRUVIII(P["Y"], P["Y"][:300], P["types"][:300], P["ctl"], k=5, fullalpha=res["fullalpha"], return_info=True)
+    ref_adj = orc.pseudoRUVIII(P["Y"], P["Y"][:300], P["types"][:300], P["ctl"], 5, fullalpha=ref["fullalpha"])
+    assert orc.rel_frobenius(adj["newY"], ref_adj["newY"]) < TOL_NEWY
+    assert np.allclose(adj["adjusted_means"], P["Y"].mean(axis=0), rtol=1e-12)
+    bad = P["Y"].copy()
+    bad[4321, 17] = np.inf  # NA/Inf in a late chunk is still caught (R/fastRUVIII.R:52-60)
+    with pytest.raises(ValueError, match="missing values or infinities"):
+        sm.fastRUVIII(bad, P["types"], P["ctl"], k=7)
+
+
 def test_w_output_and_device_resident(sm, ctx, sim):
     from scmerge_b200.ruv import _adjust
     ref = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, return_info=True)
