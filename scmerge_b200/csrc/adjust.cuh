@@ -379,10 +379,17 @@ inline int adjust_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, 
     return 0;
 }
 
+// TMA-staged variant (adjust_tma.cuh): returns 1 when not applicable
+inline int adjust_tma(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* c, double* d_out, int64_t ldo);
+
 inline int adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* c,
                   const int32_t* d_subset, int32_t nsub, double* d_out, int64_t ldo, double* d_W) {
     if (!c || c->n != n) return fail(SCM_ERR_INVALID, "adjust: coefficient object does not match n=%lld", (long long)n);
     if (m <= 0) return 0;
+    if (!d_subset && !d_W) {
+        const int trc = adjust_tma(ctx, d_Y, m, n, ld, c, d_out, ldo);
+        if (trc <= 0) return trc;
+    }
     Scratch ws(ctx);
     const bool subset = d_subset != nullptr;
     double* W = d_W;

@@ -1,5 +1,6 @@
 // C ABI of libscmerge_b200 (see include/scmerge_b200.h).  Single translation unit: all kernels are header-only.
 #include "adjust.cuh"
+#include "adjust_tma.cuh"
 #include "common.cuh"
 #include "eig_topk.cuh"
 #include "gemm_f64.cuh"
