@@ -85,20 +85,22 @@ __global__ void coef_frag_kernel(const double* __restrict__ Bmat, const double* 
     const int gb = blockIdx.x, lane = threadIdx.x;
     if (lane >= 32) return;
     const int gid = lane >> 2, tig = lane & 3;
-    double* bf = Bfrag + ((int64_t)gb * 32 + lane) * KT * 4;
+    // layout [block][q][lane] in 16-byte units (q < 2*KT): a warp-wide 16-byte load of unit q is 512 contiguous bytes
+    // in global memory and conflict-free in shared memory
+    double* bf = Bfrag + (int64_t)gb * KT * 128;
     for (int nt = 0; nt < KT; nt++)
         for (int j = 0; j < 4; j++) {
             const int64_t gene = (int64_t)gb * 16 + 4 * tig + j;
             const int kk = 8 * nt + gid;
-            bf[nt * 4 + j] = (gene < n && kk < k) ? Bmat[gene * k + kk] : 0.0;
+            bf[((nt * 2 + (j >> 1)) * 32 + lane) * 2 + (j & 1)] = (gene < n && kk < k) ? Bmat[gene * k + kk] : 0.0;
         }
-    double* af = Afrag + ((int64_t)gb * 32 + lane) * KT * 4;
+    double* af = Afrag + (int64_t)gb * KT * 128;
     for (int tau = 0; tau < 2; tau++)
         for (int nt = 0; nt < KT; nt++)
             for (int e = 0; e < 2; e++) {
                 const int64_t gene = (int64_t)gb * 16 + 4 * (gid >> 1) + 2 * tau + (gid & 1);
                 const int kk = 8 * nt + 2 * tig + e;
-                af[(tau * KT + nt) * 2 + e] = (gene < n && kk < k) ? Amat[(int64_t)kk * n + gene] : 0.0;
+                af[((tau * KT + nt) * 32 + lane) * 2 + e] = (gene < n && kk < k) ? Amat[(int64_t)kk * n + gene] : 0.0;
             }
 }
 __global__ void coef_ctlblocks_kernel(const uint8_t* __restrict__ ctl, int64_t n, int nblk, int32_t* __restrict__ blocks,
@@ -250,10 +252,10 @@ adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, co
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) w[mt][nt][0] = w[mt][nt][1] = 0.0;
     auto pass_a_block = [&](const double (&y)[MT][4], int gb) {
-        const double2* bf = reinterpret_cast<const double2*>(Bfrag + ((int64_t)gb * 32 + lane) * KT * 4);
+        const double2* bf = reinterpret_cast<const double2*>(Bfrag + (int64_t)gb * KT * 128) + lane;
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) {
-            const double2 b01 = __ldg(bf + nt * 2), b23 = __ldg(bf + nt * 2 + 1);
+            const double2 b01 = __ldg(bf + (nt * 2) * 32), b23 = __ldg(bf + (nt * 2 + 1) * 32);
             const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -312,10 +314,10 @@ adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, co
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) outp[mt] = out + (rowok[mt] ? row0 + mt * 8 + gid : 0) * ldo;
         auto pass_b_block = [&](double (&y)[MT][4], int gb) {
-            const double2* af = reinterpret_cast<const double2*>(Afrag + ((int64_t)gb * 32 + lane) * KT * 4);
+            const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)gb * KT * 128) + lane;
             double2 a[2 * KT];
 #pragma unroll
-            for (int i = 0; i < 2 * KT; i++) a[i] = __ldg(af + i);
+            for (int i = 0; i < 2 * KT; i++) a[i] = __ldg(af + i * 32);
 #pragma unroll
             for (int tau = 0; tau < 2; tau++)
 #pragma unroll

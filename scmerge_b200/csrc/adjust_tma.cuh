@@ -30,14 +30,24 @@ template <int KT, int MT>
 struct AdjTile {
     static constexpr int ROWS = 8 * MT;
     static constexpr int BOX_BYTES = ROWS * 128;
-    static constexpr int STAGE_BYTES = AT_CONSUMERS * BOX_BYTES;
-    // ring depth chosen so that two CTAs (ring + W partials) fit the 227 KB of shared memory of an SM
-    static constexpr int STAGES = MT == 4 ? (KT <= 3 ? 5 : 4) : 6;
+    static constexpr int FRAG_BYTES = KT * 1024;  // one block of B (pass A) or A (pass B) fragments: 2*KT x 32 lanes x 16 B
+    static constexpr int STAGE_BYTES = AT_CONSUMERS * (BOX_BYTES + FRAG_BYTES);
     static constexpr int PART_DOUBLES = AT_CONSUMERS * MT * KT * 2 * 32;
+    // ring depth chosen so that two CTAs (ring + W partials) fit the 227 KB of shared memory of an SM
+    static constexpr int BUDGET = 112 * 1024 - 1024 - 256 - PART_DOUBLES * 8;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES >= 6 ? 6 : (BUDGET / STAGE_BYTES >= 2 ? BUDGET / STAGE_BYTES : 2);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + PART_DOUBLES * 8 + 64;
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// contiguous global -> shared bulk copy (SASS UBLKCP), completion counted on an mbarrier like the tensor copies
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 
 template <int KT, int MT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -74,10 +84,14 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const int slot = g % AT_STAGES;
                     if (g >= AT_STAGES) mbar_wait(&empty[slot], ((g / AT_STAGES) - 1) & 1);
                     const int nbox = min(AT_CONSUMERS, nb - i * AT_CONSUMERS);
-                    mbar_expect_tx(&full[slot], nbox * TL::BOX_BYTES);
+                    mbar_expect_tx(&full[slot], nbox * (TL::BOX_BYTES + TL::FRAG_BYTES));
+                    uint8_t* stage = smem + slot * TL::STAGE_BYTES;
+                    const double* frag = pass == 0 ? Bfrag : Afrag;
                     for (int w = 0; w < nbox; w++) {
                         const int blk = pass == 0 ? ctl_blocks[i * AT_CONSUMERS + w] : i * AT_CONSUMERS + w;
-                        tma_load_2d(smem + slot * TL::STAGE_BYTES + w * TL::BOX_BYTES, &tmap, blk * 16, row, &full[slot]);
+                        tma_load_2d(stage + w * TL::BOX_BYTES, &tmap, blk * 16, row, &full[slot]);
+                        bulk_load(stage + AT_CONSUMERS * TL::BOX_BYTES + w * TL::FRAG_BYTES, frag + (int64_t)blk * KT * 128,
+                                  TL::FRAG_BYTES, &full[slot]);
                     }
                 }
             }
@@ -113,10 +127,11 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const double2 b = *reinterpret_cast<const double2*>(box + mt * 1024 + o1);
                     y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = b.x; y[mt][3] = b.y;
                 }
-                const double2* bf = reinterpret_cast<const double2*>(Bfrag + ((int64_t)gb * 32 + lane) * KT * 4);
+                const double2* bf = reinterpret_cast<const double2*>(smem + slot * TL::STAGE_BYTES + AT_CONSUMERS * TL::BOX_BYTES +
+                                                                     warp * TL::FRAG_BYTES) + lane;
 #pragma unroll
                 for (int nt = 0; nt < KT; nt++) {
-                    const double2 b01 = __ldg(bf + nt * 2), b23 = __ldg(bf + nt * 2 + 1);
+                    const double2 b01 = bf[(nt * 2) * 32], b23 = bf[(nt * 2 + 1) * 32];
                     const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
                     for (int j = 0; j < 4; j++)
@@ -168,12 +183,13 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const double2 b = *reinterpret_cast<const double2*>(box + mt * 1024 + o1);
                     y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = b.x; y[mt][3] = b.y;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);  // the box is in registers: release the slot before the math
-                const double2* af = reinterpret_cast<const double2*>(Afrag + ((int64_t)gb * 32 + lane) * KT * 4);
+                const double2* af = reinterpret_cast<const double2*>(smem + slot * TL::STAGE_BYTES + AT_CONSUMERS * TL::BOX_BYTES +
+                                                                     warp * TL::FRAG_BYTES) + lane;
                 double2 a[2 * KT];
 #pragma unroll
-                for (int q = 0; q < 2 * KT; q++) a[q] = __ldg(af + q);
+                for (int q = 0; q < 2 * KT; q++) a[q] = af[q * 32];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);  // box and fragments are in registers: release the slot before the math
 #pragma unroll
                 for (int tau = 0; tau < 2; tau++)
 #pragma unroll
