@@ -6,15 +6,22 @@
 // HBM half idle (long-scoreboard stalls, ncu profiles/r01).  Here the cell rows are streamed through a shared
 // memory ring by the TMA unit instead:
 //   * persistent CTAs (2 per SM), each walks row tiles of 8*MT cells; a producer warp issues
-//     `cp.async.bulk.tensor.2d` boxes of [8*MT cells x 16 genes] (SWIZZLE_128B) into a 6-stage ring of 4 boxes
-//     (one per consumer warp), running ahead across pass and tile boundaries -- ~100 KB per CTA in flight,
+//     `cp.async.bulk.tensor.2d` boxes of [8*MT cells x 16 genes] (SWIZZLE_128B) into a ring of stages of 4 boxes
+//     (one per consumer warp), running ahead across pass and tile boundaries,
 //   * 4 consumer warps: warp w owns box w of every stage.  Pass A (W += Y_blk B_blk over the control-gene
 //     blocks) and pass B (out_blk = Y_blk - W A_blk) read their DMMA fragments from the swizzled box with two
 //     conflict-free LDS.128 per 8-cell m-tile; pass B writes the result straight to global memory
 //     (8 full 128-byte lines per warp store),
+//   * the small-operand fragments (one KT-KB block of B or A per box, L2 resident) are prefetched one box ahead
+//     by the consumer warp itself with `cp.async` into a private double buffer: every lane copies exactly the
+//     16-byte pieces it will read, so `cp.async.wait_group` is the only synchronisation needed.  (Staging them
+//     with `cp.async.bulk` on the ring's mbarrier produced rare stale fragments -- ~2 % of launches had one wrong
+//     16-gene block, tools/probe/stress_adjust.py -- and was dropped.)
 //   * the four partial W tiles are combined through shared memory between the passes (named barrier of the 128
 //     consumer threads, fixed order => deterministic),
-//   * pass B re-reads from L2 what pass A fetched (one tile's control-gene columns per CTA: <= 8*MT*c*8 bytes).
+//   * pass B re-reads from L2 what pass A fetched (one tile's control-gene columns per CTA: <= 8*MT*c*8 bytes),
+//   * a ring slot is handed back to the producer only after the (volatile, ordered) DMMAs that consume its
+//     shared-memory loads have issued.
 // Needs ld % 2 == 0 and 16-byte aligned bases (TMA); otherwise, and for the subset / W-output variants, the
 // register-staged kernel is used.
 #pragma once
@@ -31,23 +38,16 @@ struct AdjTile {
     static constexpr int ROWS = 8 * MT;
     static constexpr int BOX_BYTES = ROWS * 128;
     static constexpr int FRAG_BYTES = KT * 1024;  // one block of B (pass A) or A (pass B) fragments: 2*KT x 32 lanes x 16 B
-    static constexpr int STAGE_BYTES = AT_CONSUMERS * (BOX_BYTES + FRAG_BYTES);
+    static constexpr int STAGE_BYTES = AT_CONSUMERS * BOX_BYTES;
+    static constexpr int FRAGBUF_BYTES = AT_CONSUMERS * 2 * FRAG_BYTES;  // per-warp double buffer
     static constexpr int PART_DOUBLES = AT_CONSUMERS * MT * KT * 2 * 32;
-    // ring depth chosen so that two CTAs (ring + W partials) fit the 227 KB of shared memory of an SM
-    static constexpr int BUDGET = 112 * 1024 - 1024 - 256 - PART_DOUBLES * 8;
+    // ring depth chosen so that two CTAs (ring + fragment buffers + W partials) fit the 227 KB of an SM
+    static constexpr int BUDGET = 112 * 1024 - 1024 - 256 - PART_DOUBLES * 8 - FRAGBUF_BYTES;
     static constexpr int STAGES = BUDGET / STAGE_BYTES >= 6 ? 6 : (BUDGET / STAGE_BYTES >= 2 ? BUDGET / STAGE_BYTES : 2);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + PART_DOUBLES * 8 + 64;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + 64 + FRAGBUF_BYTES + PART_DOUBLES * 8 + 64;
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
-
-// contiguous global -> shared bulk copy (SASS UBLKCP), completion counted on an mbarrier like the tensor copies
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
 
 template <int KT, int MT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -60,7 +60,8 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + AT_STAGES * TL::STAGE_BYTES);
     uint64_t* empty = full + AT_STAGES;
-    double* s_part = reinterpret_cast<double*>(empty + AT_STAGES);  // [4][MT*KT*2][32]
+    uint8_t* fragbuf = smem + AT_STAGES * TL::STAGE_BYTES + ((2 * AT_STAGES * 8 + 63) & ~63);
+    double* s_part = reinterpret_cast<double*>(fragbuf + TL::FRAGBUF_BYTES);  // [4][MT*KT*2][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     if (tid == 0) {
@@ -84,14 +85,10 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const int slot = g % AT_STAGES;
                     if (g >= AT_STAGES) mbar_wait(&empty[slot], ((g / AT_STAGES) - 1) & 1);
                     const int nbox = min(AT_CONSUMERS, nb - i * AT_CONSUMERS);
-                    mbar_expect_tx(&full[slot], nbox * (TL::BOX_BYTES + TL::FRAG_BYTES));
-                    uint8_t* stage = smem + slot * TL::STAGE_BYTES;
-                    const double* frag = pass == 0 ? Bfrag : Afrag;
+                    mbar_expect_tx(&full[slot], nbox * TL::BOX_BYTES);
                     for (int w = 0; w < nbox; w++) {
                         const int blk = pass == 0 ? ctl_blocks[i * AT_CONSUMERS + w] : i * AT_CONSUMERS + w;
-                        tma_load_2d(stage + w * TL::BOX_BYTES, &tmap, blk * 16, row, &full[slot]);
-                        bulk_load(stage + AT_CONSUMERS * TL::BOX_BYTES + w * TL::FRAG_BYTES, frag + (int64_t)blk * KT * 128,
-                                  TL::FRAG_BYTES, &full[slot]);
+                        tma_load_2d(smem + slot * TL::STAGE_BYTES + w * TL::BOX_BYTES, &tmap, blk * 16, row, &full[slot]);
                     }
                 }
             }
@@ -101,6 +98,29 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
     // ===== consumers =====
     // byte offsets of this lane's two 16-byte chunks (genes 4tig..4tig+1 and 4tig+2..4tig+3) inside an 8-row atom
     const int o0 = gid * 128 + (((2 * tig) ^ gid) << 4), o1 = gid * 128 + (((2 * tig + 1) ^ gid) << 4);
+    // this warp's periodic fragment stream: cA pass-A blocks (B fragments) then cB pass-B blocks (A fragments) per tile
+    const int cA = nblk_ctl > warp ? (nblk_ctl - warp + AT_CONSUMERS - 1) / AT_CONSUMERS : 0;
+    const int cB = nblk > warp ? (nblk - warp + AT_CONSUMERS - 1) / AT_CONSUMERS : 0;
+    uint8_t* myfrag = fragbuf + warp * 2 * TL::FRAG_BYTES + lane * 16;
+    auto issue_frag = [&](int ord, int buf) {  // ord in [0, cA + cB): copy this lane's 2*KT pieces of that block
+        const double* src = ord < cA ? Bfrag + (int64_t)ctl_blocks[warp + AT_CONSUMERS * ord] * KT * 128
+                                     : Afrag + (int64_t)(warp + AT_CONSUMERS * (ord - cA)) * KT * 128;
+#pragma unroll
+        for (int q = 0; q < 2 * KT; q++) cp_async16(myfrag + buf * TL::FRAG_BYTES + q * 512, src + (q * 32 + lane) * 2, true);
+        cp_async_commit();
+    };
+    int ford = 0, fbuf = 0;  // ordinal / buffer of the fragment block that is current (already issued)
+    if (cA + cB > 0) issue_frag(0, 0);
+    // returns this lane's fragment pointer for the current block and starts the copy of the next one
+    auto take_frag = [&]() -> const double2* {
+        cp_async_wait<0>();  // own pieces of the current block have landed (each lane reads only what it copied)
+        const double2* p = reinterpret_cast<const double2*>(myfrag + fbuf * TL::FRAG_BYTES);
+        ford = (ford + 1 == cA + cB) ? 0 : ford + 1;
+        fbuf ^= 1;
+        issue_frag(ford, fbuf);  // the buffer being overwritten was consumed (ordered DMMAs) one block ago
+        return p;
+    };
+
     uint32_t g = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * TL::ROWS;
@@ -116,9 +136,7 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
         for (int i = 0; i < nA; i++, g++) {
             const int slot = g % AT_STAGES;
             mbar_wait(&full[slot], (g / AT_STAGES) & 1);
-            const int bi = i * AT_CONSUMERS + warp;
-            if (bi < nblk_ctl) {
-                const int gb = ctl_blocks[bi];
+            if (i * AT_CONSUMERS + warp < nblk_ctl) {
                 const uint8_t* box = smem + slot * TL::STAGE_BYTES + warp * TL::BOX_BYTES;
                 double y[MT][4];
 #pragma unroll
@@ -127,8 +145,7 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const double2 b = *reinterpret_cast<const double2*>(box + mt * 1024 + o1);
                     y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = b.x; y[mt][3] = b.y;
                 }
-                const double2* bf = reinterpret_cast<const double2*>(smem + slot * TL::STAGE_BYTES + AT_CONSUMERS * TL::BOX_BYTES +
-                                                                     warp * TL::FRAG_BYTES) + lane;
+                const double2* bf = take_frag();
 #pragma unroll
                 for (int nt = 0; nt < KT; nt++) {
                     const double2 b01 = bf[(nt * 2) * 32], b23 = bf[(nt * 2 + 1) * 32];
@@ -136,7 +153,7 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
 #pragma unroll
                     for (int j = 0; j < 4; j++)
 #pragma unroll
-                        for (int mt = 0; mt < MT; mt++) dmma884(w[mt][nt][0], w[mt][nt][1], y[mt][j], b[j]);
+                        for (int mt = 0; mt < MT; mt++) dmma884_ordered(w[mt][nt][0], w[mt][nt][1], y[mt][j], b[j]);
                 }
             }
             __syncwarp();
@@ -183,22 +200,22 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
                     const double2 b = *reinterpret_cast<const double2*>(box + mt * 1024 + o1);
                     y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = b.x; y[mt][3] = b.y;
                 }
-                const double2* af = reinterpret_cast<const double2*>(smem + slot * TL::STAGE_BYTES + AT_CONSUMERS * TL::BOX_BYTES +
-                                                                     warp * TL::FRAG_BYTES) + lane;
+                const double2* af = take_frag();
                 double2 a[2 * KT];
 #pragma unroll
                 for (int q = 0; q < 2 * KT; q++) a[q] = af[q * 32];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);  // box and fragments are in registers: release the slot before the math
 #pragma unroll
                 for (int tau = 0; tau < 2; tau++)
 #pragma unroll
                     for (int nt = 0; nt < KT; nt++)
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++) {
-                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
-                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
+                            dmma884_ordered(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
+                            dmma884_ordered(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
                         }
+                // hand the slot back only after the DMMAs that consume its loads have issued
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
                 const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) store4(outp[mt], g0, n, vec_out, rowok[mt], y[mt]);
@@ -208,6 +225,7 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
             }
         }
     }
+    cp_async_wait<0>();
 }
 
 template <int KT, int MT>

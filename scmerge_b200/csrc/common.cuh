@@ -108,6 +108,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+// Ordered variant for the mbarrier-pipelined kernels: being `volatile` it cannot be moved past the (volatile)
+// mbarrier.arrive that hands a shared-memory slot back to the TMA producer, and because a DMMA only issues once its
+// source registers have arrived, "all DMMAs of the slot issued" implies "all shared-memory loads of the slot done".
+__device__ __forceinline__ void dmma884_ordered(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -89,7 +89,7 @@ __device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            for (int b = 0; b < 4; b++) dmma884_ordered(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
 }
 

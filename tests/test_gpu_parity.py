@@ -299,6 +299,48 @@ def test_host_pipeline_multichunk(sm, monkeypatch):
         sm.fastRUVIII(bad, P["types"], P["ctl"], k=7)
 
 
+def test_kernels_are_race_free_and_bit_reproducible(sm):
+    """Hundreds of launches of the pipelined (TMA + mbarrier) kernels on the same input must give bit-identical
+    results: a rare producer/consumer race shows up as one wrong 16-gene block in ~1 % of the launches
+    (this is how the cp.async.bulk fragment staging of the adjust kernel was caught)."""
+    import torch
+    from scmerge_b200 import _lib as L
+    from scmerge_b200 import ruv
+    torch.cuda.set_device(0)
+    ctx = sm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    m, n, c, k = 32768, 1000, 300, 10
+    P = orc.planted_factors(m, n, c, k, n_types=12, n_batch=4, seed=321)
+    dY = sm.DeviceMatrix.from_host(ctx, P["Y"])
+    keys, G = ruv.replicate_keys(P["types"])
+    fit = ruv._fit(ctx, dY, keys, G, 50, k, True)
+    lib = L.lib()
+    d_alpha = ctx.to_device(np.ascontiguousarray(fit.fullalpha[:k]))
+    d_ctl = ctx.to_device(P["ctl"].astype(np.uint8))
+    coef = C.c_void_p()
+    L.check(lib.scm_coef_create(ctx.handle, d_alpha.ptr, n, k, d_ctl.ptr, None, None, None, C.byref(coef)))
+    dO, dW, dG = sm.DeviceMatrix(ctx, m, n), sm.DeviceMatrix(ctx, m, n), ctx.empty((n, n))
+    tY, tO, tW, tG = (torch.as_tensor(x, device="cuda") for x in (dY.buf, dO.buf, dW.buf, dG))
+    L.check(lib.scm_adjust(ctx.handle, dY.ptr, m, n, dY.ld, coef, None, 0, dO.ptr, dO.ld, None))
+    L.check(lib.scm_gram(ctx.handle, dY.ptr, m, n, dY.ld, None, dG.ptr))
+    ctx.sync()
+    ref_adj, ref_gram = tO.clone(), tG.clone()
+    assert orc.rel_frobenius(dO.to_host(), orc.fastRUVIII_reduced(P["Y"], P["types"], P["ctl"], k)["newY"]) < TOL_NEWY
+    bad = 0
+    for it in range(400):
+        tO.zero_()
+        L.check(lib.scm_adjust(ctx.handle, dY.ptr, m, n, dY.ld, coef, None, 0, dO.ptr, dO.ld, None))  # out of place
+        tW.copy_(tY)
+        L.check(lib.scm_adjust(ctx.handle, dW.ptr, m, n, dW.ld, coef, None, 0, dW.ptr, dW.ld, None))  # in place
+        if it % 8 == 0:
+            tG.zero_()
+            L.check(lib.scm_gram(ctx.handle, dY.ptr, m, n, dY.ld, None, dG.ptr))
+            bad += int(not torch.equal(tG, ref_gram))
+        ctx.sync()
+        bad += int(not torch.equal(tO, ref_adj)) + int(not torch.equal(tW, ref_adj))
+    lib.scm_coef_destroy(ctx.handle, coef)
+    assert bad == 0
+
+
 def test_w_output_and_device_resident(sm, ctx, sim):
     from scmerge_b200.ruv import _adjust
     ref = orc.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], 20, return_info=True)
