@@ -76,9 +76,17 @@ chol_inv_kernel(const double* __restrict__ S, int l, double shift_rel, double* _
     for (int i = 0; i < l; i++) {
         if (tid < l && tid <= i) {
             const int c = tid;
-            double sum = (i == c) ? 1.0 : 0.0;
-            for (int k = 0; k < i; k++) sum -= A[i * ld + k] * X[k * ld + c];
-            X[i * ld + c] = sum / A[i * ld + i];
+            // X[k][c] = 0 for k < c; four independent partial sums break the FMA dependency chain
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = c;
+            for (; k + 3 < i; k += 4) {
+                s0 -= A[i * ld + k] * X[k * ld + c];
+                s1 -= A[i * ld + k + 1] * X[(k + 1) * ld + c];
+                s2 -= A[i * ld + k + 2] * X[(k + 2) * ld + c];
+                s3 -= A[i * ld + k + 3] * X[(k + 3) * ld + c];
+            }
+            for (; k < i; k++) s0 -= A[i * ld + k] * X[k * ld + c];
+            X[i * ld + c] = ((s0 + s1) + (s2 + s3)) / A[i * ld + i];
         }
         __syncthreads();
     }
@@ -96,15 +104,16 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
     extern __shared__ double sm[];
     const int lp = (l + 1) & ~1;  // even number of columns (a zero column pads odd l)
     double* A = sm;               // column-major: column j at A + j*lp
-    double* V = sm + lp * lp;
+    const int cs = lp + 1;        // column stride: odd, so the two half-warps of a warp hit different banks
+    double* V = sm + lp * cs;
     __shared__ int s_rot;
     __shared__ int s_order[SCM_MAX_BLOCK + 2];
     __shared__ double s_norm[SCM_MAX_BLOCK + 2];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     for (int idx = tid; idx < lp * lp; idx += nt) {
         const int j = idx / lp, i = idx % lp;
-        A[idx] = (i < l && j < l) ? 0.5 * (H[i * l + j] + H[j * l + i]) : 0.0;
-        V[idx] = (i == j) ? 1.0 : 0.0;
+        A[j * cs + i] = (i < l && j < l) ? 0.5 * (H[i * l + j] + H[j * l + i]) : 0.0;
+        V[j * cs + i] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
     // One half-warp (16 lanes) per column pair: all <= 56 disjoint pairs of a round run concurrently on the 64
@@ -118,7 +127,7 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
         if (tid == 0) s_rot = 0;
         for (int j = warp; j < lp; j += nwarp) {
             double a = 0.0;
-            for (int i = lane; i < lp; i += 32) a += A[j * lp + i] * A[j * lp + i];
+            for (int i = lane; i < lp; i += 32) a += A[j * cs + i] * A[j * cs + i];
             a = warp_sum(a);
             if (lane == 0) nrm2[j] = a;
         }
@@ -130,27 +139,35 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
                 if (hw == 0) { p = lp - 1; q = r; }
                 else { p = (r + hw) % (lp - 1); q = (r - hw + (lp - 1)) % (lp - 1); }
             }
-            double* ap = A + p * lp; double* aq = A + q * lp;
+            double* ap = A + p * cs; double* aq = A + q * cs;
             double ga = 0.0;
             if (act) for (int i = hl; i < lp; i += 16) ga += ap[i] * aq[i];
             const double al = nrm2[p], be = nrm2[q];  // read before the shuffles: they order it against lane 0's update
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);  // all lanes: warp stays converged
-            if (act) {
+            // The rotation parameters (two FP64 divisions, a sqrt and an rsqrt: ~150 FP64 pipe slots) are computed by
+            // ONE lane per pair and broadcast; doing it redundantly in all 16 lanes made this scalar math the bulk of a round.
+            double c = 1.0, s = 0.0;
+            if (act && hl == 0) {
                 // rotate unless the columns are orthogonal to rounding level (l * eps ~ 2e-14: a tighter threshold is
                 // below the rounding noise of the dot product and never lets a sweep come out clean)
                 if (fabs(ga) > 2e-14 * sqrt(al * be) && fabs(ga) > 1e-300) {
                     const double zeta = (be - al) / (2.0 * ga);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = rsqrt(1.0 + t * t), s = c * t;
-                    double* vp = V + p * lp; double* vq = V + q * lp;
-                    for (int i = hl; i < lp; i += 16) {
-                        const double x = ap[i], y = aq[i];
-                        ap[i] = c * x - s * y; aq[i] = s * x + c * y;
-                        const double vx = vp[i], vy = vq[i];
-                        vp[i] = c * vx - s * vy; vq[i] = s * vx + c * vy;
-                    }
-                    if (hl == 0) { nrm2[p] = al - t * ga; nrm2[q] = be + t * ga; s_rot = 1; }
+                    c = rsqrt(1.0 + t * t);
+                    s = c * t;
+                    nrm2[p] = al - t * ga; nrm2[q] = be + t * ga; s_rot = 1;
+                }
+            }
+            c = __shfl_sync(0xffffffffu, c, lane & 16);
+            s = __shfl_sync(0xffffffffu, s, lane & 16);
+            if (act && s != 0.0) {
+                double* vp = V + p * cs; double* vq = V + q * cs;
+                for (int i = hl; i < lp; i += 16) {
+                    const double x = ap[i], y = aq[i];
+                    ap[i] = c * x - s * y; aq[i] = s * x + c * y;
+                    const double vx = vp[i], vy = vq[i];
+                    vp[i] = c * vx - s * vy; vq[i] = s * vx + c * vy;
                 }
             }
             __syncthreads();
@@ -162,7 +179,7 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
     // column norms = eigenvalues (H is PSD); rank them descending
     for (int j = warp; j < lp; j += nwarp) {
         double a = 0.0;
-        for (int i = lane; i < lp; i += 32) a += A[j * lp + i] * A[j * lp + i];
+        for (int i = lane; i < lp; i += 32) a += A[j * cs + i] * A[j * cs + i];
         a = warp_sum(a);
         if (lane == 0) s_norm[j] = (j < l) ? sqrt(a) : -1.0;
     }
@@ -175,7 +192,7 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
     __syncthreads();
     for (int idx = tid; idx < l * l; idx += nt) {
         const int i = idx / l, jj = idx % l;
-        Q[idx] = V[s_order[jj] * lp + i];
+        Q[idx] = V[s_order[jj] * cs + i];
     }
     for (int j = tid; j < l; j += nt) theta[j] = s_norm[s_order[j]];
     if (tid == 0 && sweeps_out) *sweeps_out = sweep;
@@ -279,7 +296,7 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
     randn_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(X, nl, seed * 0x9E3779B97F4A7C15ull + 12345);
     SCM_LAUNCH_CHECK(ctx);
     SCM_TRY(cholqr2(ctx, X, Z, n, l, S, Linv, flag));
-    const size_t jsmem = sizeof(double) * 2 * ((l + 1) & ~1) * ((l + 1) & ~1);
+    const size_t jsmem = sizeof(double) * 2 * ((l + 1) & ~1) * (((l + 1) & ~1) + 1);
     const int fixed_iters = (mode == SCM_MODE_RANDOMIZED) ? 3 : 0;  // q = 2 power iterations + the final product
     double* h = ctx->h_pinned;
     int it = 0;
@@ -300,7 +317,9 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
             SCM_LAUNCH_CHECK(ctx);
             SCM_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
             SCM_CUDA(cudaMemcpyAsync(h + l, theta, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
+            SCM_CUDA(cudaMemcpyAsync(h + 2 * l, flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
             SCM_CUDA(cudaStreamSynchronize(st));
+            if (getenv("SCM_DEBUG_EIG")) fprintf(stderr, "[eig] it %d l %d jacobi sweeps %d\n", it, l, reinterpret_cast<int*>(h + 2 * l)[1]);
             // Davis-Kahan estimate of the angle between span(V[:, :kconv]) and the true invariant subspace:
             // ||R_k||_F / (theta_k - theta_{k+1}); a residual at rounding level also counts as converged.
             const double* th = h + l;
