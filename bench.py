@@ -43,12 +43,18 @@ def parse():
     p.add_argument("--types", type=int, default=20)
     p.add_argument("--batches", type=int, default=4)
     p.add_argument("--cpu-cells", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
+    p.add_argument("--workload", default="fastruviii", choices=["fastruviii", "scmerge2"],
+                   help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] (cosine norm, "
+                        "pseudobulk fit, adjust all cells; not the headline line)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     return p.parse_args()
 
 
 def workload_name(a):
+    if a.workload == "scmerge2":
+        return (f"scMerge2 core synthetic {a.cells} cells/GPU x {a.genes} genes, 8 batches, {a.types} cell types, k_pseudoBulk=30, "
+                f"ctl=all genes, ruvK={a.k}")
     return (f"fastRUVIII synthetic {a.cells} cells/GPU x {a.genes} genes, {a.ctl} ctl genes, k={a.k}, "
             f"{a.types} replicate groups, exact mode")
 
@@ -203,8 +209,18 @@ def run_ours(a):
     dOut = sm.DeviceMatrix(ctx, a.cells, a.genes)
     peak64 = fp64_peak(torch, dev) if rank == 0 else 0.0
 
-    def step():
-        return sm.fastRUVIII(dY, keys, ctl, k=a.k, out=dOut)
+    if a.workload == "scmerge2":
+        import warnings
+        warnings.simplefilter("ignore")
+        bt = np.random.default_rng(5 + rank).integers(0, 8, size=a.cells)
+        pb = sm.pseudobulk_keys(bt, keys, 30, seed=1)
+        a.no_e2e = True
+
+        def step():
+            return sm.scMerge2_core(dY, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx)
+    else:
+        def step():
+            return sm.fastRUVIII(dY, keys, ctl, k=a.k, out=dOut)
 
     for _ in range(a.warmup):
         step()

@@ -73,6 +73,12 @@ int scm_copy2d(scm_ctx* ctx, void* dst, int64_t dst_pitch, const void* src, int6
  * (the free `t()` of R/scRUVIII.R:48, R/scMerge2.R:298-299,313). */
 int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, int64_t ldi, double* d_out, int64_t ldo);
 
+/* ---- K7: per-cell cosine normalisation ---------------------------------------------
+ * out[i, :] = Y[i, :] / max(||Y[i, :]||_2, min_norm); in place allowed.  batchelor::cosineNorm as called by
+ * scMerge2 (R/scMerge2.R:193-198; un-vendored, published behaviour: each cell divided by its L2 norm, norms
+ * floored at 1e-8). */
+int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm);
+
 /* ---- K1: segmented column sums ---------------------------------------------------------------------
  * sums[g, j] = sum over rows i with key[i] == g of f(Y[i, j]),  counts[g] = #rows,
  *   f(y) = y                       (d_center == NULL)

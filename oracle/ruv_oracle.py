@@ -399,3 +399,39 @@ def sign_align(rows, ref_rows) -> np.ndarray:
     sg = np.sign(np.einsum("ij,ij->i", rows, np.asarray(ref_rows)))
     sg[sg == 0] = 1
     return rows * sg[:, None]
+
+
+# --------------------------------------------------------------------------------------------------
+# scMerge2 core (cosineNorm -> construct_pseudoBulk -> pseudoRUVIII), R/scMerge2.R:193-309
+# --------------------------------------------------------------------------------------------------
+
+
+def cosine_norm(X, min_norm=1e-8):
+    """batchelor::cosineNorm(x) for genes x cells (un-vendored; call site R/scMerge2.R:197): each cell (column)
+    divided by its L2 norm, norms floored at 1e-8."""
+    X = np.asarray(X, dtype=np.float64)
+    l2 = np.maximum(np.sqrt((X ** 2).sum(axis=0)), min_norm)
+    return X / l2
+
+
+def scmerge2_core(exprs_genes_x_cells, batch, clust, which, ctl=None, ruvK=20, k_fold=30, cosine=True, exact=False, rng=None):
+    """The arithmetic of scMerge2 between clustering and output for the supervised replicate structure
+    (pseudobulks of the same cluster label are replicates): cosineNorm (R/scMerge2.R:193-198), create_pseudoBulk per
+    batch (R/scMerge2_utilis.R:259-263,461-486), pseudoRUVIII (R/scMerge2.R:298-309).  `which`: fold id per cell."""
+    X = np.asarray(exprs_genes_x_cells, dtype=np.float64)
+    if cosine:
+        X = cosine_norm(X)
+    batch, clust, which = np.asarray(batch), np.asarray(clust), np.asarray(which)
+    n = X.shape[0]
+    ctl = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
+    bulks, names, rep = [], [], []
+    for b in np.unique(batch):
+        sel = batch == b
+        bulk, nm = create_pseudobulk(X[:, sel], clust[sel], which[sel], k_fold=k_fold)
+        bulks.append(bulk)
+        names += [f"{b}_{x}" for x in nm]
+        rep += [x.rsplit("_", 1)[0] for x in nm]
+    Yp = np.concatenate(bulks)
+    res = pseudoRUVIII(X.T, Yp, np.array(rep), ctl, ruvK, exact=exact, rng=rng)
+    res["bulkExprs"], res["names"] = Yp, names
+    return res

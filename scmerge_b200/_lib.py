@@ -37,6 +37,7 @@ SIGNATURES = {
     "scm_d2h": [_vp, _vp, _vp, _i64],
     "scm_copy2d": [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _int],
     "scm_transpose": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "scm_cosine_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _dbl],
     "scm_seg_colsum": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "scm_seg_colmean": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp],
     "scm_gram": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],

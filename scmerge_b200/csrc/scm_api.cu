@@ -73,6 +73,61 @@ __global__ void fullalpha_kernel(const double* __restrict__ vals, const double* 
     if (j == 0 && sigma) sigma[r] = sg;
 }
 
+// K7: per-cell cosine normalisation  out[i, :] = Y[i, :] / max(||Y[i, :]||_2, min_norm)   (batchelor::cosineNorm,
+// call site R/scMerge2.R:193-198).  One CTA per cell: the row is held in registers between the norm and the scale, so
+// the traffic is the algorithmic 8*m*n read + 8*m*n written.
+template <int PER>
+__global__ void __launch_bounds__(256)
+cosine_rows_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, double* __restrict__ out, int64_t ldo,
+                   double min_norm) {
+    __shared__ double red[8];
+    __shared__ double s_inv;
+    for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
+        const double* src = Y + row * ld;
+        double v[PER];
+        double ss = 0.0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int64_t c = (int64_t)j * 256 + threadIdx.x;
+            v[j] = c < n ? src[c] : 0.0;
+            ss += v[j] * v[j];
+        }
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += red[w];
+            s_inv = 1.0 / fmax(sqrt(t), min_norm);
+        }
+        __syncthreads();
+        const double inv = s_inv;
+        double* dst = out + row * ldo;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int64_t c = (int64_t)j * 256 + threadIdx.x;
+            if (c < n) dst[c] = v[j] * inv;
+        }
+        __syncthreads();
+    }
+}
+
+inline int cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm) {
+    if (m <= 0 || n <= 0) return 0;
+    const int per = (int)ceil_div(n, 256);
+    const unsigned grid = (unsigned)(m < (int64_t)ctx->num_sms * 16 ? m : (int64_t)ctx->num_sms * 16);
+#define COS_LAUNCH(P) cosine_rows_kernel<P><<<grid, 256, 0, ctx->stream>>>(d_Y, m, n, ld, d_out, ldo, min_norm)
+    if (per <= 4) COS_LAUNCH(4);
+    else if (per <= 8) COS_LAUNCH(8);
+    else if (per <= 16) COS_LAUNCH(16);
+    else if (per <= 32) COS_LAUNCH(32);
+    else if (per <= 96) COS_LAUNCH(96);
+    else return fail(SCM_ERR_UNSUPPORTED, "cosine_rows: more than 24576 genes per cell");
+#undef COS_LAUNCH
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
     if (ctx->world <= 1 || !ctx->allreduce) return 0;
     StageTimer t(ctx, ST_COMM);
@@ -213,6 +268,11 @@ int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, 
     transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(d_in, rows, cols, ldi, d_out, ldo);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm) {
+    SCM_REQUIRE_CTX(ctx);
+    return cosine_rows(ctx, d_Y, m, n, ld, d_out, ldo, min_norm);
 }
 
 int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,

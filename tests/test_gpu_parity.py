@@ -355,3 +355,35 @@ def test_w_output_and_device_resident(sm, ctx, sim):
     res = sm.fastRUVIII(dY, sim["M"], sim["ctl"], k=20)  # device in -> device out
     assert isinstance(res, sm.DeviceMatrix)
     assert orc.rel_frobenius(res.to_host(), ref["newY"]) < TOL_NEWY
+
+
+def test_scmerge2_core_cosine_pseudobulk_ruv(sm):
+    """BASELINE.json configs[2] in miniature: cosine-normalised cells, pseudobulks over (batch, fold, cluster),
+    RUV-III fit on the pseudobulks, every cell adjusted -- against the oracle's scMerge2 core."""
+    from scmerge_b200.scmerge2 import cosineNorm, pseudobulk_keys, scMerge2_core
+    P = orc.planted_factors(6000, 320, 320, 6, n_types=5, n_batch=4, seed=2024)
+    Y = np.abs(P["Y"]) + 0.1  # expression-like, non-negative
+    batch = np.array([f"batch{b}" for b in P["batch"]])
+    clust = np.array([f"ct{t}" for t in P["types"]])
+    keys, npb, names, pb_t, pb_b = pseudobulk_keys(batch, clust, 10, seed=3)
+    # fold ids implied by the keys (what cvFolds' `which` would be): recover them from the names for the oracle
+    fold_of_key = np.array([int(nm.rsplit("_", 1)[1]) for nm in names])
+    which = fold_of_key[keys]
+    ctx = sm.default_context()
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    cosineNorm(dY)
+    assert np.allclose(dY.to_host(), orc.cosine_norm(Y.T).T, rtol=1e-14, atol=0)
+    out = scMerge2_core(Y, batch, clust, ruvK=6, k_pseudoBulk=10, which=which, BSPARAM=sm.ExactParam())
+    ref = orc.scmerge2_core(Y.T, batch, clust, which, ruvK=6, k_fold=10, exact=True)
+    assert out["pseudobulk_names"] == ref["names"]                      # pseudobulk indices bit-exact
+    assert np.allclose(out["bulkExprs"], ref["bulkExprs"], rtol=1e-12, atol=1e-15)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(out["fullalpha"][:6], ref["fullalpha"][:6]).max() < 1e-6
+    # scMerge2's default (RandomParam): reference rule asks for min(P - G, n) rows -> truncated + converged
+    with pytest.warns(UserWarning, match="truncated"):
+        rnd = scMerge2_core(Y, batch, clust, ruvK=6, k_pseudoBulk=10, which=which)
+    assert mean_rel_diff(ref["newY"], rnd["newY"]) < 0.02
+    # device-resident, in place
+    dY2 = sm.DeviceMatrix.from_host(ctx, Y)
+    res = scMerge2_core(dY2, batch, clust, ruvK=6, k_pseudoBulk=10, which=which, BSPARAM=sm.ExactParam())
+    assert res["newY"] is dY2 and orc.rel_frobenius(dY2.to_host(), ref["newY"]) < TOL_NEWY
