@@ -107,20 +107,28 @@ def make_data(a, ctx, rank, torch):
     gc = torch.Generator(device=dev)
     gc.manual_seed(777 + rank)  # per-rank: cell-level draws
     types = torch.randint(0, T, (m,), generator=gc, device=dev)
+    if a.workload == "scmerge2":
+        Bt = 8
     batch = torch.randint(0, Bt, (m,), generator=gc, device=dev)
     dY = sm.DeviceMatrix(ctx, m, n)
     Yt = torch.as_tensor(dY.buf, device=dev).view(m, dY.ld)
     nb = min(Bt - 1, k)  # one-hot columns for all batches but the last (full column rank after centring)
+    # scmerge2 workload: the unwanted factors are (batch x cell type) effects, so they survive pseudobulk averaging
+    Rbt = torch.randn(Bt, T, k, generator=gs, device=dev, dtype=torch.float64)
     for r0 in range(0, m, 100_000):
         r1 = min(m, r0 + 100_000)
-        Wb = torch.zeros(r1 - r0, k, device=dev, dtype=torch.float64)
         b = batch[r0:r1]
-        hit = torch.nonzero(b < nb).squeeze(1)
-        Wb[hit, b[hit]] = 1.0
-        if k > nb:
-            Wb[:, nb:] = torch.randn(r1 - r0, k - nb, generator=gc, device=dev, dtype=torch.float64)
+        if a.workload == "scmerge2":
+            Wb = Rbt[b, types[r0:r1]]
+        else:
+            Wb = torch.zeros(r1 - r0, k, device=dev, dtype=torch.float64)
+            hit = torch.nonzero(b < nb).squeeze(1)
+            Wb[hit, b[hit]] = 1.0
+            if k > nb:
+                Wb[:, nb:] = torch.randn(r1 - r0, k - nb, generator=gc, device=dev, dtype=torch.float64)
         Yt[r0:r1, :n] = offs + theta[types[r0:r1]] + Wb @ A + 0.5 * torch.randn(r1 - r0, n, generator=gc, device=dev,
                                                                                dtype=torch.float64)
+    a._batch = batch.to(torch.int32).cpu().numpy()
     torch.cuda.synchronize()
     ctl = np.zeros(n, dtype=bool)
     ctl[:c] = True
@@ -212,12 +220,11 @@ def run_ours(a):
     if a.workload == "scmerge2":
         import warnings
         warnings.simplefilter("ignore")
-        bt = np.random.default_rng(5 + rank).integers(0, 8, size=a.cells)
-        pb = sm.pseudobulk_keys(bt, keys, 30, seed=1)
+        pb = sm.pseudobulk_keys(a._batch, keys, 30, seed=1)
         a.no_e2e = True
 
         def step():
-            return sm.scMerge2_core(dY, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx)
+            return sm.scMerge2_core(dY, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx, out=dOut)
     else:
         def step():
             return sm.fastRUVIII(dY, keys, ctl, k=a.k, out=dOut)

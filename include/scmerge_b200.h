@@ -98,6 +98,10 @@ int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_
 int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld,
                     const int32_t* d_key, int32_t G, double* d_means, int64_t* d_counts, int32_t* d_nonfinite);
 
+/* Column means of ALL cells recovered from group means and counts: out[j] = sum_g counts[g] means[g, j] / sum_g counts[g].
+ * scMerge2 needs both the pseudobulk means and colMeans(Y) (R/scMerge2_utilis.R:97); this saves the second pass over Y. */
+int scm_group_colmean(scm_ctx* ctx, const double* d_means, const int64_t* d_counts, int32_t G, int64_t n, int64_t ldm, double* d_out);
+
 /* ---- K3: Gram of the shifted matrix -----------------------------------------------------------------
  * gram[n x n] = sum_i (y_i - shift)(y_i - shift)'   (shift may be NULL), full symmetric output.
  * FP64 tensor-core (DMMA) SYRK over lower-triangular 128x128 tiles, split over cells, deterministic.

@@ -40,6 +40,7 @@ SIGNATURES = {
     "scm_cosine_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _dbl],
     "scm_seg_colsum": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "scm_seg_colmean": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp],
+    "scm_group_colmean": [_vp, _vp, _vp, _i32, _i64, _i64, _vp],
     "scm_gram": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
     "scm_gram_residual": [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp],
     "scm_eig_topk": [_vp, _vp, _i64, _i32, _i32, _int, _dbl, _i32, _u64, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],

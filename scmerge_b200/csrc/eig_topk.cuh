@@ -329,6 +329,9 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
             double gap = (kconv < l) ? th[kconv - 1] - th[kconv] : th[kconv - 1];
             if (!(gap > 1e-300)) gap = 1e-300;
             worst = sqrt(r2) / gap;
+            if (getenv("SCM_DEBUG_EIG"))
+                fprintf(stderr, "[eig] it %d angle_est %.3e rmax/top %.3e gap/top %.3e theta1 %.3e theta_k %.3e theta_l %.3e\n", it, worst,
+                        rmax / top, gap / top, th[0], th[kconv - 1], th[l - 1]);
             if (fixed_iters || worst <= tol || rmax <= 1e-14 * top) { converged = true; break; }
             hist[it % 16] = worst;
             // hopeless case (theta_k ~ theta_{k+1}: the k-th factor is not separated, the reference's own answer

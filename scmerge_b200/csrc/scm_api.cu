@@ -41,6 +41,17 @@ __global__ void colmean_kernel(const double* __restrict__ sums, int32_t G, int64
     mean[j] = s / (double)meta[1];
 }
 
+// out[j] = sum_g counts[g] * means[g, j] / sum_g counts[g]: the column means of all cells from the group means
+__global__ void weighted_colmean_kernel(const double* __restrict__ means, const int64_t* __restrict__ counts, int32_t G, int64_t n,
+                                        int64_t ldm, double* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    int64_t tot = 0;
+    for (int g = 0; g < G; g++) { const int64_t c = counts[g]; tot += c; s += (double)c * means[(int64_t)g * ldm + j]; }
+    out[j] = tot > 0 ? s / (double)tot : 0.0;
+}
+
 // sums[g, :] /= counts[g]  (empty groups -> 0)
 __global__ void groupmean_kernel(double* __restrict__ sums, const int64_t* __restrict__ counts, int32_t G, int64_t n) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,6 +300,13 @@ int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64
     StageTimer t(ctx, ST_SEG);
     SCM_TRY(seg_colsum(ctx, d_Y, m, n, ld, d_key, G, nullptr, d_means, d_counts, d_nonfinite));
     groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, n);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_group_colmean(scm_ctx* ctx, const double* d_means, const int64_t* d_counts, int32_t G, int64_t n, int64_t ldm, double* d_out) {
+    SCM_REQUIRE_CTX(ctx);
+    weighted_colmean_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, ctx->stream>>>(d_means, d_counts, G, n, ldm, d_out);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }

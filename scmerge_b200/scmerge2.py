@@ -61,17 +61,24 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
 
 def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: int = 30, cosine: bool = True, BSPARAM=None,
                   which=None, seed=1, replicate_of=None, return_subset_genes=None, ctx: Context | None = None,
-                  pb=None, return_bulk=True):
+                  pb=None, return_bulk=True, out: DeviceMatrix | None = None):
     """cosineNorm -> construct_pseudoBulk -> pseudoRUVIII (R/scMerge2.R:193-309) for cells x genes `exprs`
     (numpy: copied to the device; DeviceMatrix: normalised IN PLACE, result returned as a DeviceMatrix).
-    `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
+    With `out` (a DeviceMatrix of the same shape) a device-resident input is left untouched: the normalised cells are
+    written to `out` and adjusted there.  `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
     Returns {'newY', 'fullalpha', 'bulkExprs' (P x genes), 'pseudobulk_names', 'replicate_vector', 'adjusted_means'}."""
     ctx = ctx or (exprs.ctx if isinstance(exprs, DeviceMatrix) else default_context())
     host_in = not isinstance(exprs, DeviceMatrix)
     dY = DeviceMatrix.from_host(ctx, np.asarray(exprs, dtype=np.float64)) if host_in else exprs
     n = dY.n
     ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)  # scMerge2's default ctl = all genes
-    if cosine:
+    if out is not None and not host_in:
+        if cosine:
+            cosineNorm(dY, out)
+        else:
+            L.check(L.lib().scm_copy2d(ctx.handle, out.ptr, out.ld * 8, dY.ptr, dY.ld * 8, n * 8, dY.m, 2))
+        dY = out
+    elif cosine:
         cosineNorm(dY)
     if pb is None:
         pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed)
@@ -86,6 +93,11 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
         L.check(L.lib().scm_copy2d(ctx.handle, dP.ptr, dP.ld * 8, tmp.ptr, n * 8, n * 8, P, 2))
         tmp.free()
     d_keys.free()
+    # colMeans(Y) of all cells from the pseudobulk means and counts (no second pass over Y); skipped keys would break it
+    d_mean = ctx.empty((n,))
+    L.check(L.lib().scm_group_colmean(ctx.handle, dP.ptr, d_cnt.ptr, P, n, dP.ld, d_mean.ptr))
+    means = d_mean.to_host()
+    d_mean.free()
     d_cnt.free()
     bulk = dP.to_host() if (return_bulk or replicate_of is not None) else None
     rep = pb_type if replicate_of is None else np.asarray(replicate_of(names, bulk))
@@ -97,7 +109,6 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     s_dev, exact_dev = _device_rows_cap(s, ruvK, exact)
     fit = _fit(ctx, dP, rkeys, G, s_dev, int(ruvK), exact_dev)
     dP.free()
-    means = column_means(dY)
     sub = None if return_subset_genes is None else np.nonzero(tological(return_subset_genes, n))[0]
     dout, _ = _adjust(ctx, dY, fit.fullalpha, int(ruvK), ctl_mask, center=means, subset=sub, out=dY if sub is None else None)
     if host_in:
