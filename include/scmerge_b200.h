@@ -79,6 +79,18 @@ int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, 
  * floored at 1e-8). */
 int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm);
 
+/* ---- K8: sparse ingest -------------------------------------------------------------
+ * scMerge2 holds its matrix as a dgCMatrix of genes x cells (R/scMerge2.R:164-166), i.e. compressed by CELL: in the
+ * canonical cells x genes layout every cell is a sparse row with offsets p[m+1] (@p widened to int64), 0-based gene
+ * indices i[nnz] (@i) and values x[nnz] (@x).  Produces the dense cell rows on the device,
+ *     out[cell, :] = scatter(x_cell) / (cosine ? max(||x_cell||_2, min_norm) : 1),
+ * fusing batchelor::cosineNorm (R/scMerge2.R:193-198) into the densification.  Indices need not be sorted; equal
+ * indices inside a cell must be adjacent (they are summed).  d_inv_norm (optional, m) receives the applied scale,
+ * d_nonfinite (optional int32[1]) is set to 1 when a stored value is NA/NaN/Inf.  Fails with SCM_ERR_INVALID on a
+ * corrupt index structure (offsets decreasing / outside [0, nnz], gene index outside [0, n)). */
+int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
+                     int64_t nnz, int cosine, double min_norm, double* d_out, int64_t ldo, double* d_inv_norm, int32_t* d_nonfinite);
+
 /* ---- K1: segmented column sums ---------------------------------------------------------------------
  * sums[g, j] = sum over rows i with key[i] == g of f(Y[i, j]),  counts[g] = #rows,
  *   f(y) = y                       (d_center == NULL)
@@ -180,6 +192,12 @@ int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t
                   int32_t maxit, uint64_t seed, const double* h_fullalpha_in, int32_t s_in, int center_mode,
                   const double* h_center, double* h_out, int64_t ldo, double* h_fullalpha, double* h_sigma, double* h_mean,
                   double* h_sd, int32_t* iters_out, double* resid_out);
+
+/* The download half of the host drivers for a DEVICE-resident matrix: K6 runs chunk by chunk IN PLACE on d_Y and every
+ * finished chunk is copied to the (page-locked) host matrix h_out on a second stream while the next chunk is adjusted
+ * (the chunked `bplapply` adjust + rbind of pseudoRUVIII, R/scMerge2_utilis.R:104-137, with the PCIe copy overlapped).
+ * d_Y holds newY afterwards.  Synchronises. */
+int scm_adjust_to_host(scm_ctx* ctx, double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out, int64_t ldo);
 
 /* Stage timers (ms, CUDA events on the context stream) of the last scm_ruv3_fit / scm_adjust:
  * 0 seg_colsum, 1 gram (SYRK + split reduce), 2 allreduce, 3 eig, 4 coef, 5 adjust, 6 standardise,

@@ -38,6 +38,8 @@ SIGNATURES = {
     "scm_copy2d": [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _int],
     "scm_transpose": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "scm_cosine_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _dbl],
+    "scm_csc_to_dense": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _dbl, _vp, _i64, _vp, _vp],
+    "scm_adjust_to_host": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64],
     "scm_seg_colsum": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "scm_seg_colmean": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp],
     "scm_group_colmean": [_vp, _vp, _vp, _i32, _i64, _i64, _vp],

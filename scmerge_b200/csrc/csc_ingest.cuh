@@ -1,0 +1,124 @@
+// K8: sparse ingest.  scMerge2 holds its expression matrix as a dgCMatrix (genes x cells, compressed by CELL:
+// R/scMerge2.R:164-166 coerces dense input to CsparseMatrix), i.e. every cell is a sparse row of the canonical
+// cells x genes layout: p[m+1] offsets, i[nnz] gene indices, x[nnz] values.  Shipping that over PCIe instead of the
+// dense matrix cuts the upload by the sparsity factor (~10x for single-cell data); the dense cell rows the fit and
+// the rank-k update stream are produced here, on the device, fused with batchelor::cosineNorm
+// (R/scMerge2.R:193-198): out[i, :] = scatter(x_i) / max(||x_i||_2, min_norm).
+//
+// One CTA per cell (grid-stride): the cell's nonzeros are read once (12 bytes each) for the norm and once more
+// (L1/L2 hits) for the scatter into a zeroed shared-memory image of the row, which then leaves with 16-byte streaming
+// stores, so HBM sees 12*nnz bytes read + 8*m*n written -- the algorithmic traffic.  Rows longer than the shared
+// image (CSC_SLAB genes) are produced slab by slab.  Duplicate gene indices inside a cell are summed in index order
+// by a single thread (dgCMatrix never has them; scipy's un-canonical matrices may).
+#pragma once
+#include "common.cuh"
+
+namespace scm {
+
+constexpr int CSC_SLAB = 4096;  // genes per shared-memory row image (32 KB: 7 CTAs per SM)
+constexpr int CSC_THREADS = 256;
+
+__global__ void __launch_bounds__(CSC_THREADS)
+csc_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t m,
+                   int64_t n, int cosine, double min_norm, double* __restrict__ out, int64_t ldo, int vec_out,
+                   double* __restrict__ inv_norm_out, int32_t* __restrict__ flag) {
+    __shared__ __align__(16) double row[CSC_SLAB];
+    __shared__ double red[CSC_THREADS / 32];
+    __shared__ double s_inv;
+    const int tid = threadIdx.x;
+    for (int64_t cell = blockIdx.x; cell < m; cell += gridDim.x) {
+        const int64_t p0 = indptr[cell], p1 = indptr[cell + 1];
+        double inv = 1.0;
+        bool bad = false;
+        if (cosine) {
+            double ss = 0.0;
+            for (int64_t p = p0 + tid; p < p1; p += CSC_THREADS) {
+                const double v = val[p];
+                bad |= nonfinite(v);
+                ss += v * v;
+            }
+            ss = warp_sum(ss);
+            if ((tid & 31) == 0) red[tid >> 5] = ss;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < CSC_THREADS / 32; w++) t += red[w];  // fixed order: deterministic
+                s_inv = 1.0 / fmax(sqrt(t), min_norm);
+                if (inv_norm_out) inv_norm_out[cell] = s_inv;
+            }
+            __syncthreads();
+            inv = s_inv;
+        }
+        double* dst = out + cell * ldo;
+        for (int64_t g0 = 0; g0 < n; g0 += CSC_SLAB) {
+            const int width = (int)((n - g0) < CSC_SLAB ? (n - g0) : CSC_SLAB);
+            for (int j = tid * 2; j < width; j += CSC_THREADS * 2) *reinterpret_cast<double2*>(row + j) = make_double2(0.0, 0.0);
+            __syncthreads();
+            for (int64_t p = p0 + tid; p < p1; p += CSC_THREADS) {
+                const int64_t g = (int64_t)idx[p] - g0;
+                if (g >= 0 && g < width) {
+                    const double v = val[p];
+                    if (!cosine) bad |= nonfinite(v);
+                    // canonical matrices: unique indices, plain store.  A duplicate is detected by the neighbour test
+                    // below (sorted input) and folded by the owner of the first occurrence.
+                    const bool dup_prev = p > p0 && idx[p - 1] == idx[p];
+                    if (!dup_prev) {
+                        double acc = v;
+                        for (int64_t q = p + 1; q < p1 && idx[q] == idx[p]; q++) acc += val[q];
+                        row[g] = acc * inv;
+                    }
+                }
+            }
+            __syncthreads();
+            if (vec_out) {
+                for (int j = tid * 2; j < width; j += CSC_THREADS * 2) {
+                    if (j + 1 < width) stg_stream2(dst + g0 + j, *reinterpret_cast<const double2*>(row + j));
+                    else dst[g0 + j] = row[j];
+                }
+            } else {
+                for (int j = tid; j < width; j += CSC_THREADS) dst[g0 + j] = row[j];
+            }
+            __syncthreads();
+        }
+        if (bad && flag) *flag = 1;
+    }
+}
+
+// Validates the index structure on the device (what a corrupt dgCMatrix would otherwise turn into silent garbage or an
+// out-of-bounds shared-memory store): offsets non-decreasing and inside [0, nnz], gene indices inside [0, n).
+__global__ void csc_check_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t m, int64_t n,
+                                 int64_t nnz, int32_t* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = i; c < m; c += stride)
+        if (indptr[c] > indptr[c + 1] || indptr[c] < 0 || indptr[c + 1] > nnz) *bad = 1;
+    for (int64_t p = i; p < nnz; p += stride)
+        if (idx[p] < 0 || idx[p] >= n) *bad = 2;
+}
+
+inline int csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
+                        int64_t nnz, int cosine, double min_norm, double* d_out, int64_t ldo, double* d_inv_norm, int32_t* d_nonfinite) {
+    if (m <= 0 || n <= 0) return 0;
+    if (!d_indptr || !d_out || ldo < n || (nnz > 0 && (!d_idx || !d_val))) return fail(SCM_ERR_INVALID, "csc_to_dense: bad arguments");
+    cudaStream_t st = ctx->stream;
+    Scratch ws(ctx);
+    int32_t* bad;
+    SCM_TRY(ws.alloc(&bad, 1));
+    SCM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+    csc_check_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_indptr, d_idx, m, n, nnz, bad);
+    SCM_LAUNCH_CHECK(ctx);
+    int32_t hbad = 0;
+    SCM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    if (hbad) return fail(SCM_ERR_INVALID, hbad == 1 ? "csc_to_dense: column pointers are not a non-decreasing sequence inside [0, nnz]"
+                                                      : "csc_to_dense: a gene index is outside [0, n)");
+    const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    const int64_t want = (int64_t)ctx->num_sms * 7;
+    const unsigned grid = (unsigned)(m < want ? m : want);
+    csc_densify_kernel<<<grid, CSC_THREADS, 0, st>>>(d_indptr, d_idx, d_val, m, n, cosine, min_norm, d_out, ldo, vec_out, d_inv_norm,
+                                                     d_nonfinite);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace scm

@@ -35,6 +35,52 @@ __global__ void reciprocal_kernel(const double* __restrict__ x, double* __restri
     if (i < n) y[i] = 1.0 / x[i];
 }
 
+// Rows per PCIe chunk: ~512 MB, a multiple of 1024 rows (test hook SCM_HOST_CHUNK_ROWS forces several chunks on small inputs).
+inline int64_t host_chunk_rows(int64_t ld) {
+    int64_t rows_per_chunk = ((int64_t)512 << 20) / (ld * 8);
+    rows_per_chunk = rows_per_chunk / 1024 * 1024;
+    if (rows_per_chunk < 4096) rows_per_chunk = 4096;
+    if (const char* e = getenv("SCM_HOST_CHUNK_ROWS")) {
+        const long v = atol(e);
+        if (v >= 16) rows_per_chunk = v;
+    }
+    return rows_per_chunk;
+}
+
+// The download half of the host drivers: the fused adjust kernel (K6) runs chunk by chunk IN PLACE on the device-resident
+// matrix and every finished chunk goes back over PCIe (copy stream) while the next one is being adjusted.  d_Y holds newY
+// afterwards.  Returns after the last byte has landed in h_out.
+inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out,
+                           int64_t ldo, int64_t rows_per_chunk) {
+    if (!dY || !h_out || !coef || ldo < n) return fail(SCM_ERR_INVALID, "adjust_download: bad arguments");
+    cudaStream_t st = ctx->stream;
+    if (!ctx->copy_stream) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream;
+    if (rows_per_chunk <= 0) rows_per_chunk = host_chunk_rows(ld);
+    const int nchunks = (int)ceil_div(m, rows_per_chunk);
+    std::vector<cudaEvent_t> ev(nchunks + 1);
+    for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    struct EvGuard {
+        std::vector<cudaEvent_t>& v;
+        ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
+    } guard{ev};
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+        {
+            StageTimer t(ctx, ST_ADJUST);
+            SCM_TRY(adjust(ctx, dY + r0 * ld, rows, n, ld, coef, nullptr, 0, dY + r0 * ld, ld, nullptr));
+        }
+        SCM_CUDA(cudaEventRecord(ev[c], st));
+        SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
+        SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+    }
+    SCM_CUDA(cudaEventRecord(ev[nchunks], cs));
+    SCM_CUDA(cudaStreamWaitEvent(st, ev[nchunks], 0));  // later stream-ordered frees of d_Y must wait for the downloads
+    SCM_CUDA(cudaStreamSynchronize(cs));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 struct HostArgs {
     const double* h_Y; int64_t m, n, ldh;
     const int32_t* h_group; int32_t G;
@@ -58,13 +104,7 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     if (!ctx->copy_stream) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     cudaStream_t cs = ctx->copy_stream;
     const int64_t ld = (n + 1) & ~(int64_t)1;
-    int64_t rows_per_chunk = ((int64_t)512 << 20) / (ld * 8);
-    rows_per_chunk = rows_per_chunk / 1024 * 1024;
-    if (rows_per_chunk < 4096) rows_per_chunk = 4096;
-    if (const char* e = getenv("SCM_HOST_CHUNK_ROWS")) {  // test hook: force several chunks on small inputs
-        const long v = atol(e);
-        if (v >= 16) rows_per_chunk = v;
-    }
+    const int64_t rows_per_chunk = host_chunk_rows(ld);
     const int nchunks = (int)ceil_div(m, rows_per_chunk);
     std::vector<cudaEvent_t> ev(nchunks);
     for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -202,22 +242,11 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         if (crc != 0) return crc;
     }
     // ---- adjust in place chunk by chunk, each finished chunk goes back to the host while the next is computed
-    for (int c = 0; c < nchunks; c++) {
-        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-        {
-            StageTimer t(ctx, ST_ADJUST);
-            int arc = adjust(ctx, dY + r0 * ld, rows, n, ld, coef, nullptr, 0, dY + r0 * ld, ld, nullptr);
-            if (arc != 0) { coef_destroy(ctx, coef); return arc; }
-        }
-        SCM_CUDA(cudaEventRecord(ev[c], st));
-        SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
-        SCM_CUDA(cudaMemcpy2DAsync(a.h_out + r0 * a.ldo, a.ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+    {
+        const int arc = adjust_download(ctx, dY, m, n, ld, coef, a.h_out, a.ldo, rows_per_chunk);
+        coef_destroy(ctx, coef);
+        if (arc != 0) return arc;
     }
-    SCM_CUDA(cudaEventRecord(ev_done, cs));
-    SCM_CUDA(cudaStreamWaitEvent(st, ev_done, 0));  // scratch is freed in stream order on `st`: wait for the downloads
-    coef_destroy(ctx, coef);
-    SCM_CUDA(cudaStreamSynchronize(cs));
-    SCM_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
 

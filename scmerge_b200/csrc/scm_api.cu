@@ -2,6 +2,7 @@
 #include "adjust.cuh"
 #include "adjust_tma.cuh"
 #include "common.cuh"
+#include "csc_ingest.cuh"
 #include "eig_topk.cuh"
 #include "gemm_f64.cuh"
 #include "gram_syrk.cuh"
@@ -284,6 +285,19 @@ int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, 
 int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm) {
     SCM_REQUIRE_CTX(ctx);
     return cosine_rows(ctx, d_Y, m, n, ld, d_out, ldo, min_norm);
+}
+
+int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
+                     int64_t nnz, int cosine, double min_norm, double* d_out, int64_t ldo, double* d_inv_norm, int32_t* d_nonfinite) {
+    SCM_REQUIRE_CTX(ctx);
+    return csc_to_dense(ctx, d_indptr, d_idx, d_val, m, n, nnz, cosine, min_norm, d_out, ldo, d_inv_norm, d_nonfinite);
+}
+
+int scm_adjust_to_host(scm_ctx* ctx, double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!coef || coef->n != n) return fail(SCM_ERR_INVALID, "scm_adjust_to_host: coefficient object does not match n");
+    if (m <= 0) return 0;
+    return adjust_download(ctx, d_Y, m, n, ld, coef, h_out, ldo, 0);
 }
 
 int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,

@@ -17,13 +17,52 @@ from . import _lib as L
 from .device import Context, DeviceMatrix, default_context
 from .ruv import _adjust, _device_rows_cap, _fit, _is_exact, _svd_k, column_means, replicate_keys, segmented_sums, tological
 
-__all__ = ["cosineNorm", "pseudobulk_keys", "scMerge2_core"]
+__all__ = ["cosineNorm", "csc_to_device", "pseudobulk_keys", "scMerge2_core"]
 
 
 def cosineNorm(dY: DeviceMatrix, out: DeviceMatrix | None = None, min_norm: float = 1e-8) -> DeviceMatrix:
     """batchelor::cosineNorm (R/scMerge2.R:197) on a cells x genes device matrix; in place unless `out` is given."""
     out = out or dY
     L.check(L.lib().scm_cosine_rows(dY.ctx.handle, dY.ptr, dY.m, dY.n, dY.ld, out.ptr, out.ld, float(min_norm)))
+    return out
+
+
+def _is_sparse(x) -> bool:
+    return hasattr(x, "indptr") and hasattr(x, "indices") and hasattr(x, "data") and hasattr(x, "shape")
+
+
+def csc_to_device(ctx: Context, X, cosine: bool = True, min_norm: float = 1e-8, out: DeviceMatrix | None = None,
+                  check_finite: bool = True) -> DeviceMatrix:
+    """Sparse ingest (K8, scm_csc_to_dense).  `X` is the expression matrix compressed by CELL: a scipy.sparse CSR matrix of
+    cells x genes, or equivalently the CSC of genes x cells -- the dgCMatrix scMerge2 holds (R/scMerge2.R:164-166), whose
+    (@p, @i, @x) slots are exactly (indptr, indices, data).  Only the three sparse arrays cross PCIe; the dense cell rows
+    are produced on the device, fused with batchelor::cosineNorm when `cosine` (R/scMerge2.R:193-198)."""
+    fmt = getattr(X, "format", None)
+    if fmt == "csc":  # genes x cells compressed by column == cells x genes compressed by row
+        n, m = X.shape
+    elif fmt == "csr":
+        m, n = X.shape
+    else:
+        raise TypeError("expected a scipy.sparse csr (cells x genes) or csc (genes x cells) matrix")
+    if hasattr(X, "has_canonical_format") and not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+    idx = np.ascontiguousarray(X.indices, dtype=np.int32)
+    val = np.ascontiguousarray(X.data, dtype=np.float64)
+    nnz = int(indptr[-1]) if indptr.shape[0] else 0
+    d_p, d_i, d_x = ctx.to_device(indptr), ctx.to_device(idx[:nnz]), ctx.to_device(val[:nnz])
+    d_flag = ctx.to_device(np.zeros(1, dtype=np.int32)) if check_finite else None
+    out = out or DeviceMatrix(ctx, m, n)
+    try:
+        L.check(L.lib().scm_csc_to_dense(ctx.handle, d_p.ptr, d_i.ptr, d_x.ptr, m, n, nnz, int(bool(cosine)), float(min_norm),
+                                         out.ptr, out.ld, None, d_flag.ptr if d_flag is not None else None))
+        if d_flag is not None and int(d_flag.to_host()[0]):
+            raise L.NonFiniteError(L.ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.")
+    finally:
+        for a in (d_p, d_i, d_x, d_flag):
+            if a is not None:
+                a.free()
     return out
 
 
@@ -59,17 +98,48 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
     return keys, int(ids.shape[0]), names, pb_t.astype(np.int32), pb_b.astype(np.int32)
 
 
+def _adjust_to_host(ctx: Context, dY: DeviceMatrix, fullalpha, k: int, ctl_mask, center, host_out: np.ndarray) -> np.ndarray:
+    """scm_coef_create + scm_adjust_to_host: adjust the resident matrix in place chunk by chunk, downloads overlapped."""
+    lib = L.lib()
+    n = dY.n
+    assert host_out.shape == (dY.m, n) and host_out.dtype == np.float64 and host_out.flags.c_contiguous
+    kk = int(min(k, fullalpha.shape[0]))
+    d_alpha = ctx.to_device(np.ascontiguousarray(fullalpha[:kk], dtype=np.float64))
+    d_ctl = ctx.to_device(np.ascontiguousarray(ctl_mask, dtype=np.uint8))
+    d_cen = ctx.to_device(np.ascontiguousarray(center, dtype=np.float64))
+    coef = C.c_void_p()
+    try:
+        L.check(lib.scm_coef_create(ctx.handle, d_alpha.ptr, n, kk, d_ctl.ptr, d_cen.ptr, None, None, C.byref(coef)))
+        L.check(lib.scm_adjust_to_host(ctx.handle, dY.ptr, dY.m, n, dY.ld, coef, host_out.ctypes.data_as(C.c_void_p), n))
+    finally:
+        if coef:
+            lib.scm_coef_destroy(ctx.handle, coef)
+        for a in (d_alpha, d_ctl, d_cen):
+            a.free()
+    return host_out
+
+
 def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: int = 30, cosine: bool = True, BSPARAM=None,
                   which=None, seed=1, replicate_of=None, return_subset_genes=None, ctx: Context | None = None,
                   pb=None, return_bulk=True, out: DeviceMatrix | None = None):
     """cosineNorm -> construct_pseudoBulk -> pseudoRUVIII (R/scMerge2.R:193-309) for cells x genes `exprs`
-    (numpy: copied to the device; DeviceMatrix: normalised IN PLACE, result returned as a DeviceMatrix).
+    (numpy: copied to the device; scipy.sparse CSR cells x genes / CSC genes x cells, i.e. the reference's dgCMatrix:
+    only the sparse arrays are uploaded and the dense normalised rows are built on the device (K8);
+    DeviceMatrix: normalised IN PLACE, result returned as a DeviceMatrix).  For host inputs `out` may be a (page-locked)
+    numpy cells x genes array: the adjusted chunks are then downloaded while the next chunk is computed.
     With `out` (a DeviceMatrix of the same shape) a device-resident input is left untouched: the normalised cells are
     written to `out` and adjusted there.  `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
     Returns {'newY', 'fullalpha', 'bulkExprs' (P x genes), 'pseudobulk_names', 'replicate_vector', 'adjusted_means'}."""
     ctx = ctx or (exprs.ctx if isinstance(exprs, DeviceMatrix) else default_context())
     host_in = not isinstance(exprs, DeviceMatrix)
-    dY = DeviceMatrix.from_host(ctx, np.asarray(exprs, dtype=np.float64)) if host_in else exprs
+    host_out = out if (host_in and isinstance(out, np.ndarray)) else None
+    if host_in:
+        out = None
+    if _is_sparse(exprs):
+        dY = csc_to_device(ctx, exprs, cosine=cosine)
+        cosine = False  # already applied during the densification
+    else:
+        dY = DeviceMatrix.from_host(ctx, np.asarray(exprs, dtype=np.float64)) if host_in else exprs
     n = dY.n
     ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)  # scMerge2's default ctl = all genes
     if out is not None and not host_in:
@@ -110,9 +180,14 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     fit = _fit(ctx, dP, rkeys, G, s_dev, int(ruvK), exact_dev)
     dP.free()
     sub = None if return_subset_genes is None else np.nonzero(tological(return_subset_genes, n))[0]
+    if host_out is not None and sub is None:
+        newY = _adjust_to_host(ctx, dY, fit.fullalpha, int(ruvK), ctl_mask, means, host_out)
+        dY.free()
+        return {"newY": newY, "fullalpha": fit.fullalpha, "bulkExprs": bulk, "pseudobulk_names": names, "replicate_vector": rep,
+                "adjusted_means": means}
     dout, _ = _adjust(ctx, dY, fit.fullalpha, int(ruvK), ctl_mask, center=means, subset=sub, out=dY if sub is None else None)
     if host_in:
-        newY = dout.to_host()
+        newY = dout.to_host(host_out)
         if dout is not dY:
             dout.free()
         dY.free()

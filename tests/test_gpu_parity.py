@@ -387,3 +387,97 @@ def test_scmerge2_core_cosine_pseudobulk_ruv(sm):
     dY2 = sm.DeviceMatrix.from_host(ctx, Y)
     res = scMerge2_core(dY2, batch, clust, ruvK=6, k_pseudoBulk=10, which=which, BSPARAM=sm.ExactParam())
     assert res["newY"] is dY2 and orc.rel_frobenius(dY2.to_host(), ref["newY"]) < TOL_NEWY
+
+
+# ---- K8: sparse (dgCMatrix) ingest ---------------------------------------------------------------------
+def _sparse_case(m, n, density, seed, empty_cells=()):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    X = sp.random(m, n, density=density, format="csr", random_state=rng, data_rvs=lambda k: rng.gamma(2.0, 1.0, k) + 0.05)
+    X = X.tolil()
+    for r in empty_cells:
+        X.rows[r], X.data[r] = [], []
+    return X.tocsr()
+
+
+@pytest.mark.parametrize("m,n,density,cosine", [(700, 257, 0.1, True), (300, 5000, 0.02, True), (64, 33, 0.5, False),
+                                                (2000, 4097, 0.05, True)])
+def test_csc_to_dense_bit_exact(sm, ctx, m, n, density, cosine):
+    """Densification is a scatter: bit-exact against the host; the fused cosine scale matches batchelor's formula
+    (x / max(||x||, 1e-8)) to the last few ulps (the squared norm is summed in a different order)."""
+    X = _sparse_case(m, n, density, seed=m + n, empty_cells=(0, m // 2))
+    D = X.toarray()
+    d = sm.csc_to_device(ctx, X, cosine=cosine)
+    got = d.to_host()
+    d.free()
+    if not cosine:
+        assert np.array_equal(got, D)
+    else:
+        ref = orc.cosine_norm(D.T).T
+        assert np.array_equal(got != 0, D != 0)                      # sparsity pattern (gene indices) bit-exact
+        assert np.allclose(got, ref, rtol=1e-14, atol=0)
+        assert np.all(got[0] == 0) and np.all(got[m // 2] == 0)      # empty cells stay all-zero (norm floored, no NaN)
+    # the CSC view of genes x cells is the same three arrays
+    d2 = sm.csc_to_device(ctx, X.T.tocsc(), cosine=cosine)
+    assert np.array_equal(d2.to_host(), got)
+    d2.free()
+
+
+def test_csc_ingest_rejects_corrupt_and_nonfinite(sm, ctx):
+    X = _sparse_case(200, 64, 0.2, seed=5)
+    bad = X.copy()
+    bad.indices = bad.indices.copy()
+    bad.indices[3] = 64                                             # gene index out of range
+    with pytest.raises(sm.ScmError, match="gene index"):
+        sm.csc_to_device(ctx, bad)
+    bad = X.copy()
+    bad.indptr = bad.indptr.copy()
+    bad.indptr[5] = bad.indptr[6] + 1                               # decreasing offsets
+    with pytest.raises(sm.ScmError, match="column pointers"):
+        sm.csc_to_device(ctx, bad)
+    nf = X.copy()
+    nf.data = nf.data.copy()
+    nf.data[7] = np.inf
+    with pytest.raises(sm.NonFiniteError):
+        sm.csc_to_device(ctx, nf)
+    dup = X.copy()                                                  # un-canonical input: duplicates are summed
+    dup.indices = dup.indices.copy()
+    p0 = dup.indptr[10]
+    if dup.indptr[11] - p0 >= 2:
+        dup.indices[p0 + 1] = dup.indices[p0]
+        dup.has_canonical_format = False
+        d = sm.csc_to_device(ctx, dup, cosine=False)
+        assert np.array_equal(d.to_host(), dup.toarray())
+        d.free()
+
+
+def test_scmerge2_core_sparse_input_matches_dense(sm):
+    """scMerge2 on the dgCMatrix it actually holds (R/scMerge2.R:164-166): same result as the dense path / the oracle,
+    with the adjusted matrix streamed into a page-locked host buffer."""
+    from scmerge_b200.scmerge2 import pseudobulk_keys, scMerge2_core
+    m, n = 5000, 300
+    rng = np.random.default_rng(99)
+    batch = rng.integers(0, 3, m)
+    clust = rng.integers(0, 4, m)
+    X = _sparse_case(m, n, 0.15, seed=17).tolil()
+    # cell-type and batch x cell-type signal on top of the sparse noise so that the fit has factors to find
+    T = rng.gamma(2.0, 1.0, (4, n)) * (rng.random((4, n)) < 0.2)
+    Bf = rng.gamma(2.0, 0.5, (3, 4, n)) * (rng.random((3, 4, n)) < 0.1)
+    D = X.toarray() + T[clust] + Bf[batch, clust]
+    import scipy.sparse as sp
+    Xs = sp.csr_matrix(D)
+    # 3 batches x 4 types -> 8 batch-by-type factors: ruvK = 8 sits at the spectral gap (sigma_8 / sigma_9 ~ 4)
+    keys, npb, names, pb_t, pb_b = pseudobulk_keys(batch, clust, 8, seed=3)
+    which = np.array([int(nm.rsplit("_", 1)[1]) for nm in names])[keys]
+    ref = orc.scmerge2_core(D.T, batch, clust, which, ruvK=8, k_fold=8, exact=True)
+    host_out = sm.pinned_empty((m, n))
+    out = scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam(), out=host_out)
+    assert out["newY"] is host_out
+    assert out["pseudobulk_names"] == ref["names"]
+    assert np.allclose(out["bulkExprs"], ref["bulkExprs"], rtol=1e-12, atol=1e-15)
+    assert orc.rel_frobenius(host_out, ref["newY"]) < TOL_NEWY
+    dense = scMerge2_core(D, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
+    assert orc.rel_frobenius(dense["newY"], host_out) < 1e-12
+    # genes x cells CSC (the reference's orientation) gives the same answer
+    out2 = scMerge2_core(Xs.T.tocsc(), batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
+    assert orc.rel_frobenius(out2["newY"], host_out) < 1e-13
