@@ -153,6 +153,10 @@ int scm_fullalpha(scm_ctx* ctx, const double* d_vals, const double* d_vecs, int3
  * Fails with SCM_ERR_SINGULAR when ac ac' is not positive definite. */
 int scm_coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, const uint8_t* d_ctl,
                     const double* d_center, const double* d_pre, const double* d_post, scm_coef** out);
+/* Coefficient object from explicit factors B (n x k, row-major; rows of genes with d_rows[g] == 0 must be zero) and
+ * A (k x n): newY = Y - ((Y - center) B) A.  Used by scRUVg (B = 1[ctl] V diag(1/sigma), A = alpha, R/scRUVg.R:77-80). */
+int scm_coef_from_factors(scm_ctx* ctx, const double* d_B, const double* d_A, int64_t n, int32_t k, const uint8_t* d_rows,
+                          const double* d_center, scm_coef** out);
 int scm_coef_destroy(scm_ctx* ctx, scm_coef* coef);
 
 /* ---- K6: fused rank-k adjustment --------------------------------------------------------------------
@@ -175,6 +179,16 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
                  const int32_t* d_group, int32_t G, const int32_t* d_batch, int32_t Bt,
                  int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
                  double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd,
+                 int32_t* iters_out, double* resid_out);
+
+/* scm_ruvg_fit: the fit half of scRUVg (R/scRUVg.R:30-85 with Z = 1, eta = NULL) on a device-resident,
+ * cell-sharded Y: column means (my_residop(Y, 1), :61-63), the top-k left singular vectors of the centred control block
+ * (:66-73) through the Gram of the centred cells and its control block (K3 + K4; the m x m cross product of the >= 5:1
+ * aspect-ratio branch is never formed), alpha = W'Y0 (:78).  Outputs d_alpha (k x n), d_center (n), d_sigma (k, optional:
+ * singular values of Y0[, ctl]) and the coefficient object: scm_adjust(..., coef, ..., d_W) then gives newY (:80) and W (:77).
+ * Errors: SCM_ERR_INVALID when k exceeds the number of controls (:56-58), SCM_ERR_SINGULAR when the control block has rank < k. */
+int scm_ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const uint8_t* d_ctl, int32_t k, int mode,
+                 double tol, int32_t maxit, uint64_t seed, double* d_alpha, double* d_center, double* d_sigma, scm_coef** coef_out,
                  int32_t* iters_out, double* resid_out);
 
 /* scm_ruv3_host: the whole closure on HOST matrices (what `.Call` hands over), with the PCIe copies overlapped with

@@ -334,6 +334,28 @@ def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, 
 # --------------------------------------------------------------------------------------------------
 
 
+def scRUVg(Y, ctl, k):
+    """R/scRUVg.R:30-85 with the default Z = 1, eta = NULL (literal: svd of Y0[, ctl] or of its m x m cross product when
+    the aspect ratio is >= 5, :66-73).  Returns dict(newY, W, alpha)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    m, n = Y.shape
+    ctl = tological(ctl, n)
+    if k > ctl.sum():  # :56-58
+        raise ValueError("k must not be larger than the number of controls")
+    Z = np.ones((m, 1))  # :37-41, design.matrix of an intercept
+    q = 1
+    Y0 = my_residop(Y, Z)  # :61-63 (RUV1 is the identity for eta = NULL)
+    Y0ctl = Y0[:, ctl]
+    mat = Y0ctl
+    if max(mat.shape) / min(mat.shape) >= 5:  # :68-71
+        mat = Y0ctl @ Y0ctl.T
+    u = np.linalg.svd(mat, full_matrices=False)[0]  # :72
+    fullW = u[:, : min(m - q, int(ctl.sum()))]  # :73
+    W = fullW[:, :k]  # :77
+    alpha = np.linalg.solve(W.T @ W, W.T) @ Y0  # :78
+    return {"newY": Y - W @ alpha, "W": W, "alpha": alpha}  # :80
+
+
 def ruv_simulate(m=100, n=5000, nc=None, n_celltypes=3, n_batch=2, k=20, lam=0.1, rng=None):
     """Distribution of R/ruvSimulate.R:41-84 with NumPy's RNG (R's RNG stream is not reproducible here)."""
     rng = np.random.default_rng(0) if rng is None else rng

@@ -7,7 +7,7 @@ from ._lib import LIB_PATH, NonFiniteError, NotConvergedWarning, ScmError, Singu
 from .device import Context, DeviceArray, DeviceMatrix, default_context, pinned_empty  # noqa: F401
 from .ruv import (ExactParam, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
                   create_pseudoBulk, fastRUVIII, getAdjustedMat, pseudoRUVIII, replicate_keys, replicate_matrix,
-                  scRUVIII, tological)
+                  scRUVg, scRUVIII, tological)
 
 from .scmerge2 import cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402
 

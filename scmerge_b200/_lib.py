@@ -49,6 +49,9 @@ SIGNATURES = {
     "scm_fullalpha": [_vp, _vp, _vp, _i32, _i64, _vp],
     "scm_coef_create": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _pp],
     "scm_coef_destroy": [_vp, _vp],
+    "scm_coef_from_factors": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _pp],
+    "scm_ruvg_fit": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _int, _dbl, _i32, _u64, _vp, _vp, _vp, _pp, C.POINTER(_i32),
+                     C.POINTER(_dbl)],
     "scm_adjust": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i64, _vp],
     "scm_ruv3_fit": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _int, _dbl, _i32, _u64,
                      _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],

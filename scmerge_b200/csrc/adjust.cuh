@@ -136,10 +136,10 @@ inline int coef_destroy(scm_ctx* ctx, scm_coef* c) {
     return 0;
 }
 
-inline int coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, const uint8_t* d_ctl,
-                       const double* d_center, const double* d_pre, const double* d_post, scm_coef** out) {
-    if (k <= 0 || k > SCM_MAX_K) return fail(SCM_ERR_UNSUPPORTED, "coef_create: k=%d outside 1..%d", k, SCM_MAX_K);
-    if (n <= 0 || !d_alpha || !d_ctl) return fail(SCM_ERR_INVALID, "coef_create: bad arguments");
+// Allocates the coefficient object (Bmat / Amat uninitialised).
+inline int coef_alloc(scm_ctx* ctx, int64_t n, int32_t k, scm_coef** out) {
+    if (k <= 0 || k > SCM_MAX_K) return fail(SCM_ERR_UNSUPPORTED, "coef: k=%d outside 1..%d", k, SCM_MAX_K);
+    if (n <= 0) return fail(SCM_ERR_INVALID, "coef: bad n");
     cudaStream_t st = ctx->stream;
     scm_coef* c = new scm_coef();
     c->n = n; c->k = k; c->KT = (k + 7) / 8; c->nblk = (int32_t)ceil_div(n, 16);
@@ -155,6 +155,34 @@ inline int coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k
     rc |= dalloc((void**)&c->Afrag, sizeof(double) * (int64_t)c->nblk * 32 * c->KT * 4);
     rc |= dalloc((void**)&c->ctl_blocks, sizeof(int32_t) * (c->nblk + 1));
     if (rc) { coef_destroy(ctx, c); return SCM_ERR_CUDA; }
+    *out = c;
+    return 0;
+}
+
+// From Bmat / Amat: w0 = center' B, the fragment-ordered copies and the list of 16-gene blocks pass A must visit
+// (`d_rows` marks the genes whose row of B may be non-zero).  Synchronises the stream (reads back the block count).
+inline int coef_finalize(scm_ctx* ctx, scm_coef* c, const uint8_t* d_rows, const double* d_center) {
+    cudaStream_t st = ctx->stream;
+    coef_w0_kernel<<<1, 1024, 0, st>>>(c->Bmat, d_center, c->n, c->k, c->w0);
+    SCM_LAUNCH_CHECK(ctx);
+    coef_frag_kernel<<<c->nblk, 32, 0, st>>>(c->Bmat, c->Amat, c->n, c->k, c->KT, c->nblk, c->Bfrag, c->Afrag);
+    SCM_LAUNCH_CHECK(ctx);
+    coef_ctlblocks_kernel<<<1, 1024, 0, st>>>(d_rows, c->n, c->nblk, c->ctl_blocks, c->ctl_blocks + c->nblk);
+    SCM_LAUNCH_CHECK(ctx);
+    int h = 0;
+    SCM_CUDA(cudaMemcpyAsync(&h, c->ctl_blocks + c->nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    c->nblk_ctl = h;
+    return 0;
+}
+
+inline int coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, const uint8_t* d_ctl,
+                       const double* d_center, const double* d_pre, const double* d_post, scm_coef** out) {
+    if (n <= 0 || !d_alpha || !d_ctl) return fail(SCM_ERR_INVALID, "coef_create: bad arguments");
+    cudaStream_t st = ctx->stream;
+    scm_coef* c = nullptr;
+    SCM_TRY(coef_alloc(ctx, n, k, &c));
+    struct Guard { scm_ctx* ctx; scm_coef*& c; bool ok = false; ~Guard() { if (!ok) coef_destroy(ctx, c); } } guard{ctx, c};
     Scratch ws(ctx);
     double *AU, *ACU, *N, *Linv, *Ninv;
     int* flag;
@@ -177,21 +205,28 @@ inline int coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k
     SCM_TRY(gemm(ctx, (int)n, k, k, 1.0, transposed(ACU, n), rowmajor(Ninv, k), 0.0, c->Bmat, k));
     coef_scale_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(c->Bmat, c->Amat, AU, n, k, d_pre, d_post);
     SCM_LAUNCH_CHECK(ctx);
-    coef_w0_kernel<<<1, 1024, 0, st>>>(c->Bmat, d_center, n, k, c->w0);
-    SCM_LAUNCH_CHECK(ctx);
-    coef_frag_kernel<<<c->nblk, 32, 0, st>>>(c->Bmat, c->Amat, n, k, c->KT, c->nblk, c->Bfrag, c->Afrag);
-    SCM_LAUNCH_CHECK(ctx);
-    coef_ctlblocks_kernel<<<1, 1024, 0, st>>>(d_ctl, n, c->nblk, c->ctl_blocks, c->ctl_blocks + c->nblk);
-    SCM_LAUNCH_CHECK(ctx);
-    int h[3];
-    SCM_CUDA(cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SCM_CUDA(cudaMemcpyAsync(h + 1, c->ctl_blocks + c->nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SCM_CUDA(cudaStreamSynchronize(st));
-    c->nblk_ctl = h[1];
-    if (h[0]) {
-        coef_destroy(ctx, c);
+    int h = 0;
+    SCM_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCM_TRY(coef_finalize(ctx, c, d_ctl, d_center));  // synchronises: h is valid afterwards
+    if (h)
         return fail(SCM_ERR_SINGULAR, "coef_create: ac %%*%% t(ac) is not positive definite (k=%d exceeds the rank of the control-gene block?)", k);
-    }
+    guard.ok = true;
+    *out = c;
+    return 0;
+}
+
+// Coefficient object from explicit factors: newY = Y - ((Y - center) B) A with B (n x k, rows outside `d_rows` must be
+// zero) and A (k x n) given by the caller (scRUVg: B = 1[ctl] V diag(1/sigma), A = alpha).
+inline int coef_from_factors(scm_ctx* ctx, const double* d_B, const double* d_A, int64_t n, int32_t k, const uint8_t* d_rows,
+                             const double* d_center, scm_coef** out) {
+    if (!d_B || !d_A || !d_rows || !out) return fail(SCM_ERR_INVALID, "coef_from_factors: bad arguments");
+    scm_coef* c = nullptr;
+    SCM_TRY(coef_alloc(ctx, n, k, &c));
+    cudaError_t e1 = cudaMemcpyAsync(c->Bmat, d_B, sizeof(double) * n * k, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaError_t e2 = cudaMemcpyAsync(c->Amat, d_A, sizeof(double) * n * k, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { coef_destroy(ctx, c); return fail(SCM_ERR_CUDA, "coef_from_factors: copy failed"); }
+    const int rc = coef_finalize(ctx, c, d_rows, d_center);
+    if (rc != 0) { coef_destroy(ctx, c); return rc; }
     *out = c;
     return 0;
 }

@@ -151,6 +151,7 @@ inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
 }  // namespace scm
 
 #include "host_pipeline.cuh"
+#include "ruvg.cuh"
 
 using namespace scm;
 
@@ -358,6 +359,18 @@ int scm_coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k, c
     if (!out) return fail(SCM_ERR_INVALID, "scm_coef_create: out is NULL");
     StageTimer t(ctx, ST_COEF);
     return coef_create(ctx, d_alpha, n, k, d_ctl, d_center, d_pre, d_post, out);
+}
+int scm_coef_from_factors(scm_ctx* ctx, const double* d_B, const double* d_A, int64_t n, int32_t k, const uint8_t* d_rows,
+                          const double* d_center, scm_coef** out) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_COEF);
+    return coef_from_factors(ctx, d_B, d_A, n, k, d_rows, d_center, out);
+}
+int scm_ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const uint8_t* d_ctl, int32_t k, int mode,
+                 double tol, int32_t maxit, uint64_t seed, double* d_alpha, double* d_center, double* d_sigma, scm_coef** coef_out,
+                 int32_t* iters_out, double* resid_out) {
+    SCM_REQUIRE_CTX(ctx);
+    return ruvg_fit(ctx, d_Y, m_local, n, ld, d_ctl, k, mode, tol, maxit, seed, d_alpha, d_center, d_sigma, coef_out, iters_out, resid_out);
 }
 int scm_coef_destroy(scm_ctx* ctx, scm_coef* coef) {
     SCM_REQUIRE_CTX(ctx);

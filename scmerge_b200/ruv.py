@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib as L
 from .device import Context, DeviceArray, DeviceMatrix, default_context
 
-__all__ = ["fastRUVIII", "scRUVIII", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
+__all__ = ["fastRUVIII", "scRUVIII", "scRUVg", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
            "replicate_matrix", "replicate_keys", "tological", "createChunk", "RUVFit", "ExactParam", "RandomParam",
            "IrlbaParam"]
 
@@ -377,6 +377,54 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     res = dict(results[ks[0]])
     res["optimal_ruvK"] = optimal
     return res
+
+
+def scRUVg(Y, ctl, k, Z=1, eta=None, include_intercept=True, fullW=None, svdyc=None, BSPARAM=None, ctx: Context | None = None):
+    """R/scRUVg.R:30-85.  Y: m x n (cells x genes, numpy or DeviceMatrix).  Returns {'newY', 'W' (m x k), 'alpha' (k x n)}.
+    Only the default covariate structure is implemented on the device (Z = 1: an intercept, eta = NULL), which is what
+    every documented call uses; `fullW` / `svdyc` (re-use of a previous decomposition) are not supported.  Columns of W
+    (and the matching rows of alpha) are defined up to sign, exactly like the reference's `svd`."""
+    del include_intercept
+    if eta is not None or not (np.isscalar(Z) and Z == 1):
+        raise NotImplementedError("scRUVg on the device supports Z = 1 (intercept only) and eta = NULL")
+    if fullW is not None or svdyc is not None:
+        raise NotImplementedError("fullW / svdyc re-use is not supported on the device path")
+    ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
+    m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
+    ctlm = tological(ctl, n)
+    k = int(k)
+    if k > int(ctlm.sum()):
+        raise ValueError("k must not be larger than the number of controls")  # R/scRUVg.R:56-58
+    if k > min(L.MAX_K, m - 1):
+        raise L.ScmError(L.ERR_UNSUPPORTED, f"k = {k} outside 1..min({L.MAX_K}, m - 1)")
+    lib = L.lib()
+    dY, copied = _as_device(ctx, Y)
+    d_ctl = ctx.to_device(np.ascontiguousarray(ctlm, dtype=np.uint8))
+    d_alpha, d_center, d_sigma = ctx.empty((k, n)), ctx.empty((n,)), ctx.empty((k,))
+    coef = C.c_void_p()
+    iters, resid = C.c_int32(0), C.c_double(0.0)
+    try:
+        rc = lib.scm_ruvg_fit(ctx.handle, dY.ptr, m, n, dY.ld, d_ctl.ptr, k, L.MODE_EXACT if _is_exact(BSPARAM) else L.MODE_RANDOMIZED,
+                              1e-10, 500, 1, d_alpha.ptr, d_center.ptr, d_sigma.ptr, C.byref(coef), C.byref(iters), C.byref(resid))
+        if rc == L.ERR_NOCONV:
+            warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=2)
+        else:
+            L.check(rc)
+        dout = DeviceMatrix(ctx, m, n)
+        d_W = ctx.empty((m, k))
+        L.check(lib.scm_adjust(ctx.handle, dY.ptr, m, n, dY.ld, coef, None, 0, dout.ptr, dout.ld, d_W.ptr))
+        ctx.sync()
+        W, alpha = d_W.to_host(), d_alpha.to_host()
+        d_W.free()
+    finally:
+        if coef:
+            lib.scm_coef_destroy(ctx.handle, coef)
+        for a in (d_ctl, d_alpha, d_center, d_sigma):
+            a.free()
+    newY = _finish(dout, copied)
+    if copied:
+        dY.free()
+    return {"newY": newY, "W": W, "alpha": alpha}
 
 
 def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, inputcheck=True, fullalpha=None,

@@ -424,31 +424,39 @@ def test_csc_to_dense_bit_exact(sm, ctx, m, n, density, cosine):
 
 
 def test_csc_ingest_rejects_corrupt_and_nonfinite(sm, ctx):
+    from types import SimpleNamespace
     X = _sparse_case(200, 64, 0.2, seed=5)
-    bad = X.copy()
-    bad.indices = bad.indices.copy()
-    bad.indices[3] = 64                                             # gene index out of range
+
+    def raw(indptr=None, indices=None, data=None):  # the three dgCMatrix slots without scipy's own validation
+        return SimpleNamespace(format="csr", shape=X.shape, indptr=X.indptr.copy() if indptr is None else indptr,
+                               indices=X.indices.copy() if indices is None else indices,
+                               data=X.data.copy() if data is None else data)
+
+    idx = X.indices.copy()
+    idx[3] = 64                                                     # gene index out of range
     with pytest.raises(sm.ScmError, match="gene index"):
-        sm.csc_to_device(ctx, bad)
-    bad = X.copy()
-    bad.indptr = bad.indptr.copy()
-    bad.indptr[5] = bad.indptr[6] + 1                               # decreasing offsets
+        sm.csc_to_device(ctx, raw(indices=idx))
+    ptr = X.indptr.copy()
+    ptr[5] = ptr[6] + 1                                             # decreasing offsets
     with pytest.raises(sm.ScmError, match="column pointers"):
-        sm.csc_to_device(ctx, bad)
-    nf = X.copy()
-    nf.data = nf.data.copy()
-    nf.data[7] = np.inf
+        sm.csc_to_device(ctx, raw(indptr=ptr))
+    val = X.data.copy()
+    val[7] = np.inf
     with pytest.raises(sm.NonFiniteError):
-        sm.csc_to_device(ctx, nf)
-    dup = X.copy()                                                  # un-canonical input: duplicates are summed
-    dup.indices = dup.indices.copy()
-    p0 = dup.indptr[10]
-    if dup.indptr[11] - p0 >= 2:
-        dup.indices[p0 + 1] = dup.indices[p0]
-        dup.has_canonical_format = False
-        d = sm.csc_to_device(ctx, dup, cosine=False)
-        assert np.array_equal(d.to_host(), dup.toarray())
-        d.free()
+        sm.csc_to_device(ctx, raw(data=val))
+    with pytest.raises(sm.NonFiniteError):                          # also without the norm pass
+        sm.csc_to_device(ctx, raw(data=val), cosine=False)
+    # un-canonical input (adjacent duplicates) is summed on the device
+    p0 = int(X.indptr[10])
+    assert X.indptr[11] - p0 >= 2
+    idx = X.indices.copy()
+    idx[p0 + 1] = idx[p0]
+    want = np.zeros(X.shape)
+    rows = np.repeat(np.arange(X.shape[0]), np.diff(X.indptr))
+    np.add.at(want, (rows, idx), X.data)
+    d = sm.csc_to_device(ctx, raw(indices=idx), cosine=False)
+    assert np.allclose(d.to_host(), want, rtol=1e-15, atol=0)
+    d.free()
 
 
 def test_scmerge2_core_sparse_input_matches_dense(sm):
@@ -481,3 +489,28 @@ def test_scmerge2_core_sparse_input_matches_dense(sm):
     # genes x cells CSC (the reference's orientation) gives the same answer
     out2 = scMerge2_core(Xs.T.tocsc(), batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
     assert orc.rel_frobenius(out2["newY"], host_out) < 1e-13
+
+
+# ---- scRUVg ---------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,nc,k", [(80, 1000, 50, 20), (3000, 400, 120, 10)])
+def test_scruvg_vs_oracle(sm, m, n, nc, k):
+    """R/scRUVg.R:30-85 on the device (Gram of the centred cells -> eigenpairs of its control block -> fused rank-k
+    update) against the literal oracle; the reference's own assertion is abs(W) == abs(RUV2 W) (test-scRUVg.R:7)."""
+    L = orc.ruv_simulate(m=m, n=n, nc=nc, n_celltypes=5, rng=np.random.default_rng(1234 + m))
+    ref = orc.scRUVg(L["Y"], L["ctl"], k)
+    got = sm.scRUVg(L["Y"], L["ctl"], k)
+    assert orc.rel_frobenius(got["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(got["W"].T, ref["W"].T).max() < 1e-6
+    assert orc.principal_angles(got["alpha"], ref["alpha"]).max() < 1e-6
+    assert np.allclose(got["W"].T @ got["W"], np.eye(k), atol=1e-9)            # W orthonormal like svd's u
+    sgn = np.sign(np.sum(got["W"] * ref["W"], axis=0))
+    # individual columns match up to sign where the singular values are separated
+    s = np.linalg.svd((L["Y"] - L["Y"].mean(0))[:, orc.tological(L["ctl"], n)], compute_uv=False)
+    sep = np.minimum(np.abs(np.diff(s[: k + 1])), np.r_[np.inf, np.abs(np.diff(s[:k]))]) / s[0] > 1e-3
+    assert np.allclose((got["W"] * sgn)[:, sep], ref["W"][:, sep], atol=1e-6)
+    with pytest.raises(ValueError, match="number of controls"):
+        sm.scRUVg(L["Y"], L["ctl"], nc + 1)
+    # device-resident in -> device-resident out
+    dY = sm.DeviceMatrix.from_host(sm.default_context(), L["Y"])
+    res = sm.scRUVg(dY, L["ctl"], k)
+    assert isinstance(res["newY"], sm.DeviceMatrix) and orc.rel_frobenius(res["newY"].to_host(), ref["newY"]) < TOL_NEWY

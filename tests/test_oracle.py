@@ -155,3 +155,29 @@ def test_golden_sim(golden_dir):
     out = orc.fastRUVIII(g["sim_Y"].astype(np.float64), g["sim_M"].astype(np.float64), g["sim_ctl"], 20)
     assert orc.rel_frobenius(out[:16], g["sim_newY_rows"]) < 1e-10
     assert abs(np.linalg.norm(out) / g["sim_newY_fro"] - 1) < 1e-12
+
+
+def test_scruvg_literal_vs_reduced_and_ruv2():
+    """scRUVg (R/scRUVg.R:30-85): the reference's own test pins abs(W) to ruv::RUV2's W, i.e. the first k left singular
+    vectors of the centred control block (tests/testthat/test-scRUVg.R:7); the Gram-space form used on the device agrees."""
+    L = orc.ruv_simulate(m=80, n=1000, nc=50, n_celltypes=10, rng=np.random.default_rng(1234))
+    Y, ctl = L["Y"], orc.tological(L["ctl"], 1000)
+    r = orc.scRUVg(Y, ctl, 20)
+    Y0 = Y - Y.mean(axis=0)
+    u = np.linalg.svd(Y0[:, ctl], full_matrices=False)[0][:, :20]       # RUV2's W (Z = 1)
+    assert np.allclose(np.abs(r["W"]), np.abs(u), atol=1e-10)
+    G = Y0.T @ Y0
+    lam, V = np.linalg.eigh(G[np.ix_(ctl, ctl)])
+    lam, V = lam[::-1][:20], V[:, ::-1][:, :20]
+    B = np.zeros((1000, 20))
+    B[ctl] = V / np.sqrt(lam)
+    A = (V / np.sqrt(lam)).T @ G[ctl]
+    assert orc.rel_frobenius(Y - (Y0 @ B) @ A, r["newY"]) < 1e-12
+    # tall case takes the m x m cross-product branch (aspect ratio >= 5): same answer
+    L2 = orc.ruv_simulate(m=400, n=300, nc=40, n_celltypes=4, rng=np.random.default_rng(7))
+    r2 = orc.scRUVg(L2["Y"], L2["ctl"], 8)
+    Y02 = L2["Y"] - L2["Y"].mean(axis=0)
+    u2 = np.linalg.svd(Y02[:, orc.tological(L2["ctl"], 300)], full_matrices=False)[0][:, :8]
+    assert np.allclose(np.abs(r2["W"]), np.abs(u2), atol=1e-8)
+    with pytest.raises(ValueError, match="number of controls"):
+        orc.scRUVg(Y, ctl, 51)
