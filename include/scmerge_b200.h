@@ -163,7 +163,8 @@ int scm_coef_destroy(scm_ctx* ctx, scm_coef* coef);
  * out[i, :] = Y[i, :] - ((Y[i, :] - center) B) A      (in place allowed: d_out == d_Y)
  * d_subset (int32[nsub], optional): only these gene columns are produced, out is m x nsub
  * (return_subset_genes, R/scMerge2_utilis.R:117-121, R/scMerge2.R:402-406).
- * d_W (optional, m x k row-major): emits W = (Y - center) B (R/fastRUVIII.R:99).  Rank-local. */
+ * d_W (optional, m x k row-major): emits W = (Y - center) B (R/fastRUVIII.R:99).  d_out == NULL with d_W given runs
+ * the projection only.  Rank-local. */
 int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef,
                const int32_t* d_subset, int32_t nsub, double* d_out, int64_t ldo, double* d_W);
 
@@ -180,6 +181,34 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
                  int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
                  double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd,
                  int32_t* iters_out, double* resid_out);
+
+/* scm_ruv3_fit with two more outputs (either may be NULL): d_gram_centred (n x n) = sum over ALL cells of
+ * (y - ybar)(y - ybar)' and d_colmean (n) = ybar, the inputs of scm_pca_scores (no extra pass over the cells). */
+int scm_ruv3_fit_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld,
+                      const int32_t* d_group, int32_t G, const int32_t* d_batch, int32_t Bt,
+                      int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                      double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd,
+                      int32_t* iters_out, double* resid_out, double* d_gram_centred, double* d_colmean);
+
+/* ---- choice of ruvK (scRUVIII with several k, R/scRUVIII.R:80-114,182-199) --------------------------------------------
+ * scm_pca_scores: BiocSingular::runPCA(newY, rank, center = TRUE, scale = TRUE)$x (R/scRUVIII.R:183-184) of the ADJUSTED
+ * matrix newY = Y - ((Y - center) B) A described by `coef` (NULL: of Y itself) WITHOUT materialising newY: its centred Gram
+ * is (I - BA)' Gc (I - BA), expanded in the rank-k factors; after scaling to unit variance (n - 1 denominator) the top
+ * `rank` eigenpairs (K4, converged to `tol`) give the scores with one projection pass (K6 pass A) over the local rows of Y:
+ * d_scores (m_local x rank, row-major; columns defined up to sign), d_sing (rank, optional: singular values of the centred,
+ * scaled matrix).  m_total = number of cells over all ranks, d_colmean = their column means (scm_ruv3_fit_gram). */
+int scm_pca_scores(scm_ctx* ctx, const double* d_gram_centred, int64_t n, int64_t m_total, const scm_coef* coef, const double* d_colmean,
+                   int32_t rank, const double* d_Y, int64_t m_local, int64_t ld, double* d_scores, double* d_sing, double tol,
+                   int32_t maxit, int32_t* iters_out, double* resid_out);
+
+/* scm_silhouette: kBET_batch_sil (R/scRUVIII.R:192-199) = summary(cluster::silhouette(labels, dist(x)))$avg.width, exact
+ * (all m^2 Euclidean distances, O(m) memory).  d_X: m x d scores of ALL cells (d <= 16), labels 0-based in [0, C).  One
+ * distance pass serves two labelings (cell type and batch; d_lab_b may be NULL).  Returns in h_sum_a / h_sum_b the SUM of
+ * the widths s_i over the cells at positions [i0, i1) of the order by (label_a, label_b): ranks take disjoint ranges and
+ * add the sums; avg.width = total / m.  s_i = 0 for singleton clusters (cluster::silhouette) and when fewer than two
+ * clusters are populated (the reference would return NA). */
+int scm_silhouette(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t ldx, const int32_t* d_lab_a, int32_t Ca,
+                   const int32_t* d_lab_b, int32_t Cb, int64_t i0, int64_t i1, double* h_sum_a, double* h_sum_b);
 
 /* scm_ruvg_fit: the fit half of scRUVg (R/scRUVg.R:30-85 with Z = 1, eta = NULL) on a device-resident,
  * cell-sharded Y: column means (my_residop(Y, 1), :61-63), the top-k left singular vectors of the centred control block

@@ -209,10 +209,50 @@ def standardize2(Y, batch):
     return {"stand_Y": stand_Y, "stand_mean": stand_mean, "stand_var": stand_var}
 
 
-def scRUVIII(Y, M, ctl, k, batch, fullalpha=None, exact=True, svd_k=50, rng=None):
-    """R/scRUVIII.R:41-137 without the silhouette-based k selection (:80-114, out of scope).
-    Y is genes x cells.  `k` may be an int or a sequence; returns {k: {newY (cells x genes), fullalpha}}
-    plus 'optimal_ruvK' = k[0] for a single k (f_score = 1, :80-82)."""
+def silhouette_avg_width(X, labels):
+    """summary(cluster::silhouette(labels, dist(X)))$avg.width as used by kBET_batch_sil (R/scRUVIII.R:192-199; `cluster` is
+    un-vendored, this is its published definition): s_i = (b_i - a_i) / max(a_i, b_i), a_i = mean distance to the OTHER
+    members of i's cluster, b_i = smallest mean distance to another cluster, s_i = 0 for singleton clusters."""
+    X = np.asarray(X, dtype=np.float64)
+    lev, lab = np.unique(np.asarray(labels), return_inverse=True)
+    C, m = lev.shape[0], X.shape[0]
+    if C < 2:
+        return float("nan")
+    D = np.empty((m, m))
+    for r0 in range(0, m, 512):  # dist(): plain Euclidean distances from coordinate differences
+        diff = X[r0:r0 + 512, None, :] - X[None, :, :]
+        D[r0:r0 + 512] = np.sqrt((diff * diff).sum(axis=2))
+    onehot = np.zeros((m, C))
+    onehot[np.arange(m), lab] = 1.0
+    S = D @ onehot  # sum of distances to every cluster
+    cnt = onehot.sum(axis=0)
+    own = cnt[lab]
+    a = S[np.arange(m), lab] / np.maximum(own - 1, 1)
+    other = S / cnt[None, :]
+    other[np.arange(m), lab] = np.inf
+    b = other.min(axis=1)
+    s = np.where(own > 1, (b - a) / np.maximum(a, b), 0.0)
+    return float(s.mean())
+
+
+def calculate_sil(newY, cell_type, batch, rank=10):
+    """calculateSil (R/scRUVIII.R:182-190): BiocSingular::runPCA(newY, rank = 10, center = TRUE, scale = TRUE) -- scores
+    x = U D of the column-centred, unit-variance (n - 1 denominator) matrix -- then the average silhouette width of the
+    cell types and of the batches in the first 10 PCs (Euclidean `dist`)."""
+    Y = np.asarray(newY, dtype=np.float64)
+    Xc = Y - Y.mean(axis=0)
+    Xs = Xc / Y.std(axis=0, ddof=1)
+    U, S, _ = np.linalg.svd(Xs, full_matrices=False)
+    r = min(rank, S.shape[0])
+    x = U[:, :r] * S[:r]
+    return silhouette_avg_width(x, cell_type), silhouette_avg_width(x, batch)
+
+
+def scRUVIII(Y, M, ctl, k, batch, fullalpha=None, exact=True, svd_k=50, rng=None, cell_type=None):
+    """R/scRUVIII.R:41-137.  Y is genes x cells.  `k` may be an int or a sequence; returns {k: {newY (cells x genes),
+    fullalpha}} plus 'optimal_ruvK': k[0] for a single k (f_score = 1, :80-82), otherwise the k maximising the F-score of
+    the cell-type and (1 - batch) silhouette coefficients (:83-105; computed on the standardised adjusted matrices, i.e.
+    BEFORE the mean / sd are added back at :117-119), with 'f_score' and 'sil' (2 x len(k))."""
     ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
     sc = standardize2(Y, batch)
     stand_tY = sc["stand_Y"].T
@@ -223,11 +263,22 @@ def scRUVIII(Y, M, ctl, k, batch, fullalpha=None, exact=True, svd_k=50, rng=None
     out = {ks[0]: first}
     for kk in ks[1:]:  # :70-74 re-use fullalpha
         out[kk] = fastRUVIII(stand_tY, M, ctl, kk, fullalpha=first["fullalpha"], return_info=True)
+    if len(ks) == 1:
+        f_score = np.ones(1)  # :80-82
+    else:
+        if cell_type is None:  # :89-92 replicate structure stands in for the cell types
+            cell_type = group_ids(replicate_matrix(M))
+        sil = np.array([calculate_sil(out[kk]["newY"], cell_type, batch) for kk in ks]).T  # :94-96, 2 x len(k)
+        zo = (sil + 1.0) / 2.0  # zeroOneScale :143-146
+        ct, bt = zo[0], 1.0 - zo[1]
+        f_score = 2.0 * ct * bt / (ct + bt)  # f_measure :177-180
+        out["sil"] = sil
     for kk in ks:  # :117-119
         r = dict(out[kk])
         r["newY"] = (r["newY"].T * stand_sd[:, None] + stand_mean[:, None]).T
         out[kk] = r
-    out["optimal_ruvK"] = ks[0] if len(ks) == 1 else None
+    out["f_score"] = f_score
+    out["optimal_ruvK"] = ks[int(np.argmax(f_score))]
     out["stand_mean"], out["stand_sd"] = stand_mean, stand_sd
     return out
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "scm_adjust": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _i64, _vp],
     "scm_ruv3_fit": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _int, _dbl, _i32, _u64,
                      _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
+    "scm_ruv3_fit_gram": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _int, _dbl, _i32, _u64,
+                          _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp],
+    "scm_pca_scores": [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _dbl, _i32, C.POINTER(_i32), C.POINTER(_dbl)],
+    "scm_silhouette": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i64, _i64, C.POINTER(_dbl), C.POINTER(_dbl)],
     "scm_ruv3_host": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _int, _dbl, _i32, _u64, _vp, _i32, _int,
                       _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
     "scm_timers": [_vp, C.POINTER(_dbl), _int],

@@ -423,6 +423,7 @@ inline int adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t
                   const int32_t* d_subset, int32_t nsub, double* d_out, int64_t ldo, double* d_W) {
     if (!c || c->n != n) return fail(SCM_ERR_INVALID, "adjust: coefficient object does not match n=%lld", (long long)n);
     if (m <= 0) return 0;
+    if (!d_out && (d_subset || !d_W)) return fail(SCM_ERR_INVALID, "adjust: no output requested");
     if (!d_subset && !d_W) {
         const int trc = adjust_tma(ctx, d_Y, m, n, ld, c, d_out, ldo);
         if (trc <= 0) return trc;
@@ -431,7 +432,7 @@ inline int adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t
     const bool subset = d_subset != nullptr;
     double* W = d_W;
     if (subset && !W) SCM_TRY(ws.alloc(&W, m * c->k));
-    const bool pass_b = !subset;
+    const bool pass_b = !subset && d_out != nullptr;  // d_out == NULL: projection only (W = (Y - center) B)
     int rc;
     switch (c->KT) {
         case 1: rc = adjust_launch<1, 4>(ctx, d_Y, m, n, ld, c, pass_b, d_out, ldo, W); break;

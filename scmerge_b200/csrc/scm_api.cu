@@ -152,6 +152,7 @@ inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
 
 #include "host_pipeline.cuh"
 #include "ruvg.cuh"
+#include "select_k.cuh"
 
 using namespace scm;
 
@@ -384,9 +385,10 @@ int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld
     return adjust(ctx, d_Y, m, n, ld, coef, d_subset, nsub, d_out, ldo, d_W);
 }
 
-int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const int32_t* d_group, int32_t G,
-                 const int32_t* d_batch, int32_t Bt, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
-                 double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd, int32_t* iters_out, double* resid_out) {
+static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const int32_t* d_group, int32_t G,
+                         const int32_t* d_batch, int32_t Bt, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                         double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd, int32_t* iters_out, double* resid_out,
+                         double* d_gram_centred, double* d_colmean) {
     SCM_REQUIRE_CTX(ctx);
     if (!d_Y || !d_group || G <= 0 || n <= 0 || s <= 0 || !d_fullalpha)
         return fail(SCM_ERR_INVALID, "scm_ruv3_fit: bad arguments");
@@ -433,6 +435,9 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
         SCM_TRY(gram(ctx, d_Y, m_local, n, ld, shift, Gm, true));
     }
     SCM_TRY(allreduce(ctx, Gm, n * n, 0));
+    // the shift is the global column mean, so at this point Gm is the centred Gram of ALL cells (PCA of Y / of any newY)
+    if (d_gram_centred) SCM_CUDA(cudaMemcpyAsync(d_gram_centred, Gm, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+    if (d_colmean) SCM_CUDA(cudaMemcpyAsync(d_colmean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, G, shift, inv_sd));
     int64_t hmeta[2];
     SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
@@ -449,6 +454,34 @@ int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
     }
     SCM_CUDA(cudaStreamSynchronize(st));
     return rc;
+}
+
+int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const int32_t* d_group, int32_t G,
+                 const int32_t* d_batch, int32_t Bt, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                 double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd, int32_t* iters_out, double* resid_out) {
+    return ruv3_fit_impl(ctx, d_Y, m_local, n, ld, d_group, G, d_batch, Bt, s, kconv, mode, tol, maxit, seed, d_fullalpha, d_sigma,
+                         d_mean, d_sd, iters_out, resid_out, nullptr, nullptr);
+}
+int scm_ruv3_fit_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const int32_t* d_group, int32_t G,
+                      const int32_t* d_batch, int32_t Bt, int32_t s, int32_t kconv, int mode, double tol, int32_t maxit, uint64_t seed,
+                      double* d_fullalpha, double* d_sigma, double* d_mean, double* d_sd, int32_t* iters_out, double* resid_out,
+                      double* d_gram_centred, double* d_colmean) {
+    return ruv3_fit_impl(ctx, d_Y, m_local, n, ld, d_group, G, d_batch, Bt, s, kconv, mode, tol, maxit, seed, d_fullalpha, d_sigma,
+                         d_mean, d_sd, iters_out, resid_out, d_gram_centred, d_colmean);
+}
+
+int scm_pca_scores(scm_ctx* ctx, const double* d_gram_centred, int64_t n, int64_t m_total, const scm_coef* coef, const double* d_colmean,
+                   int32_t rank, const double* d_Y, int64_t m_local, int64_t ld, double* d_scores, double* d_sing, double tol,
+                   int32_t maxit, int32_t* iters_out, double* resid_out) {
+    SCM_REQUIRE_CTX(ctx);
+    return pca_scores(ctx, d_gram_centred, n, m_total, coef, d_colmean, rank, d_Y, m_local, ld, d_scores, d_sing, tol, maxit, iters_out,
+                      resid_out);
+}
+
+int scm_silhouette(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t ldx, const int32_t* d_lab_a, int32_t Ca,
+                   const int32_t* d_lab_b, int32_t Cb, int64_t i0, int64_t i1, double* h_sum_a, double* h_sum_b) {
+    SCM_REQUIRE_CTX(ctx);
+    return silhouette(ctx, d_X, m, d, ldx, d_lab_a, Ca, d_lab_b, Cb, i0, i1, h_sum_a, h_sum_b);
 }
 
 int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,

@@ -150,13 +150,18 @@ class RUVFit:
         self.fullalpha, self.sigma = fullalpha, sigma
         self.stand_mean, self.stand_sd = stand_mean, stand_sd
         self.iters, self.resid = iters, resid
+        self.d_gram = self.d_colmean = None  # device-resident centred Gram / column means (only with keep_gram)
 
 
 # ---- device drivers -----------------------------------------------------------------------------------
 def _fit(ctx: Context, dY: DeviceMatrix, keys: np.ndarray, G: int, s: int, k: int, exact: bool, batch_keys=None, Bt=0,
-         tol=1e-10, maxit=500, seed=1) -> RUVFit:
+         tol=1e-10, maxit=500, seed=1, keep_gram=False) -> RUVFit:
+    """scm_ruv3_fit.  keep_gram: the centred Gram of all cells (n x n) and their column means stay on the device as
+    `fit.d_gram` / `fit.d_colmean` (inputs of the ruvK selection, scm_pca_scores); the caller frees them."""
     lib = L.lib()
     n = dY.n
+    d_gram = ctx.empty((n, n)) if keep_gram else None
+    d_colmean = ctx.empty((n,)) if keep_gram else None
     d_keys = ctx.to_device(np.ascontiguousarray(keys, dtype=np.int32))
     d_batch = ctx.to_device(np.ascontiguousarray(batch_keys, dtype=np.int32)) if batch_keys is not None else None
     d_fa = ctx.empty((s, n))
@@ -164,9 +169,9 @@ def _fit(ctx: Context, dY: DeviceMatrix, keys: np.ndarray, G: int, s: int, k: in
     d_mean = ctx.empty((n,)) if d_batch is not None else None
     d_sd = ctx.empty((n,)) if d_batch is not None else None
     iters, resid = C.c_int32(0), C.c_double(0.0)
-    rc = lib.scm_ruv3_fit(ctx.handle, dY.ptr, dY.m, n, dY.ld, d_keys.ptr, G, _dptr(d_batch), Bt, s, min(k, s),
-                          L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, d_fa.ptr, d_sig.ptr,
-                          _dptr(d_mean), _dptr(d_sd), C.byref(iters), C.byref(resid))
+    rc = lib.scm_ruv3_fit_gram(ctx.handle, dY.ptr, dY.m, n, dY.ld, d_keys.ptr, G, _dptr(d_batch), Bt, s, min(k, s),
+                               L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, d_fa.ptr, d_sig.ptr,
+                               _dptr(d_mean), _dptr(d_sd), C.byref(iters), C.byref(resid), _dptr(d_gram), _dptr(d_colmean))
     if rc == L.ERR_NOCONV:
         warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
     else:
@@ -176,7 +181,47 @@ def _fit(ctx: Context, dY: DeviceMatrix, keys: np.ndarray, G: int, s: int, k: in
     for a in (d_keys, d_batch, d_fa, d_sig, d_mean, d_sd):
         if a is not None:
             a.free()
+    fit.d_gram, fit.d_colmean = d_gram, d_colmean
     return fit
+
+
+class _Coef:
+    """scm_coef_create / scm_coef_destroy as a context manager: the device-side (B, A, center) of
+    newY = Y - ((Y - center) B) A for alpha = the first k rows of fullalpha."""
+
+    def __init__(self, ctx: Context, n: int, fullalpha: np.ndarray, k: int, ctl: np.ndarray, center=None, pre=None, post=None):
+        self.ctx, self.n = ctx, n
+        self.k = int(min(k, fullalpha.shape[0]))
+        if self.k > L.MAX_K:
+            raise L.ScmError(L.ERR_UNSUPPORTED, f"ruvK = {self.k} > {L.MAX_K} is not supported by the fused adjust kernel")
+        self._args = (np.ascontiguousarray(fullalpha[:self.k], dtype=np.float64), np.ascontiguousarray(ctl, dtype=np.uint8),
+                      center, pre, post)
+        self.handle = C.c_void_p()
+        self._bufs = []
+
+    def __enter__(self):
+        ctx, lib = self.ctx, L.lib()
+        alpha, ctl, center, pre, post = self._args
+        d_alpha, d_ctl = ctx.to_device(alpha), ctx.to_device(ctl)
+        vecs = [ctx.to_device(np.ascontiguousarray(v, dtype=np.float64)) if v is not None else None for v in (center, pre, post)]
+        self._bufs = [d_alpha, d_ctl] + vecs
+        try:
+            L.check(lib.scm_coef_create(ctx.handle, d_alpha.ptr, self.n, self.k, d_ctl.ptr, _dptr(vecs[0]), _dptr(vecs[1]),
+                                        _dptr(vecs[2]), C.byref(self.handle)))
+        except Exception:
+            self.__exit__(None, None, None)
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        if self.handle:
+            L.lib().scm_coef_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+        for a in self._bufs:
+            if a is not None:
+                a.free()
+        self._bufs = []
+        return False
 
 
 def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: np.ndarray, center=None, pre=None,
@@ -184,16 +229,7 @@ def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: 
     """newY = Y - ((Y - center) B) A on the device (scm_coef_create + scm_adjust)."""
     lib = L.lib()
     n = dY.n
-    kk = int(min(k, fullalpha.shape[0]))
-    if kk > L.MAX_K:
-        raise L.ScmError(L.ERR_UNSUPPORTED, f"ruvK = {kk} > {L.MAX_K} is not supported by the fused adjust kernel")
-    d_alpha = ctx.to_device(np.ascontiguousarray(fullalpha[:kk], dtype=np.float64))
-    d_ctl = ctx.to_device(np.ascontiguousarray(ctl, dtype=np.uint8))
-    vecs = [ctx.to_device(np.ascontiguousarray(v, dtype=np.float64)) if v is not None else None for v in (center, pre, post)]
-    coef = C.c_void_p()
-    try:
-        L.check(lib.scm_coef_create(ctx.handle, d_alpha.ptr, n, kk, d_ctl.ptr, _dptr(vecs[0]), _dptr(vecs[1]), _dptr(vecs[2]),
-                                    C.byref(coef)))
+    with _Coef(ctx, n, fullalpha, k, ctl, center, pre, post) as coef:
         d_sub, nsub = None, 0
         if subset is not None:
             sub = np.ascontiguousarray(subset, dtype=np.int32)
@@ -201,17 +237,40 @@ def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: 
         n_out = nsub if d_sub is not None else n
         if out is None:
             out = DeviceMatrix(ctx, dY.m, n_out)
-        d_W = ctx.empty((dY.m, kk)) if want_W else None
-        L.check(lib.scm_adjust(ctx.handle, dY.ptr, dY.m, n, dY.ld, coef, _dptr(d_sub), nsub, out.ptr, out.ld, _dptr(d_W)))
+        d_W = ctx.empty((dY.m, coef.k)) if want_W else None
+        L.check(lib.scm_adjust(ctx.handle, dY.ptr, dY.m, n, dY.ld, coef.handle, _dptr(d_sub), nsub, out.ptr, out.ld, _dptr(d_W)))
         ctx.sync()
         W = d_W.to_host() if d_W is not None else None
-    finally:
-        if coef:
-            lib.scm_coef_destroy(ctx.handle, coef)
-        for a in [d_alpha, d_ctl] + vecs:
+        for a in (d_sub, d_W):
             if a is not None:
                 a.free()
     return out, W
+
+
+def _silhouette_pair(ctx: Context, fit: RUVFit, dY: DeviceMatrix, coef: _Coef | None, ct_keys: np.ndarray, n_ct: int,
+                     b_keys: np.ndarray, n_b: int, rank: int = 10):
+    """calculateSil (R/scRUVIII.R:182-190) for one candidate k: PC scores of the adjusted matrix (scm_pca_scores, no newY
+    is materialised) and the average silhouette widths of the cell types and of the batches (scm_silhouette)."""
+    lib = L.lib()
+    m, n = dY.m, dY.n
+    r = int(min(rank, n, m - 1))
+    d_scores = ctx.empty((m, r))
+    d_ct, d_b = ctx.to_device(np.ascontiguousarray(ct_keys, dtype=np.int32)), ctx.to_device(np.ascontiguousarray(b_keys, dtype=np.int32))
+    iters, resid = C.c_int32(0), C.c_double(0.0)
+    sa, sb = C.c_double(0.0), C.c_double(0.0)
+    try:
+        rc = lib.scm_pca_scores(ctx.handle, fit.d_gram.ptr, n, m, coef.handle if coef is not None else None, fit.d_colmean.ptr, r,
+                                dY.ptr, m, dY.ld, d_scores.ptr, None, 1e-9, 500, C.byref(iters), C.byref(resid))
+        if rc == L.ERR_NOCONV:
+            warnings.warn("PCA for the ruvK selection: " + lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
+        else:
+            L.check(rc)
+        L.check(lib.scm_silhouette(ctx.handle, d_scores.ptr, m, r, r, d_ct.ptr, int(n_ct), d_b.ptr, int(n_b), 0, m,
+                                   C.byref(sa), C.byref(sb)))
+    finally:
+        for a in (d_scores, d_ct, d_b):
+            a.free()
+    return sa.value / m, sb.value / m
 
 
 def _is_host_matrix(Y) -> bool:
@@ -315,9 +374,11 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
              BSPARAM=None, svd_k=50, ctx: Context | None = None):
     """R/scRUVIII.R:41-137.  Y: genes x cells (numpy) -- byte-identical to the device layout cells x genes.
     Standardisation and de-standardisation (R/scRUVIII.R:47-50,117-119) are fused into the Gram scaling and the
-    adjust coefficients, so Y is read but never rewritten.  The silhouette-based choice among several k
-    (R/scRUVIII.R:80-114) is out of scope: with several k every result is returned and optimal_ruvK is None."""
-    del BPPARAM, cell_type
+    adjust coefficients, so Y is read but never rewritten.  With several k the silhouette-based choice of
+    R/scRUVIII.R:80-114 runs on the device (PC scores of every candidate from the centred Gram the fit already has, exact
+    silhouette widths of cell types and batches; nothing is plotted): 'optimal_ruvK', 'f_score' and 'sil' (2 x len(k)) are
+    returned, and with return_all_RUV=False only the optimal matrix is produced."""
+    del BPPARAM
     if batch is None:
         raise ValueError("batch is required")
     ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
@@ -358,24 +419,41 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     if G >= m or ks[0] == 0:
         raise NotImplementedError("degenerate replicate structure (ncol(M) >= m): nothing to adjust")
     s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
+    select = len(ks) > 1
     if fullalpha is None:
-        fit = _fit(ctx, dY, keys, G, s_dev, ks[0], exact_dev, batch_keys=bkeys, Bt=Bt)
+        fit = _fit(ctx, dY, keys, G, s_dev, ks[0], exact_dev, batch_keys=bkeys, Bt=Bt, keep_gram=select)
     else:  # still need stand_mean / stand_sd: run the standardisation passes only via a fit with s = 1
-        fit0 = _fit(ctx, dY, keys, G, 1, 1, True, batch_keys=bkeys, Bt=Bt, maxit=2, tol=1.0)
+        fit0 = _fit(ctx, dY, keys, G, 1, 1, True, batch_keys=bkeys, Bt=Bt, maxit=2, tol=1.0, keep_gram=select)
         fit = RUVFit(np.asarray(fullalpha, dtype=np.float64), None, fit0.stand_mean, fit0.stand_sd)
-    for kk in ks:
+        fit.d_gram, fit.d_colmean = fit0.d_gram, fit0.d_colmean
+    f_score, sil = np.ones(1), None
+    if select:
+        # R/scRUVIII.R:83-105: silhouette of the cell types (the replicate structure when cell_type is NULL, :89-92) and of
+        # the batches in the first 10 PCs of every candidate's adjusted matrix, F-score of the two, which.max
+        ct_keys, n_ct = (keys, G) if cell_type is None else replicate_keys(np.asarray(cell_type))
+        sil = np.empty((2, len(ks)))
+        for i, kk in enumerate(ks):
+            with _Coef(ctx, n, fit.fullalpha, kk, ctl, fit.stand_mean, 1.0 / fit.stand_sd, fit.stand_sd) as coef:
+                sil[:, i] = _silhouette_pair(ctx, fit, dY, coef, ct_keys, n_ct, bkeys, Bt)
+        zo = (sil + 1.0) / 2.0
+        ctv, btv = zo[0], 1.0 - zo[1]
+        f_score = 2.0 * ctv * btv / (ctv + btv)
+        fit.d_gram.free()
+        fit.d_colmean.free()
+    optimal = ks[int(np.argmax(f_score))]
+    for kk in (ks if return_all_RUV else [optimal]):
         dout, _ = _adjust(ctx, dY, fit.fullalpha, kk, ctl, center=fit.stand_mean, pre=1.0 / fit.stand_sd, post=fit.stand_sd)
         newY = _finish(dout, copied)
         results[kk] = {"newY": newY, "M": M, "fullalpha": fit.fullalpha}
     if copied:
         dY.free()
-    optimal = ks[0] if len(ks) == 1 else None
+    extras = {"optimal_ruvK": optimal, "f_score": f_score, "sil": sil}
     if return_all_RUV:
-        results["optimal_ruvK"] = optimal
+        results.update(extras)
         results["stand_mean"], results["stand_sd"] = fit.stand_mean, fit.stand_sd
         return results
-    res = dict(results[ks[0]])
-    res["optimal_ruvK"] = optimal
+    res = dict(results[optimal])
+    res.update(extras)
     return res
 
 

@@ -211,15 +211,104 @@ def test_golden_example_scruviii(sm, golden_dir):
 
 
 def test_scruviii_multi_k(sm):
+    """scRUVIII with several k (R/scRUVIII.R:64-114): every adjusted matrix, the two silhouette coefficients per k, the
+    F-scores and the chosen k against the oracle (exact PCA + all-pairs silhouette on the materialised matrices)."""
     L_ = orc.ruv_simulate(m=200, n=300, nc=100, rng=np.random.default_rng(1234))
     Y = np.log2(L_["Y"] + 1).T
     keep = Y.var(axis=1) > 0
     Y, ctl = Y[keep], L_["ctl"][keep]
-    res = sm.scRUVIII(Y, L_["M"], ctl, k=[5, 10], batch=L_["batch"])
-    ref = orc.scRUVIII(Y, L_["M"], ctl, [5, 10], L_["batch"])
-    for kk in (5, 10):
+    ks = [2, 5, 10]
+    res = sm.scRUVIII(Y, L_["M"], ctl, k=ks, batch=L_["batch"], cell_type=L_["cellTypes"])
+    ref = orc.scRUVIII(Y, L_["M"], ctl, ks, L_["batch"], cell_type=L_["cellTypes"])
+    for kk in ks:
         assert orc.rel_frobenius(res[kk]["newY"], ref[kk]["newY"]) < TOL_NEWY
-    assert res["optimal_ruvK"] is None
+    assert np.allclose(res["sil"], ref["sil"], rtol=0, atol=1e-7)
+    assert np.allclose(res["f_score"], ref["f_score"], rtol=0, atol=1e-7)
+    assert res["optimal_ruvK"] == ref["optimal_ruvK"]
+    # cell_type = NULL: the replicate structure stands in (R/scRUVIII.R:89-92); only the optimal matrix is produced
+    one = sm.scRUVIII(Y, L_["M"], ctl, k=ks, batch=L_["batch"], return_all_RUV=False)
+    ref2 = orc.scRUVIII(Y, L_["M"], ctl, ks, L_["batch"])
+    assert one["optimal_ruvK"] == ref2["optimal_ruvK"]
+    assert orc.rel_frobenius(one["newY"], ref2[ref2["optimal_ruvK"]]["newY"]) < TOL_NEWY
+
+
+@pytest.mark.parametrize("m,d,Ca,Cb", [(500, 10, 4, 3), (1300, 3, 7, 1), (257, 16, 2, 2), (900, 10, 12, 5)])
+def test_silhouette_vs_oracle(sm, ctx, m, d, Ca, Cb):
+    """scm_silhouette == summary(cluster::silhouette(labels, dist(x)))$avg.width for both labelings from one distance pass;
+    singleton clusters (s_i = 0), unused label ids and a split over cell ranges (the multi-rank decomposition) included."""
+    rng = np.random.default_rng(m + d)
+    la = rng.integers(0, Ca - 1, m).astype(np.int32)       # id Ca - 1 is used exactly once -> singleton cluster
+    la[5] = Ca - 1
+    lb = rng.integers(0, Cb, m).astype(np.int32)
+    if Cb > 2:
+        lb[lb == 1] = 0                                     # label id 1 unused
+    X = rng.normal(size=(m, d)) + 1.5 * rng.normal(size=(Ca, d))[la]
+    dX, dla, dlb = ctx.to_device(X), ctx.to_device(la), ctx.to_device(lb)
+    sa, sb = C.c_double(), C.c_double()
+    lib = sm.lib()
+
+    def run(i0, i1, with_b=True):
+        rc = lib.scm_silhouette(ctx.handle, dX.ptr, m, d, d, dla.ptr, Ca, dlb.ptr if with_b else None, Cb, i0, i1,
+                                C.byref(sa), C.byref(sb))
+        assert rc == 0, lib.scm_last_error()
+        return sa.value, sb.value
+    ta, tb = run(0, m)
+    assert abs(ta / m - orc.silhouette_avg_width(X, la)) < 1e-12
+    if len(np.unique(lb)) > 1:
+        assert abs(tb / m - orc.silhouette_avg_width(X, lb)) < 1e-12
+    else:
+        assert tb == 0.0
+    pa, pb = run(0, m // 3)
+    qa, qb = run(m // 3, m)
+    assert abs(pa + qa - ta) < 1e-9 and abs(pb + qb - tb) < 1e-9
+    assert abs(run(0, m, with_b=False)[0] - ta) < 1e-9
+    assert run(0, m) == (ta, tb)                            # deterministic
+    bad = ctx.to_device(np.full(m, Ca, dtype=np.int32))
+    assert lib.scm_silhouette(ctx.handle, dX.ptr, m, d, d, bad.ptr, Ca, None, 1, 0, m, C.byref(sa), C.byref(sb)) == -1
+
+
+def test_pca_scores_of_adjusted_matrix(sm, ctx):
+    """scm_pca_scores: runPCA(newY, rank = 10, center, scale)$x of the adjusted matrix from the centred Gram of Y and the
+    rank-k factors, without materialising newY -- against the SVD of the materialised, centred, scaled oracle matrix."""
+    from scmerge_b200.ruv import _Coef, _fit
+    P = orc.planted_factors(4000, 200, 60, 6, n_types=4, n_batch=3, seed=11)
+    Y, ctlm = P["Y"], orc.tological(P["ctl"], 200)
+    ref = orc.fastRUVIII(Y, P["types"], ctlm, 6, return_info=True)
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    fit = _fit(ctx, dY, P["types"].astype(np.int32), 4, 50, 6, True, keep_gram=True)
+    Yc = Y - Y.mean(axis=0)
+    assert np.allclose(fit.d_gram.to_host(), Yc.T @ Yc, rtol=1e-10, atol=1e-8 * np.abs(Yc.T @ Yc).max())
+    assert np.allclose(fit.d_colmean.to_host(), Y.mean(axis=0), rtol=1e-13)
+    lib = sm.lib()
+    for coef_k in (6, None):
+        target = ref["newY"] if coef_k else Y
+        Xs = (target - target.mean(axis=0)) / target.std(axis=0, ddof=1)
+        U, S, Vt = np.linalg.svd(Xs, full_matrices=False)
+        want = U[:, :10] * S[:10]
+        d_scores, d_sing = ctx.empty((4000, 10)), ctx.empty((10,))
+        it, rs = C.c_int32(), C.c_double()
+
+        def call(h):
+            rc = lib.scm_pca_scores(ctx.handle, fit.d_gram.ptr, 200, 4000, h, fit.d_colmean.ptr, 10, dY.ptr, 4000, dY.ld,
+                                    d_scores.ptr, d_sing.ptr, 1e-10, 500, C.byref(it), C.byref(rs))
+            assert rc == 0, lib.scm_last_error()
+        if coef_k:
+            with _Coef(ctx, 200, fit.fullalpha, coef_k, ctlm) as coef:
+                call(coef.handle)
+        else:
+            call(None)
+        got = d_scores.to_host()
+        assert np.allclose(d_sing.to_host(), S[:10], rtol=1e-9)
+        sgn = np.sign(np.sum(got * want, axis=0))
+        gaps = np.minimum(np.abs(np.diff(S[:11])), np.r_[np.inf, np.abs(np.diff(S[:10]))]) / S[0]
+        ok = gaps > 1e-3                                     # individual PCs are defined where the spectrum is separated
+        assert ok.sum() >= 3
+        assert np.allclose((got * sgn)[:, ok], want[:, ok], rtol=0, atol=1e-7 * np.abs(want).max())
+        # pairwise distances (all the silhouette sees) are invariant to rotations inside near-degenerate PC groups
+        idx = np.random.default_rng(0).integers(0, 4000, (200, 2))
+        dg = np.linalg.norm(got[idx[:, 0]] - got[idx[:, 1]], axis=1)
+        dw = np.linalg.norm(want[idx[:, 0]] - want[idx[:, 1]], axis=1)
+        assert np.allclose(dg, dw, rtol=1e-7, atol=1e-9)
 
 
 def _pseudo_case(seed=777, m=1200, n=300, c=120, k=8):

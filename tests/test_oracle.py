@@ -181,3 +181,34 @@ def test_scruvg_literal_vs_reduced_and_ruv2():
     assert np.allclose(np.abs(r2["W"]), np.abs(u2), atol=1e-8)
     with pytest.raises(ValueError, match="number of controls"):
         orc.scRUVg(Y, ctl, 51)
+
+
+def test_silhouette_and_k_selection():
+    """kBET_batch_sil / calculateSil / f_measure (R/scRUVIII.R:83-105,177-199) restated: brute-force check of the
+    silhouette definition, and the selection picks the k with the largest F-score."""
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(60, 4))
+    lab = rng.integers(0, 3, 60)
+    lab[0] = 7  # singleton cluster -> s_i = 0
+    s = []
+    for i in range(60):
+        d = np.sqrt(((X - X[i]) ** 2).sum(axis=1))
+        own = lab == lab[i]
+        if own.sum() == 1:
+            s.append(0.0)
+            continue
+        a = d[own].sum() / (own.sum() - 1)
+        b = min(d[lab == c].mean() for c in set(lab) if c != lab[i])
+        s.append((b - a) / max(a, b))
+    assert abs(np.mean(s) - orc.silhouette_avg_width(X, lab)) < 1e-14
+    assert np.isnan(orc.silhouette_avg_width(X, np.zeros(60)))
+    L = orc.ruv_simulate(m=120, n=200, nc=60, rng=np.random.default_rng(4))
+    Y = np.log2(L["Y"] + 1).T
+    keep = Y.var(axis=1) > 0
+    res = orc.scRUVIII(Y[keep], L["M"], L["ctl"][keep], [2, 6], L["batch"], cell_type=L["cellTypes"])
+    assert res["sil"].shape == (2, 2) and res["optimal_ruvK"] == [2, 6][int(np.argmax(res["f_score"]))]
+    zo = (res["sil"] + 1) / 2
+    assert np.allclose(res["f_score"], 2 * zo[0] * (1 - zo[1]) / (zo[0] + 1 - zo[1]))
+    # runPCA(center, scale) is invariant to the per-gene de-standardisation: same silhouettes on the final matrices
+    for i, kk in enumerate((2, 6)):
+        assert np.allclose(orc.calculate_sil(res[kk]["newY"], L["cellTypes"], L["batch"]), res["sil"][:, i], atol=1e-10)
