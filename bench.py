@@ -49,19 +49,28 @@ def parse():
     p.add_argument("--k", type=int, default=20)
     p.add_argument("--types", type=int, default=20)
     p.add_argument("--batches", type=int, default=4)
-    p.add_argument("--cpu-cells", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
+    p.add_argument("--cpu-cells", type=int, default=None,
+                   help="cells in the bounded CPU-baseline sample (default 20000; 50000 for the scmerge2 workload, whose fit cost "
+                        "does not depend on the number of cells)")
     p.add_argument("--workload", default="fastruviii", choices=["fastruviii", "scmerge2"],
                    help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] (cosine norm, "
                         "pseudobulk fit, adjust all cells; not the headline line)")
+    p.add_argument("--density", type=float, default=0.1,
+                   help="scmerge2 workload: fraction of non-zero entries of the (sparse, dgCMatrix-like) expression matrix")
+    p.add_argument("--dense-input", action="store_true", help="scmerge2 workload: dense device matrix instead of the sparse one")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.cpu_cells is None:
+        a.cpu_cells = 50000 if a.workload == "scmerge2" else 20000
+    return a
 
 
 def workload_name(a):
     if a.workload == "scmerge2":
+        inp = "dense input" if a.dense_input else f"sparse (dgCMatrix) input, density {a.density}"
         return (f"scMerge2 core synthetic {a.cells} cells/GPU x {a.genes} genes, 8 batches, {a.types} cell types, k_pseudoBulk=30, "
-                f"ctl=all genes, ruvK={a.k}")
+                f"ctl=all genes, ruvK={a.k}, {inp}")
     return (f"fastRUVIII synthetic {a.cells} cells/GPU x {a.genes} genes, {a.ctl} ctl genes, k={a.k}, "
             f"{a.types} replicate groups, exact mode")
 
@@ -142,6 +151,40 @@ def make_data(a, ctx, rank, torch):
     return dY, types.to(torch.int32).cpu().numpy(), ctl
 
 
+def sparsify(a, ctx, dY, rank, torch):
+    """scmerge2 workload: Bernoulli dropout mask on the dense generator output (single-cell matrices are ~90 % zeros; the
+    low-rank structure survives in expectation), then the three dgCMatrix slots of the cells-compressed matrix in
+    page-locked host memory.  Returns a namespace with format / shape / indptr / indices / data (what scMerge2_core takes)."""
+    from types import SimpleNamespace
+
+    import scmerge_b200 as sm
+    m, n = a.cells, a.genes
+    dev = torch.device("cuda", ctx.device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242 + rank)
+    Yt = torch.as_tensor(dY.buf, device=dev).view(m, dY.ld)
+    counts = torch.empty(m, dtype=torch.int64, device=dev)
+    step = 50_000
+    for r0 in range(0, m, step):
+        r1 = min(m, r0 + step)
+        blk = Yt[r0:r1, :n]
+        blk *= (torch.rand(r1 - r0, n, generator=g, device=dev) < a.density)
+        counts[r0:r1] = (blk != 0).sum(dim=1)
+    indptr = np.zeros(m + 1, dtype=np.int64)
+    indptr[1:] = torch.cumsum(counts, 0).cpu().numpy()
+    nnz = int(indptr[-1])
+    idx, val = sm.pinned_empty((nnz,), np.int32), sm.pinned_empty((nnz,), np.float64)
+    for r0 in range(0, m, step):
+        r1 = min(m, r0 + step)
+        blk = Yt[r0:r1, :n]
+        nzr, nzc = torch.nonzero(blk, as_tuple=True)  # row-major order: sorted by cell, then gene
+        p0, p1 = int(indptr[r0]), int(indptr[r1])
+        idx[p0:p1] = nzc.to(torch.int32).cpu().numpy()
+        val[p0:p1] = blk[nzr, nzc].cpu().numpy()
+    torch.cuda.synchronize()
+    return SimpleNamespace(format="csr", shape=(m, n), indptr=indptr, indices=idx, data=val, nnz=nnz)
+
+
 def fp64_peak(torch, dev):
     """cuBLAS DGEMM 8192^3 best of 5 (MEASURED_PEAKS.json has no fp64 entry; same method as its bf16 one)."""
     N = 8192
@@ -159,17 +202,53 @@ def fp64_peak(torch, dev):
     return 2 * N ** 3 / (best * 1e-3) * 1e-12
 
 
+def pcie_probe(sm, ctx, torch, pinned):
+    """Measured pinned-host <-> device copy bandwidth (GB/s) of this box: the bound of the end-to-end number."""
+    nb = min(pinned.nbytes, 2 << 30)
+    d = ctx.empty((nb // 8,))
+    lib = sm.lib()
+    import ctypes as C
+    hp = pinned.ctypes.data_as(C.c_void_p)
+    out = {}
+    for name, fn in (("h2d_gbs", lambda: lib.scm_h2d(ctx.handle, d.ptr, hp, nb)), ("d2h_gbs", lambda: lib.scm_d2h(ctx.handle, hp, d.ptr, nb))):
+        fn()
+        ctx.sync()
+        t0 = time.perf_counter()
+        fn()
+        ctx.sync()
+        out[name] = nb / (time.perf_counter() - t0) * 1e-9
+    d.free()
+    return out
+
+
 # ---- CPU arms ---------------------------------------------------------------------------------------------
 def cpu_sample(a):
     from oracle import ruv_oracle as orc
-    P = orc.planted_factors(a.cpu_cells, a.genes, a.ctl, a.k, n_types=a.types, n_batch=a.batches, seed=20241)
+    nb = 8 if a.workload == "scmerge2" else a.batches
+    P = orc.planted_factors(a.cpu_cells, a.genes, a.ctl, a.k, n_types=a.types, n_batch=nb, seed=20241)
+    if a.workload == "scmerge2":
+        from scmerge_b200.scmerge2 import pseudobulk_keys  # host-side index construction only (no device, no arithmetic)
+        keys, _npb, names, _t, _b = pseudobulk_keys(P["batch"], P["types"], 30, seed=1)
+        P["which"] = np.array([int(nm.rsplit("_", 1)[1]) for nm in names])[keys]
+        P["Yt"] = np.ascontiguousarray(P["Y"].T)
     return orc, P
 
 
 def cpu_time_once(a, orc, P):
     t0 = time.perf_counter()
-    orc.fastRUVIII(P["Y"], P["types"], P["ctl"], a.k)
+    if a.workload == "scmerge2":
+        orc.scmerge2_core(P["Yt"], P["batch"], P["types"], P["which"], ruvK=a.k, k_fold=30, exact=False,
+                          rng=np.random.default_rng(1))
+    else:
+        orc.fastRUVIII(P["Y"], P["types"], P["ctl"], a.k)
     return time.perf_counter() - t0
+
+
+def cpu_what(a):
+    if a.workload == "scmerge2":
+        return ("NumPy/LAPACK restatement of scMerge2's arithmetic core (R/scMerge2.R:193-309: cosineNorm, pseudobulk means, "
+                "pseudoRUVIII with rsvd, adjust of every cell); R is not installable here")
+    return "NumPy/LAPACK literal restatement of R/fastRUVIII.R:41-129 (dense residop + thin dgesdd + adjust); R is not installable here"
 
 
 def run_reference(a):
@@ -188,7 +267,7 @@ def run_reference(a):
            "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a)},
            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
-                            "what": "NumPy/LAPACK literal restatement of R/fastRUVIII.R:41-129 (R is not installable here)"},
+                            "what": cpu_what(a)},
            "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
@@ -224,14 +303,24 @@ def run_ours(a):
     dOut = sm.DeviceMatrix(ctx, a.cells, a.genes)
     peak64 = fp64_peak(torch, dev) if rank == 0 else 0.0
 
+    Xh = None
     if a.workload == "scmerge2":
         import warnings
         warnings.simplefilter("ignore")
         pb = sm.pseudobulk_keys(a._batch, keys, 30, seed=1)
-        a.no_e2e = True
+        if a.dense_input:
+            a.no_e2e = True
+            src = dY
+        else:
+            # the matrix scMerge2 actually holds: sparse, compressed by cell (R/scMerge2.R:164-166).  Device-resident value:
+            # the three sparse arrays are in HBM; every step densifies + cosine-normalises them into dOut (K8), builds the
+            # pseudobulks, fits and adjusts dOut in place.
+            Xh = sparsify(a, ctx, dY, rank, torch)
+            dY.free()
+            src = sm.DeviceCSC(ctx, Xh.indptr, Xh.indices, Xh.data, a.cells, a.genes)
 
         def step():
-            return sm.scMerge2_core(dY, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx, out=dOut)
+            return sm.scMerge2_core(src, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx, out=dOut)
     else:
         def step():
             return sm.fastRUVIII(dY, keys, ctl, k=a.k, out=dOut)
@@ -262,29 +351,44 @@ def run_ours(a):
     clk = clocks.summary(tw0, tw1) if clocks else None
     stages = {k2: v / a.steps for k2, v in stage_acc.items()}
 
-    # ---- end to end: pinned host Y in, pinned host newY out, through the same public call
+    # ---- end to end: pinned host input, pinned host newY out, through the same public call
     e2e = None
     if not a.no_e2e:
-        Yh = sm.pinned_empty((a.cells, a.genes))
-        Oh = sm.pinned_empty((a.cells, a.genes))
-        dY.to_host(Yh)
-        dOut.free()
         n_e2e = max(1, min(a.steps, 3))
-        sm.fastRUVIII(Yh, keys, ctl, k=a.k, out=Oh, ctx=ctx)  # warm-up
+        nbytes = a.cells * a.genes * 8
+        Oh = sm.pinned_empty((a.cells, a.genes))
+        if a.workload == "scmerge2":
+            src.free()
+            dOut.free()
+
+            def call():
+                sm.scMerge2_core(Xh, None, None, ctl=None, ruvK=a.k, pb=pb, return_bulk=False, ctx=ctx, out=Oh)
+            h2d = Xh.nnz * 12 + (a.cells + 1) * 8 + 4 * a.cells
+            d2h = nbytes + 8 * a.k * a.genes
+            api = "scmerge_b200.scMerge2_core(sparse cells-compressed host matrix (pinned), pb keys, ruvK, out=numpy pinned)"
+        else:
+            Yh = sm.pinned_empty((a.cells, a.genes))
+            dY.to_host(Yh)
+            dOut.free()
+
+            def call():
+                sm.fastRUVIII(Yh, keys, ctl, k=a.k, out=Oh, ctx=ctx)
+            h2d = nbytes + 4 * a.cells
+            d2h = nbytes + 8 * 50 * a.genes
+            api = "scmerge_b200.fastRUVIII(numpy pinned Y, keys, ctl, k, out=numpy pinned)"
+        call()  # warm-up
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(n_e2e):
-            sm.fastRUVIII(Yh, keys, ctl, k=a.k, out=Oh, ctx=ctx)
+            call()
         f1.record()
         barrier()
         t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        nbytes = a.cells * a.genes * 8
         e2e = {"value": a.cells * world * n_e2e / (float(t2.item()) * 1e-3), "unit": "cells/s", "steps": n_e2e,
-               "h2d_bytes_per_step": nbytes + 4 * a.cells, "d2h_bytes_per_step": nbytes + 8 * 50 * a.genes,
-               "api": "scmerge_b200.fastRUVIII(numpy pinned Y, keys, ctl, k, out=numpy pinned)"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api, "pcie": pcie_probe(sm, ctx, torch, Oh)}
 
     if rank == 0:
         m, n = a.cells, a.genes
@@ -302,6 +406,12 @@ def run_ours(a):
         if stages.get("seg_colsum", 0) > 0:
             gb = 8.0 * m * n / (stages["seg_colsum"] * 1e-3) * 1e-9
             sec["seg_colsum"] = {"bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "ms": stages["seg_colsum"]}
+        if stages.get("ingest", 0) > 0 and a.workload == "scmerge2":
+            by = (12.0 * Xh.nnz + 8.0 * m * n) if Xh is not None else 16.0 * m * n
+            gb = by / (stages["ingest"] * 1e-3) * 1e-9
+            sec["ingest_densify_cosine" if Xh is not None else "cosine_rows"] = {
+                "bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "ms": stages["ingest"],
+                "algorithmic": "12*nnz read + 8*m*n written" if Xh is not None else "8*m*n read + 8*m*n written"}
         if stages.get("adjust", 0) > 0:
             gb = 16.0 * m * n / (stages["adjust"] * 1e-3) * 1e-9
             sec["adjust_rank_k"] = {"bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "ms": stages["adjust"]}
@@ -341,7 +451,7 @@ def run_ours(a):
             orc, P = cpu_sample(a)
             tcpu = cpu_time_once(a, orc, P)
             out["cpu_baseline"] = {"value": a.cpu_cells / tcpu, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{a.cpu_cells} cells x {a.genes} genes, one pass of the NumPy oracle (dense residop + thin dgesdd + adjust)",
+                                   "sample": f"{a.cpu_cells} cells x {a.genes} genes, one pass of the NumPy oracle", "what": cpu_what(a),
                                    "seconds": tcpu}
         emit(out)
     if world > 1:

@@ -9,6 +9,6 @@ from .ruv import (ExactParam, IrlbaParam, RandomParam, RUVFit, aggregate_matrix,
                   create_pseudoBulk, fastRUVIII, getAdjustedMat, pseudoRUVIII, replicate_keys, replicate_matrix,
                   scRUVg, scRUVIII, tological)
 
-from .scmerge2 import cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402
+from .scmerge2 import DeviceCSC, cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -286,12 +286,14 @@ int scm_transpose(scm_ctx* ctx, const double* d_in, int64_t rows, int64_t cols, 
 
 int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, double* d_out, int64_t ldo, double min_norm) {
     SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_INGEST);
     return cosine_rows(ctx, d_Y, m, n, ld, d_out, ldo, min_norm);
 }
 
 int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
                      int64_t nnz, int cosine, double min_norm, double* d_out, int64_t ldo, double* d_inv_norm, int32_t* d_nonfinite) {
     SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_INGEST);
     return csc_to_dense(ctx, d_indptr, d_idx, d_val, m, n, nnz, cosine, min_norm, d_out, ldo, d_inv_norm, d_nonfinite);
 }
 

@@ -42,9 +42,9 @@ class Context:
         return n.value
 
     def timers(self) -> dict:
-        ms = (C.c_double * 8)()
-        L.check(L.lib().scm_timers(self._h, ms, 8))
-        names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel"]
+        ms = (C.c_double * 9)()
+        L.check(L.lib().scm_timers(self._h, ms, 9))
+        names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel", "ingest"]
         return dict(zip(names, list(ms)))
 
     def set_allreduce(self, fn, world_size: int):

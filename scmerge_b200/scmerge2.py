@@ -17,7 +17,7 @@ from . import _lib as L
 from .device import Context, DeviceMatrix, default_context
 from .ruv import _adjust, _device_rows_cap, _fit, _is_exact, _svd_k, column_means, replicate_keys, segmented_sums, tological
 
-__all__ = ["cosineNorm", "csc_to_device", "pseudobulk_keys", "scMerge2_core"]
+__all__ = ["cosineNorm", "csc_to_device", "DeviceCSC", "pseudobulk_keys", "scMerge2_core"]
 
 
 def cosineNorm(dY: DeviceMatrix, out: DeviceMatrix | None = None, min_norm: float = 1e-8) -> DeviceMatrix:
@@ -31,39 +31,69 @@ def _is_sparse(x) -> bool:
     return hasattr(x, "indptr") and hasattr(x, "indices") and hasattr(x, "data") and hasattr(x, "shape")
 
 
+class DeviceCSC:
+    """The three dgCMatrix slots (@p widened to int64, @i, @x) of a cells-compressed expression matrix, resident in HBM."""
+
+    def __init__(self, ctx: Context, indptr, indices, data, m: int, n: int):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        if indptr.shape[0] != m + 1:
+            raise ValueError("indptr must have one entry per cell plus one")
+        self.ctx, self.m, self.n = ctx, int(m), int(n)
+        self.nnz = int(indptr[-1]) if m > 0 else 0
+        self.indptr = ctx.to_device(indptr)
+        self.indices = ctx.to_device(np.ascontiguousarray(indices[:self.nnz], dtype=np.int32))
+        self.data = ctx.to_device(np.ascontiguousarray(data[:self.nnz], dtype=np.float64))
+
+    @classmethod
+    def from_scipy(cls, ctx: Context, X) -> "DeviceCSC":
+        """`X`: scipy.sparse CSR of cells x genes or, equivalently, CSC of genes x cells (the reference's dgCMatrix)."""
+        fmt = getattr(X, "format", None)
+        if fmt == "csc":  # genes x cells compressed by column == cells x genes compressed by row
+            n, m = X.shape
+        elif fmt == "csr":
+            m, n = X.shape
+        else:
+            raise TypeError("expected a scipy.sparse csr (cells x genes) or csc (genes x cells) matrix")
+        if hasattr(X, "has_canonical_format") and not X.has_canonical_format:
+            X = X.copy()
+            X.sum_duplicates()
+        return cls(ctx, X.indptr, X.indices, X.data, m, n)
+
+    def to_dense(self, cosine: bool = True, min_norm: float = 1e-8, out: DeviceMatrix | None = None,
+                 check_finite: bool = True) -> DeviceMatrix:
+        """K8 (scm_csc_to_dense): dense cell rows on the device, fused with batchelor::cosineNorm when `cosine`."""
+        ctx = self.ctx
+        out = out or DeviceMatrix(ctx, self.m, self.n)
+        if (out.m, out.n) != (self.m, self.n):
+            raise ValueError("out has the wrong shape")
+        d_flag = ctx.to_device(np.zeros(1, dtype=np.int32)) if check_finite else None
+        try:
+            L.check(L.lib().scm_csc_to_dense(ctx.handle, self.indptr.ptr, self.indices.ptr, self.data.ptr, self.m, self.n, self.nnz,
+                                             int(bool(cosine)), float(min_norm), out.ptr, out.ld, None,
+                                             d_flag.ptr if d_flag is not None else None))
+            if d_flag is not None and int(d_flag.to_host()[0]):
+                raise L.NonFiniteError(L.ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.")
+        finally:
+            if d_flag is not None:
+                d_flag.free()
+        return out
+
+    def free(self):
+        for a in (self.indptr, self.indices, self.data):
+            a.free()
+
+
 def csc_to_device(ctx: Context, X, cosine: bool = True, min_norm: float = 1e-8, out: DeviceMatrix | None = None,
                   check_finite: bool = True) -> DeviceMatrix:
     """Sparse ingest (K8, scm_csc_to_dense).  `X` is the expression matrix compressed by CELL: a scipy.sparse CSR matrix of
     cells x genes, or equivalently the CSC of genes x cells -- the dgCMatrix scMerge2 holds (R/scMerge2.R:164-166), whose
     (@p, @i, @x) slots are exactly (indptr, indices, data).  Only the three sparse arrays cross PCIe; the dense cell rows
     are produced on the device, fused with batchelor::cosineNorm when `cosine` (R/scMerge2.R:193-198)."""
-    fmt = getattr(X, "format", None)
-    if fmt == "csc":  # genes x cells compressed by column == cells x genes compressed by row
-        n, m = X.shape
-    elif fmt == "csr":
-        m, n = X.shape
-    else:
-        raise TypeError("expected a scipy.sparse csr (cells x genes) or csc (genes x cells) matrix")
-    if hasattr(X, "has_canonical_format") and not X.has_canonical_format:
-        X = X.copy()
-        X.sum_duplicates()
-    indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
-    idx = np.ascontiguousarray(X.indices, dtype=np.int32)
-    val = np.ascontiguousarray(X.data, dtype=np.float64)
-    nnz = int(indptr[-1]) if indptr.shape[0] else 0
-    d_p, d_i, d_x = ctx.to_device(indptr), ctx.to_device(idx[:nnz]), ctx.to_device(val[:nnz])
-    d_flag = ctx.to_device(np.zeros(1, dtype=np.int32)) if check_finite else None
-    out = out or DeviceMatrix(ctx, m, n)
+    d = DeviceCSC.from_scipy(ctx, X)
     try:
-        L.check(L.lib().scm_csc_to_dense(ctx.handle, d_p.ptr, d_i.ptr, d_x.ptr, m, n, nnz, int(bool(cosine)), float(min_norm),
-                                         out.ptr, out.ld, None, d_flag.ptr if d_flag is not None else None))
-        if d_flag is not None and int(d_flag.to_host()[0]):
-            raise L.NonFiniteError(L.ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.")
+        return d.to_dense(cosine=cosine, min_norm=min_norm, out=out, check_finite=check_finite)
     finally:
-        for a in (d_p, d_i, d_x, d_flag):
-            if a is not None:
-                a.free()
-    return out
+        d.free()
 
 
 def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
@@ -130,12 +160,15 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     With `out` (a DeviceMatrix of the same shape) a device-resident input is left untouched: the normalised cells are
     written to `out` and adjusted there.  `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
     Returns {'newY', 'fullalpha', 'bulkExprs' (P x genes), 'pseudobulk_names', 'replicate_vector', 'adjusted_means'}."""
-    ctx = ctx or (exprs.ctx if isinstance(exprs, DeviceMatrix) else default_context())
-    host_in = not isinstance(exprs, DeviceMatrix)
+    ctx = ctx or (exprs.ctx if isinstance(exprs, (DeviceMatrix, DeviceCSC)) else default_context())
+    host_in = not isinstance(exprs, (DeviceMatrix, DeviceCSC))
     host_out = out if (host_in and isinstance(out, np.ndarray)) else None
     if host_in:
         out = None
-    if _is_sparse(exprs):
+    if isinstance(exprs, DeviceCSC):  # device-resident sparse input: the dense rows go to `out` (or a new matrix)
+        dY = exprs.to_dense(cosine=cosine, out=out, check_finite=False)
+        cosine, out = False, None
+    elif _is_sparse(exprs):
         dY = csc_to_device(ctx, exprs, cosine=cosine)
         cosine = False  # already applied during the densification
     else:
