@@ -50,7 +50,8 @@ struct scm_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // PCIe transfers of the host-matrix drivers (created on first use)
+    cudaStream_t copy_stream = nullptr;      // host -> device bulk transfers of the host-matrix drivers (created on first use)
+    cudaStream_t copy_stream_d2h = nullptr;  // device -> host bulk transfers (a separate stream per direction, see host_pipeline.cuh)
     bool own_stream = false;
     int64_t launches = 0;
     scm_allreduce_fn allreduce = nullptr;
@@ -98,6 +99,33 @@ struct StageTimer {
 };
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Small device-side zero fill / copy as KERNELS.  cudaMemsetAsync / device-to-device cudaMemcpyAsync may be executed by a
+// copy engine, where they queue behind every bulk PCIe transfer already submitted by another stream: in the chunked host
+// drivers one such call stalled the whole fit until the last H2D chunk had landed (measured with SCM_HOST_TRACE=1:
+// 144 ms at 1M x 2000).  Anything issued on the compute stream while bulk copies are in flight uses these instead.
+__global__ void zero_u32_kernel(uint32_t* __restrict__ p, int64_t nwords) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+__global__ void copy_u32_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int64_t nwords) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+inline int zero_async(scm_ctx* ctx, void* p, int64_t bytes) {  // bytes must be a multiple of 4
+    if (bytes <= 0) return 0;
+    const int64_t nw = bytes / 4;
+    const int64_t blocks = ceil_div(nw, 256);
+    zero_u32_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, ctx->stream>>>((uint32_t*)p, nw);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+inline int copy_async(scm_ctx* ctx, void* dst, const void* src, int64_t bytes) {  // bytes must be a multiple of 4
+    if (bytes <= 0) return 0;
+    const int64_t nw = bytes / 4;
+    const int64_t blocks = ceil_div(nw, 256);
+    copy_u32_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, ctx->stream>>>((uint32_t*)dst, (const uint32_t*)src, nw);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 // ---- device helpers ---------------------------------------------------------------------------------
 

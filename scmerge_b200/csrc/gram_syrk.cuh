@@ -258,7 +258,7 @@ inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t l
     if (m < 0 || n <= 0 || ld < n) return fail(SCM_ERR_INVALID, "gram: bad shape m=%lld n=%lld ld=%lld", (long long)m, (long long)n, (long long)ld);
     cudaStream_t st = ctx->stream;
     if (m == 0) {
-        if (!accumulate) SCM_CUDA(cudaMemsetAsync(d_gram, 0, sizeof(double) * n * n, st));
+        if (!accumulate) SCM_TRY(zero_async(ctx, d_gram, sizeof(double) * n * n));
         return 0;
     }
     static bool attr_set = false;

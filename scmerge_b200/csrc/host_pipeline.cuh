@@ -7,8 +7,16 @@
 //   solve   : Gram correction, top-s eigenpairs, coefficients (small, latency bound),
 //   download: the fused adjust kernel (K6) runs chunk by chunk IN PLACE and each finished chunk goes back over
 //             PCIe while the next one is being adjusted.
+// Two things keep the overlap real (both found with SCM_HOST_TRACE=1, which prints the per-chunk device timeline):
+//   * nothing that a copy engine might execute (cudaMemsetAsync, small cudaMemcpyAsync) is issued on the compute stream
+//     while bulk copies are in flight, and the compute stream is moved back to the compute engine by a trivial kernel
+//     before the first bulk copy: otherwise its next operation is arbitrated behind ALL queued bulk copies,
+//   * uploads and downloads use separate copy streams, and chunks are handed over by the host (event wait) with at most
+//     two bulk copies queued.
 // Included by scm_api.cu after the small helper kernels (meta_kernel, colmean_kernel, ...).
 #pragma once
+#include <chrono>
+
 #include "adjust.cuh"
 #include "common.cuh"
 #include "eig_topk.cuh"
@@ -54,8 +62,8 @@ inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64
                            int64_t ldo, int64_t rows_per_chunk) {
     if (!dY || !h_out || !coef || ldo < n) return fail(SCM_ERR_INVALID, "adjust_download: bad arguments");
     cudaStream_t st = ctx->stream;
-    if (!ctx->copy_stream) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    cudaStream_t cs = ctx->copy_stream;
+    if (!ctx->copy_stream_d2h) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream_d2h, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream_d2h;
     if (rows_per_chunk <= 0) rows_per_chunk = host_chunk_rows(ld);
     const int nchunks = (int)ceil_div(m, rows_per_chunk);
     std::vector<cudaEvent_t> ev(nchunks + 1);
@@ -64,18 +72,43 @@ inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64
         std::vector<cudaEvent_t>& v;
         ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
     } guard{ev};
+    const bool trace = getenv("SCM_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tl_adj, tl_copy;
+    cudaEvent_t tl_zero = nullptr;
+    if (trace) {
+        tl_adj.resize(nchunks); tl_copy.resize(nchunks);
+        for (int c = 0; c < nchunks; c++) { cudaEventCreate(&tl_adj[c]); cudaEventCreate(&tl_copy[c]); }
+        cudaEventCreate(&tl_zero);
+        cudaEventRecord(tl_zero, st);
+    }
     for (int c = 0; c < nchunks; c++) {
         const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
         {
             StageTimer t(ctx, ST_ADJUST);
             SCM_TRY(adjust(ctx, dY + r0 * ld, rows, n, ld, coef, nullptr, 0, dY + r0 * ld, ld, nullptr));
         }
+        if (trace) cudaEventRecord(tl_adj[c], st);
         SCM_CUDA(cudaEventRecord(ev[c], st));
         SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
-        SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+        if (ldo == n && ld == n)
+            SCM_CUDA(cudaMemcpyAsync(h_out + r0 * ldo, dY + r0 * ld, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
+        else
+            SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+        if (trace) cudaEventRecord(tl_copy[c], cs);
     }
-    SCM_CUDA(cudaEventRecord(ev[nchunks], cs));
-    SCM_CUDA(cudaStreamWaitEvent(st, ev[nchunks], 0));  // later stream-ordered frees of d_Y must wait for the downloads
+    if (trace) {
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(st);
+        for (int c = 0; c < nchunks; c++) {
+            float ta = 0.f, tc = 0.f;
+            cudaEventElapsedTime(&ta, tl_zero, tl_adj[c]);
+            cudaEventElapsedTime(&tc, tl_zero, tl_copy[c]);
+            if (c < 4 || c >= nchunks - 2) fprintf(stderr, "[adjust_download]   chunk %2d: adjusted %8.2f ms, D2H landed %8.2f ms\n", c, ta, tc);
+            cudaEventDestroy(tl_adj[c]); cudaEventDestroy(tl_copy[c]);
+        }
+        cudaEventDestroy(tl_zero);
+    }
+    // the host waits for the downloads: stream-ordered frees of d_Y issued after this function returns are safe
     SCM_CUDA(cudaStreamSynchronize(cs));
     SCM_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -94,7 +127,20 @@ struct HostArgs {
     int32_t* iters_out; double* resid_out;
 };
 
+// SCM_HOST_TRACE=1: wall-clock phase marks of the host driver on stderr (diagnostics only)
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    HostTrace() : on(getenv("SCM_HOST_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) const {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[scm_ruv3_host] %8.2f ms  %s\n", ms, what);
+    }
+};
+
 inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
+    const HostTrace trace;
     const int64_t m = a.m, n = a.n;
     if (!a.h_Y || !a.h_out || m <= 0 || n <= 0 || a.ldh < n || a.ldo < n || !a.h_ctl) return fail(SCM_ERR_INVALID, "scm_ruv3_host: bad arguments");
     const bool do_fit = a.h_fullalpha_in == nullptr;
@@ -108,13 +154,10 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     const int nchunks = (int)ceil_div(m, rows_per_chunk);
     std::vector<cudaEvent_t> ev(nchunks);
     for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaEvent_t ev_alloc, ev_done;
-    SCM_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
-    SCM_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     struct EvGuard {
-        std::vector<cudaEvent_t>& v; cudaEvent_t a, b;
-        ~EvGuard() { for (auto e : v) cudaEventDestroy(e); cudaEventDestroy(a); cudaEventDestroy(b); }
-    } guard{ev, ev_alloc, ev_done};
+        std::vector<cudaEvent_t>& v;
+        ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
+    } guard{ev};
 
     Scratch ws(ctx);
     double *dY, *gsums = nullptr, *tsums = nullptr, *shift = nullptr, *Gm = nullptr, *vals = nullptr, *vecs = nullptr, *fa = nullptr;
@@ -149,20 +192,50 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         SCM_TRY(ws.alloc(&bcounts, a.Bt)); SCM_TRY(ws.alloc(&sd, n)); SCM_TRY(ws.alloc(&inv_sd, n));
         SCM_CUDA(cudaMemcpyAsync(dbatch, a.h_batch, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
     }
-    SCM_CUDA(cudaEventRecord(ev_alloc, st));
-    SCM_CUDA(cudaStreamWaitEvent(cs, ev_alloc, 0));  // the copy stream may touch the pool allocations from here on
+    // The small uploads / memsets above are copy-engine work of the COMPUTE stream.  While its channel still targets the copy
+    // engine, its next operation (even an event record) is arbitrated behind every bulk copy of the copy stream: measured with
+    // SCM_HOST_TRACE=1, the whole fit then only started when the last H2D chunk had landed (+144 ms at 1M x 2000).  A trivial
+    // kernel moves the channel back to the compute engine, and the host waits for it before the first bulk copy is issued
+    // (this also makes the pool allocations visible to the copy stream).
+    SCM_TRY(zero_async(ctx, flag, 4));
+    SCM_CUDA(cudaStreamSynchronize(st));
 
+    trace.mark("allocated");
+    // trace mode: device timeline of every chunk (H2D landed / fit work done), relative to the first enqueue
+    std::vector<cudaEvent_t> tl_copy, tl_comp, tl_wait, tl_seg;
+    cudaEvent_t tl_zero = nullptr;
+    if (trace.on) {
+        tl_copy.resize(nchunks); tl_comp.resize(nchunks); tl_wait.resize(nchunks); tl_seg.resize(nchunks);
+        for (int c = 0; c < nchunks; c++) { cudaEventCreate(&tl_copy[c]); cudaEventCreate(&tl_comp[c]); cudaEventCreate(&tl_wait[c]); cudaEventCreate(&tl_seg[c]); }
+        cudaEventCreate(&tl_zero);
+        cudaEventRecord(tl_zero, st);
+    }
     // ---- upload, with the fit accumulating behind it
     const bool need_sums = do_fit || a.center_mode == 1;
+    const bool copy_1d = a.ldh == n && ld == n;
+    auto issue_copy = [&](int c) -> int {
+        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+        if (copy_1d) SCM_CUDA(cudaMemcpyAsync(dY + r0 * ld, a.h_Y + r0 * a.ldh, (size_t)rows * n * 8, cudaMemcpyHostToDevice, cs));
+        else SCM_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, a.h_Y + r0 * a.ldh, a.ldh * 8, n * 8, rows, cudaMemcpyHostToDevice, cs));
+        if (trace.on) cudaEventRecord(tl_copy[c], cs);
+        SCM_CUDA(cudaEventRecord(ev[c], cs));
+        return 0;
+    };
+    SCM_TRY(issue_copy(0));
+    if (nchunks > 1) SCM_TRY(issue_copy(1));
     for (int c = 0; c < nchunks; c++) {
         const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-        SCM_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, a.h_Y + r0 * a.ldh, a.ldh * 8, n * 8, rows, cudaMemcpyHostToDevice, cs));
-        SCM_CUDA(cudaEventRecord(ev[c], cs));
-        SCM_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
+        if (trace.on && c > 0) cudaEventRecord(tl_comp[c - 1], st);
+        // host-mediated hand-over with two bulk copies in flight: chunk c is in HBM when the event has fired, its fit work
+        // is enqueued right away and copy c + 2 joins the queue (the copy engine never idles, the queue never grows)
+        SCM_CUDA(cudaEventSynchronize(ev[c]));
+        if (c + 2 < nchunks) SCM_TRY(issue_copy(c + 2));
+        if (trace.on) cudaEventRecord(tl_wait[c], st);
         if (!need_sums) continue;
         {
             StageTimer t(ctx, ST_SEG);
             SCM_TRY(seg_colsum(ctx, dY + r0 * ld, rows, n, ld, dgroup + r0, Gk, nullptr, tsums, tcounts, flag));
+            if (trace.on) cudaEventRecord(tl_seg[c], st);
             add_f64_kernel<<<(unsigned)ceil_div((int64_t)Gk * n, 256), 256, 0, st>>>(gsums, tsums, (int64_t)Gk * n);
             SCM_LAUNCH_CHECK(ctx);
             add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcounts, tcounts, Gk);
@@ -175,8 +248,8 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
             // shift = column mean of the first chunk (summed over ranks so that every rank uses the same vector)
             int64_t* m0;
             SCM_TRY(ws.alloc(&m0, 2));
-            SCM_CUDA(cudaMemcpyAsync(m0, meta, 16, cudaMemcpyDeviceToDevice, st));
-            SCM_CUDA(cudaMemcpyAsync(tsums, gsums, sizeof(double) * Gk * n, cudaMemcpyDeviceToDevice, st));
+            SCM_TRY(copy_async(ctx, m0, meta, 16));  // kernels, not cudaMemcpyAsync: see common.cuh (copy-engine queueing)
+            SCM_TRY(copy_async(ctx, tsums, gsums, sizeof(double) * Gk * n));
             SCM_TRY(allreduce(ctx, tsums, (int64_t)Gk * n, 0));
             SCM_TRY(allreduce(ctx, m0, 2, 1));
             colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, m0, shift);
@@ -184,6 +257,23 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         }
         StageTimer t(ctx, ST_GRAM);
         SCM_TRY(gram(ctx, dY + r0 * ld, rows, n, ld, shift, Gm, c == nchunks - 1, c > 0));
+    }
+    trace.mark("upload + fit chunks enqueued");
+    if (trace.on) {
+        cudaEventRecord(tl_comp[nchunks - 1], st);
+        cudaStreamSynchronize(cs); trace.mark("H2D done"); cudaStreamSynchronize(st); trace.mark("chunk Gram / sums done");
+        for (int c = 0; c < nchunks; c++) {
+            float t_copy = 0.f, t_comp = 0.f, t_wait = 0.f, t_seg = 0.f;
+            cudaEventElapsedTime(&t_copy, tl_zero, tl_copy[c]);
+            cudaEventElapsedTime(&t_comp, tl_zero, tl_comp[c]);
+            cudaEventElapsedTime(&t_wait, tl_zero, tl_wait[c]);
+            if (need_sums) cudaEventElapsedTime(&t_seg, tl_zero, tl_seg[c]);
+            if (c < 6 || c >= nchunks - 3)
+                fprintf(stderr, "[scm_ruv3_host]   chunk %2d: H2D landed %8.2f ms, wait released %8.2f, sums done %8.2f, fit work done %8.2f ms\n", c,
+                        t_copy, t_wait, t_seg, t_comp);
+            cudaEventDestroy(tl_copy[c]); cudaEventDestroy(tl_comp[c]); cudaEventDestroy(tl_wait[c]); cudaEventDestroy(tl_seg[c]);
+        }
+        cudaEventDestroy(tl_zero);
     }
     int rc = 0;
     scm_coef* coef = nullptr;
@@ -211,6 +301,7 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
         SCM_CUDA(cudaStreamSynchronize(st));
         if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+        trace.mark("Gram residual done (sync)");
         {
             StageTimer t(ctx, ST_EIG);
             const int32_t kconv = a.k < s ? a.k : s;
@@ -241,12 +332,14 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         int crc = coef_create(ctx, fa, n, kk, dctl, c_center, sc ? inv_sd : nullptr, sc ? sd : nullptr, &coef);
         if (crc != 0) return crc;
     }
+    trace.mark("eig + coefficients done");
     // ---- adjust in place chunk by chunk, each finished chunk goes back to the host while the next is computed
     {
         const int arc = adjust_download(ctx, dY, m, n, ld, coef, a.h_out, a.ldo, rows_per_chunk);
         coef_destroy(ctx, coef);
         if (arc != 0) return arc;
     }
+    trace.mark("adjust + D2H done");
     return rc;
 }
 

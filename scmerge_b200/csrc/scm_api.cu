@@ -206,6 +206,8 @@ int scm_ctx_destroy(scm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev0[i]); cudaEventDestroy(ctx->ev1[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream_d2h) cudaStreamDestroy(ctx->copy_stream_d2h);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
     return 0;

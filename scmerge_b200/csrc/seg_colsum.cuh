@@ -163,8 +163,8 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     cudaStream_t st = ctx->stream;
     Scratch ws(ctx);
     if (m == 0) {
-        SCM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * G * n, st));
-        if (d_counts) SCM_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * G, st));
+        SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * n));
+        if (d_counts) SCM_TRY(zero_async(ctx, d_counts, sizeof(int64_t) * G));
         return 0;
     }
     uint32_t *skey_in, *skey_out;
@@ -175,7 +175,7 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     SCM_TRY(ws.alloc(&sval_in, m)); SCM_TRY(ws.alloc(&perm, m));
     SCM_TRY(ws.alloc(&cnt, (int64_t)G + 1)); SCM_TRY(ws.alloc(&chunk_off, (int64_t)G + 1));
     SCM_TRY(ws.alloc(&pslot_off, (int64_t)G + 1)); SCM_TRY(ws.alloc(&seg_start, (int64_t)G + 1));
-    SCM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((int64_t)G + 1), st));
+    SCM_TRY(zero_async(ctx, cnt, sizeof(int) * ((int64_t)G + 1)));
     const int use_smem = G < 4096;
     seg_prepare_kernel<<<(unsigned)ceil_div(m, SEG_PREP_ROWS), 256, use_smem ? sizeof(int) * (G + 1) : 0, st>>>(
         d_key, m, G, skey_in, sval_in, cnt, use_smem);
@@ -194,7 +194,7 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     const int64_t max_slots = 2 * ceil_div(m, SEG_R) + 1;
     double* partial;
     SCM_TRY(ws.alloc(&partial, max_slots * n));
-    SCM_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * G * n, st));  // empty groups stay 0
+    SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * n));  // empty groups stay 0
     const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
     const int vec = vec2 ? 2 : 1;
     dim3 grid((unsigned)ceil_div(n, (int64_t)SEG_THREADS * vec), 1);
