@@ -36,3 +36,18 @@ fastRUVIII <- function(Y, M, ctl, k = NULL, eta = NULL, svd_k = 50, include.inte
   }
   if (!return.info) newY else list(newY = newY, M = M, fullalpha = fullalpha)
 }
+
+## scRUVg (R/scRUVg.R:30-85) with the default Z = 1, eta = NULL
+scRUVg <- function(Y, ctl, k, Z = 1, eta = NULL, include.intercept = TRUE, fullW = NULL, svdyc = NULL) {
+  stopifnot(is.null(eta), identical(Z, 1), is.null(fullW), is.null(svdyc))
+  n <- ncol(Y); ctl2 <- rep(FALSE, n); ctl2[ctl] <- TRUE
+  if (k > sum(ctl2)) stop("k must not be larger than the number of controls")
+  res <- .Call("scm_ruvg", .Call("scm_upload", as.matrix(Y), 1L), ctl2, as.integer(k))
+  list(newY = DelayedArray::DelayedArray(t(res[[1]])), W = t(res[[2]]), alpha = t(res[[3]]))
+}
+
+## inside scRUVIII (R/scRUVIII.R:83-105), for length(k) > 1:
+##   sil_res <- sapply(k, function(kk) .Call("scm_sil", dY, fit$gram, fit$colmean, t(fullalpha[seq_len(kk), ]), kk, ctl2,
+##                                           stand_mean, 1 / stand_sd, stand_sd, ct_key, n_ct, batch_key, n_batch, 10L))
+##   f_score <- f_measure(zeroOneScale(sil_res[1, ]), 1 - zeroOneScale(sil_res[2, ]))
+## inside scMerge2 (R/scMerge2.R:164-198): dY <- .Call("scm_upload_sparse", exprsMat@p, exprsMat@i, exprsMat@x, dim(exprsMat), cosineNorm)

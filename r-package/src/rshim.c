@@ -7,6 +7,10 @@
  *   scRUVIII    (R/scRUVIII.R:41-137)        -> scm_fit() with batch keys, scm_adjust_() with center/pre/post
  *   pseudoRUVIII (R/scMerge2_utilis.R:17-150), getAdjustedMat (R/scMerge2.R:368-410) -> same two calls
  *   create_pseudoBulk / aggregate.Matrix (R/scMerge2_utilis.R:325-346,461-486)       -> scm_segmean()
+ *   as(., "CsparseMatrix") + batchelor::cosineNorm (R/scMerge2.R:164-166,193-198)     -> scm_upload_sparse()
+ *   scRUVg (R/scRUVg.R:30-85)                                                         -> scm_ruvg()
+ *   calculateSil / kBET_batch_sil (R/scRUVIII.R:182-199)                              -> scm_sil()   (scm_fit_gram, the scm_fit
+ *     variant that also keeps the centred Gram and the column means on the device via scm_ruv3_fit_gram, is analogous to scm_fit)
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -117,7 +121,84 @@ SEXP scm_segmean(SEXP Yp, SEXP key, SEXP G_) {
     return out;
 }
 
+/* dgCMatrix (genes x cells: slots @p int, @i int, @x double, @Dim) -> dense, cosine-normalised cell rows on the device (K8).
+ * Replaces methods::as(., "CsparseMatrix") + batchelor::cosineNorm (R/scMerge2.R:164-166,193-198) + the dense upload. */
+SEXP scm_upload_sparse(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP cosine) {
+    int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1], nnz = Rf_xlength(x);
+    int64_t* hp = (int64_t*)R_alloc(m + 1, 8);
+    for (int64_t c = 0; c <= m; c++) hp[c] = INTEGER(p)[c];               /* @p is 32-bit in R: widen */
+    int64_t* dp = (int64_t*)to_dev(hp, (m + 1) * 8);
+    int32_t* di = (int32_t*)to_dev(INTEGER(i), nnz * 4);
+    double* dx = (double*)to_dev(REAL(x), nnz * 8);
+    int32_t hflag = 0, *dflag = (int32_t*)to_dev(&hflag, 4);
+    dmat* d = R_Calloc(1, dmat);
+    d->m = m; d->n = n; d->ld = (n + 1) / 2 * 2;
+    CHECK(scm_dev_alloc(ctx(), d->m * d->ld * 8, (void**)&d->p));
+    CHECK(scm_csc_to_dense(ctx(), dp, di, dx, m, n, nnz, Rf_asLogical(cosine), 1e-8, d->p, d->ld, NULL, dflag));
+    CHECK(scm_d2h(ctx(), &hflag, dflag, 4));
+    scm_dev_free(ctx(), dp); scm_dev_free(ctx(), di); scm_dev_free(ctx(), dx); scm_dev_free(ctx(), dflag);
+    if (hflag) Rf_warning("Y contains missing values or infinities.");       /* pseudoRUVIII only warns, R/scMerge2_utilis.R:49-52 */
+    SEXP out = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(out, dmat_fin, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+
+/* scRUVg (R/scRUVg.R:30-85, Z = 1, eta = NULL): list(newY genes x cells image, W (k x m image), alpha (n x k image)) */
+SEXP scm_ruvg(SEXP Yp, SEXP ctl, SEXP k_) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int k = Rf_asInteger(k_);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    double *dal, *dce, *dout, *dW; scm_coef* coef; int32_t iters; double resid;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)k * d->n * 8, (void**)&dal)); CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dce));
+    CHECK(scm_dev_alloc(ctx(), d->m * d->ld * 8, (void**)&dout)); CHECK(scm_dev_alloc(ctx(), d->m * k * 8, (void**)&dW));
+    CHECK(scm_ruvg_fit(ctx(), d->p, d->m, d->n, d->ld, dc, k, SCM_MODE_EXACT, 1e-10, 500, 1, dal, dce, NULL, &coef, &iters, &resid));
+    CHECK(scm_adjust(ctx(), d->p, d->m, d->n, d->ld, coef, NULL, 0, dout, d->ld, dW));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP ny = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, (int)d->m));
+    CHECK(scm_copy2d(ctx(), REAL(ny), d->n * 8, dout, d->ld * 8, d->n * 8, d->m, 1)); SET_VECTOR_ELT(out, 0, ny);
+    SEXP W = PROTECT(Rf_allocMatrix(REALSXP, k, (int)d->m)); CHECK(scm_d2h(ctx(), REAL(W), dW, d->m * k * 8)); SET_VECTOR_ELT(out, 1, W);
+    SEXP al = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, k)); CHECK(scm_d2h(ctx(), REAL(al), dal, (int64_t)k * d->n * 8)); SET_VECTOR_ELT(out, 2, al);
+    scm_coef_destroy(ctx(), coef);
+    scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dal); scm_dev_free(ctx(), dce); scm_dev_free(ctx(), dout); scm_dev_free(ctx(), dW);
+    UNPROTECT(4);
+    return out;
+}
+
+/* choice of ruvK (R/scRUVIII.R:83-105): for the candidate described by (alpha, k, ctl, center, pre, post) returns
+ * c(silhouette(cell_type), silhouette(batch)) in the first `rank` PCs of the adjusted matrix.  gram / colmean are the external
+ * pointers returned by scm_fit_gram (scm_ruv3_fit_gram); labels are 0-based ints. */
+SEXP scm_sil(SEXP Yp, SEXP gram, SEXP colmean, SEXP alpha, SEXP k_, SEXP ctl, SEXP center, SEXP pre, SEXP post, SEXP ct, SEXP nct,
+             SEXP bt, SEXP nbt, SEXP rank_) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int k = Rf_asInteger(k_), rank = Rf_asInteger(rank_);
+    double* da = (double*)to_dev(REAL(alpha), (int64_t)k * d->n * 8);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    double* dce = Rf_isNull(center) ? NULL : (double*)to_dev(REAL(center), d->n * 8);
+    double* dpr = Rf_isNull(pre) ? NULL : (double*)to_dev(REAL(pre), d->n * 8);
+    double* dpo = Rf_isNull(post) ? NULL : (double*)to_dev(REAL(post), d->n * 8);
+    int32_t* dct = (int32_t*)to_dev(INTEGER(ct), d->m * 4);
+    int32_t* dbt = (int32_t*)to_dev(INTEGER(bt), d->m * 4);
+    scm_coef* coef; CHECK(scm_coef_create(ctx(), da, d->n, k, dc, dce, dpr, dpo, &coef));
+    double* dsc; CHECK(scm_dev_alloc(ctx(), d->m * rank * 8, (void**)&dsc));
+    int32_t iters; double resid, sa, sb;
+    CHECK(scm_pca_scores(ctx(), (const double*)R_ExternalPtrAddr(gram), d->n, d->m, coef, (const double*)R_ExternalPtrAddr(colmean), rank,
+                         d->p, d->m, d->ld, dsc, NULL, 1e-9, 500, &iters, &resid));
+    CHECK(scm_silhouette(ctx(), dsc, d->m, rank, rank, dct, Rf_asInteger(nct), dbt, Rf_asInteger(nbt), 0, d->m, &sa, &sb));
+    scm_coef_destroy(ctx(), coef);
+    scm_dev_free(ctx(), da); scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dce); scm_dev_free(ctx(), dpr); scm_dev_free(ctx(), dpo);
+    scm_dev_free(ctx(), dct); scm_dev_free(ctx(), dbt); scm_dev_free(ctx(), dsc);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 2));
+    REAL(out)[0] = sa / (double)d->m; REAL(out)[1] = sb / (double)d->m;
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
     {"scm_upload", (DL_FUNC)&scm_upload, 2}, {"scm_fit", (DL_FUNC)&scm_fit, 8},
-    {"scm_adjust_", (DL_FUNC)&scm_adjust_, 8}, {"scm_segmean", (DL_FUNC)&scm_segmean, 3}, {NULL, NULL, 0}};
+    {"scm_adjust_", (DL_FUNC)&scm_adjust_, 8}, {"scm_segmean", (DL_FUNC)&scm_segmean, 3},
+    {"scm_upload_sparse", (DL_FUNC)&scm_upload_sparse, 5}, {"scm_ruvg", (DL_FUNC)&scm_ruvg, 3}, {"scm_sil", (DL_FUNC)&scm_sil, 14},
+    {NULL, NULL, 0}};
 void R_init_scMergeB200(DllInfo* dll) { R_registerRoutines(dll, NULL, calls, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

@@ -5,19 +5,92 @@
 // the rank-k update stream are produced here, on the device, fused with batchelor::cosineNorm
 // (R/scMerge2.R:193-198): out[i, :] = scatter(x_i) / max(||x_i||_2, min_norm).
 //
-// One CTA per cell (grid-stride): the cell's nonzeros are read once (12 bytes each) for the norm and once more
-// (L1/L2 hits) for the scatter into a zeroed shared-memory image of the row, which then leaves with 16-byte streaming
-// stores, so HBM sees 12*nnz bytes read + 8*m*n written -- the algorithmic traffic.  Rows longer than the shared
-// image (CSC_SLAB genes) are produced slab by slab.  Duplicate gene indices inside a cell are summed in index order
-// by a single thread (dgCMatrix never has them; scipy's un-canonical matrices may).
+// One CTA per cell (grid-stride): the cell's non-zeros are read once (12 bytes each), the norm is reduced, the scaled
+// values are scattered into a zeroed shared-memory image of the row, which then leaves with 16-byte streaming stores, so
+// HBM sees 12*nnz bytes read + 8*m*n written -- the algorithmic traffic.  Rows longer than the shared image are produced
+// slab by slab (generic kernel).  Indices need not be sorted; duplicate gene indices inside a cell are summed.
 #pragma once
 #include "common.cuh"
 
 namespace scm {
 
-constexpr int CSC_SLAB = 4096;  // genes per shared-memory row image (32 KB: 7 CTAs per SM)
+constexpr int CSC_SLAB = 4096;  // genes per shared-memory row image of the generic kernel (32 KB: 7 CTAs per SM)
 constexpr int CSC_THREADS = 256;
+constexpr int CSC_REG = 2;      // non-zeros per thread the fast kernel keeps in registers (cells with more loop over the rest)
 
+// Fast path (n <= slab, i.e. the whole row fits one shared-memory image): the cell's non-zeros are read from global memory
+// ONCE into registers (the loads of the next cell are issued before the current row is written out), the row image is
+// double-buffered, and a cell costs two __syncthreads.  Duplicate indices are summed (shared-memory atomicAdd on the zeroed
+// image; a canonical matrix has none, so every value is stored exactly).
+__global__ void __launch_bounds__(CSC_THREADS)
+csc_densify_fast_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t m,
+                        int n, int slab, int cosine, double min_norm, double* __restrict__ out, int64_t ldo, int vec_out,
+                        double* __restrict__ inv_norm_out, int32_t* __restrict__ flag) {
+    extern __shared__ __align__(16) double csc_smem[];
+    double* rowbuf[2] = {csc_smem, csc_smem + slab};
+    double* red = csc_smem + 2 * slab;  // [2][8]
+    const int tid = threadIdx.x;
+    int32_t ci[CSC_REG];
+    double cv[CSC_REG];
+    int64_t p0 = 0, p1 = 0;
+    auto prefetch = [&](int64_t cell) {
+        if (cell < m) {
+            p0 = indptr[cell]; p1 = indptr[cell + 1];
+#pragma unroll
+            for (int r = 0; r < CSC_REG; r++) {
+                const int64_t p = p0 + (int64_t)r * CSC_THREADS + tid;
+                const bool ok = p < p1;
+                ci[r] = ok ? idx[p] : -1;
+                cv[r] = ok ? val[p] : 0.0;
+            }
+        }
+    };
+    int buf = 0;
+    bool bad = false;
+    prefetch(blockIdx.x);
+    for (int64_t cell = blockIdx.x; cell < m; cell += gridDim.x, buf ^= 1) {
+        double* row = rowbuf[buf];
+        const int64_t q0 = p0, q1 = p1;  // this cell's range (prefetch overwrites p0 / p1)
+        for (int j = tid * 2; j < n; j += CSC_THREADS * 2) *reinterpret_cast<double2*>(row + j) = make_double2(0.0, 0.0);
+        double ss = 0.0;
+#pragma unroll
+        for (int r = 0; r < CSC_REG; r++) { bad |= nonfinite(cv[r]); ss += cv[r] * cv[r]; }
+        for (int64_t p = q0 + (int64_t)CSC_REG * CSC_THREADS + tid; p < q1; p += CSC_THREADS) {  // rare: > 512 non-zeros
+            const double v = val[p];
+            bad |= nonfinite(v);
+            ss += v * v;
+        }
+        ss = warp_sum(ss);
+        if ((tid & 31) == 0) red[buf * 8 + (tid >> 5)] = ss;
+        __syncthreads();  // row image zeroed, partial norms visible
+        double inv = 1.0;
+        if (cosine) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < CSC_THREADS / 32; w++) t += red[buf * 8 + w];  // fixed order: deterministic
+            inv = 1.0 / fmax(sqrt(t), min_norm);
+            if (tid == 0 && inv_norm_out) inv_norm_out[cell] = inv;
+        }
+#pragma unroll
+        for (int r = 0; r < CSC_REG; r++)
+            if (ci[r] >= 0) atomicAdd(row + ci[r], cv[r] * inv);
+        for (int64_t p = q0 + (int64_t)CSC_REG * CSC_THREADS + tid; p < q1; p += CSC_THREADS) atomicAdd(row + idx[p], val[p] * inv);
+        __syncthreads();  // scatter complete
+        prefetch(cell + gridDim.x);  // next cell's loads fly while this row is written out
+        double* dst = out + cell * ldo;
+        if (vec_out) {
+            for (int j = tid * 2; j < n; j += CSC_THREADS * 2) {
+                if (j + 1 < n) stg_stream2(dst + j, *reinterpret_cast<const double2*>(row + j));
+                else dst[j] = row[j];
+            }
+        } else {
+            for (int j = tid; j < n; j += CSC_THREADS) dst[j] = row[j];
+        }
+    }
+    if (bad && flag) *flag = 1;
+}
+
+// Generic path (rows longer than one shared-memory image are produced slab by slab).
 __global__ void __launch_bounds__(CSC_THREADS)
 csc_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t m,
                    int64_t n, int cosine, double min_norm, double* __restrict__ out, int64_t ldo, int vec_out,
@@ -59,14 +132,7 @@ csc_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
                 if (g >= 0 && g < width) {
                     const double v = val[p];
                     if (!cosine) bad |= nonfinite(v);
-                    // canonical matrices: unique indices, plain store.  A duplicate is detected by the neighbour test
-                    // below (sorted input) and folded by the owner of the first occurrence.
-                    const bool dup_prev = p > p0 && idx[p - 1] == idx[p];
-                    if (!dup_prev) {
-                        double acc = v;
-                        for (int64_t q = p + 1; q < p1 && idx[q] == idx[p]; q++) acc += val[q];
-                        row[g] = acc * inv;
-                    }
+                    atomicAdd(row + g, v * inv);  // duplicates are summed; unique indices are stored exactly (0 + x)
                 }
             }
             __syncthreads();
@@ -113,6 +179,24 @@ inline int csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_
     if (hbad) return fail(SCM_ERR_INVALID, hbad == 1 ? "csc_to_dense: column pointers are not a non-decreasing sequence inside [0, nnz]"
                                                       : "csc_to_dense: a gene index is outside [0, n)");
     const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    if (n <= 6144 && !getenv("SCM_CSC_GENERIC")) {
+        const int slab = (int)((n + 1) & ~(int64_t)1);
+        const int smem = (2 * slab + 16) * (int)sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            SCM_CUDA(cudaFuncSetAttribute(csc_densify_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 6144 + 16) * 8));
+            attr_set = true;
+        }
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t want = (int64_t)ctx->num_sms * per_sm;
+        const unsigned grid = (unsigned)(m < want ? m : want);
+        csc_densify_fast_kernel<<<grid, CSC_THREADS, smem, st>>>(d_indptr, d_idx, d_val, m, (int)n, slab, cosine, min_norm, d_out, ldo,
+                                                                 vec_out, d_inv_norm, d_nonfinite);
+        SCM_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     const int64_t want = (int64_t)ctx->num_sms * 7;
     const unsigned grid = (unsigned)(m < want ? m : want);
     csc_densify_kernel<<<grid, CSC_THREADS, 0, st>>>(d_indptr, d_idx, d_val, m, n, cosine, min_norm, d_out, ldo, vec_out, d_inv_norm,
