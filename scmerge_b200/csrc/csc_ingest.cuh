@@ -20,14 +20,14 @@ constexpr int CSC_REG = 2;      // non-zeros per thread the fast kernel keeps in
 
 // Fast path (n <= slab, i.e. the whole row fits one shared-memory image): the cell's non-zeros are read from global memory
 // ONCE into registers (the loads of the next cell are issued before the current row is written out), the row image is
-// double-buffered, and a cell costs two __syncthreads.  Duplicate indices are summed (shared-memory atomicAdd on the zeroed
-// image; a canonical matrix has none, so every value is stored exactly).
+// double-buffered, and a cell costs two __syncthreads.  Requires unique indices inside a cell (csc_check_kernel verifies
+// "strictly increasing", which every dgCMatrix satisfies); anything else takes the generic kernel, whose scatter sums
+// duplicates with shared-memory atomics (a CAS loop for f64: ATOMS.CAST.SPIN in SASS, hence not on the fast path).
 __global__ void __launch_bounds__(CSC_THREADS)
 csc_densify_fast_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t m,
                         int n, int slab, int cosine, double min_norm, double* __restrict__ out, int64_t ldo, int vec_out,
                         double* __restrict__ inv_norm_out, int32_t* __restrict__ flag) {
     extern __shared__ __align__(16) double csc_smem[];
-    double* rowbuf[2] = {csc_smem, csc_smem + slab};
     double* red = csc_smem + 2 * slab;  // [2][8]
     const int tid = threadIdx.x;
     int32_t ci[CSC_REG];
@@ -49,7 +49,7 @@ csc_densify_fast_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     bool bad = false;
     prefetch(blockIdx.x);
     for (int64_t cell = blockIdx.x; cell < m; cell += gridDim.x, buf ^= 1) {
-        double* row = rowbuf[buf];
+        double* row = csc_smem + buf * slab;
         const int64_t q0 = p0, q1 = p1;  // this cell's range (prefetch overwrites p0 / p1)
         for (int j = tid * 2; j < n; j += CSC_THREADS * 2) *reinterpret_cast<double2*>(row + j) = make_double2(0.0, 0.0);
         double ss = 0.0;
@@ -73,8 +73,8 @@ csc_densify_fast_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         }
 #pragma unroll
         for (int r = 0; r < CSC_REG; r++)
-            if (ci[r] >= 0) atomicAdd(row + ci[r], cv[r] * inv);
-        for (int64_t p = q0 + (int64_t)CSC_REG * CSC_THREADS + tid; p < q1; p += CSC_THREADS) atomicAdd(row + idx[p], val[p] * inv);
+            if (ci[r] >= 0) row[ci[r]] = cv[r] * inv;  // canonical input (checked by the caller): indices are unique
+        for (int64_t p = q0 + (int64_t)CSC_REG * CSC_THREADS + tid; p < q1; p += CSC_THREADS) row[idx[p]] = val[p] * inv;
         __syncthreads();  // scatter complete
         prefetch(cell + gridDim.x);  // next cell's loads fly while this row is written out
         double* dst = out + cell * ldo;
@@ -151,15 +151,22 @@ csc_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
 }
 
 // Validates the index structure on the device (what a corrupt dgCMatrix would otherwise turn into silent garbage or an
-// out-of-bounds shared-memory store): offsets non-decreasing and inside [0, nnz], gene indices inside [0, n).
+// out-of-bounds shared-memory store): offsets non-decreasing and inside [0, nnz], gene indices inside [0, n).  One warp per
+// cell; also reports whether every cell's indices are strictly increasing (canonical: sorted, no duplicates).
+// flags[0] = 1 bad offsets / 2 bad index, flags[1] = 1 when some cell is not canonical.
 __global__ void csc_check_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, int64_t m, int64_t n,
-                                 int64_t nnz, int32_t* __restrict__ bad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t c = i; c < m; c += stride)
-        if (indptr[c] > indptr[c + 1] || indptr[c] < 0 || indptr[c + 1] > nnz) *bad = 1;
-    for (int64_t p = i; p < nnz; p += stride)
-        if (idx[p] < 0 || idx[p] >= n) *bad = 2;
+                                 int64_t nnz, int32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < m; c += nwarps) {
+        const int64_t p0 = indptr[c], p1 = indptr[c + 1];
+        if (p0 > p1 || p0 < 0 || p1 > nnz) { if (lane == 0) flags[0] = 1; continue; }
+        for (int64_t p = p0 + lane; p < p1; p += 32) {
+            const int32_t g = idx[p];
+            if (g < 0 || g >= n) flags[0] = 2;
+            if (p > p0 && idx[p - 1] >= g) flags[1] = 1;
+        }
+    }
 }
 
 inline int csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
@@ -169,17 +176,18 @@ inline int csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_
     cudaStream_t st = ctx->stream;
     Scratch ws(ctx);
     int32_t* bad;
-    SCM_TRY(ws.alloc(&bad, 1));
-    SCM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+    SCM_TRY(ws.alloc(&bad, 2));
+    SCM_TRY(zero_async(ctx, bad, 8));
     csc_check_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_indptr, d_idx, m, n, nnz, bad);
     SCM_LAUNCH_CHECK(ctx);
-    int32_t hbad = 0;
-    SCM_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int32_t hbad[2] = {0, 0};
+    SCM_CUDA(cudaMemcpyAsync(hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st));
     SCM_CUDA(cudaStreamSynchronize(st));
-    if (hbad) return fail(SCM_ERR_INVALID, hbad == 1 ? "csc_to_dense: column pointers are not a non-decreasing sequence inside [0, nnz]"
-                                                      : "csc_to_dense: a gene index is outside [0, n)");
+    if (hbad[0]) return fail(SCM_ERR_INVALID, hbad[0] == 1 ? "csc_to_dense: column pointers are not a non-decreasing sequence inside [0, nnz]"
+                                                         : "csc_to_dense: a gene index is outside [0, n)");
+    const bool canonical = hbad[1] == 0;
     const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
-    if (n <= 6144 && !getenv("SCM_CSC_GENERIC")) {
+    if (n <= 6144 && canonical && !getenv("SCM_CSC_GENERIC")) {
         const int slab = (int)((n + 1) & ~(int64_t)1);
         const int smem = (2 * slab + 16) * (int)sizeof(double);
         static bool attr_set = false;
