@@ -387,8 +387,11 @@ def run_ours(a):
         t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        pcie = pcie_probe(sm, ctx, torch, Oh)
+        bound_s = h2d / (pcie["h2d_gbs"] * 1e9) + d2h / (pcie["d2h_gbs"] * 1e9)  # the fit needs every cell before the first adjusted byte exists
         e2e = {"value": a.cells * world * n_e2e / (float(t2.item()) * 1e-3), "unit": "cells/s", "steps": n_e2e,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api, "pcie": pcie_probe(sm, ctx, torch, Oh)}
+               "ms_per_step": float(t2.item()) / n_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api, "pcie": pcie,
+               "pcie_bound_ms_per_step": bound_s * 1e3, "pcie_bound_cells_per_s": a.cells * world / bound_s}
 
     if rank == 0:
         m, n = a.cells, a.genes

@@ -91,6 +91,29 @@ int scm_cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64
 int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, int64_t m, int64_t n,
                      int64_t nnz, int cosine, double min_norm, double* d_out, int64_t ldo, double* d_inv_norm, int32_t* d_nonfinite);
 
+/* ---- sparse-native scMerge2 passes (the dense normalised matrix is never an input) ------------------------------------
+ * For cells-compressed input with CANONICAL cells (gene indices strictly increasing inside every cell: every dgCMatrix) the
+ * three passes over the cells read 12 bytes per non-zero instead of 8 bytes per entry:
+ *   scm_csc_check        validates the index structure (SCM_ERR_INVALID when corrupt) and reports `canonical` (0/1)
+ *   scm_csc_rownorm      d_inv_norm[i] = cosine ? 1 / max(||x_i||_2, min_norm) : 1     (batchelor::cosineNorm, R/scMerge2.R:193-198)
+ *   scm_csc_seg_colmean  means[g, :] = mean over the cells with key g of inv_i x_i      (create_pseudoBulk, R/scMerge2_utilis.R:461-486;
+ *                        G x ldn row-major with ldn >= n even, deterministic)
+ *   scm_csc_adjust       out[i, :] = inv_i x_i - ((inv_i x_i - center) B) A, dense m x n (pseudoRUVIII's adjust of every cell,
+ *                        R/scMerge2_utilis.R:97-137): sparse gather for W, DMMA rank-k update on shared-memory tiles of the scaled
+ *                        sparse rows, newY written once.  k <= 32.
+ * Un-canonical input: use scm_csc_to_dense and the dense kernels. */
+int scm_csc_check(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, int64_t m, int64_t n, int64_t nnz, int32_t* canonical);
+int scm_csc_rownorm(scm_ctx* ctx, const int64_t* d_indptr, const double* d_val, int64_t m, int cosine, double min_norm, double* d_inv_norm,
+                    int32_t* d_nonfinite);
+int scm_csc_seg_colmean(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm,
+                        int64_t m, int64_t n, const int32_t* d_key, int32_t G, double* d_means, int64_t ldn, int64_t* d_counts);
+int scm_csc_adjust(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm, int64_t m,
+                   int64_t n, const scm_coef* coef, double* d_out, int64_t ldo);
+/* scm_csc_adjust with the result streamed to the (page-locked) host matrix h_out chunk by chunk through two device staging
+ * buffers while the next chunk is computed: the dense matrix never exists on the device.  Synchronises. */
+int scm_csc_adjust_to_host(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm,
+                           int64_t m, int64_t n, const scm_coef* coef, double* h_out, int64_t ldo);
+
 /* ---- K1: segmented column sums ---------------------------------------------------------------------
  * sums[g, j] = sum over rows i with key[i] == g of f(Y[i, j]),  counts[g] = #rows,
  *   f(y) = y                       (d_center == NULL)

@@ -39,6 +39,11 @@ SIGNATURES = {
     "scm_transpose": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "scm_cosine_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _dbl],
     "scm_csc_to_dense": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _dbl, _vp, _i64, _vp, _vp],
+    "scm_csc_check": [_vp, _vp, _vp, _i64, _i64, _i64, C.POINTER(_i32)],
+    "scm_csc_rownorm": [_vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp],
+    "scm_csc_seg_colmean": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp],
+    "scm_csc_adjust": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64],
+    "scm_csc_adjust_to_host": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64],
     "scm_adjust_to_host": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64],
     "scm_seg_colsum": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "scm_seg_colmean": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp],

@@ -1,0 +1,350 @@
+// Sparse-native scMerge2 path: the cosine-normalised dense matrix is never materialised as an INPUT.
+//
+// For the dgCMatrix scMerge2 holds (cells compressed, ~10 % non-zero) the three passes over the cells
+//     (a) cosine norms            batchelor::cosineNorm                       R/scMerge2.R:193-198
+//     (b) pseudobulk means        create_pseudoBulk / aggregate.Matrix        R/scMerge2_utilis.R:325-346,461-486
+//     (c) newY = Y - ((Y - c) B) A  pseudoRUVIII's chunked adjust             R/scMerge2_utilis.R:97-137
+// read 12 bytes per NON-ZERO instead of 8 bytes per ENTRY; only (c) touches dense memory, and only to WRITE newY once.
+// HBM traffic per cell x gene entry drops from 8 (densify, written) + 8 (K1) + 16 + 8 (K6 with all genes as controls:
+// two reads, one write) = 40 bytes to 8 bytes + 3 x 12 x density.
+//
+//   csc_rownorm_kernel      one warp per cell: inv[i] = 1 / max(||x_i||_2, min_norm), NA/Inf scan
+//   csc_seg_partial_kernel  K1 on sparse rows: cells ordered by key (same plumbing as the dense K1), one CTA per chunk of
+//                           <= 128 cells, every warp sums ITS cells (fixed order) into a private shared-memory accumulator
+//                           row (no atomics: indices inside a cell are unique), the warp rows are added in warp order and
+//                           the chunk partial goes through the same ordered final reduction: deterministic
+//   csc_adjust_kernel       K6 on sparse rows, 32 cells per CTA: pass A is a sparse gather W_i = s_i sum_nz x_ij B[j, :] - c'B
+//                           (lanes over the k factors, B rows are 8k-byte L1/L2 hits), pass B builds 32 x 256 tiles of the
+//                           scaled sparse rows in shared memory (zero fill + scatter through per-cell cursors: indices are
+//                           sorted) and adds (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out.
+// All three require canonical cells (indices strictly increasing, what csc_check_kernel verifies); otherwise the caller
+// falls back to densify + the dense kernels.
+#pragma once
+#include "adjust.cuh"
+#include "common.cuh"
+#include "csc_ingest.cuh"
+#include "seg_colsum.cuh"
+
+namespace scm {
+
+__global__ void __launch_bounds__(256)
+csc_rownorm_kernel(const int64_t* __restrict__ indptr, const double* __restrict__ val, int64_t m, int cosine, double min_norm,
+                   double* __restrict__ inv, int32_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (int64_t c = warp; c < m; c += nwarps) {
+        const int64_t p0 = indptr[c], p1 = indptr[c + 1];
+        double ss = 0.0;
+        for (int64_t p = p0 + lane; p < p1; p += 32) {
+            const double v = val[p];
+            bad |= nonfinite(v);
+            ss += v * v;
+        }
+        ss = warp_sum(ss);  // xor butterfly: every lane holds the same, order-fixed sum
+        if (lane == 0) inv[c] = cosine ? 1.0 / fmax(sqrt(ss), min_norm) : 1.0;
+    }
+    if (bad && flag) *flag = 1;
+}
+
+constexpr int CSG_THREADS = 128;  // 4 warps, each with a private accumulator row of n doubles in shared memory
+
+// One CTA per chunk (grid-stride).  acc: [nwarp][n] doubles (dynamic shared memory).
+__global__ void __launch_bounds__(CSG_THREADS)
+csc_seg_partial_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                       const double* __restrict__ inv, int n, const int32_t* __restrict__ perm, const int64_t* __restrict__ seg_start,
+                       const int* __restrict__ chunk_off, const int* __restrict__ pslot_off, int32_t G, int nwarp,
+                       double* __restrict__ partial, double* __restrict__ sums) {
+    extern __shared__ __align__(16) double csg_acc[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = chunk_off[G];
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        int lo = 0, hi = G;  // largest g with chunk_off[g] <= chunk
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (chunk_off[mid] <= chunk) lo = mid; else hi = mid;
+        }
+        const int g = lo, j = chunk - chunk_off[g];
+        const int64_t start = seg_start[g] + (int64_t)j * SEG_R;
+        const int len = (int)min((int64_t)SEG_R, seg_start[g + 1] - start);
+        for (int e = tid * 2; e < nwarp * n; e += CSG_THREADS * 2) {  // n is even-padded by the host
+            *reinterpret_cast<double2*>(csg_acc + e) = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (warp < nwarp) {
+            double* acc = csg_acc + (int64_t)warp * n;
+            // warp w takes cells w, w + nwarp, ... of the chunk, one after the other: a fixed summation order per gene
+            for (int r = warp; r < len; r += nwarp) {
+                const int64_t cell = perm[start + r];
+                const int64_t p0 = indptr[cell], p1 = indptr[cell + 1];
+                const double s = inv[cell];
+                for (int64_t pb = p0 + lane; pb < p1; pb += 128) {  // 4 independent loads in flight per lane
+                    int32_t gi[4];
+                    double gv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int64_t p = pb + 32 * u;
+                        gi[u] = p < p1 ? idx[p] : -1;
+                        gv[u] = p < p1 ? val[p] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (gi[u] >= 0) acc[gi[u]] += gv[u] * s;  // unique indices inside a cell: no conflicts
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int nch = chunk_off[g + 1] - chunk_off[g];
+        double* dst = (nch == 1) ? (sums + (int64_t)g * n) : (partial + (int64_t)(pslot_off[g] + j) * n);
+        for (int e = tid; e < n; e += CSG_THREADS) {
+            double t = 0.0;
+            for (int w = 0; w < nwarp; w++) t += csg_acc[(int64_t)w * n + e];
+            dst[e] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// Segmented column sums of the scaled sparse rows: sums[g, :] = sum over cells i with key g of inv[i] * x_i (G x ldn, ldn = n
+// rounded up to even), counts[g].  Deterministic.  Rows of empty groups are 0.
+inline int csc_seg_colsum(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
+                          int64_t m, int64_t n, const int32_t* d_key, int32_t G, double* d_sums, int64_t ldn, int64_t* d_counts) {
+    if (m < 0 || n <= 0 || G <= 0 || ldn < n || (ldn & 1)) return fail(SCM_ERR_INVALID, "csc_seg_colsum: bad shape");
+    if (m >= (int64_t)1 << 31) return fail(SCM_ERR_UNSUPPORTED, "csc_seg_colsum: m >= 2^31");
+    if (ldn > 24576) return fail(SCM_ERR_UNSUPPORTED, "csc_seg_colsum: more than 24576 genes");
+    cudaStream_t st = ctx->stream;
+    Scratch ws(ctx);
+    SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * ldn));
+    if (m == 0) {
+        if (d_counts) SCM_TRY(zero_async(ctx, d_counts, sizeof(int64_t) * G));
+        return 0;
+    }
+    SegPlan sp;
+    SCM_TRY(seg_plan_build(ctx, ws, d_key, m, G, d_counts, sp));
+    const int64_t max_slots = 2 * ceil_div(m, SEG_R) + 1;
+    double* partial;
+    SCM_TRY(ws.alloc(&partial, max_slots * ldn));
+    int nwarp = (int)((200 * 1024) / (ldn * 8));
+    if (nwarp > CSG_THREADS / 32) nwarp = CSG_THREADS / 32;
+    if (nwarp < 1) nwarp = 1;
+    const int smem = (int)(nwarp * ldn * 8);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        SCM_CUDA(cudaFuncSetAttribute(csc_seg_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const int64_t max_chunks = ceil_div(m, SEG_R) + G;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t grid = (int64_t)ctx->num_sms * per_sm;
+    if (grid > max_chunks) grid = max_chunks;
+    csc_seg_partial_kernel<<<(unsigned)grid, CSG_THREADS, smem, st>>>(d_indptr, d_idx, d_val, d_inv, (int)ldn, sp.perm, sp.seg_start,
+                                                                     sp.chunk_off, sp.pslot_off, G, nwarp, partial, d_sums);
+    SCM_LAUNCH_CHECK(ctx);
+    dim3 fgrid((unsigned)G, (unsigned)ceil_div(ldn, 256));
+    seg_final_kernel<<<fgrid, 256, 0, st>>>(partial, sp.chunk_off, sp.pslot_off, ldn, d_sums);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---- K6 on sparse rows ----------------------------------------------------------------------------------------------
+constexpr int CSA_WARPS = 4, CSA_MT = 4, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256;  // 32 cells x 256 genes x 8 B = 64 KB tile
+
+template <int KT>
+__global__ void __launch_bounds__(CSA_WARPS * 32, 3)
+csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                  const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Bmat, const double* __restrict__ Afrag,
+                  const double* __restrict__ w0, int k, int nblk, double* __restrict__ out, int64_t ldo, int vec_out) {
+    extern __shared__ __align__(16) uint8_t csa_smem[];
+    double* tile = reinterpret_cast<double*>(csa_smem);                       // [32][CSA_SLAB + 2] (padded: conflict-free fragment reads)
+    constexpr int TLD = CSA_SLAB + 2;
+    double* Wsm = tile + CSA_ROWS * TLD;                                      // [32][KT * 8]
+    int64_t* cur = reinterpret_cast<int64_t*>(Wsm + CSA_ROWS * KT * 8);       // [32] cursor into the cell's non-zeros
+    int64_t* endp = cur + CSA_ROWS;                                           // [32]
+    double* sc = reinterpret_cast<double*>(endp + CSA_ROWS);                  // [32] scale of the cell
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t ntiles = ceil_div(m, CSA_ROWS);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * CSA_ROWS;
+        __syncthreads();  // previous tile fully consumed
+        if (tid < CSA_ROWS) {
+            const int64_t cell = row0 + tid;
+            const bool ok = cell < m;
+            cur[tid] = ok ? indptr[cell] : 0;
+            endp[tid] = ok ? indptr[cell + 1] : 0;
+            sc[tid] = ok ? inv[cell] : 0.0;
+        }
+        __syncthreads();
+        // ---- pass A: W[cell, a] = s * sum_nz x B[idx, a] - w0[a]; warp w owns cells 8w .. 8w+7, lanes run over a
+        for (int r = 0; r < 8; r++) {
+            const int c = warp * 8 + r;
+            const int64_t p0 = cur[c], p1 = endp[c];
+            double acc = 0.0, acc1 = 0.0;
+            for (int64_t pb = p0; pb < p1; pb += 32) {
+                const int64_t p = pb + lane;
+                const int32_t gi = p < p1 ? idx[p] : 0;
+                const double gv = p < p1 ? val[p] : 0.0;
+                const int cnt = (int)min((int64_t)32, p1 - pb);
+#pragma unroll 4
+                for (int q = 0; q < cnt; q++) {  // shuffles are executed by the whole warp; only the first k lanes accumulate
+                    const int32_t g = __shfl_sync(0xffffffffu, gi, q);
+                    const double v = __shfl_sync(0xffffffffu, gv, q);
+                    if (lane < k) {
+                        const double b = __ldg(Bmat + (int64_t)g * k + lane);
+                        if (q & 1) acc1 = fma(v, b, acc1); else acc = fma(v, b, acc);
+                    }
+                }
+            }
+            acc += acc1;
+            if (lane < KT * 8) Wsm[c * (KT * 8) + lane] = lane < k ? acc * sc[c] - w0[lane] : 0.0;
+        }
+        __syncthreads();
+        double w[CSA_MT][KT][2];
+#pragma unroll
+        for (int mt = 0; mt < CSA_MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < KT; nt++) {
+                const double2 v = *reinterpret_cast<const double2*>(Wsm + (mt * 8 + gid) * (KT * 8) + 8 * nt + 2 * tig);
+                w[mt][nt][0] = -v.x; w[mt][nt][1] = -v.y;  // pass B adds (-W) A
+            }
+        // ---- pass B, slab by slab
+        for (int64_t g0 = 0; g0 < n; g0 += CSA_SLAB) {
+            const int width = (int)min((int64_t)CSA_SLAB, n - g0);
+            __syncthreads();  // previous slab consumed
+            for (int e = tid; e < CSA_ROWS * (TLD / 2); e += CSA_WARPS * 32) *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(0.0, 0.0);
+            __syncthreads();
+            // scatter: warp w walks the cursors of its 8 cells (indices are sorted: the slab's non-zeros are a contiguous run)
+            for (int r = 0; r < 8; r++) {
+                const int c = warp * 8 + r;
+                int64_t p = cur[c];
+                const int64_t p1 = endp[c];
+                const double s = sc[c];
+                while (true) {
+                    const int64_t q = p + lane;
+                    int32_t g = q < p1 ? idx[q] : INT32_MAX;
+                    const bool in = g < g0 + width;
+                    if (in) tile[c * TLD + (g - (int32_t)g0)] = val[q] * s;
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    p += __popc(mask);
+                    if (mask != 0xffffffffu) break;
+                }
+                __syncwarp();
+                if (lane == 0) cur[c] = p;
+            }
+            __syncthreads();
+            // DMMA over this slab's 16-gene blocks, warps round-robin
+            const int nb_slab = (width + 15) / 16;
+            for (int b = warp; b < nb_slab; b += CSA_WARPS) {
+                const int gb = (int)(g0 / 16) + b;
+                double y[CSA_MT][4];
+#pragma unroll
+                for (int mt = 0; mt < CSA_MT; mt++) {
+                    const double* src = tile + (mt * 8 + gid) * TLD + b * 16 + 4 * tig;
+                    const double2 a = *reinterpret_cast<const double2*>(src), c2 = *reinterpret_cast<const double2*>(src + 2);
+                    y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = c2.x; y[mt][3] = c2.y;
+                }
+                const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)gb * KT * 128) + lane;
+                double2 a[2 * KT];
+#pragma unroll
+                for (int i = 0; i < 2 * KT; i++) a[i] = __ldg(af + i * 32);
+#pragma unroll
+                for (int tau = 0; tau < 2; tau++)
+#pragma unroll
+                    for (int nt = 0; nt < KT; nt++)
+#pragma unroll
+                        for (int mt = 0; mt < CSA_MT; mt++) {
+                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
+                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
+                        }
+                const int64_t gg = (int64_t)gb * 16 + 4 * tig;
+#pragma unroll
+                for (int mt = 0; mt < CSA_MT; mt++) {
+                    const int64_t cell = row0 + mt * 8 + gid;
+                    store4(out + (cell < m ? cell : 0) * ldo, gg, n, vec_out, cell < m, y[mt]);
+                }
+            }
+        }
+    }
+}
+
+template <int KT>
+inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
+                             int64_t m, int64_t n, const scm_coef* c, double* d_out, int64_t ldo) {
+    const int smem = (CSA_ROWS * (CSA_SLAB + 2) + CSA_ROWS * KT * 8) * 8 + CSA_ROWS * (8 + 8 + 8);
+    SCM_CUDA(cudaFuncSetAttribute(csc_adjust_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t ntiles = ceil_div(m, CSA_ROWS);
+    int64_t grid = (int64_t)ctx->num_sms * 3;
+    if (grid > ntiles) grid = ntiles;
+    const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, c->Bmat, c->Afrag, c->w0,
+                                                                                c->k, c->nblk, d_out, ldo, vec_out);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// out[i, :] = s_i x_i - ((s_i x_i - center) B) A for cells-compressed sparse input (s = d_inv).  out is dense m x n.
+inline int csc_adjust(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv, int64_t m,
+                      int64_t n, const scm_coef* c, double* d_out, int64_t ldo) {
+    if (!c || c->n != n) return fail(SCM_ERR_INVALID, "csc_adjust: coefficient object does not match n=%lld", (long long)n);
+    if (!d_indptr || !d_inv || !d_out || ldo < n) return fail(SCM_ERR_INVALID, "csc_adjust: bad arguments");
+    if (m <= 0) return 0;
+    if (n >= ((int64_t)1 << 31) - CSA_SLAB) return fail(SCM_ERR_UNSUPPORTED, "csc_adjust: too many genes");
+    switch (c->KT) {
+        case 1: return csc_adjust_launch<1>(ctx, d_indptr, d_idx, d_val, d_inv, m, n, c, d_out, ldo);
+        case 2: return csc_adjust_launch<2>(ctx, d_indptr, d_idx, d_val, d_inv, m, n, c, d_out, ldo);
+        case 3: return csc_adjust_launch<3>(ctx, d_indptr, d_idx, d_val, d_inv, m, n, c, d_out, ldo);
+        case 4: return csc_adjust_launch<4>(ctx, d_indptr, d_idx, d_val, d_inv, m, n, c, d_out, ldo);
+        default: return fail(SCM_ERR_UNSUPPORTED, "csc_adjust: k=%d > 32 is not supported on the sparse path (densify first)", c->k);
+    }
+}
+
+// Sparse rows in, adjusted dense rows straight to the host: the rank-k update runs chunk by chunk into two staging buffers and
+// every finished chunk goes down the copy stream while the next one is computed -- the dense matrix never exists on the device.
+inline int64_t host_chunk_rows(int64_t ld);
+inline int csc_adjust_download(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
+                               int64_t m, int64_t n, const scm_coef* c, double* h_out, int64_t ldo) {
+    if (!h_out || ldo < n) return fail(SCM_ERR_INVALID, "csc_adjust_download: bad arguments");
+    if (m <= 0) return 0;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->copy_stream_d2h) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream_d2h, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream_d2h;
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    int64_t rows_per_chunk = host_chunk_rows(ld);
+    if (rows_per_chunk > m) rows_per_chunk = m;
+    const int nchunks = (int)ceil_div(m, rows_per_chunk);
+    Scratch ws(ctx);
+    double* stage[2];
+    SCM_TRY(ws.alloc(&stage[0], rows_per_chunk * ld));
+    SCM_TRY(ws.alloc(&stage[1], rows_per_chunk * ld));
+    cudaEvent_t evk[2], evc[2];
+    for (int i = 0; i < 2; i++) {
+        SCM_CUDA(cudaEventCreateWithFlags(&evk[i], cudaEventDisableTiming));
+        SCM_CUDA(cudaEventCreateWithFlags(&evc[i], cudaEventDisableTiming));
+    }
+    struct Guard { cudaEvent_t *a, *b; ~Guard() { for (int i = 0; i < 2; i++) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); } } } guard{evk, evc};
+    SCM_CUDA(cudaStreamSynchronize(st));  // staging buffers allocated (stream-ordered) before the copy stream touches them
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int b = ch & 1;
+        const int64_t r0 = (int64_t)ch * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+        if (ch >= 2) SCM_CUDA(cudaEventSynchronize(evc[b]));  // host-mediated: the staging buffer has been downloaded
+        {
+            StageTimer t(ctx, ST_ADJUST);
+            SCM_TRY(csc_adjust(ctx, d_indptr + r0, d_idx, d_val, d_inv + r0, rows, n, c, stage[b], ld));
+        }
+        SCM_CUDA(cudaEventRecord(evk[b], st));
+        SCM_CUDA(cudaStreamWaitEvent(cs, evk[b], 0));
+        if (ldo == n && ld == n)
+            SCM_CUDA(cudaMemcpyAsync(h_out + r0 * ldo, stage[b], (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
+        else
+            SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, stage[b], ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+        SCM_CUDA(cudaEventRecord(evc[b], cs));
+    }
+    SCM_CUDA(cudaStreamSynchronize(cs));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace scm

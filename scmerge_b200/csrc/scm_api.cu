@@ -153,6 +153,7 @@ inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
 #include "host_pipeline.cuh"
 #include "ruvg.cuh"
 #include "select_k.cuh"
+#include "csc_sparse.cuh"
 
 using namespace scm;
 
@@ -297,6 +298,62 @@ int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx
     SCM_REQUIRE_CTX(ctx);
     StageTimer t(ctx, ST_INGEST);
     return csc_to_dense(ctx, d_indptr, d_idx, d_val, m, n, nnz, cosine, min_norm, d_out, ldo, d_inv_norm, d_nonfinite);
+}
+
+int scm_csc_check(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, int64_t m, int64_t n, int64_t nnz, int32_t* canonical) {
+    SCM_REQUIRE_CTX(ctx);
+    if (m < 0 || n <= 0 || !d_indptr || (nnz > 0 && !d_idx)) return fail(SCM_ERR_INVALID, "scm_csc_check: bad arguments");
+    Scratch ws(ctx);
+    int32_t* flags;
+    SCM_TRY(ws.alloc(&flags, 2));
+    SCM_TRY(zero_async(ctx, flags, 8));
+    if (m > 0) {
+        csc_check_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_indptr, d_idx, m, n, nnz, flags);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    int32_t h[2] = {0, 0};
+    SCM_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[0]) return fail(SCM_ERR_INVALID, h[0] == 1 ? "scm_csc_check: column pointers are not a non-decreasing sequence inside [0, nnz]"
+                                                     : "scm_csc_check: a gene index is outside [0, n)");
+    if (canonical) *canonical = h[1] == 0;
+    return 0;
+}
+
+int scm_csc_rownorm(scm_ctx* ctx, const int64_t* d_indptr, const double* d_val, int64_t m, int cosine, double min_norm, double* d_inv_norm,
+                    int32_t* d_nonfinite) {
+    SCM_REQUIRE_CTX(ctx);
+    if (m <= 0) return 0;
+    if (!d_indptr || !d_inv_norm) return fail(SCM_ERR_INVALID, "scm_csc_rownorm: bad arguments");
+    StageTimer t(ctx, ST_INGEST);
+    csc_rownorm_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_indptr, d_val, m, cosine, min_norm, d_inv_norm, d_nonfinite);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_csc_seg_colmean(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm,
+                        int64_t m, int64_t n, const int32_t* d_key, int32_t G, double* d_means, int64_t ldn, int64_t* d_counts) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!d_counts) return fail(SCM_ERR_INVALID, "scm_csc_seg_colmean: d_counts is required");
+    StageTimer t(ctx, ST_SEG);
+    SCM_TRY(csc_seg_colsum(ctx, d_indptr, d_idx, d_val, d_inv_norm, m, n, d_key, G, d_means, ldn, d_counts));
+    groupmean_kernel<<<(unsigned)ceil_div(ldn, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, ldn);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int scm_csc_adjust(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm, int64_t m,
+                   int64_t n, const scm_coef* coef, double* d_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    StageTimer t(ctx, ST_ADJUST);
+    return csc_adjust(ctx, d_indptr, d_idx, d_val, d_inv_norm, m, n, coef, d_out, ldo);
+}
+
+int scm_csc_adjust_to_host(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv_norm,
+                           int64_t m, int64_t n, const scm_coef* coef, double* h_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!coef || coef->n != n) return fail(SCM_ERR_INVALID, "scm_csc_adjust_to_host: coefficient object does not match n");
+    return csc_adjust_download(ctx, d_indptr, d_idx, d_val, d_inv_norm, m, n, coef, h_out, ldo);
 }
 
 int scm_adjust_to_host(scm_ctx* ctx, double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out, int64_t ldo) {

@@ -156,17 +156,17 @@ __global__ void seg_final_kernel(const double* __restrict__ partial, const int* 
     sums[(int64_t)g * n + col] = acc;
 }
 
-inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key,
-                      int32_t G, const double* d_center, double* d_sums, int64_t* d_counts, int32_t* d_nonfinite) {
-    if (m < 0 || n <= 0 || G <= 0 || ld < n) return fail(SCM_ERR_INVALID, "seg_colsum: bad shape m=%lld n=%lld ld=%lld G=%d", (long long)m, (long long)n, (long long)ld, G);
-    if (m >= (int64_t)1 << 31) return fail(SCM_ERR_UNSUPPORTED, "seg_colsum: m >= 2^31 rows per rank");
+// Index plumbing shared by the dense and the sparse segmented sums: rows ordered by key (stable radix sort), group starts,
+// chunk / partial-slot offsets.  All buffers live in the caller's Scratch.
+struct SegPlan {
+    int32_t* perm = nullptr;       // row order by key (m)
+    int64_t* seg_start = nullptr;  // G + 1
+    int* chunk_off = nullptr;      // G + 1
+    int* pslot_off = nullptr;      // G + 1
+};
+
+inline int seg_plan_build(scm_ctx* ctx, Scratch& ws, const int32_t* d_key, int64_t m, int32_t G, int64_t* d_counts, SegPlan& sp) {
     cudaStream_t st = ctx->stream;
-    Scratch ws(ctx);
-    if (m == 0) {
-        SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * n));
-        if (d_counts) SCM_TRY(zero_async(ctx, d_counts, sizeof(int64_t) * G));
-        return 0;
-    }
     uint32_t *skey_in, *skey_out;
     int32_t *sval_in, *perm;
     int *cnt, *chunk_off, *pslot_off;
@@ -190,6 +190,26 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     SCM_TRY(ws.alloc(&tmp, (int64_t)tmp_bytes));
     SCM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, skey_in, skey_out, sval_in, perm, (int)m, 0, end_bit, st));
     ctx->launches += 3;
+    sp.perm = perm; sp.seg_start = seg_start; sp.chunk_off = chunk_off; sp.pslot_off = pslot_off;
+    return 0;
+}
+
+inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key,
+                      int32_t G, const double* d_center, double* d_sums, int64_t* d_counts, int32_t* d_nonfinite) {
+    if (m < 0 || n <= 0 || G <= 0 || ld < n) return fail(SCM_ERR_INVALID, "seg_colsum: bad shape m=%lld n=%lld ld=%lld G=%d", (long long)m, (long long)n, (long long)ld, G);
+    if (m >= (int64_t)1 << 31) return fail(SCM_ERR_UNSUPPORTED, "seg_colsum: m >= 2^31 rows per rank");
+    cudaStream_t st = ctx->stream;
+    Scratch ws(ctx);
+    if (m == 0) {
+        SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * n));
+        if (d_counts) SCM_TRY(zero_async(ctx, d_counts, sizeof(int64_t) * G));
+        return 0;
+    }
+    SegPlan sp;
+    SCM_TRY(seg_plan_build(ctx, ws, d_key, m, G, d_counts, sp));
+    int32_t* perm = sp.perm;
+    int64_t* seg_start = sp.seg_start;
+    int *chunk_off = sp.chunk_off, *pslot_off = sp.pslot_off;
 
     const int64_t max_slots = 2 * ceil_div(m, SEG_R) + 1;
     double* partial;

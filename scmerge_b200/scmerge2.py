@@ -43,6 +43,7 @@ class DeviceCSC:
         self.indptr = ctx.to_device(indptr)
         self.indices = ctx.to_device(np.ascontiguousarray(indices[:self.nnz], dtype=np.int32))
         self.data = ctx.to_device(np.ascontiguousarray(data[:self.nnz], dtype=np.float64))
+        self._canonical = None
 
     @classmethod
     def from_scipy(cls, ctx: Context, X) -> "DeviceCSC":
@@ -77,6 +78,30 @@ class DeviceCSC:
             if d_flag is not None:
                 d_flag.free()
         return out
+
+    def is_canonical(self) -> bool:
+        """scm_csc_check: raises on a corrupt index structure; True when every cell's gene indices are strictly increasing
+        (sorted, no duplicates -- every dgCMatrix), which the sparse-native kernels require."""
+        if self._canonical is None:
+            flag = C.c_int32(0)
+            L.check(L.lib().scm_csc_check(self.ctx.handle, self.indptr.ptr, self.indices.ptr, self.m, self.n, self.nnz, C.byref(flag)))
+            self._canonical = bool(flag.value)
+        return self._canonical
+
+    def row_scales(self, cosine: bool = True, min_norm: float = 1e-8, check_finite: bool = True):
+        """scm_csc_rownorm: device vector of 1 / max(||x_i||, min_norm) (all ones when not `cosine`)."""
+        ctx = self.ctx
+        d_inv = ctx.empty((self.m,))
+        d_flag = ctx.to_device(np.zeros(1, dtype=np.int32)) if check_finite else None
+        L.check(L.lib().scm_csc_rownorm(ctx.handle, self.indptr.ptr, self.data.ptr, self.m, int(bool(cosine)), float(min_norm), d_inv.ptr,
+                                        d_flag.ptr if d_flag is not None else None))
+        if d_flag is not None:
+            bad = int(d_flag.to_host()[0])
+            d_flag.free()
+            if bad:
+                d_inv.free()
+                raise L.NonFiniteError(L.ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.")
+        return d_inv
 
     def free(self):
         for a in (self.indptr, self.indices, self.data):
@@ -149,28 +174,90 @@ def _adjust_to_host(ctx: Context, dY: DeviceMatrix, fullalpha, k: int, ctl_mask,
     return host_out
 
 
+def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: int, k_pseudoBulk, cosine, BSPARAM, which, seed,
+                     replicate_of, pb, return_bulk, out: DeviceMatrix | None, host_out, check_finite=True):
+    """scMerge2 core on the sparse rows themselves (scm_csc_rownorm / scm_csc_seg_colmean / scm_csc_adjust[_to_host])."""
+    lib = L.lib()
+    m, n = dcsc.m, dcsc.n
+    ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
+    if pb is None:
+        pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed)
+    keys, P, names, pb_type, _pb_batch = pb
+    d_inv = dcsc.row_scales(cosine=cosine, check_finite=check_finite)
+    dP = DeviceMatrix(ctx, P, n)
+    d_keys, d_cnt = ctx.to_device(np.ascontiguousarray(keys, dtype=np.int32)), ctx.empty((P,), np.int64)
+    coef = None
+    try:
+        L.check(lib.scm_csc_seg_colmean(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, d_keys.ptr, P,
+                                        dP.ptr, dP.ld, d_cnt.ptr))
+        d_mean = ctx.empty((n,))
+        L.check(lib.scm_group_colmean(ctx.handle, dP.ptr, d_cnt.ptr, P, n, dP.ld, d_mean.ptr))
+        means = d_mean.to_host()
+        d_mean.free()
+        bulk = dP.to_host() if (return_bulk or replicate_of is not None) else None
+        rep = pb_type if replicate_of is None else np.asarray(replicate_of(names, bulk))
+        rkeys, G = replicate_keys(rep)
+        exact = _is_exact(BSPARAM) if BSPARAM is not None else False
+        s = _svd_k(P, G, int(ctl_mask.sum()), exact, ruvK)
+        if G >= P or ruvK == 0:
+            raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
+        s_dev, exact_dev = _device_rows_cap(s, ruvK, exact)
+        fit = _fit(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
+        from .ruv import _Coef
+        with _Coef(ctx, n, fit.fullalpha, ruvK, ctl_mask, center=means) as coef:
+            if host_out is not None:
+                assert host_out.shape == (m, n) and host_out.dtype == np.float64 and host_out.flags.c_contiguous
+                L.check(lib.scm_csc_adjust_to_host(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n,
+                                                   coef.handle, host_out.ctypes.data_as(C.c_void_p), n))
+                newY = host_out
+            else:
+                dout = out or DeviceMatrix(ctx, m, n)
+                L.check(lib.scm_csc_adjust(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, coef.handle,
+                                           dout.ptr, dout.ld))
+                ctx.sync()
+                newY = dout
+    finally:
+        for a in (d_inv, d_keys, d_cnt):
+            a.free()
+        dP.free()
+    return {"newY": newY, "fullalpha": fit.fullalpha, "bulkExprs": bulk, "pseudobulk_names": names, "replicate_vector": rep,
+            "adjusted_means": means}
+
+
 def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: int = 30, cosine: bool = True, BSPARAM=None,
                   which=None, seed=1, replicate_of=None, return_subset_genes=None, ctx: Context | None = None,
-                  pb=None, return_bulk=True, out: DeviceMatrix | None = None):
+                  pb=None, return_bulk=True, out: DeviceMatrix | None = None, sparse_native: bool = True):
     """cosineNorm -> construct_pseudoBulk -> pseudoRUVIII (R/scMerge2.R:193-309) for cells x genes `exprs`
     (numpy: copied to the device; scipy.sparse CSR cells x genes / CSC genes x cells, i.e. the reference's dgCMatrix:
     only the sparse arrays are uploaded and the dense normalised rows are built on the device (K8);
     DeviceMatrix: normalised IN PLACE, result returned as a DeviceMatrix).  For host inputs `out` may be a (page-locked)
     numpy cells x genes array: the adjusted chunks are then downloaded while the next chunk is computed.
+    Sparse input with canonical cells (sorted unique indices: every dgCMatrix) takes the sparse-native kernels
+    (`sparse_native`): norms, pseudobulk means and the rank-k update read 12 bytes per non-zero, the dense matrix is only
+    ever written (newY), and with a host `out` it never exists on the device at all.
     With `out` (a DeviceMatrix of the same shape) a device-resident input is left untouched: the normalised cells are
     written to `out` and adjusted there.  `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
     Returns {'newY', 'fullalpha', 'bulkExprs' (P x genes), 'pseudobulk_names', 'replicate_vector', 'adjusted_means'}."""
     ctx = ctx or (exprs.ctx if isinstance(exprs, (DeviceMatrix, DeviceCSC)) else default_context())
     host_in = not isinstance(exprs, (DeviceMatrix, DeviceCSC))
-    host_out = out if (host_in and isinstance(out, np.ndarray)) else None
-    if host_in:
+    host_out = out if isinstance(out, np.ndarray) else None
+    if host_out is not None and isinstance(exprs, DeviceMatrix):
+        raise TypeError("a numpy `out` needs a host or DeviceCSC input (a DeviceMatrix input is adjusted on the device)")
+    if host_in or host_out is not None:
         out = None
-    if isinstance(exprs, DeviceCSC):  # device-resident sparse input: the dense rows go to `out` (or a new matrix)
-        dY = exprs.to_dense(cosine=cosine, out=out, check_finite=False)
-        cosine, out = False, None
-    elif _is_sparse(exprs):
-        dY = csc_to_device(ctx, exprs, cosine=cosine)
-        cosine = False  # already applied during the densification
+    if isinstance(exprs, DeviceCSC) or _is_sparse(exprs):
+        dcsc = exprs if isinstance(exprs, DeviceCSC) else DeviceCSC.from_scipy(ctx, exprs)
+        try:
+            if sparse_native and ruvK <= 32 and return_subset_genes is None and dcsc.is_canonical():
+                # the dense normalised matrix is never an input: norms, pseudobulks and the rank-k update read the sparse rows
+                return _scmerge2_sparse(ctx, dcsc, batch, clust, ctl, int(ruvK), k_pseudoBulk, cosine, BSPARAM, which, seed,
+                                        replicate_of, pb, return_bulk, out if not host_in else None, host_out,
+                                        check_finite=host_in)
+            dY = dcsc.to_dense(cosine=cosine, out=out if not host_in else None, check_finite=host_in)
+        finally:
+            if dcsc is not exprs:
+                dcsc.free()
+        cosine, out = False, None  # already applied during the densification
     else:
         dY = DeviceMatrix.from_host(ctx, np.asarray(exprs, dtype=np.float64)) if host_in else exprs
     n = dY.n

@@ -574,10 +574,81 @@ def test_scmerge2_core_sparse_input_matches_dense(sm):
     assert np.allclose(out["bulkExprs"], ref["bulkExprs"], rtol=1e-12, atol=1e-15)
     assert orc.rel_frobenius(host_out, ref["newY"]) < TOL_NEWY
     dense = scMerge2_core(D, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
-    assert orc.rel_frobenius(dense["newY"], host_out) < 1e-12
-    # genes x cells CSC (the reference's orientation) gives the same answer
+    assert orc.rel_frobenius(dense["newY"], host_out) < 1e-10
+    # the densify-first path (what un-canonical input takes) agrees with the sparse-native kernels
+    dens = scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam(), sparse_native=False)
+    assert orc.rel_frobenius(dens["newY"], host_out) < 1e-10
+    assert np.allclose(dens["bulkExprs"], out["bulkExprs"], rtol=1e-13, atol=1e-16)
+    # genes x cells CSC (the reference's orientation) gives the same answer, bit for bit (deterministic kernels)
     out2 = scMerge2_core(Xs.T.tocsc(), batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
-    assert orc.rel_frobenius(out2["newY"], host_out) < 1e-13
+    assert np.array_equal(out2["newY"], host_out)
+    # device-resident sparse input -> device-resident dense output
+    ctx = sm.default_context()
+    dcsc = sm.DeviceCSC.from_scipy(ctx, Xs)
+    res = scMerge2_core(dcsc, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
+    assert isinstance(res["newY"], sm.DeviceMatrix) and np.array_equal(res["newY"].to_host(), host_out)
+    dcsc.free()
+
+
+@pytest.mark.parametrize("m,n,density,k,G", [(3000, 257, 0.1, 5, 40), (5000, 2000, 0.05, 20, 700), (700, 4500, 0.02, 32, 3),
+                                             (64, 96, 0.5, 8, 64)])
+def test_sparse_native_kernels_vs_dense(sm, ctx, m, n, density, k, G):
+    """scm_csc_rownorm / scm_csc_seg_colmean / scm_csc_adjust against the dense kernels on the densified matrix: norms and
+    group counts bit-exact, means and the adjusted matrix to rounding (different summation order), empty cells / groups,
+    ragged tiles, odd n and a control subset included."""
+    from scmerge_b200.ruv import _Coef
+    X = _sparse_case(m, n, density, seed=m + k, empty_cells=(1, m - 1))
+    rng = np.random.default_rng(k)
+    keys = rng.integers(0, G, m).astype(np.int32)
+    keys[keys == 1] = 0                                             # group 1 is empty
+    dcsc = sm.DeviceCSC.from_scipy(ctx, X)
+    assert dcsc.is_canonical()
+    d_inv = dcsc.row_scales(cosine=True)
+    D = X.toarray()
+    nrm = np.sqrt((D * D).sum(axis=1))
+    assert np.allclose(d_inv.to_host(), 1.0 / np.maximum(nrm, 1e-8), rtol=1e-14)
+    Dn = orc.cosine_norm(D.T).T
+    lib = sm.lib()
+    dP = sm.DeviceMatrix(ctx, G, n)
+    d_keys, d_cnt = ctx.to_device(keys), ctx.empty((G,), np.int64)
+    assert lib.scm_csc_seg_colmean(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, d_keys.ptr, G,
+                                   dP.ptr, dP.ld, d_cnt.ptr) == 0, lib.scm_last_error()
+    cnt = np.bincount(keys, minlength=G)
+    assert np.array_equal(d_cnt.to_host(), cnt)
+    want = np.zeros((G, n))
+    np.add.at(want, keys, Dn)
+    want[cnt > 0] /= cnt[cnt > 0, None]
+    got = dP.to_host()
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-16) and np.all(got[1] == 0)
+    again = sm.DeviceMatrix(ctx, G, n)
+    assert lib.scm_csc_seg_colmean(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, d_keys.ptr, G,
+                                   again.ptr, again.ld, d_cnt.ptr) == 0
+    assert np.array_equal(again.to_host(), got)                     # deterministic
+    # rank-k update: random factor rows, controls = every third gene, centre = column means
+    alpha = rng.normal(size=(k, n))
+    ctl = np.zeros(n, bool)
+    ctl[::3] = True
+    center = Dn.mean(axis=0)
+    ac = alpha[:, ctl]
+    W = (Dn - center)[:, ctl] @ ac.T @ np.linalg.inv(ac @ ac.T)
+    ref = Dn - W @ alpha
+    dout = sm.DeviceMatrix(ctx, m, n)
+    with _Coef(ctx, n, alpha, k, ctl, center=center) as coef:
+        assert lib.scm_csc_adjust(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, coef.handle,
+                                  dout.ptr, dout.ld) == 0, lib.scm_last_error()
+        ctx.sync()
+        assert orc.rel_frobenius(dout.to_host(), ref) < 1e-11
+        host = sm.pinned_empty((m, n))
+        os.environ["SCM_HOST_CHUNK_ROWS"] = "100"                   # several staging chunks
+        try:
+            assert lib.scm_csc_adjust_to_host(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n,
+                                              coef.handle, host.ctypes.data_as(C.c_void_p), n) == 0, lib.scm_last_error()
+        finally:
+            del os.environ["SCM_HOST_CHUNK_ROWS"]
+        assert np.array_equal(host, dout.to_host())
+    for a in (d_inv, d_keys, d_cnt):
+        a.free()
+    dcsc.free()
 
 
 # ---- scRUVg (SURVEY.md 8f rank 3) ---------------------------------------------------------------------------
