@@ -28,6 +28,7 @@ struct scm_coef {
     double* w0 = nullptr;    // k       center' B
     double* Bfrag = nullptr; // [nblk][32][KT][4]
     double* Afrag = nullptr; // [nblk][32][2][KT][2]
+    double* Bpad = nullptr;  // n x (KT*8), rows of Bmat zero-padded to a multiple of 8 (16-byte vector loads, sparse pass A)
     int32_t* ctl_blocks = nullptr;
 };
 
@@ -127,10 +128,19 @@ __global__ void coef_ctlblocks_kernel(const uint8_t* __restrict__ ctl, int64_t n
     if (threadIdx.x == 0) *count = s_base;
 }
 
+// Bpad[g, a] = a < k ? Bmat[g, a] : 0
+__global__ void coef_bpad_kernel(const double* __restrict__ Bmat, int64_t n, int k, int KP, double* __restrict__ Bpad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * KP) return;
+    const int64_t g = e / KP;
+    const int a = (int)(e % KP);
+    Bpad[e] = a < k ? Bmat[g * k + a] : 0.0;
+}
+
 inline int coef_destroy(scm_ctx* ctx, scm_coef* c) {
     if (!c) return 0;
     cudaStream_t st = ctx->stream;
-    void* ptrs[] = {c->Bmat, c->Amat, c->w0, c->Bfrag, c->Afrag, c->ctl_blocks};
+    void* ptrs[] = {c->Bmat, c->Amat, c->w0, c->Bfrag, c->Afrag, c->Bpad, c->ctl_blocks};
     for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
     delete c;
     return 0;
@@ -153,6 +163,7 @@ inline int coef_alloc(scm_ctx* ctx, int64_t n, int32_t k, scm_coef** out) {
     rc |= dalloc((void**)&c->w0, sizeof(double) * k);
     rc |= dalloc((void**)&c->Bfrag, sizeof(double) * (int64_t)c->nblk * 32 * c->KT * 4);
     rc |= dalloc((void**)&c->Afrag, sizeof(double) * (int64_t)c->nblk * 32 * c->KT * 4);
+    rc |= dalloc((void**)&c->Bpad, sizeof(double) * n * c->KT * 8);
     rc |= dalloc((void**)&c->ctl_blocks, sizeof(int32_t) * (c->nblk + 1));
     if (rc) { coef_destroy(ctx, c); return SCM_ERR_CUDA; }
     *out = c;
@@ -166,6 +177,8 @@ inline int coef_finalize(scm_ctx* ctx, scm_coef* c, const uint8_t* d_rows, const
     coef_w0_kernel<<<1, 1024, 0, st>>>(c->Bmat, d_center, c->n, c->k, c->w0);
     SCM_LAUNCH_CHECK(ctx);
     coef_frag_kernel<<<c->nblk, 32, 0, st>>>(c->Bmat, c->Amat, c->n, c->k, c->KT, c->nblk, c->Bfrag, c->Afrag);
+    SCM_LAUNCH_CHECK(ctx);
+    coef_bpad_kernel<<<(unsigned)ceil_div(c->n * c->KT * 8, 256), 256, 0, st>>>(c->Bmat, c->n, c->k, c->KT * 8, c->Bpad);
     SCM_LAUNCH_CHECK(ctx);
     coef_ctlblocks_kernel<<<1, 1024, 0, st>>>(d_rows, c->n, c->nblk, c->ctl_blocks, c->ctl_blocks + c->nblk);
     SCM_LAUNCH_CHECK(ctx);

@@ -14,7 +14,9 @@
 //                           row (no atomics: indices inside a cell are unique), the warp rows are added in warp order and
 //                           the chunk partial goes through the same ordered final reduction: deterministic
 //   csc_adjust_kernel       K6 on sparse rows, 32 cells per CTA: pass A is a sparse gather W_i = s_i sum_nz x_ij B[j, :] - c'B
-//                           (lanes over the k factors, B rows are 8k-byte L1/L2 hits), pass B builds 32 x 256 tiles of the
+//                           (a quad of lanes per non-zero, 16-byte loads of zero-padded B rows, 2 sectors per row and load;
+//                           v1 ran lanes over the k factors with shuffles: 26 ms; v2 one lane per non-zero: L1TEX-bound at
+//                           12 sector look-ups per non-zero, 14 ms), pass B builds 32 x 256 tiles of the
 //                           scaled sparse rows in shared memory (zero fill + scatter through per-cell cursors: indices are
 //                           sorted) and adds (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out.
 // All three require canonical cells (indices strictly increasing, what csc_check_kernel verifies); otherwise the caller
@@ -155,7 +157,7 @@ constexpr int CSA_WARPS = 4, CSA_MT = 4, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256; 
 template <int KT>
 __global__ void __launch_bounds__(CSA_WARPS * 32, 3)
 csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                  const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Bmat, const double* __restrict__ Afrag,
+                  const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Bpad, const double* __restrict__ Afrag,
                   const double* __restrict__ w0, int k, int nblk, double* __restrict__ out, int64_t ldo, int vec_out) {
     extern __shared__ __align__(16) uint8_t csa_smem[];
     double* tile = reinterpret_cast<double*>(csa_smem);                       // [32][CSA_SLAB + 2] (padded: conflict-free fragment reads)
@@ -178,28 +180,42 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
             sc[tid] = ok ? inv[cell] : 0.0;
         }
         __syncthreads();
-        // ---- pass A: W[cell, a] = s * sum_nz x B[idx, a] - w0[a]; warp w owns cells 8w .. 8w+7, lanes run over a
+        // ---- pass A: W[cell, a] = s * sum_nz x B[idx, a] - w0[a].  Warp w owns cells 8w .. 8w+7.  A QUAD of lanes shares one
+        // non-zero (8 non-zeros per warp step): lane `sub` of the quad loads the 16-byte pieces sub, sub + 4, ... of the
+        // zero-padded B row, so one warp-wide load touches 2 sectors per row (the minimum: 6 sector look-ups per non-zero; the
+        // kernel is L1TEX-bound, ncu profiles/r01) and accumulates 2 KT private partial sums; three xor-shuffles over the 8 quads
+        // finish the column totals.
+        constexpr int KP = KT * 8;
+        const int sub = lane & 3, grp = lane >> 2;
         for (int r = 0; r < 8; r++) {
             const int c = warp * 8 + r;
             const int64_t p0 = cur[c], p1 = endp[c];
-            double acc = 0.0, acc1 = 0.0;
-            for (int64_t pb = p0; pb < p1; pb += 32) {
-                const int64_t p = pb + lane;
-                const int32_t gi = p < p1 ? idx[p] : 0;
-                const double gv = p < p1 ? val[p] : 0.0;
-                const int cnt = (int)min((int64_t)32, p1 - pb);
-#pragma unroll 4
-                for (int q = 0; q < cnt; q++) {  // shuffles are executed by the whole warp; only the first k lanes accumulate
-                    const int32_t g = __shfl_sync(0xffffffffu, gi, q);
-                    const double v = __shfl_sync(0xffffffffu, gv, q);
-                    if (lane < k) {
-                        const double b = __ldg(Bmat + (int64_t)g * k + lane);
-                        if (q & 1) acc1 = fma(v, b, acc1); else acc = fma(v, b, acc);
-                    }
+            double v[2 * KT];
+#pragma unroll
+            for (int i = 0; i < 2 * KT; i++) v[i] = 0.0;
+#pragma unroll 2
+            for (int64_t p = p0 + grp; p < p1; p += 8) {
+                const double x = val[p];
+                const double2* brow = reinterpret_cast<const double2*>(Bpad + (int64_t)idx[p] * KP) + sub;
+                double2 b[KT];
+#pragma unroll
+                for (int i = 0; i < KT; i++) b[i] = __ldg(brow + 4 * i);
+#pragma unroll
+                for (int i = 0; i < KT; i++) { v[2 * i] = fma(x, b[i].x, v[2 * i]); v[2 * i + 1] = fma(x, b[i].y, v[2 * i + 1]); }
+            }
+#pragma unroll
+            for (int off = 4; off <= 16; off <<= 1)
+#pragma unroll
+                for (int i = 0; i < 2 * KT; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+            if (grp == 0) {
+                const double s = sc[c];
+#pragma unroll
+                for (int i = 0; i < KT; i++) {
+                    const int col = 2 * (sub + 4 * i);
+                    Wsm[c * KP + col] = col < k ? v[2 * i] * s - w0[col] : 0.0;
+                    Wsm[c * KP + col + 1] = col + 1 < k ? v[2 * i + 1] * s - w0[col + 1] : 0.0;
                 }
             }
-            acc += acc1;
-            if (lane < KT * 8) Wsm[c * (KT * 8) + lane] = lane < k ? acc * sc[c] - w0[lane] : 0.0;
         }
         __syncthreads();
         double w[CSA_MT][KT][2];
@@ -279,7 +295,7 @@ inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_
     int64_t grid = (int64_t)ctx->num_sms * 3;
     if (grid > ntiles) grid = ntiles;
     const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
-    csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, c->Bmat, c->Afrag, c->w0,
+    csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, c->Bpad, c->Afrag, c->w0,
                                                                                 c->k, c->nblk, d_out, ldo, vec_out);
     SCM_LAUNCH_CHECK(ctx);
     return 0;

@@ -175,7 +175,7 @@ def _adjust_to_host(ctx: Context, dY: DeviceMatrix, fullalpha, k: int, ctl_mask,
 
 
 def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: int, k_pseudoBulk, cosine, BSPARAM, which, seed,
-                     replicate_of, pb, return_bulk, out: DeviceMatrix | None, host_out, check_finite=True):
+                     replicate_of, pb, return_bulk, out: DeviceMatrix | None, host_out, check_finite=True, to_host=False):
     """scMerge2 core on the sparse rows themselves (scm_csc_rownorm / scm_csc_seg_colmean / scm_csc_adjust[_to_host])."""
     lib = L.lib()
     m, n = dcsc.m, dcsc.n
@@ -216,6 +216,9 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
                                            dout.ptr, dout.ld))
                 ctx.sync()
                 newY = dout
+                if to_host:  # host input without a caller-supplied buffer: hand back numpy like every other host path
+                    newY = dout.to_host()
+                    dout.free()
     finally:
         for a in (d_inv, d_keys, d_cnt):
             a.free()
@@ -252,7 +255,7 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
                 # the dense normalised matrix is never an input: norms, pseudobulks and the rank-k update read the sparse rows
                 return _scmerge2_sparse(ctx, dcsc, batch, clust, ctl, int(ruvK), k_pseudoBulk, cosine, BSPARAM, which, seed,
                                         replicate_of, pb, return_bulk, out if not host_in else None, host_out,
-                                        check_finite=host_in)
+                                        check_finite=host_in, to_host=host_in)
             dY = dcsc.to_dense(cosine=cosine, out=out if not host_in else None, check_finite=host_in)
         finally:
             if dcsc is not exprs:
