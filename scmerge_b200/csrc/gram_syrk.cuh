@@ -198,26 +198,34 @@ gram_syrk_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld,
 }
 
 // gram[i][j] = sum_s partial[s][tile(i,j)][..] for j-tile <= i-tile, mirrored for the upper triangle.
-// One CTA per lower tile; writes both (ti,tj) and its transpose.
+// One CTA per lower tile; writes both (ti,tj) and its transpose.  tri != 0: the partials of DIAGONAL tiles hold only the
+// 8x8 blocks on or below the diagonal (lean TMA kernel); the blocks above are filled by mirroring.
 __global__ void __launch_bounds__(256)
-gram_reduce_kernel(const double* __restrict__ partial, int T, int S, int64_t n, double* __restrict__ gram, int accumulate) {
+gram_reduce_kernel(const double* __restrict__ partial, int T, int S, int64_t n, double* __restrict__ gram, int accumulate, int tri) {
     __shared__ double tile[32][33];
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const int bi = (blockIdx.y >> 2) * 32, bj = (blockIdx.y & 3) * 32;  // 32x32 sub-block of the tile
+    const bool dtile = tri && ti == tj;
+    if (dtile && bi < bj) return;  // entirely above the diagonal: written as the mirror image of sub-block (bj, bi)
     for (int r = ty; r < 32; r += 8) {
         const int i = bi + r, j = bj + tx;
+        const bool valid = !dtile || (i >> 3) >= (j >> 3);
         const int64_t gi = (int64_t)ti * GR_BT + i, gj = (int64_t)tj * GR_BT + j;
-        double acc = (accumulate && gi < n && gj < n) ? gram[gi * n + gj] : 0.0;  // chunked fits add into the running Gram
-        for (int s = 0; s < S; s++) acc += partial[((int64_t)s * T + blockIdx.x) * (GR_BT * GR_BT) + i * GR_BT + j];
+        double acc = 0.0;
+        if (valid) {
+            if (accumulate && gi < n && gj < n) acc = gram[gi * n + gj];  // chunked fits add into the running Gram
+            for (int s = 0; s < S; s++) acc += partial[((int64_t)s * T + blockIdx.x) * (GR_BT * GR_BT) + i * GR_BT + j];
+            if (gi < n && gj < n) gram[gi * n + gj] = acc;
+        }
         tile[r][tx] = acc;
-        if (gi < n && gj < n) gram[gi * n + gj] = acc;
     }
     __syncthreads();
-    if (ti != tj) {
+    if (ti != tj || dtile) {
         for (int r = ty; r < 32; r += 8) {
             const int j = bj + r, i = bi + tx;  // transposed write: row = gene j, col = gene i
+            if (dtile && (i >> 3) <= (j >> 3)) continue;  // only the strictly-lower blocks are mirrored
             const int64_t gi = (int64_t)ti * GR_BT + i, gj = (int64_t)tj * GR_BT + j;
             if (gi < n && gj < n) gram[gj * n + gi] = tile[tx][r];
         }
@@ -282,7 +290,8 @@ inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t l
         gram_syrk_kernel<1><<<p.grid, GR_THREADS, GR_SMEM_BYTES, st>>>(d_Y, m, n, ld, d_shift, p.T, p.S, p.rows_per_split, partial);
     if (timed) { cudaEventRecord(ctx->ev1[ST_SYRK], st); ctx->ev_used[ST_SYRK] = true; }
     SCM_LAUNCH_CHECK(ctx);
-    gram_reduce_kernel<<<dim3(p.T, 16), 256, 0, st>>>(partial, p.T, p.S, n, d_gram, accumulate ? 1 : 0);
+    gram_reduce_kernel<<<dim3(p.T, 16), 256, 0, st>>>(partial, p.T, p.S, n, d_gram, accumulate ? 1 : 0,
+                                                      (tma_rc == 0 && (ctx->gram_lean & 2)) ? 1 : 0);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -93,13 +93,74 @@ __device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const
     }
 }
 
+// Fragment of gene strip `t` (8 genes: rows t*8 .. t*8+7 of the tile) for k-step parity p / cell half `half`.
+__device__ __forceinline__ double gram_frag(const uint8_t* __restrict__ tile, int t, int half, const int (&off)[2][2], int p) {
+    return *reinterpret_cast<const double*>(tile + (t >> 1) * GT_SLAB_BYTES + half + off[p][t & 1]);
+}
+
+// THIN unit (last tile row when n is not a multiple of 128): only the first `na` 8-gene strips of the A side hold genes
+// (na <= GT_THIN_NA), the rest is padding.  The 8 warps split the B side instead (2 strips each): na x 2 DMMA per k-step
+// and warp instead of 8 x 4, i.e. the unit costs na/16 of a full one.
+constexpr int GT_THIN_NA = 10;
+template <bool TAIL>
+__device__ __forceinline__ void gram_chunk_thin(const uint8_t* __restrict__ sa, const uint8_t* __restrict__ sb, const int (&off)[2][2],
+                                                int warp, int tig, int na, const double (&sA)[GT_THIN_NA], const double (&sB)[2],
+                                                int rows_valid, double (&acc)[GT_THIN_NA][2][2]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        const int p = ks & 1;
+        const int half = (ks >> 1) * 1024;
+        const double msk = (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
+        double af[GT_THIN_NA], bf[2];
+#pragma unroll
+        for (int a = 0; a < GT_THIN_NA; a++) af[a] = gram_frag(sa, a, half, off, p) - msk * sA[a];  // strips >= na are zero padding
+#pragma unroll
+        for (int b = 0; b < 2; b++) bf[b] = gram_frag(sb, 2 * warp + b, half, off, p) - msk * sB[b];
+#pragma unroll
+        for (int a = 0; a < GT_THIN_NA; a++)
+            if (a < na) {
+#pragma unroll
+                for (int b = 0; b < 2; b++) dmma884_ordered(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+    }
+}
+
+// DIAG unit (ti == tj): only the lower triangle is needed.  In 8-gene strips the triangle has 16 * 17 / 2 = 136 strip pairs
+// instead of 256; warp w takes the row strips w and 15 - w ((w + 1) + (16 - w) = 17 pairs each, perfectly balanced), so a
+// diagonal unit costs 17/32 of a full one.  `nvs` = number of strips that hold genes (16, less in the corner tile).
+template <bool TAIL>
+__device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, const int (&off)[2][2], int t0, int t1, int nvs, int tig,
+                                                double s0, double s1, const double (&sS)[16], int rows_valid, double (&acc0)[16][2],
+                                                double (&acc1)[16][2]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        const int p = ks & 1;
+        const int half = (ks >> 1) * 1024;
+        const double msk = (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
+        const double a0 = gram_frag(sa, t0, half, off, p) - msk * s0;
+        const double a1 = gram_frag(sa, t1, half, off, p) - msk * s1;
+        const bool v0 = t0 < nvs, v1 = t1 < nvs;
+#pragma unroll
+        for (int jb = 0; jb < 16; jb += 8) {  // two batches of 8 strips: all loads of a batch are issued before its DMMAs
+            double f[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = gram_frag(sa, jb + j, half, off, p) - msk * sS[jb + j];  // always in bounds (padding strips are zero)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (v0 && jb + j <= t0) dmma884_ordered(acc0[jb + j][0], acc0[jb + j][1], a0, f[j]);
+                if (v1 && jb + j <= t1) dmma884_ordered(acc1[jb + j][0], acc1[jb + j][1], a1, f[j]);
+            }
+        }
+    }
+}
+
 // 3 warpgroups: 8 consumer warps (setmaxnreg.inc -> 232 registers) + one producer warpgroup (setmaxnreg.dec -> 40;
 // only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
 constexpr int GT_THREADS = 384;
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, const double* __restrict__ shift, int T, int S,
-                int64_t rows_per_split, double* __restrict__ partial) {
+                int64_t rows_per_split, double* __restrict__ partial, int ntile, int na_last, int lean) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_BYTES);
@@ -165,11 +226,67 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
         const int64_t row_end = min(m, row_begin + rows_per_split);
         const int nchunk = row_end > row_begin ? (int)ceil_div(row_end - row_begin, GT_KC) : 0;
         const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
+        double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
+        const bool last_row = ti == ntile - 1;
+        auto shift_at = [&](int64_t g) -> double { return (shift && g < n) ? shift[g] : 0.0; };
+        if ((lean & 2) && diag) {
+            // ---- lower triangle only (see gram_chunk_diag)
+            const int t0 = warp, t1 = 15 - warp, nvs = last_row ? na_last : 16;
+            double sS[16], acc0[16][2], acc1[16][2];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { sS[j] = shift_at(colA0 + j * 8 + gid); acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0; }
+            const double s0 = shift_at(colA0 + t0 * 8 + gid), s1 = shift_at(colA0 + t1 * 8 + gid);
+            for (int c = 0; c < nchunk; c++) {
+                const int slot = gu % GT_STAGES;
+                mbar_wait(&full[slot], (gu / GT_STAGES) & 1);
+                const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
+                const int64_t r0 = row_begin + (int64_t)c * GT_KC;
+                if (r0 + GT_KC <= row_end) gram_chunk_diag<false>(sa, off, t0, t1, nvs, tig, s0, s1, sS, GT_KC, acc0, acc1);
+                else gram_chunk_diag<true>(sa, off, t0, t1, nvs, tig, s0, s1, sS, (int)(row_end - r0), acc0, acc1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                gu++;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j <= t0) *reinterpret_cast<double2*>(out + (t0 * 8 + gid) * GR_BT + j * 8 + 2 * tig) = make_double2(acc0[j][0], acc0[j][1]);
+                if (j <= t1) *reinterpret_cast<double2*>(out + (t1 * 8 + gid) * GR_BT + j * 8 + 2 * tig) = make_double2(acc1[j][0], acc1[j][1]);
+            }
+            continue;
+        }
+        if ((lean & 1) && !diag && last_row && na_last <= GT_THIN_NA) {
+            // ---- padded last tile row: na_last strips x 2 strips per warp (see gram_chunk_thin)
+            double sA[GT_THIN_NA], sB[2], acc[GT_THIN_NA][2][2];
+#pragma unroll
+            for (int a = 0; a < GT_THIN_NA; a++) { sA[a] = shift_at(colA0 + a * 8 + gid); acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.0; }
+#pragma unroll
+            for (int b = 0; b < 2; b++) sB[b] = shift_at(colB0 + (2 * warp + b) * 8 + gid);
+            for (int c = 0; c < nchunk; c++) {
+                const int slot = gu % GT_STAGES;
+                mbar_wait(&full[slot], (gu / GT_STAGES) & 1);
+                const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
+                const uint8_t* sb = sa + GT_TILE_BYTES;
+                const int64_t r0 = row_begin + (int64_t)c * GT_KC;
+                if (r0 + GT_KC <= row_end) gram_chunk_thin<false>(sa, sb, off, warp, tig, na_last, sA, sB, GT_KC, acc);
+                else gram_chunk_thin<true>(sa, sb, off, warp, tig, na_last, sA, sB, (int)(row_end - r0), acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                gu++;
+            }
+#pragma unroll
+            for (int a = 0; a < GT_THIN_NA; a++)
+                if (a < na_last) {
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+                        *reinterpret_cast<double2*>(out + (a * 8 + gid) * GR_BT + (2 * warp + b) * 8 + 2 * tig) = make_double2(acc[a][b][0], acc[a][b][1]);
+                }
+            continue;
+        }
         double sA[8], sB[4];
 #pragma unroll
-        for (int a = 0; a < 8; a++) { const int64_t g = colA0 + wm * 64 + a * 8 + gid; sA[a] = (shift && g < n) ? shift[g] : 0.0; }
+        for (int a = 0; a < 8; a++) sA[a] = shift_at(colA0 + wm * 64 + a * 8 + gid);
 #pragma unroll
-        for (int b = 0; b < 4; b++) { const int64_t g = colB0 + wn * 32 + b * 8 + gid; sB[b] = (shift && g < n) ? shift[g] : 0.0; }
+        for (int b = 0; b < 4; b++) sB[b] = shift_at(colB0 + wn * 32 + b * 8 + gid);
         double acc[8][4][2];
 #pragma unroll
         for (int a = 0; a < 8; a++)
@@ -188,7 +305,6 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
             if (lane == 0) mbar_arrive(&empty[slot]);
             gu++;
         }
-        double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
@@ -235,7 +351,9 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
         SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
         attr_set = true;
     }
-    gram_tma_kernel<<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial);
+    const int valid_last = (int)(n - (int64_t)(p.ntile - 1) * GR_BT);
+    gram_tma_kernel<<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial, p.ntile,
+                                                                        (valid_last + 7) / 8, ctx->gram_lean);
     return 0;
 }
 

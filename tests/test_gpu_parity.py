@@ -71,8 +71,11 @@ def test_seg_colsum_nonfinite_flag(sm, ctx):
 
 
 @pytest.mark.parametrize("m,n,shift", [(1000, 128, False), (777, 300, True), (5000, 257, True), (40, 513, False),
-                                       (70000, 260, True)])
+                                       (70000, 260, True), (3000, 2000, True), (1500, 3000, True), (900, 240, True),
+                                       (500, 64, False), (333, 1000, True), (2000, 56, True), (129, 208, True)])
 def test_gram(sm, ctx, m, n, shift):
+    """K3 against NumPy for every unit type of the TMA kernel: full tiles, the triangular diagonal units, the thin last tile
+    row (n mod 128 <= 80: 300, 257, 513, 260, 2000, 3000, 208) and a padded last row that stays full (240, 1000)."""
     from scmerge_b200 import _lib as L
     rng = np.random.default_rng(m * 7 + n)
     Y = rng.normal(size=(m, n)) + 2.0

@@ -6,7 +6,7 @@ import scmerge_b200 as sm
 from scmerge_b200 import ruv
 import bench
 class A: pass
-a = A(); a.cells=int(sys.argv[1]) if len(sys.argv)>1 else 1_000_000; a.genes=2000; a.ctl=500; a.k=20; a.types=20; a.batches=4
+a = A(); a.cells=int(sys.argv[1]) if len(sys.argv)>1 else 1_000_000; a.genes=2000; a.ctl=500; a.k=20; a.types=20; a.batches=4; a.workload="fastruviii"
 torch.cuda.set_device(0)
 ctx = sm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
 dY, keys, ctl = bench.make_data(a, ctx, 0, torch)
