@@ -57,10 +57,13 @@ def replicate_matrix(a) -> np.ndarray:
     return M
 
 
-def replicate_keys(M):
+def replicate_keys(M, spare: int | None = None):
     """Replicate structure -> (int32 group id per cell, number of groups).  A numeric matrix must be a one-hot
     partition (every row exactly one 1): the device path implements the residual operator as a segmented
-    mean, which is what my_residop (R/fastRUVIII.R:121-129) computes for such M; a general M is rejected."""
+    mean, which is what my_residop (R/fastRUVIII.R:121-129) computes for such M; a general M is rejected.
+    `spare`: for non-negative integer labels with m - (max + 1) >= spare the O(m) histogram that drops unused label
+    values (R's factor levels) is skipped and G = max + 1 is returned: unused ids are empty groups, which change nothing
+    in the arithmetic, and with that much slack the svd_k rule min(m - G, n_ctl, cap) does not depend on G either."""
     if isinstance(M, DeviceArray):
         raise TypeError("pass replicate keys as a host array")
     a = np.asarray(M)
@@ -78,6 +81,8 @@ def replicate_keys(M):
         raise ValueError("M must be a replicate matrix or a label vector")
     if np.issubdtype(a.dtype, np.integer) and a.shape[0] > 0:
         lo, hi = int(a.min()), int(a.max())
+        if spare is not None and lo >= 0 and a.shape[0] - (hi + 1) >= spare:
+            return a.astype(np.int32, copy=False), hi + 1
         if lo >= 0 and hi < 4 * a.shape[0] + 1024:  # O(m) path for integer labels (sorted level order = numeric order)
             present = np.bincount(a, minlength=hi + 1) > 0
             if present.all():
@@ -333,7 +338,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if k is None:
         raise TypeError("k must be given (the reference fails on k = NULL, R/fastRUVIII.R:78)")
     m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
-    keys, G = replicate_keys(M)
+    keys, G = replicate_keys(M, spare=n)
     if keys.shape[0] != m:
         raise ValueError("M must have one row per row of Y")
     ctl = tological(ctl, n)

@@ -68,6 +68,13 @@ def test_replicate_keys_and_matrix():
     assert G3 == 2 and keys3.tolist() == [0, 1, 0]
     keys4, G4 = replicate_keys(np.array([3, 3, 7, 5], dtype=np.int64))  # integer labels
     assert G4 == 3 and keys4.tolist() == [0, 0, 2, 1]
+    # `spare`: with enough slack the histogram that drops unused label values is skipped (empty groups are harmless) ...
+    lab = np.array([0, 2, 2, 5] * 50, dtype=np.int32)
+    k5, G5 = replicate_keys(lab, spare=100)
+    assert G5 == 6 and k5 is lab
+    # ... but not when m - G could enter the svd_k rule: then the levels are compacted like R's factor()
+    k6, G6 = replicate_keys(lab, spare=198)
+    assert G6 == 3 and k6.tolist()[:4] == [0, 1, 1, 2]
     with pytest.raises(ValueError, match="one-hot"):
         replicate_keys(np.array([[1.0, 1.0], [0.0, 1.0]]))
     with pytest.raises(ValueError, match="one-hot"):
