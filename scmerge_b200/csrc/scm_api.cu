@@ -184,6 +184,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_LEAN")) c->gram_lean = atoi(e) & 3;
+    if (const char* e = getenv("SCM_GRAM_ORDER")) c->gram_order = atoi(e) & 1;
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < ST_COUNT; i++) {

@@ -27,6 +27,7 @@ class Context:
         self.device = int(device)
         self.stream = stream
         self._cb = None  # keep the ctypes callback alive
+        self.world, self.rank, self._ar_fn = 1, None, None
         self._fin = weakref.finalize(self, L.lib().scm_ctx_destroy, self._h)
 
     @property
@@ -47,8 +48,11 @@ class Context:
         names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel", "ingest"]
         return dict(zip(names, list(ms)))
 
-    def set_allreduce(self, fn, world_size: int):
-        """fn(dev_ptr:int, count:int, dtype:int(0 f64, 1 i64), stream:int) -> None; sums in place across ranks."""
+    def set_allreduce(self, fn, world_size: int, rank: int | None = None):
+        """fn(dev_ptr:int, count:int, dtype:int(0 f64, 1 i64), stream:int) -> None; sums in place across ranks.
+        `rank` (this process's index among the `world_size` ranks sharing the cells) is only needed by the host-side
+        gathers of the ruvK selection (scRUVIII with several k)."""
+        self.world, self.rank, self._ar_fn = int(world_size), rank, fn
         def _cb(ptr, count, dtype, stream, _user):
             try:
                 fn(ptr, count, dtype, stream)
@@ -60,6 +64,16 @@ class Context:
                 return 1
         self._cb = L.ALLREDUCE_FN(_cb)
         L.check(L.lib().scm_ctx_set_allreduce(self._h, self._cb, None, int(world_size)))
+
+    def allreduce(self, arr: "DeviceArray"):
+        """Sum a float64 / int64 device array in place over the ranks (no-op for a single rank)."""
+        if self.world <= 1 or self._ar_fn is None:
+            return
+        if arr.dtype not in (np.dtype(np.float64), np.dtype(np.int64)):
+            raise TypeError("all-reduce supports float64 and int64")
+        self.sync()
+        self._ar_fn(arr.address, int(np.prod(arr.shape, dtype=np.int64)), 0 if arr.dtype == np.dtype(np.float64) else 1, 0)
+        self.sync()
 
     # ---- memory -------------------------------------------------------------------------------
     def empty(self, shape, dtype=np.float64) -> "DeviceArray":

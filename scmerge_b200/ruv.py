@@ -255,27 +255,69 @@ def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: 
 def _silhouette_pair(ctx: Context, fit: RUVFit, dY: DeviceMatrix, coef: _Coef | None, ct_keys: np.ndarray, n_ct: int,
                      b_keys: np.ndarray, n_b: int, rank: int = 10):
     """calculateSil (R/scRUVIII.R:182-190) for one candidate k: PC scores of the adjusted matrix (scm_pca_scores, no newY
-    is materialised) and the average silhouette widths of the cell types and of the batches (scm_silhouette)."""
+    is materialised) and the average silhouette widths of the cell types and of the batches (scm_silhouette).
+    Multi-rank: every rank computes the scores of its cells, scores and labels are gathered with the sum all-reduce
+    (disjoint slices of a zero buffer), each rank takes a slice of the cells for the O(m^2) distance pass and the
+    width sums are all-reduced: every rank returns the same pair."""
+    from .dist import shard_rows
     lib = L.lib()
     m, n = dY.m, dY.n
-    r = int(min(rank, n, m - 1))
+    world = ctx.world
+    off, m_total = 0, m
+    if world > 1:
+        if ctx.rank is None:
+            raise ValueError("the ruvK selection on several ranks needs Context.set_allreduce(fn, world_size, rank)")
+        cnt = np.zeros(world, dtype=np.int64)
+        cnt[ctx.rank] = m
+        d_cnt = ctx.to_device(cnt)
+        ctx.allreduce(d_cnt)
+        cnt = d_cnt.to_host()
+        d_cnt.free()
+        off, m_total = int(cnt[:ctx.rank].sum()), int(cnt.sum())
+    r = int(min(rank, n, m_total - 1))
     d_scores = ctx.empty((m, r))
-    d_ct, d_b = ctx.to_device(np.ascontiguousarray(ct_keys, dtype=np.int32)), ctx.to_device(np.ascontiguousarray(b_keys, dtype=np.int32))
     iters, resid = C.c_int32(0), C.c_double(0.0)
     sa, sb = C.c_double(0.0), C.c_double(0.0)
+    bufs = [d_scores]
     try:
-        rc = lib.scm_pca_scores(ctx.handle, fit.d_gram.ptr, n, m, coef.handle if coef is not None else None, fit.d_colmean.ptr, r,
+        rc = lib.scm_pca_scores(ctx.handle, fit.d_gram.ptr, n, m_total, coef.handle if coef is not None else None, fit.d_colmean.ptr, r,
                                 dY.ptr, m, dY.ld, d_scores.ptr, None, 1e-9, 500, C.byref(iters), C.byref(resid))
         if rc == L.ERR_NOCONV:
             warnings.warn("PCA for the ruvK selection: " + lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
         else:
             L.check(rc)
-        L.check(lib.scm_silhouette(ctx.handle, d_scores.ptr, m, r, r, d_ct.ptr, int(n_ct), d_b.ptr, int(n_b), 0, m,
+        ct32, b32 = np.ascontiguousarray(ct_keys, dtype=np.int32), np.ascontiguousarray(b_keys, dtype=np.int32)
+        if world > 1:
+            d_all = ctx.to_device(np.zeros((m_total, r)))
+            bufs.append(d_all)
+            if m:
+                L.check(lib.scm_copy2d(ctx.handle, C.c_void_p(d_all.address + off * r * 8), r * 8, d_scores.ptr, r * 8, r * 8, m, 2))
+            ctx.allreduce(d_all)
+            lab = np.zeros((2, m_total), dtype=np.int64)
+            lab[0, off:off + m], lab[1, off:off + m] = ct32, b32
+            d_lab = ctx.to_device(lab)
+            ctx.allreduce(d_lab)
+            lab = d_lab.to_host()
+            d_lab.free()
+            ct32, b32 = lab[0].astype(np.int32), lab[1].astype(np.int32)
+            i0, i1 = shard_rows(m_total, world, ctx.rank)
+            d_x = d_all
+        else:
+            i0, i1, d_x = 0, m, d_scores
+        d_ct, d_b = ctx.to_device(ct32), ctx.to_device(b32)
+        bufs += [d_ct, d_b]
+        L.check(lib.scm_silhouette(ctx.handle, d_x.ptr, m_total, r, r, d_ct.ptr, int(n_ct), d_b.ptr, int(n_b), i0, i1,
                                    C.byref(sa), C.byref(sb)))
+        sums = np.array([sa.value, sb.value])
+        if world > 1:
+            d_s = ctx.to_device(sums)
+            ctx.allreduce(d_s)
+            sums = d_s.to_host()
+            d_s.free()
     finally:
-        for a in (d_scores, d_ct, d_b):
+        for a in bufs:
             a.free()
-    return sa.value / m, sb.value / m
+    return sums[0] / m_total, sums[1] / m_total
 
 
 def _is_host_matrix(Y) -> bool:

@@ -9,6 +9,9 @@
                          M = one-hot(cellTypes), the deterministic stand-in for scReplicate).
   golden_sim.npz       : oracle outputs on a seeded ruvSimulate-distribution matrix (fastRUVIII exact,
                          the shape of tests/testthat/test-fastRUVIII.R:3-6) and a pseudoRUVIII case.
+  golden_select.npz    : oracle outputs on the bundled fixture for the rows added later: scRUVIII with several ruvK
+                         (silhouette coefficients, F-scores, chosen k; R/scRUVIII.R:80-114) and scRUVg (R/scRUVg.R:30-85).
+                         `python tests/golden/make_golden.py select` writes only this file.
 
 Usage: python tests/golden/make_golden.py
 """
@@ -27,7 +30,23 @@ from oracle import ruv_oracle as orc  # noqa: E402
 REF = "/root/reference/data"
 
 
+def make_select():
+    d = np.load(os.path.join(HERE, "example_sce.npz"))
+    lc, ct, batch, ctl = d["logcounts"], d["cellTypes"], d["batch"], d["ctl"]
+    ks = [5, 10, 20]
+    res = orc.scRUVIII(lc, ct, ctl, ks, batch, cell_type=ct)
+    g = orc.scRUVg(lc.T, ctl, 10)
+    np.savez_compressed(os.path.join(HERE, "golden_select.npz"), ks=np.array(ks), sil=res["sil"], f_score=res["f_score"],
+                        optimal=res["optimal_ruvK"], newY5_colsum=res[5]["newY"].sum(axis=0), newY5_fro=np.linalg.norm(res[5]["newY"]),
+                        ruvg_newY_rows=g["newY"][:16], ruvg_newY_fro=np.linalg.norm(g["newY"]), ruvg_absW_colsum=np.abs(g["W"]).sum(axis=0),
+                        ruvg_alpha_rownorm=np.linalg.norm(g["alpha"], axis=1))
+    print("golden_select.npz", os.path.getsize(os.path.join(HERE, "golden_select.npz")) // 1024, "KiB", "sil", res["sil"],
+          "f", res["f_score"], "optimal", res["optimal_ruvK"])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "select":
+        return make_select()
     sce = read_rda(os.path.join(REF, "example_sce.rda"))["example_sce"].attrs()
     assays = sce["assays"].attrs()[".xData"].value[".->data"].attrs()["listData"]
     names = assays.attrs()["names"].value
@@ -78,6 +97,7 @@ def main():
                         ps_newY_fro=np.linalg.norm(pr["newY"]), ps_fullalpha=pr["fullalpha"])
     for f in ("example_sce.npz", "golden_example.npz", "golden_sim.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+    make_select()
 
 
 if __name__ == "__main__":

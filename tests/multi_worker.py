@@ -20,7 +20,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = sm.Context(local, stream=torch.cuda.current_stream().cuda_stream)
-    ctx.set_allreduce(torch_allreduce_hook(local), world)
+    ctx.set_allreduce(torch_allreduce_hook(local), world, rank)
     P = orc.planted_factors(9000, 384, 128, 10, n_types=6, n_batch=3, seed=31)
     lo, hi = shard_rows(9000, world, rank)
     ok = True
@@ -34,13 +34,23 @@ def main():
     res = sm.scRUVIII(P["Y"][lo:hi].T, P["types"][lo:hi], P["ctl"], k=10, batch=batch[lo:hi], ctx=ctx)
     ref2 = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 10, batch)
     e2 = orc.rel_frobenius(res[10]["newY"], ref2[10]["newY"][lo:hi])
+    # ruvK selection across ranks (scores and labels gathered, distance pass split over the ranks) and scRUVg
+    sel = sm.scRUVIII(P["Y"][lo:hi].T, P["types"][lo:hi], P["ctl"], k=[4, 10], batch=batch[lo:hi], cell_type=P["types"][lo:hi], ctx=ctx)
+    rsel = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], [4, 10], batch, cell_type=P["types"])
+    e3 = float(np.abs(sel["sil"] - rsel["sil"]).max())
+    same_k = sel["optimal_ruvK"] == rsel["optimal_ruvK"]
+    e4 = orc.rel_frobenius(sel[4]["newY"], rsel[4]["newY"][lo:hi])
+    rg = sm.scRUVg(P["Y"][lo:hi], P["ctl"], 8, ctx=ctx)
+    refg = orc.scRUVg(P["Y"], P["ctl"], 8)
+    e5 = orc.rel_frobenius(rg["newY"], refg["newY"][lo:hi])
     # every rank must hold bit-identical fullalpha (no broadcast in the design)
     fa = torch.from_numpy(out["fullalpha"].copy()).cuda()
     lst = [torch.empty_like(fa) for _ in range(world)]
     dist.all_gather(lst, fa)
     same = all(torch.equal(lst[0], t) for t in lst)
-    ok = e1 < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same
-    print(f"rank {rank}/{world}: rows [{lo},{hi}) fast err {e1:.2e} angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same}", flush=True)
+    ok = e1 < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8
+    print(f"rank {rank}/{world}: rows [{lo},{hi}) fast err {e1:.2e} angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same} "
+          f"selection sil err {e3:.2e} same_k {same_k} newY err {e4:.2e} scRUVg err {e5:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

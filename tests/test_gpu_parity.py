@@ -677,3 +677,43 @@ def test_scruvg_vs_oracle(sm, m, n, nc, k):
     dY = sm.DeviceMatrix.from_host(sm.default_context(), L["Y"])
     res = sm.scRUVg(dY, L["ctl"], k)
     assert isinstance(res["newY"], sm.DeviceMatrix) and orc.rel_frobenius(res["newY"].to_host(), ref["newY"]) < TOL_NEWY
+
+
+def test_golden_select_and_ruvg_on_example_sce(sm, golden_dir):
+    """BASELINE.json configs[0] (the reference's bundled example_sce) through scMerge(ruvK = c(5, 10, 20))'s arithmetic:
+    the device selection (PC scores from the centred Gram + exact silhouette) against the committed oracle fixture, and
+    scRUVg on the same data."""
+    d = np.load(os.path.join(golden_dir, "example_sce.npz"))
+    g = np.load(os.path.join(golden_dir, "golden_select.npz"))
+    ks = [int(k) for k in g["ks"]]
+    res = sm.scRUVIII(d["logcounts"], d["cellTypes"], d["ctl"], k=ks, batch=d["batch"], cell_type=d["cellTypes"])
+    assert np.allclose(res["sil"], g["sil"], rtol=0, atol=1e-7)
+    assert np.allclose(res["f_score"], g["f_score"], rtol=0, atol=1e-7)
+    assert res["optimal_ruvK"] == int(g["optimal"])
+    assert abs(np.linalg.norm(res[5]["newY"]) - float(g["newY5_fro"])) / float(g["newY5_fro"]) < 1e-9
+    assert np.allclose(res[5]["newY"].sum(axis=0), g["newY5_colsum"], rtol=1e-8, atol=1e-8)
+    r = sm.scRUVg(d["logcounts"].T, d["ctl"], 10)
+    assert orc.rel_frobenius(r["newY"][:16], g["ruvg_newY_rows"]) < TOL_NEWY
+    assert abs(np.linalg.norm(r["newY"]) - float(g["ruvg_newY_fro"])) / float(g["ruvg_newY_fro"]) < 1e-9
+    assert np.allclose(np.linalg.norm(r["alpha"], axis=1), g["ruvg_alpha_rownorm"], rtol=1e-7)
+
+
+def test_scmerge2_core_is_deterministic(sm):
+    """The reference pins scMerge2 on seed-determinism (tests/testthat/test-scMerge2.R:68-77,131-136): same seed, same
+    result.  Here the pseudobulk folds come from a seeded generator and every kernel is order-deterministic, so two runs are
+    bit-identical, on the dense and on the sparse path."""
+    import scipy.sparse as sp
+    from scmerge_b200.scmerge2 import scMerge2_core
+    rng = np.random.default_rng(7)
+    m, n = 3000, 200
+    batch, clust = rng.integers(0, 3, m), rng.integers(0, 4, m)
+    D = rng.gamma(2.0, 1.0, (m, n)) * (rng.random((m, n)) < 0.3) + rng.gamma(2.0, 1.0, (4, n))[clust] * (rng.random((4, n)) < 0.3)[clust]
+    D += (rng.gamma(2.0, 0.5, (3, 4, n)) * (rng.random((3, 4, n)) < 0.2))[batch, clust]
+    runs = [scMerge2_core(D, batch, clust, ruvK=6, k_pseudoBulk=6, seed=11, BSPARAM=sm.ExactParam()) for _ in range(2)]
+    assert np.array_equal(runs[0]["newY"], runs[1]["newY"]) and runs[0]["pseudobulk_names"] == runs[1]["pseudobulk_names"]
+    Xs = sp.csr_matrix(D)
+    sruns = [scMerge2_core(Xs, batch, clust, ruvK=6, k_pseudoBulk=6, seed=11, BSPARAM=sm.ExactParam()) for _ in range(2)]
+    assert np.array_equal(sruns[0]["newY"], sruns[1]["newY"])
+    assert orc.rel_frobenius(sruns[0]["newY"], runs[0]["newY"]) < 1e-9
+    other = scMerge2_core(D, batch, clust, ruvK=6, k_pseudoBulk=6, seed=12, BSPARAM=sm.ExactParam())
+    assert not np.array_equal(other["newY"], runs[0]["newY"])        # a different seed draws different folds

@@ -212,3 +212,15 @@ def test_silhouette_and_k_selection():
     # runPCA(center, scale) is invariant to the per-gene de-standardisation: same silhouettes on the final matrices
     for i, kk in enumerate((2, 6)):
         assert np.allclose(orc.calculate_sil(res[kk]["newY"], L["cellTypes"], L["batch"]), res["sil"][:, i], atol=1e-10)
+
+
+def test_golden_select(golden_dir):
+    """The oracle reproduces the committed fixture for the ruvK selection and scRUVg on the reference's bundled example_sce."""
+    d = np.load(os.path.join(golden_dir, "example_sce.npz"))
+    g = np.load(os.path.join(golden_dir, "golden_select.npz"))
+    res = orc.scRUVIII(d["logcounts"], d["cellTypes"], d["ctl"], [int(k) for k in g["ks"]], d["batch"], cell_type=d["cellTypes"])
+    assert np.allclose(res["sil"], g["sil"], atol=1e-9) and np.allclose(res["f_score"], g["f_score"], atol=1e-9)
+    assert res["optimal_ruvK"] == int(g["optimal"])
+    r = orc.scRUVg(d["logcounts"].T, d["ctl"], 10)
+    assert orc.rel_frobenius(r["newY"][:16], g["ruvg_newY_rows"]) < 1e-9
+    assert np.allclose(np.abs(r["W"]).sum(axis=0), g["ruvg_absW_colsum"], rtol=1e-8)
