@@ -10,6 +10,8 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)  # a rank stuck in a collective prints where, instead of hanging the test
     import torch
     import torch.distributed as dist
 
@@ -41,8 +43,11 @@ def main():
     same_k = sel["optimal_ruvK"] == rsel["optimal_ruvK"]
     e4 = orc.rel_frobenius(sel[4]["newY"], rsel[4]["newY"][lo:hi])
     rg = sm.scRUVg(P["Y"][lo:hi], P["ctl"], 8, ctx=ctx)
-    refg = orc.scRUVg(P["Y"], P["ctl"], 8)
-    e5 = orc.rel_frobenius(rg["newY"], refg["newY"][lo:hi])
+    # reference: the definition (first k left singular vectors of the centred control block, alpha = W'Y0) without the
+    # oracle's literal m x m cross product of the >= 5:1 branch (9000 x 9000 here; equality of the two is a CPU test)
+    Y0 = P["Y"] - P["Y"].mean(axis=0)
+    U = np.linalg.svd(Y0[:, orc.tological(P["ctl"], 384)], full_matrices=False)[0][:, :8]
+    e5 = orc.rel_frobenius(rg["newY"], (P["Y"] - U @ (U.T @ Y0))[lo:hi])
     # every rank must hold bit-identical fullalpha (no broadcast in the design)
     fa = torch.from_numpy(out["fullalpha"].copy()).cuda()
     lst = [torch.empty_like(fa) for _ in range(world)]
