@@ -717,3 +717,23 @@ def test_scmerge2_core_is_deterministic(sm):
     assert orc.rel_frobenius(sruns[0]["newY"], runs[0]["newY"]) < 1e-9
     other = scMerge2_core(D, batch, clust, ruvK=6, k_pseudoBulk=6, seed=12, BSPARAM=sm.ExactParam())
     assert not np.array_equal(other["newY"], runs[0]["newY"])        # a different seed draws different folds
+
+
+def test_scruviii_reference_test_shape(sm):
+    """The shape of the reference's own scRUVIII test (tests/testthat/test-scRUVIII.R:3-7): ruvSimulate(m = 200, n = 1000,
+    nc = 100, nCelltypes = 3, nBatch = 2, lambda = 0.1), Y = t(log2(Y + 1)), k = c(5, 10, 15, 20), M a one-hot matrix and no
+    cell_type (the replicate structure stands in, R/scRUVIII.R:89-92).  The reference only checks that it runs; here every
+    output is compared with the oracle."""
+    L_ = orc.ruv_simulate(m=200, n=1000, nc=100, n_celltypes=3, n_batch=2, lam=0.1, rng=np.random.default_rng(1234))
+    Y = np.log2(L_["Y"] + 1).T
+    keep = Y.var(axis=1) > 0                       # standardize2 has no zero-variance guard (R/scRUVIII.R:171)
+    Y, ctl = Y[keep], L_["ctl"][keep]
+    ks = [5, 10, 15, 20]
+    res = sm.scRUVIII(Y, L_["M"], ctl, k=ks, batch=L_["batch"])
+    ref = orc.scRUVIII(Y, L_["M"], ctl, ks, L_["batch"])
+    for kk in ks:
+        assert orc.rel_frobenius(res[kk]["newY"], ref[kk]["newY"]) < TOL_NEWY
+    assert np.allclose(res["sil"], ref["sil"], rtol=0, atol=1e-7)
+    assert np.allclose(res["f_score"], ref["f_score"], rtol=0, atol=1e-7)
+    assert res["optimal_ruvK"] == ref["optimal_ruvK"]
+    assert set(res.keys()) >= set(ks) | {"optimal_ruvK"}       # list named by k + $optimal_ruvK (R/scRUVIII.R:77,126-136)
