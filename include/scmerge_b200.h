@@ -56,6 +56,10 @@ int scm_version(void);
 int scm_ctx_create(int device, void* cuda_stream /* NULL = own stream */, scm_ctx** out);
 int scm_ctx_destroy(scm_ctx* ctx);
 int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size);
+/* Additional subspace dimensions the EXACT eigensolver has to converge in the following fits (besides `kconv`): scRUVIII with
+ * several ruvK (R/scRUVIII.R:64-75) re-uses ONE fullalpha for every k, so the top-k subspace must be accurate for each of
+ * them.  nk = 0 resets. */
+int scm_ctx_set_conv_ranks(scm_ctx* ctx, const int32_t* ks, int32_t nk);
 int scm_ctx_sync(scm_ctx* ctx);
 int scm_ctx_launch_count(scm_ctx* ctx, int64_t* n_launches); /* kernels launched by this library so far */
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "scm_ctx_create": [_int, _vp, _pp],
     "scm_ctx_destroy": [_vp],
     "scm_ctx_set_allreduce": [_vp, ALLREDUCE_FN, _vp, _int],
+    "scm_ctx_set_conv_ranks": [_vp, _vp, _i32],
     "scm_ctx_sync": [_vp],
     "scm_ctx_launch_count": [_vp, C.POINTER(_i64)],
     "scm_dev_alloc": [_vp, _i64, _pp],

@@ -60,9 +60,10 @@ struct scm_ctx {
     cudaEvent_t ev0[scm::ST_COUNT], ev1[scm::ST_COUNT];
     bool ev_used[scm::ST_COUNT];
     bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
-    int gram_order = 0;          // Gram TMA kernel: unit order (0 interleaved classes, 1 class-ordered; env SCM_GRAM_ORDER), see gram_tma.cuh
     int gram_lean = 3;           // Gram TMA kernel: bit 0 thin last tile row, bit 1 triangular diagonal units (env SCM_GRAM_LEAN)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
+    int conv_ranks[16];          // additional subspace dimensions the EXACT eigensolver must converge (scm_ctx_set_conv_ranks)
+    int n_conv_ranks = 0;
 };
 
 namespace scm {

@@ -329,16 +329,25 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
             // Davis-Kahan estimate of the angle between span(V[:, :kconv]) and the true invariant subspace:
             // ||R_k||_F / (theta_k - theta_{k+1}); a residual at rounding level also counts as converged.
             const double* th = h + l;
-            double r2 = 0.0, rmax = 0.0;
-            for (int i = 0; i < kconv; i++) { r2 += h[i] * h[i]; rmax = rmax > h[i] ? rmax : h[i]; }
             const double top = th[0] > 0 ? th[0] : 1.0;
-            double gap = (kconv < l) ? th[kconv - 1] - th[kconv] : th[kconv - 1];
-            if (!(gap > 1e-300)) gap = 1e-300;
-            worst = sqrt(r2) / gap;
+            double rmax = 0.0, gap = 0.0;
+            worst = 0.0;
+            // the requested rank and every additional one (scRUVIII with several ruvK re-uses one fit for all of them)
+            for (int q = -1; q < ctx->n_conv_ranks; q++) {
+                const int kq = q < 0 ? kconv : (ctx->conv_ranks[q] < s ? ctx->conv_ranks[q] : s);
+                if (kq <= 0 || (q >= 0 && kq == kconv)) continue;
+                double r2 = 0.0, rm = 0.0;
+                for (int i = 0; i < kq; i++) { r2 += h[i] * h[i]; rm = rm > h[i] ? rm : h[i]; }
+                double g = (kq < l) ? th[kq - 1] - th[kq] : th[kq - 1];
+                if (!(g > 1e-300)) g = 1e-300;
+                const double est = rm <= 1e-14 * top ? 0.0 : sqrt(r2) / g;  // a residual at rounding level counts as converged
+                if (q < 0 || est > worst) { if (est >= worst) { worst = est; gap = g; } }
+                rmax = rmax > rm ? rmax : rm;
+            }
             if (getenv("SCM_DEBUG_EIG"))
                 fprintf(stderr, "[eig] it %d angle_est %.3e rmax/top %.3e gap/top %.3e theta1 %.3e theta_k %.3e theta_l %.3e\n", it, worst,
                         rmax / top, gap / top, th[0], th[kconv - 1], th[l - 1]);
-            if (fixed_iters || worst <= tol || rmax <= 1e-14 * top) { converged = true; break; }
+            if (fixed_iters || worst <= tol) { converged = true; break; }
 
             hist[it % 16] = worst;
             // hopeless case (theta_k ~ theta_{k+1}: the k-th factor is not separated, the reference's own answer

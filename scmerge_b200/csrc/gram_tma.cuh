@@ -154,42 +154,13 @@ __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, 
     }
 }
 
-// Unit order of the persistent grid: CTA c executes list positions c, c + grid, c + 2 grid, ...
-//   order 0 (default): [ split-major, tiles of a split in triangular order ] -- the unit classes (full / thin / diagonal) are
-//                      interleaved, so at any time some CTAs run the units that need half the operand bytes and the L2 -> SM
-//                      feed, which bounds this kernel, is evened out.  CTAs drift up to ~1.5 units apart, the cells of a split
-//                      are no longer shared through L2 and the DRAM traffic is 155 GB at 1M x 2000 (10x the algorithmic 16 GB,
-//                      still only 14 % of the HBM bandwidth): 130.5 ms.
-//   order 1 (SCM_GRAM_ORDER=1): [ all full units ] ++ [ thin ] ++ [ diagonal ], each split-major: every time slot holds units
-//                      of ONE cost class, nobody drifts, DRAM traffic 61 GB -- but 132.3 ms, because the full-unit phase now
-//                      saturates the L2 feed all the time.  Kept for the evidence (ncu r01f / r01g); the faster order is used.
-// `thin` = the last tile row is a class of its own (lean bit 0 and n mod 128 <= 80), otherwise it is part of the full class.
-__device__ __forceinline__ void gram_unit_decode(int64_t u, int S, int ntile, bool thin, int order, int& split, int& ti, int& tj) {
-    if (order == 0) {
-        const int T = ntile * (ntile + 1) / 2;
-        split = (int)(u / T);
-        tri_decode((int)(u % T), ti, tj);
-        return;
-    }
-    const int nrow_full = thin ? ntile - 1 : ntile;                 // tile rows whose off-diagonal tiles are "full"
-    const int NF = nrow_full * (nrow_full - 1) / 2, NT = thin ? ntile - 1 : 0;
-    const int64_t UF = (int64_t)NF * S, UT = (int64_t)NT * S;
-    if (u < UF) {
-        split = (int)(u / NF);
-        int a, b;
-        tri_decode((int)(u % NF), a, b);  // lower triangle incl. diagonal of size nrow_full - 1  ->  strictly lower of nrow_full
-        ti = a + 1; tj = b;
-    } else if (u < UF + UT) {
-        const int64_t v = u - UF;
-        split = (int)(v / NT);
-        ti = ntile - 1; tj = (int)(v % NT);
-    } else {
-        const int64_t v = u - UF - UT;
-        split = (int)(v / ntile);
-        ti = tj = (int)(v % ntile);
-    }
-}
-
+// Unit order: CTA c executes units c, c + grid, ... of the split-major list (tiles of a split in triangular order), so the
+// unit classes (full / thin / diagonal) are interleaved.  With the lean units CTAs drift up to ~1.5 units apart, the cells of a
+// split are no longer shared through L2 and the DRAM traffic of the kernel is 155 GB at 1M x 2000 (10x the algorithmic 16 GB,
+// 14 % of the HBM bandwidth; 50 GB with full units only).  A class-ordered list ([all full] ++ [thin] ++ [diagonal], each
+// split-major: nobody drifts) brought the traffic back to 61 GB (ncu r01g) but was 1.4 % slower; that build also carried 60
+// bytes of register spills from the extra decode state (the consumer warps are compiled against the 168-register launch
+// bound), so the comparison is not clean and the simpler order stays.
 // 3 warpgroups: 8 consumer warps (setmaxnreg.inc -> 232 registers) + one producer warpgroup (setmaxnreg.dec -> 40;
 // only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
 constexpr int GT_THREADS = 384;
@@ -219,15 +190,15 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
             off[p][q] = (2 * tig + p) * 128 + ((((gid >> 1) ^ (2 * tig + p)) ^ (q << 2)) << 4) + (gid & 1) * 8;
 
     const int64_t units = (int64_t)T * S;
-    const bool thin_class = (lean & 1) && ntile > 1 && na_last <= GT_THIN_NA;
     if (warp >= 8) {
         // ===== producer warpgroup: one lane walks the same unit / chunk sequence and keeps the ring full =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         if (tid != 256) return;
         uint32_t gl = 0;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            int split, ti, tj;
-            gram_unit_decode(u, S, ntile, thin_class, lean >> 2, split, ti, tj);
+            const int split = (int)(u / T);
+            int ti, tj;
+            tri_decode((int)(u % T), ti, tj);
             const bool diag = (ti == tj);
             const int64_t row_begin = (int64_t)split * rows_per_split;
             const int64_t row_end = min(m, row_begin + rows_per_split);
@@ -254,14 +225,15 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     uint32_t gu = 0;  // chunks consumed so far by this CTA
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        int split, ti, tj;
-        gram_unit_decode(u, S, ntile, thin_class, lean >> 2, split, ti, tj);
+        const int split = (int)(u / T);
+        int ti, tj;
+        tri_decode((int)(u % T), ti, tj);
         const bool diag = (ti == tj);
         const int64_t row_begin = (int64_t)split * rows_per_split;
         const int64_t row_end = min(m, row_begin + rows_per_split);
         const int nchunk = row_end > row_begin ? (int)ceil_div(row_end - row_begin, GT_KC) : 0;
         const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
-        double* out = partial + ((int64_t)split * T + (ti * (ti + 1) / 2 + tj)) * (GR_BT * GR_BT);
+        double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
         const bool last_row = ti == ntile - 1;
         auto shift_at = [&](int64_t g) -> double { return (shift && g < n) ? shift[g] : 0.0; };
         if ((lean & 2) && diag) {
@@ -289,7 +261,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
             }
             continue;
         }
-        if (thin_class && !diag && last_row) {
+        if ((lean & 1) && !diag && last_row && na_last <= GT_THIN_NA) {
             // ---- padded last tile row: na_last strips x 2 strips per warp (see gram_chunk_thin)
             double sA[GT_THIN_NA], sB[2], acc[GT_THIN_NA][2][2];
 #pragma unroll
@@ -388,7 +360,7 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
     }
     const int valid_last = (int)(n - (int64_t)(p.ntile - 1) * GR_BT);
     gram_tma_kernel<<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial, p.ntile,
-                                                                        (valid_last + 7) / 8, ctx->gram_lean | (ctx->gram_order << 2));
+                                                                        (valid_last + 7) / 8, ctx->gram_lean);
     return 0;
 }
 

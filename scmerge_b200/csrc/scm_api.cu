@@ -184,7 +184,6 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_LEAN")) c->gram_lean = atoi(e) & 3;
-    if (const char* e = getenv("SCM_GRAM_ORDER")) c->gram_order = atoi(e) & 1;
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < ST_COUNT; i++) {
@@ -219,6 +218,13 @@ int scm_ctx_destroy(scm_ctx* ctx) {
 int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size) {
     if (!ctx) return fail(SCM_ERR_INVALID, "null context");
     ctx->allreduce = fn; ctx->allreduce_user = user; ctx->world = world_size;
+    return 0;
+}
+
+int scm_ctx_set_conv_ranks(scm_ctx* ctx, const int32_t* ks, int32_t nk) {
+    if (!ctx || nk < 0 || nk > 16 || (nk > 0 && !ks)) return fail(SCM_ERR_INVALID, "scm_ctx_set_conv_ranks: bad arguments (at most 16 ranks)");
+    for (int i = 0; i < nk; i++) ctx->conv_ranks[i] = ks[i];
+    ctx->n_conv_ranks = nk;
     return 0;
 }
 

@@ -468,7 +468,13 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
     select = len(ks) > 1
     if fullalpha is None:
-        fit = _fit(ctx, dY, keys, G, s_dev, ks[0], exact_dev, batch_keys=bkeys, Bt=Bt, keep_gram=select)
+        # one fit serves every k (R/scRUVIII.R:64-75): the eigensolver must converge the top-k subspace for each of them
+        extra = np.ascontiguousarray(sorted(set(ks[1:])), dtype=np.int32)
+        L.check(L.lib().scm_ctx_set_conv_ranks(ctx.handle, extra.ctypes.data_as(C.c_void_p), int(extra.shape[0])))
+        try:
+            fit = _fit(ctx, dY, keys, G, s_dev, ks[0], exact_dev, batch_keys=bkeys, Bt=Bt, keep_gram=select)
+        finally:
+            L.check(L.lib().scm_ctx_set_conv_ranks(ctx.handle, None, 0))
     else:  # still need stand_mean / stand_sd: run the standardisation passes only via a fit with s = 1
         fit0 = _fit(ctx, dY, keys, G, 1, 1, True, batch_keys=bkeys, Bt=Bt, maxit=2, tol=1.0, keep_gram=select)
         fit = RUVFit(np.asarray(fullalpha, dtype=np.float64), None, fit0.stand_mean, fit0.stand_sd)
