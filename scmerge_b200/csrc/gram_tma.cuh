@@ -159,8 +159,8 @@ __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, 
 // split are no longer shared through L2 and the DRAM traffic of the kernel is 155 GB at 1M x 2000 (10x the algorithmic 16 GB,
 // 14 % of the HBM bandwidth; 50 GB with full units only).  A class-ordered list ([all full] ++ [thin] ++ [diagonal], each
 // split-major: nobody drifts) brought the traffic back to 61 GB (ncu r01g) but was 1.4 % slower; that build also carried 60
-// bytes of register spills from the extra decode state (the consumer warps are compiled against the 168-register launch
-// bound), so the comparison is not clean and the simpler order stays.
+// bytes of register spills from the extra decode state (the consumer warps already fill their 232 registers: 128
+// accumulators + fragments + shifts + addressing), so the comparison is not clean and the simpler order stays.
 // 3 warpgroups: 8 consumer warps (setmaxnreg.inc -> 232 registers) + one producer warpgroup (setmaxnreg.dec -> 40;
 // only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
 constexpr int GT_THREADS = 384;
