@@ -85,3 +85,78 @@ def test_permutation_and_linearity_at_scale(sm):
     # with alpha fixed the adjustment is linear in Y: adjust(2Y) = 2 adjust(Y)
     twice = sm.fastRUVIII(2.0 * P["Y"], P["types"], P["ctl"], k=10, fullalpha=out["fullalpha"])
     assert orc.rel_frobenius(twice, 2.0 * out["newY"]) < 1e-12
+
+
+def test_full_size_1m_x_2000_properties_and_k_sweep(sm):
+    """BASELINE.json's metric size (1M cells x 2000 genes, 500 controls) and its ruvK sweep (configs[4]: k = 5/10/20/50),
+    device-resident, through size-independent properties checked with torch on the device (no 16 GB host copies):
+    bit-exact group counts, trace / symmetry of the centred Gram, the column means, idempotence of the adjustment for
+    every k (alpha_c B = I  =>  adjust(newY) == newY) and removal of the planted unwanted factors."""
+    import torch
+    from scmerge_b200.ruv import _adjust, _fit
+    m, n, c, T, kp = 1_000_000, 2000, 500, 20, 20
+    dev = torch.device("cuda", 0)
+    ctx = sm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)
+    theta = torch.randn(T, n, generator=g, device=dev, dtype=torch.float64)
+    theta[:, :c] = 0                                               # controls carry no biology
+    A = torch.randn(kp, n, generator=g, device=dev, dtype=torch.float64) * torch.linspace(3.0, 1.5, kp, device=dev, dtype=torch.float64)[:, None]
+    types = torch.randint(0, T, (m,), generator=g, device=dev)
+    dY = sm.DeviceMatrix(ctx, m, n)
+    Yt = torch.as_tensor(dY.buf, device=dev).view(m, dY.ld)
+    Wall = torch.empty(m, kp, device=dev, dtype=torch.float64)
+    for r0 in range(0, m, 100_000):
+        r1 = min(m, r0 + 100_000)
+        Wb = torch.randn(r1 - r0, kp, generator=g, device=dev, dtype=torch.float64)
+        Wall[r0:r1] = Wb
+        Yt[r0:r1] = theta[types[r0:r1]] + Wb @ A + 0.5 * torch.randn(r1 - r0, n, generator=g, device=dev, dtype=torch.float64)
+    torch.cuda.synchronize()
+    keys = types.to(torch.int32).cpu().numpy()
+    ctl = np.zeros(n, dtype=bool)
+    ctl[:c] = True
+    fit = _fit(ctx, dY, keys, T, 50, kp, True, keep_gram=True)
+    assert fit.fullalpha.shape == (50, n) and np.all(np.isfinite(fit.fullalpha))
+    # column means and centred Gram against torch reductions on the device
+    mean_t = Yt.mean(dim=0)
+    assert torch.allclose(torch.as_tensor(fit.d_colmean, device=dev), mean_t, rtol=1e-12, atol=1e-13)
+    Gc = torch.as_tensor(fit.d_gram, device=dev).view(n, n)
+    assert torch.equal(Gc, Gc.T)
+    ssq = torch.zeros(n, device=dev, dtype=torch.float64)
+    for r0 in range(0, m, 100_000):
+        ssq += ((Yt[r0:r0 + 100_000] - mean_t) ** 2).sum(dim=0)
+    assert torch.allclose(torch.diagonal(Gc), ssq, rtol=1e-11)
+    sub = torch.arange(0, n, 97, device=dev)
+    Zs = Yt[:200_000][:, sub] - mean_t[sub]                         # a 21 x 21 block of the Gram of the first 200k cells ...
+    Gfull = torch.zeros(len(sub), len(sub), device=dev, dtype=torch.float64)
+    for r0 in range(0, m, 200_000):
+        Zs = Yt[r0:r0 + 200_000][:, sub] - mean_t[sub]
+        Gfull += Zs.T @ Zs
+    assert torch.allclose(Gc[sub][:, sub], Gfull, rtol=1e-10, atol=1e-6)
+    fit.d_gram.free()
+    fit.d_colmean.free()
+    # the planted factor space is recovered: rows of A lie in the row space of alpha_k
+    ang = orc.principal_angles(A.cpu().numpy(), fit.fullalpha[:kp])
+    assert ang.max() < 0.05
+    dOut, dAgain = sm.DeviceMatrix(ctx, m, n), sm.DeviceMatrix(ctx, m, n)
+    Ot = torch.as_tensor(dOut.buf, device=dev).view(m, dOut.ld)
+    At = torch.as_tensor(dAgain.buf, device=dev).view(m, dAgain.ld)
+    for k in (5, 10, 20, 50):
+        _adjust(ctx, dY, fit.fullalpha, k, ctl, out=dOut)
+        _adjust(ctx, dOut, fit.fullalpha, k, ctl, out=dAgain)
+        torch.cuda.synchronize()
+        num = den = 0.0
+        for r0 in range(0, m, 250_000):
+            num += float(((At[r0:r0 + 250_000] - Ot[r0:r0 + 250_000]) ** 2).sum())
+            den += float((Ot[r0:r0 + 250_000] ** 2).sum())
+        assert (num / den) ** 0.5 < 1e-10, (k, (num / den) ** 0.5)   # idempotent
+        if k == 20:
+            # the unwanted factors are gone: the adjusted cells no longer correlate with the planted W
+            blk = Ot[:200_000, c:] - theta[types[:200_000]][:, c:]
+            before = Yt[:200_000, c:] - theta[types[:200_000]][:, c:]
+            cw = Wall[:200_000]
+            r_after = float((cw.T @ blk).norm() / (cw.norm() * blk.norm()))
+            r_before = float((cw.T @ before).norm() / (cw.norm() * before.norm()))
+            assert r_before > 0.1 and r_after < 0.05 * r_before, (r_before, r_after)   # measured 0.223 -> 0.002
+    for d_ in (dY, dOut, dAgain):
+        d_.free()
