@@ -38,10 +38,6 @@ __global__ void meta_acc_kernel(const int32_t* __restrict__ flag, int64_t rows, 
     if (flag[0]) meta[0] = 1;
     meta[1] += rows;
 }
-__global__ void reciprocal_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = 1.0 / x[i];
-}
 
 // Rows per PCIe chunk: ~512 MB, a multiple of 1024 rows (test hook SCM_HOST_CHUNK_ROWS forces several chunks on small inputs).
 inline int64_t host_chunk_rows(int64_t ld) {

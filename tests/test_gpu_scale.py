@@ -160,3 +160,29 @@ def test_full_size_1m_x_2000_properties_and_k_sweep(sm):
             assert r_before > 0.1 and r_after < 0.05 * r_before, (r_before, r_after)   # measured 0.223 -> 0.002
     for d_ in (dY, dOut, dAgain):
         d_.free()
+
+
+def test_wide_matrix_20000_genes(sm):
+    """Whole-transcriptome width (n = 20000 genes, what scMerge2 is usually given): 12403 Gram tiles, 1250 gene blocks in the
+    rank-k update, shared-memory row images beyond one slab in the sparse kernels.  Small m keeps the oracle cheap."""
+    import scipy.sparse as sp
+    from scmerge_b200.scmerge2 import pseudobulk_keys, scMerge2_core
+    P = orc.planted_factors(600, 20000, 2000, 5, n_types=4, n_batch=3, seed=5)
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5, return_info=True)
+    out = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=5, return_info=True)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < 1e-8
+    assert orc.principal_angles(out["fullalpha"][:5], ref["fullalpha"][:5]).max() < 1e-6
+    # scMerge2 core on a sparse 20000-gene matrix: sparse-native kernels and the densify-first path agree with the oracle
+    rng = np.random.default_rng(3)
+    m, n = 1500, 20000
+    batch, clust = rng.integers(0, 3, m), rng.integers(0, 3, m)
+    D = rng.gamma(2.0, 1.0, (m, n)) * (rng.random((m, n)) < 0.03)
+    D += (rng.gamma(2.0, 1.0, (3, n)) * (rng.random((3, n)) < 0.05))[clust] + (rng.gamma(2.0, 0.7, (3, 3, n)) * (rng.random((3, 3, n)) < 0.03))[batch, clust]
+    keys, npb, names, pb_t, pb_b = pseudobulk_keys(batch, clust, 6, seed=1)
+    which = np.array([int(nm.rsplit("_", 1)[1]) for nm in names])[keys]
+    refs = orc.scmerge2_core(D.T, batch, clust, which, ruvK=6, k_fold=6, exact=True)
+    Xs = sp.csr_matrix(D)
+    for native in (True, False):
+        got = scMerge2_core(Xs, batch, clust, ruvK=6, k_pseudoBulk=6, which=which, BSPARAM=sm.ExactParam(), sparse_native=native)
+        assert got["pseudobulk_names"] == refs["names"]
+        assert orc.rel_frobenius(got["newY"], refs["newY"]) < 1e-8, native
