@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib as L
 from .device import Context, DeviceArray, DeviceMatrix, default_context
 
-__all__ = ["fastRUVIII", "scRUVIII", "scRUVg", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
+__all__ = ["fastRUVIII", "scRUVIII", "scRUVg", "genes_by_name", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
            "replicate_matrix", "replicate_keys", "tological", "createChunk", "RUVFit", "ExactParam", "RandomParam",
            "IrlbaParam"]
 
@@ -607,22 +607,36 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
     return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": means}
 
 
+def genes_by_name(sel, n: int, gene_names=None) -> np.ndarray:
+    """Gene selection -> boolean mask of length n.  Masks / 0-based indices as in tological(); a list of gene NAMES is
+    matched against `gene_names` (the rownames of the genes x cells matrix) like the reference's
+    `intersect(rownames(exprsMat), ctl)` / `rownames(exprsMat) %in% ctl` (R/scMerge2.R:304,382-390): names that are not in
+    the data are dropped silently and the matrix order is kept."""
+    a = np.asarray(sel)
+    if a.dtype.kind in ("U", "S", "O") and a.size and isinstance(a.reshape(-1)[0], (str, bytes)):
+        if gene_names is None:
+            raise ValueError("gene names given but the matrix has no gene_names")
+        return np.isin(np.asarray(gene_names), a)
+    return tological(a, n)
+
+
 def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, return_subset_genes=None,
-                   ctx: Context | None = None):
+                   ctx: Context | None = None, gene_names=None):
     """R/scMerge2.R:368-410.  exprsMat: genes x cells; returns genes x cells (numpy) or a DeviceMatrix (cells x genes
-    device layout, which *is* genes x cells column-major) when given one."""
+    device layout, which *is* genes x cells column-major) when given one.  `ctl` / `return_subset_genes` may be masks,
+    0-based indices or gene names (matched against `gene_names` = rownames(exprsMat), as the reference does)."""
     ctx = ctx or (exprsMat.ctx if isinstance(exprsMat, DeviceMatrix) else default_context())
     if isinstance(exprsMat, DeviceMatrix):
         dY, copied = exprsMat, False
     else:
         dY, copied = DeviceMatrix.from_host(ctx, np.asarray(exprsMat, dtype=np.float64).T), True
     n = dY.n
-    ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
+    ctl_mask = np.ones(n, dtype=bool) if ctl is None else genes_by_name(ctl, n, gene_names)
     if ctl_mask.sum() == 0:
         raise ValueError("No provided ctl genes in the data")
     sub = None
     if return_subset_genes is not None:
-        sub = np.nonzero(tological(return_subset_genes, n))[0]
+        sub = np.nonzero(genes_by_name(return_subset_genes, n, gene_names))[0]
         if sub.shape[0] == 0:
             raise ValueError("No provided return_subset_genes genes in the data")
     means = column_means(dY) if adjusted_means is None else np.asarray(adjusted_means, dtype=np.float64)

@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _lib as L
 from .device import Context, DeviceMatrix, default_context
-from .ruv import _adjust, _device_rows_cap, _fit, _is_exact, _svd_k, column_means, replicate_keys, segmented_sums, tological
+from .ruv import (_adjust, _device_rows_cap, _fit, _is_exact, _svd_k, column_means, genes_by_name, replicate_keys,
+                  segmented_sums, tological)
 
 __all__ = ["cosineNorm", "csc_to_device", "DeviceCSC", "pseudobulk_keys", "scMerge2_core"]
 
@@ -229,7 +230,7 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
 
 def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: int = 30, cosine: bool = True, BSPARAM=None,
                   which=None, seed=1, replicate_of=None, return_subset_genes=None, ctx: Context | None = None,
-                  pb=None, return_bulk=True, out: DeviceMatrix | None = None, sparse_native: bool = True):
+                  pb=None, return_bulk=True, out: DeviceMatrix | None = None, sparse_native: bool = True, gene_names=None):
     """cosineNorm -> construct_pseudoBulk -> pseudoRUVIII (R/scMerge2.R:193-309) for cells x genes `exprs`
     (numpy: copied to the device; scipy.sparse CSR cells x genes / CSC genes x cells, i.e. the reference's dgCMatrix:
     only the sparse arrays are uploaded and the dense normalised rows are built on the device (K8);
@@ -240,7 +241,13 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     ever written (newY), and with a host `out` it never exists on the device at all.
     With `out` (a DeviceMatrix of the same shape) a device-resident input is left untouched: the normalised cells are
     written to `out` and adjusted there.  `pb` may carry a precomputed `pseudobulk_keys(...)` result (the key construction is host-side index work).
+    `ctl` / `return_subset_genes` may be masks, indices or gene names (with `gene_names` = rownames of the reference's
+    genes x cells matrix; `rownames(exprsMat) %in% ctl`, R/scMerge2.R:304).
     Returns {'newY', 'fullalpha', 'bulkExprs' (P x genes), 'pseudobulk_names', 'replicate_vector', 'adjusted_means'}."""
+    if gene_names is not None:
+        n_genes = len(gene_names)
+        ctl = None if ctl is None else genes_by_name(ctl, n_genes, gene_names)
+        return_subset_genes = None if return_subset_genes is None else genes_by_name(return_subset_genes, n_genes, gene_names)
     ctx = ctx or (exprs.ctx if isinstance(exprs, (DeviceMatrix, DeviceCSC)) else default_context())
     host_in = not isinstance(exprs, (DeviceMatrix, DeviceCSC))
     host_out = out if isinstance(out, np.ndarray) else None

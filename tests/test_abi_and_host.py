@@ -115,3 +115,15 @@ def test_shard_rows_partition():
         parts = [shard_rows(m, w, r) for r in range(w)]
         assert parts[0][0] == 0 and parts[-1][1] == m
         assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+
+
+def test_gene_selection_by_name():
+    """getAdjustedMat / scMerge2 select control and subset genes by NAME (R/scMerge2.R:304,382-390): unknown names are
+    dropped, the matrix order is kept."""
+    from scmerge_b200 import genes_by_name
+    names = np.array(["g3", "g1", "g7", "g2"])
+    assert genes_by_name(["g2", "g3", "nope"], 4, names).tolist() == [True, False, False, True]
+    assert genes_by_name(np.array([1, 2]), 4).tolist() == [False, True, True, False]
+    assert genes_by_name(np.array([True, False, True, False]), 4).tolist() == [True, False, True, False]
+    with pytest.raises(ValueError, match="gene_names"):
+        genes_by_name(["g1"], 4)
