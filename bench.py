@@ -300,6 +300,7 @@ def run_ours(a):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None if os.environ.get("SCM_NO_NUMA_BIND") else sm.bind_host_to_gpu(local)  # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = sm.Context(local, stream=torch.cuda.current_stream().cuda_stream)
@@ -405,6 +406,7 @@ def run_ours(a):
         bound_s = h2d / (pcie["h2d_gbs"] * 1e9) + d2h / (pcie["d2h_gbs"] * 1e9)  # the fit needs every cell before the first adjusted byte exists
         e2e = {"value": a.cells * world * n_e2e / (float(t2.item()) * 1e-3), "unit": "cells/s", "steps": n_e2e,
                "ms_per_step": float(t2.item()) / n_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api, "pcie": pcie,
+               "host_cpus_bound_to": numa,
                "pcie_bound_ms_per_step": bound_s * 1e3, "pcie_bound_cells_per_s": a.cells * world / bound_s}
 
     if rank == 0:

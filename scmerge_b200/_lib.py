@@ -24,6 +24,7 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "scm_last_error": [],
     "scm_version": [],
+    "scm_device_pci_bus_id": [_int, C.c_char_p, _int],
     "scm_ctx_create": [_int, _vp, _pp],
     "scm_ctx_destroy": [_vp],
     "scm_ctx_set_allreduce": [_vp, ALLREDUCE_FN, _vp, _int],

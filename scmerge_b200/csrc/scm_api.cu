@@ -168,6 +168,12 @@ extern "C" {
 const char* scm_last_error(void) { return scm::g_err; }
 int scm_version(void) { return 100; }
 
+int scm_device_pci_bus_id(int device, char* buf, int len) {
+    if (!buf || len < 16) return fail(SCM_ERR_INVALID, "scm_device_pci_bus_id: buffer too small");
+    SCM_CUDA(cudaDeviceGetPCIBusId(buf, len, device));
+    return 0;
+}
+
 int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     if (!out) return fail(SCM_ERR_INVALID, "scm_ctx_create: out is NULL");
     int ndev = 0;

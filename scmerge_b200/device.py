@@ -88,6 +88,32 @@ class Context:
         return d
 
 
+def bind_host_to_gpu(device: int = 0):
+    """Pin the calling process to the CPUs of the NUMA node the GPU is attached to (sysfs `local_cpulist` of its PCI
+    device), so that page-locked buffers allocated afterwards (first touch) and the staging of pageable copies are local to
+    the GPU's PCIe root.  Returns the cpu list applied, or None when the topology cannot be read (no-op)."""
+    import os
+    buf = C.create_string_buffer(32)
+    try:
+        L.check(L.lib().scm_device_pci_bus_id(int(device), buf, 32))
+        bus = buf.value.decode().lower()
+        txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return txt
+    except Exception:
+        return None
+
+
 _default_ctx: dict = {}
 
 
