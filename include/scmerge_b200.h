@@ -108,7 +108,8 @@ int scm_csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx
  *   scm_csc_adjust       out[i, :] = inv_i x_i - ((inv_i x_i - center) B) A, dense m x n (pseudoRUVIII's adjust of every cell,
  *                        R/scMerge2_utilis.R:97-137): sparse gather for W, DMMA rank-k update on shared-memory tiles of the scaled
  *                        sparse rows, newY written once.  k <= 32.
- * Un-canonical input: use scm_csc_to_dense and the dense kernels. */
+ * Un-canonical input: use scm_csc_to_dense and the dense kernels.  scm_csc_rownorm / _seg_colmean / _adjust trust the index
+ * structure: call scm_csc_check once per matrix first (a gene index outside [0, n) would make scm_csc_adjust read out of bounds). */
 int scm_csc_check(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, int64_t m, int64_t n, int64_t nnz, int32_t* canonical);
 int scm_csc_rownorm(scm_ctx* ctx, const int64_t* d_indptr, const double* d_val, int64_t m, int cosine, double min_norm, double* d_inv_norm,
                     int32_t* d_nonfinite);
