@@ -29,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 _REAL_STDOUT = None
+_BLAS_DESC = None  # BLAS / OpenMP pools of the CPU arms (threadpoolctl), reported in cpu_baseline
 
 
 def emit(obj):
@@ -258,7 +259,10 @@ def use_all_host_threads():
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
         threadpool_limits(limits=n)
-        got = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        info = [p for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        global _BLAS_DESC
+        _BLAS_DESC = "; ".join(f"{p.get('internal_api')} {p.get('version') or ''} x{p.get('num_threads')}".strip() for p in info) or None
+        got = [p.get("num_threads", 1) for p in info]
         return max(got) if got else n
     except Exception:
         return int(os.environ.get("OMP_NUM_THREADS", n))
@@ -281,7 +285,7 @@ def run_reference(a):
            "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a)},
            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
-                            "what": cpu_what(a)},
+                            "what": cpu_what(a), "blas": _BLAS_DESC},
            "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
@@ -479,7 +483,7 @@ def run_ours(a):
             orc, P = cpu_sample(a)
             tcpu = cpu_time_once(a, orc, P)
             out["cpu_baseline"] = {"value": a.cpu_cells / tcpu, "unit": "cells/s", "cores": threads, "kind": "port",
-                                   "sample": f"{a.cpu_cells} cells x {a.genes} genes, one pass of the NumPy oracle", "what": cpu_what(a),
+                                   "sample": f"{a.cpu_cells} cells x {a.genes} genes, one pass of the NumPy oracle", "what": cpu_what(a), "blas": _BLAS_DESC,
                                    "seconds": tcpu}
         emit(out)
     if world > 1:
