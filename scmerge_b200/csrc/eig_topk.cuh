@@ -151,9 +151,11 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
             if (act && hl == 0) {
                 // rotate unless the columns are orthogonal to the requested level (jtol >= l * eps ~ 2e-14: a tighter
                 // threshold is below the rounding noise of the dot product and never lets a sweep come out clean)
-                if (fabs(ga) > jtol * sqrt(al * be) && fabs(ga) > 1e-300) {
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                if (ga * ga > jtol * jtol * al * be && fabs(ga) > 1e-300) {
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), with the inner division folded
+                    // away: one sqrt + one division + one rsqrt on the critical path of a round instead of 2 + 2 + 1
+                    const double tau = be - al;
+                    const double t = (tau < 0.0 ? -2.0 * ga : 2.0 * ga) / (fabs(tau) + sqrt(tau * tau + 4.0 * ga * ga));
                     c = rsqrt(1.0 + t * t);
                     s = c * t;
                     nrm2[p] = al - t * ga; nrm2[q] = be + t * ga; s_rot = 1;
