@@ -315,7 +315,9 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
         // measures the Jacobi tolerance instead of the subspace error (it stays rigorous for any orthonormal Q).
         const double jtol = (!fixed_iters && it == 1) ? 1e-6 : 2e-14;
 
-        jacobi_eig_kernel<<<1, 1024, jsmem, st>>>(H, l, Q, theta, 40, jtol, flag + 1);
+        // one half-warp per column pair: l / 2 pairs need 8 l threads; idle warps would only lengthen every barrier
+        const int jthreads = ((((l + 1) / 2) * 16 + 31) / 32 * 32) < 256 ? 256 : ((((l + 1) / 2) * 16 + 31) / 32 * 32);
+        jacobi_eig_kernel<<<1, jthreads, jsmem, st>>>(H, l, Q, theta, 40, jtol, flag + 1);
         SCM_LAUNCH_CHECK(ctx);
         SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(Z, l), rowmajor(Q, l), 0.0, W, l));
         SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(X, l), rowmajor(Q, l), 0.0, V, l));
