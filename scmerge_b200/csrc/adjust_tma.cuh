@@ -57,7 +57,9 @@ adjust_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n
     using TL = AdjTile<KT, MT>;
     constexpr int AT_STAGES = TL::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by POINTER arithmetic: a round trip through uintptr_t hides the shared address space from the
+    // compiler and every fragment load becomes a generic LD.E (64-bit addresses, long scoreboard) instead of LDS
+    uint8_t* smem = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + AT_STAGES * TL::STAGE_BYTES);
     uint64_t* empty = full + AT_STAGES;
     uint8_t* fragbuf = smem + AT_STAGES * TL::STAGE_BYTES + ((2 * AT_STAGES * 8 + 63) & ~63);

@@ -60,6 +60,7 @@ struct scm_ctx {
     cudaEvent_t ev0[scm::ST_COUNT], ev1[scm::ST_COUNT];
     bool ev_used[scm::ST_COUNT];
     bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
+    bool gram_preshift = true;   // fits run the Gram on a pre-shifted copy of the cells when there is room (env SCM_GRAM_PRESHIFT=0: off)
     int gram_lean = 3;           // Gram TMA kernel: bit 0 thin last tile row, bit 1 triangular diagonal units (env SCM_GRAM_LEAN)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
     int conv_ranks[16];          // additional subspace dimensions the EXACT eigensolver must converge (scm_ctx_set_conv_ranks)

@@ -10,7 +10,13 @@
 //     tensor pipe fed while another warp waits,
 //   * fragment loads read the 128B-swizzled layout conflict-free by permuting the k index of each 8-cell
 //     group (k-steps use cells {0,2,4,6} then {1,3,5,7}; any permutation of the summation index is legal),
-//   * the column shift is subtracted in registers when fragments are loaded (12 DADD per 32 DMMA).
+//   * SHIFT = true: the column shift is subtracted in registers when fragments are loaded (12 DADD per 32 DMMA).  On sm_100
+//     DADD and DMMA share the FP64 pipe and the DADDs sit in the DMMA issue stream: ncu's PC sampling puts 25 % of all samples
+//     on them (math-pipe throttle) and the kernel runs 130.6 ms at 1M x 2000.  SHIFT = false (no shift vector: the caller hands
+//     over cells that are already shifted, see ruv3_fit_impl) has no DADD at all and runs 117.3 ms = 34.1 TFLOP/s, 96 % of
+//     cuBLAS DGEMM.  Shifting ONCE per stage in shared memory with the idle warps of the producer warpgroup was tried and is
+//     slower (139.5 ms): next to two DMMA-saturating warps per scheduler a third warp's DADD waits ~110 cycles for the pipe
+//     (80 % of the shifter warps' samples), so the shifters cannot keep up (profiles/README.md, r01i).
 // Requires ld % 2 == 0 and a 16-byte aligned base (TMA global stride rule); otherwise gram_syrk.cuh is used.
 #pragma once
 #include <cuda.h>
@@ -59,7 +65,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 
 // One 16-cell chunk: 4 k-steps x (8 + 4 fragment loads, 32 DMMA).  off[p][q] are the thread's swizzled byte offsets.
-template <bool TAIL>
+template <bool TAIL, bool SHIFT>
 __device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const uint8_t* __restrict__ sb, const int (&off)[2][2],
                                            int wm, int wn, int tig, const double (&sA)[8], const double (&sB)[4], int rows_valid,
                                            double (&acc)[8][4][2]) {
@@ -74,7 +80,9 @@ __device__ __forceinline__ void gram_chunk(const uint8_t* __restrict__ sa, const
 #pragma unroll
         for (int b = 0; b < 4; b++)
             bf[b] = *reinterpret_cast<const double*>(sb + (wn * 2 + (b >> 1)) * GT_SLAB_BYTES + half + off[p][b & 1]);
-        if (TAIL) {
+        if (!SHIFT) {
+            // nothing to subtract; cells past the end of the matrix are zero-filled by the TMA unit
+        } else if (TAIL) {
             const double msk = (8 * (ks >> 1) + 2 * tig + p) < rows_valid ? 1.0 : 0.0;  // zero-filled cells stay zero
 #pragma unroll
             for (int a = 0; a < 8; a++) af[a] -= msk * sA[a];
@@ -102,7 +110,7 @@ __device__ __forceinline__ double gram_frag(const uint8_t* __restrict__ tile, in
 // (na <= GT_THIN_NA), the rest is padding.  The 8 warps split the B side instead (2 strips each): na x 2 DMMA per k-step
 // and warp instead of 8 x 4, i.e. the unit costs na/16 of a full one.
 constexpr int GT_THIN_NA = 10;
-template <bool TAIL>
+template <bool TAIL, bool SHIFT>
 __device__ __forceinline__ void gram_chunk_thin(const uint8_t* __restrict__ sa, const uint8_t* __restrict__ sb, const int (&off)[2][2],
                                                 int warp, int tig, int na, const double (&sA)[GT_THIN_NA], const double (&sB)[2],
                                                 int rows_valid, double (&acc)[GT_THIN_NA][2][2]) {
@@ -110,12 +118,12 @@ __device__ __forceinline__ void gram_chunk_thin(const uint8_t* __restrict__ sa, 
     for (int ks = 0; ks < 4; ks++) {
         const int p = ks & 1;
         const int half = (ks >> 1) * 1024;
-        const double msk = (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
+        const double msk = !SHIFT ? 0.0 : (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
         double af[GT_THIN_NA], bf[2];
 #pragma unroll
-        for (int a = 0; a < GT_THIN_NA; a++) af[a] = gram_frag(sa, a, half, off, p) - msk * sA[a];  // strips >= na are zero padding
+        for (int a = 0; a < GT_THIN_NA; a++) af[a] = SHIFT ? gram_frag(sa, a, half, off, p) - msk * sA[a] : gram_frag(sa, a, half, off, p);  // strips >= na are zero padding
 #pragma unroll
-        for (int b = 0; b < 2; b++) bf[b] = gram_frag(sb, 2 * warp + b, half, off, p) - msk * sB[b];
+        for (int b = 0; b < 2; b++) bf[b] = SHIFT ? gram_frag(sb, 2 * warp + b, half, off, p) - msk * sB[b] : gram_frag(sb, 2 * warp + b, half, off, p);
 #pragma unroll
         for (int a = 0; a < GT_THIN_NA; a++)
             if (a < na) {
@@ -128,7 +136,7 @@ __device__ __forceinline__ void gram_chunk_thin(const uint8_t* __restrict__ sa, 
 // DIAG unit (ti == tj): only the lower triangle is needed.  In 8-gene strips the triangle has 16 * 17 / 2 = 136 strip pairs
 // instead of 256; warp w takes the row strips w and 15 - w ((w + 1) + (16 - w) = 17 pairs each, perfectly balanced), so a
 // diagonal unit costs 17/32 of a full one.  `nvs` = number of strips that hold genes (16, less in the corner tile).
-template <bool TAIL>
+template <bool TAIL, bool SHIFT>
 __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, const int (&off)[2][2], int t0, int t1, int nvs, int tig,
                                                 double s0, double s1, const double (&sS)[16], int rows_valid, double (&acc0)[16][2],
                                                 double (&acc1)[16][2]) {
@@ -136,15 +144,15 @@ __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, 
     for (int ks = 0; ks < 4; ks++) {
         const int p = ks & 1;
         const int half = (ks >> 1) * 1024;
-        const double msk = (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
-        const double a0 = gram_frag(sa, t0, half, off, p) - msk * s0;
-        const double a1 = gram_frag(sa, t1, half, off, p) - msk * s1;
+        const double msk = !SHIFT ? 0.0 : (!TAIL || (8 * (ks >> 1) + 2 * tig + p) < rows_valid) ? 1.0 : 0.0;
+        const double a0 = SHIFT ? gram_frag(sa, t0, half, off, p) - msk * s0 : gram_frag(sa, t0, half, off, p);
+        const double a1 = SHIFT ? gram_frag(sa, t1, half, off, p) - msk * s1 : gram_frag(sa, t1, half, off, p);
         const bool v0 = t0 < nvs, v1 = t1 < nvs;
 #pragma unroll
         for (int jb = 0; jb < 16; jb += 8) {  // two batches of 8 strips: all loads of a batch are issued before its DMMAs
             double f[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) f[j] = gram_frag(sa, jb + j, half, off, p) - msk * sS[jb + j];  // always in bounds (padding strips are zero)
+            for (int j = 0; j < 8; j++) f[j] = SHIFT ? gram_frag(sa, jb + j, half, off, p) - msk * sS[jb + j] : gram_frag(sa, jb + j, half, off, p);  // always in bounds (padding strips are zero)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (v0 && jb + j <= t0) dmma884_ordered(acc0[jb + j][0], acc0[jb + j][1], a0, f[j]);
@@ -165,11 +173,16 @@ __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, 
 // only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
 constexpr int GT_THREADS = 384;
 
+template <bool SHIFT>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, const double* __restrict__ shift, int T, int S,
                 int64_t rows_per_split, double* __restrict__ partial, int ntile, int na_last, int lean) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment.  By pointer arithmetic the compiler keeps the shared address space and emits LDS; through uintptr_t it
+    // emits generic LD.E.  Measured on the SHIFT = true variant: generic 130.9 ms, LDS 132.6 ms (different instruction
+    // schedule around the DADDs), so that variant keeps the generic form.
+    uint8_t* smem = SHIFT ? reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023)
+                          : smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_BYTES);
     uint64_t* empty = full + GT_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,7 +248,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
         const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
         double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
         const bool last_row = ti == ntile - 1;
-        auto shift_at = [&](int64_t g) -> double { return (shift && g < n) ? shift[g] : 0.0; };
+        auto shift_at = [&](int64_t g) -> double { return (SHIFT && shift && g < n) ? shift[g] : 0.0; };
         if ((lean & 2) && diag) {
             // ---- lower triangle only (see gram_chunk_diag)
             const int t0 = warp, t1 = 15 - warp, nvs = last_row ? na_last : 16;
@@ -248,8 +261,8 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
                 mbar_wait(&full[slot], (gu / GT_STAGES) & 1);
                 const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
                 const int64_t r0 = row_begin + (int64_t)c * GT_KC;
-                if (r0 + GT_KC <= row_end) gram_chunk_diag<false>(sa, off, t0, t1, nvs, tig, s0, s1, sS, GT_KC, acc0, acc1);
-                else gram_chunk_diag<true>(sa, off, t0, t1, nvs, tig, s0, s1, sS, (int)(row_end - r0), acc0, acc1);
+                if (r0 + GT_KC <= row_end) gram_chunk_diag<false, SHIFT>(sa, off, t0, t1, nvs, tig, s0, s1, sS, GT_KC, acc0, acc1);
+                else gram_chunk_diag<SHIFT, SHIFT>(sa, off, t0, t1, nvs, tig, s0, s1, sS, (int)(row_end - r0), acc0, acc1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);
                 gu++;
@@ -274,8 +287,8 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
                 const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
                 const uint8_t* sb = sa + GT_TILE_BYTES;
                 const int64_t r0 = row_begin + (int64_t)c * GT_KC;
-                if (r0 + GT_KC <= row_end) gram_chunk_thin<false>(sa, sb, off, warp, tig, na_last, sA, sB, GT_KC, acc);
-                else gram_chunk_thin<true>(sa, sb, off, warp, tig, na_last, sA, sB, (int)(row_end - r0), acc);
+                if (r0 + GT_KC <= row_end) gram_chunk_thin<false, SHIFT>(sa, sb, off, warp, tig, na_last, sA, sB, GT_KC, acc);
+                else gram_chunk_thin<SHIFT, SHIFT>(sa, sb, off, warp, tig, na_last, sA, sB, (int)(row_end - r0), acc);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);
                 gu++;
@@ -306,8 +319,8 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
             const uint8_t* sa = smem + slot * GT_STAGE_BYTES;
             const uint8_t* sb = diag ? sa : sa + GT_TILE_BYTES;
             const int64_t r0 = row_begin + (int64_t)c * GT_KC;
-            if (r0 + GT_KC <= row_end) gram_chunk<false>(sa, sb, off, wm, wn, tig, sA, sB, GT_KC, acc);
-            else gram_chunk<true>(sa, sb, off, wm, wn, tig, sA, sB, (int)(row_end - r0), acc);
+            if (r0 + GT_KC <= row_end) gram_chunk<false, SHIFT>(sa, sb, off, wm, wn, tig, sA, sB, GT_KC, acc);
+            else gram_chunk<SHIFT, SHIFT>(sa, sb, off, wm, wn, tig, sA, sB, (int)(row_end - r0), acc);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
             gu++;
@@ -355,12 +368,17 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
     if (r != CUDA_SUCCESS) return 1;
     static bool attr_set = false;
     if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
         attr_set = true;
     }
     const int valid_last = (int)(n - (int64_t)(p.ntile - 1) * GR_BT);
-    gram_tma_kernel<<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial, p.ntile,
-                                                                        (valid_last + 7) / 8, ctx->gram_lean);
+    if (d_shift)
+        gram_tma_kernel<true><<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial,
+                                                                                  p.ntile, (valid_last + 7) / 8, ctx->gram_lean);
+    else
+        gram_tma_kernel<false><<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, nullptr, p.T, p.S, p.rows_per_split, partial,
+                                                                                   p.ntile, (valid_last + 7) / 8, ctx->gram_lean);
     return 0;
 }
 

@@ -42,6 +42,46 @@ __global__ void colmean_kernel(const double* __restrict__ sums, int32_t G, int64
     mean[j] = s / (double)meta[1];
 }
 
+// out[j] = sums[j] / count[0]  (0 when there are no rows)
+__global__ void vec_mean_kernel(const double* __restrict__ sums, const int64_t* __restrict__ count, int64_t n, double* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = count[0] > 0 ? sums[j] / (double)count[0] : 0.0;
+}
+
+// tot[j] = sum_g sums[g, j]
+__global__ void group_total_kernel(const double* __restrict__ sums, int32_t G, int64_t n, double* __restrict__ tot) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int g = 0; g < G; g++) s += sums[(int64_t)g * n + j];
+    tot[j] = s;
+}
+
+// out[i, j] = Y[i, j] - shift[j]: the pre-shifted copy of the cells the Gram kernel reads (HBM-bound: 8 m n read + 8 m n written).
+// One CTA per 8-row group (grid-stride), 16-byte accesses when both leading dimensions are even and the bases aligned.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+shift_copy_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, const double* __restrict__ shift,
+                  double* __restrict__ out, int64_t ldo) {
+    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < m; r0 += (int64_t)gridDim.x * 8) {
+        const int nr = (int)min((int64_t)8, m - r0);
+        for (int64_t j = (int64_t)threadIdx.x * VEC; j < n; j += 256 * VEC) {
+            if (VEC == 2 && j + 1 < n) {
+                const double2 s = *reinterpret_cast<const double2*>(shift + j);
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (u < nr) v[u] = ldg_stream2(Y + (r0 + u) * ld + j);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (u < nr) *reinterpret_cast<double2*>(out + (r0 + u) * ldo + j) = make_double2(v[u].x - s.x, v[u].y - s.y);
+            } else {
+                for (int u = 0; u < nr; u++) out[(r0 + u) * ldo + j] = Y[(r0 + u) * ld + j] - shift[j];
+            }
+        }
+    }
+}
+
 // out[j] = sum_g counts[g] * means[g, j] / sum_g counts[g]: the column means of all cells from the group means
 __global__ void weighted_colmean_kernel(const double* __restrict__ means, const int64_t* __restrict__ counts, int32_t G, int64_t n,
                                         int64_t ldm, double* __restrict__ out) {
@@ -190,6 +230,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_LEAN")) c->gram_lean = atoi(e) & 3;
+    if (const char* e = getenv("SCM_GRAM_PRESHIFT")) c->gram_preshift = (e[0] != '0');
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < ST_COUNT; i++) {
@@ -505,15 +546,72 @@ static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64
         SCM_LAUNCH_CHECK(ctx);
         SCM_CUDA(cudaMemcpyAsync(d_mean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     }
-    {   // Gram of the shifted cells (local), summed over ranks, then corrected to the Gram of the residual Y0
+    // Gram of the shifted cells (local), summed over ranks, then corrected to the Gram of the residual Y0.  The Gram kernel
+    // without a shift vector has no DADD in its DMMA stream and is 10 % faster (gram_tma.cuh), so it reads a PRE-SHIFTED copy
+    // of the cells.  The identity of DESIGN.md section 2 holds for ANY fixed shift: `pre` is the column mean of a strided sample
+    // of <= 4096 cells per rank (summed over the ranks: the same vector everywhere), close enough to the mean that nothing
+    // cancels, and available before the first full pass.  Without room for the copy (or with SCM_GRAM_PRESHIFT=0) the Gram
+    // kernel subtracts the exact column mean from its fragments as before.
+    struct AsyncBuf {  // stream-ordered buffer that may fail to allocate (freed on every exit path)
+        double* p = nullptr;
+        cudaStream_t st;
+        ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+    } ypre;
+    ypre.st = st;
+    double*& Ypre = ypre.p;
+    const double* gshift = shift;
+    const int64_t ldp = (n + 1) & ~(int64_t)1;
+    if (ctx->gram_preshift && ctx->use_tma) {
+        double *pre, *psum;
+        int64_t* pcount;
+        int32_t* zkey;
+        const int64_t ms = m_local < 4096 ? m_local : 4096, stride = ms > 0 ? m_local / ms : 1;
+        SCM_TRY(ws.alloc(&pre, n)); SCM_TRY(ws.alloc(&psum, n)); SCM_TRY(ws.alloc(&pcount, 1)); SCM_TRY(ws.alloc(&zkey, ms));
+        SCM_TRY(zero_async(ctx, zkey, sizeof(int32_t) * ms));
+        SCM_TRY(seg_colsum(ctx, d_Y, ms, n, ld * stride, zkey, 1, nullptr, psum, pcount, nullptr));
+        SCM_TRY(allreduce(ctx, psum, n, 0));
+        SCM_TRY(allreduce(ctx, pcount, 1, 1));
+        vec_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(psum, pcount, n, pre);
+        SCM_LAUNCH_CHECK(ctx);
+        gshift = pre;
+        if (m_local > 0) {
+            if (cudaMallocAsync((void**)&Ypre, sizeof(double) * (size_t)m_local * (size_t)ldp, st) != cudaSuccess) {
+                cudaGetLastError();  // no room for the copy: in-kernel shift (by `pre`, which every rank already agreed on)
+                Ypre = nullptr;
+            }
+        }
+    }
+    {
         StageTimer t(ctx, ST_GRAM);
-        SCM_TRY(gram(ctx, d_Y, m_local, n, ld, shift, Gm, true));
+        int grc;
+        if (Ypre) {
+            const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
+            const int64_t groups = ceil_div(m_local, 8);
+            const unsigned grid = (unsigned)(groups < (int64_t)ctx->num_sms * 16 ? groups : (int64_t)ctx->num_sms * 16);
+            if (vec2) shift_copy_kernel<2><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
+            else shift_copy_kernel<1><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
+            SCM_LAUNCH_CHECK(ctx);
+            grc = gram(ctx, Ypre, m_local, n, ldp, nullptr, Gm, true);
+        } else {
+            grc = gram(ctx, d_Y, m_local, n, ld, gshift, Gm, true);
+        }
+        SCM_TRY(grc);
     }
     SCM_TRY(allreduce(ctx, Gm, n * n, 0));
-    // the shift is the global column mean, so at this point Gm is the centred Gram of ALL cells (PCA of Y / of any newY)
-    if (d_gram_centred) SCM_CUDA(cudaMemcpyAsync(d_gram_centred, Gm, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+    if (d_gram_centred) {
+        // centred Gram of ALL cells (PCA of Y / of any newY): Gm - m (ybar - gshift)(ybar - gshift)', i.e. the residual
+        // correction for ONE group holding every cell (exactly Gm when the shift is the global mean)
+        SCM_CUDA(cudaMemcpyAsync(d_gram_centred, Gm, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+        if (gshift != shift) {
+            double* tot;
+            SCM_TRY(ws.alloc(&tot, n));
+            group_total_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, G, n, tot);
+            SCM_LAUNCH_CHECK(ctx);
+            SCM_TRY(gram_residual(ctx, d_gram_centred, n, tot, meta + 1, 1, gshift, nullptr));
+        }
+    }
     if (d_colmean) SCM_CUDA(cudaMemcpyAsync(d_colmean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, G, shift, inv_sd));
+    SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, G, gshift, inv_sd));
     int64_t hmeta[2];
     SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
     SCM_CUDA(cudaStreamSynchronize(st));
