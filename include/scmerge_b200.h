@@ -275,7 +275,8 @@ int scm_adjust_to_host(scm_ctx* ctx, double* d_Y, int64_t m, int64_t n, int64_t 
 
 /* Stage timers (ms, CUDA events on the context stream) of the last scm_ruv3_fit / scm_adjust:
  * 0 seg_colsum, 1 gram (SYRK + split reduce), 2 allreduce, 3 eig, 4 coef, 5 adjust, 6 standardise,
- * 7 the gram_syrk kernel alone, 8 ingest (scm_csc_to_dense / scm_cosine_rows). */
+ * 7 the gram_syrk kernel alone, 8 ingest (scm_csc_to_dense / scm_cosine_rows), 9 the pre-shifted copy of the cells the fit's Gram
+ * reads (part of 1; 0 when that path is off). */
 int scm_timers(scm_ctx* ctx, double* ms, int n);
 
 #ifdef __cplusplus

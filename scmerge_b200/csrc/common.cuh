@@ -42,7 +42,7 @@ inline int fail(int code, const char* fmt, ...) {
         SCM_CUDA(cudaGetLastError()); \
     } while (0)
 
-enum Stage { ST_SEG = 0, ST_GRAM = 1, ST_COMM = 2, ST_EIG = 3, ST_COEF = 4, ST_ADJUST = 5, ST_STD = 6, ST_SYRK = 7, ST_INGEST = 8, ST_COUNT = 9 };
+enum Stage { ST_SEG = 0, ST_GRAM = 1, ST_COMM = 2, ST_EIG = 3, ST_COEF = 4, ST_ADJUST = 5, ST_STD = 6, ST_SYRK = 7, ST_INGEST = 8, ST_PRESHIFT = 9, ST_COUNT = 10 };
 
 }  // namespace scm
 

@@ -518,6 +518,7 @@ static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64
     SCM_TRY(ws.alloc(&flag, 1)); SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&Gm, n * n));
     SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n));
     SCM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    ctx->ev_used[ST_PRESHIFT] = false;
     {   // residual operator, part 1: replicate-group sums (my_residop, R/fastRUVIII.R:121-129) + NA/Inf scan (:52-60)
         StageTimer t(ctx, ST_SEG);
         SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_group, G, nullptr, gsums, gcounts, flag));
@@ -588,8 +589,11 @@ static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64
             const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
             const int64_t groups = ceil_div(m_local, 8);
             const unsigned grid = (unsigned)(groups < (int64_t)ctx->num_sms * 16 ? groups : (int64_t)ctx->num_sms * 16);
-            if (vec2) shift_copy_kernel<2><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
-            else shift_copy_kernel<1><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
+            {
+                StageTimer tc(ctx, ST_PRESHIFT);
+                if (vec2) shift_copy_kernel<2><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
+                else shift_copy_kernel<1><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
+            }
             SCM_LAUNCH_CHECK(ctx);
             grc = gram(ctx, Ypre, m_local, n, ldp, nullptr, Gm, true);
         } else {

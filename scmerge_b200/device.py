@@ -43,9 +43,9 @@ class Context:
         return n.value
 
     def timers(self) -> dict:
-        ms = (C.c_double * 9)()
-        L.check(L.lib().scm_timers(self._h, ms, 9))
-        names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel", "ingest"]
+        ms = (C.c_double * 10)()
+        L.check(L.lib().scm_timers(self._h, ms, 10))
+        names = ["seg_colsum", "gram", "allreduce", "eig", "coef", "adjust", "standardise", "gram_syrk_kernel", "ingest", "preshift_copy"]
         return dict(zip(names, list(ms)))
 
     def set_allreduce(self, fn, world_size: int, rank: int | None = None):
