@@ -368,6 +368,22 @@ def _finish(out: DeviceMatrix, made_copy_in: bool, host_out=None):
     return res
 
 
+def _scruviii_degenerate(Y, M, ks, return_all_RUV):
+    """scRUVIII when fastRUVIII takes its early-out (ncol(M) >= m or k == 0, R/fastRUVIII.R:78-80): every candidate's newY is
+    the standardised matrix itself, and adding the mean and sd back (R/scRUVIII.R:117-119) returns the input, cells x genes;
+    fullalpha is NULL, f_score = 1 for a single k (R/scRUVIII.R:80-82).  With several k the reference would go on to the
+    silhouette of identical matrices (all F-scores equal, which.max picks the first k): the first k is returned without
+    touching the device."""
+    Yh = Y.to_host() if isinstance(Y, DeviceMatrix) else np.ascontiguousarray(np.asarray(Y, dtype=np.float64).T)
+    results = {kk: {"newY": Yh, "M": M, "fullalpha": None} for kk in (ks if return_all_RUV else ks[:1])}
+    if return_all_RUV:
+        results["optimal_ruvK"] = ks[0]
+        return results
+    one = dict(results[ks[0]])
+    one["optimal_ruvK"] = ks[0]
+    return one
+
+
 # ---- the reference's closures ---------------------------------------------------------------------------
 def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, average=False, BPPARAM=None,
                BSPARAM=None, fullalpha=None, return_info=False, inputcheck=True, ctx: Context | None = None, out=None):
@@ -429,18 +445,21 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     if batch is None:
         raise ValueError("batch is required")
     ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
+    keys, G = replicate_keys(M)
+    m = Y.m if isinstance(Y, DeviceMatrix) else np.shape(Y)[1]
+    if keys.shape[0] != m:
+        raise ValueError("M must have one row per cell (column of Y)")
+    if G >= m or ks[0] == 0:  # fastRUVIII's early-out (R/fastRUVIII.R:78-80): resolved before touching the device
+        return _scruviii_degenerate(Y, M, ks, return_all_RUV)
     ctx = ctx or default_context()
     if isinstance(Y, np.ndarray) and _is_host_matrix(Y.T) and len(ks) == 1 and fullalpha is None:
         # genes x cells in column-major order (R's layout) is cells x genes row-major: pipelined host path
         Yt = Y.T
         m, n = Yt.shape
-        keys, G = replicate_keys(M)
         bkeys, Bt = replicate_keys(np.asarray(batch))
         ctlm = tological(ctl, n)
         exact = _is_exact(BSPARAM)
         s = _svd_k(m, G, int(ctlm.sum()), exact, svd_k)
-        if G >= m or ks[0] == 0:
-            raise NotImplementedError("degenerate replicate structure (ncol(M) >= m): nothing to adjust")
         s_dev, exact_dev = _device_rows_cap(s, ks[0], exact)
         newY, fit = _host_pipeline(ctx, Yt, ctlm, ks[0], keys=keys, G=G, s=s_dev, exact=exact_dev, batch_keys=bkeys, Bt=Bt)
         res = {ks[0]: {"newY": newY, "M": M, "fullalpha": fit.fullalpha}, "optimal_ruvK": ks[0],
@@ -457,14 +476,11 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
         # genes x cells: C-order needs a transpose on the device, Fortran order is already cells x genes row-major
         dY, copied = DeviceMatrix.from_host(ctx, Y.T), True
     m, n = dY.m, dY.n
-    keys, G = replicate_keys(M)
     bkeys, Bt = replicate_keys(np.asarray(batch))
     ctl = tological(ctl, n)
     exact = _is_exact(BSPARAM)
     s = _svd_k(m, G, int(ctl.sum()), exact, svd_k)
     results = {}
-    if G >= m or ks[0] == 0:
-        raise NotImplementedError("degenerate replicate structure (ncol(M) >= m): nothing to adjust")
     s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
     select = len(ks) > 1
     if fullalpha is None:

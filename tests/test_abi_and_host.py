@@ -109,6 +109,37 @@ def test_early_out_needs_no_device():
         sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=1, eta=np.ones((1, 2)))
 
 
+def test_scruviii_early_out_needs_no_device():
+    """scRUVIII on a degenerate replicate structure: fastRUVIII returns its input (R/fastRUVIII.R:78-80) and the
+    de-standardisation (R/scRUVIII.R:117-119) gives the original matrix back, cells x genes, fullalpha NULL."""
+    import scmerge_b200 as sm
+    Y = np.arange(12.0).reshape(2, 6)  # genes x cells
+    res = sm.scRUVIII(Y, np.arange(6), [0], k=3, batch=np.arange(6) % 2)
+    assert res["optimal_ruvK"] == 3 and res[3]["fullalpha"] is None
+    np.testing.assert_array_equal(res[3]["newY"], Y.T)
+    one = sm.scRUVIII(Y, np.arange(6) % 2, [0], k=[0, 2], batch=np.arange(6) % 2, return_all_RUV=False)
+    assert one["optimal_ruvK"] == 0 and one["fullalpha"] is None and one["newY"].shape == (6, 2)
+    with pytest.raises(ValueError, match="one row per cell"):
+        sm.scRUVIII(Y, np.arange(5), [0], k=1, batch=np.arange(6) % 2)
+
+
+def test_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-cells", "1500", "--genes", "300", "--ctl", "100"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "RUV-III cells/sec" and d["unit"] == "cells/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
 def test_shard_rows_partition():
     from scmerge_b200.dist import shard_rows
     for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
