@@ -65,6 +65,11 @@ int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int wor
 int scm_ctx_set_conv_ranks(scm_ctx* ctx, const int32_t* ks, int32_t nk);
 int scm_ctx_sync(scm_ctx* ctx);
 int scm_ctx_launch_count(scm_ctx* ctx, int64_t* n_launches); /* kernels launched by this library so far */
+/* Scratch (Gram partials, the pre-shifted copy of the cells the fit's Gram reads: m x n doubles, ...) comes from the device's
+ * stream-ordered memory pool and stays cached there between calls (a fit re-allocates the same sizes; plain cudaFree next to a
+ * populated pool costs up to a second).  This hands the cached, unused blocks back to the driver, e.g. before another library
+ * needs the memory.  Synchronises the context's stream. */
+int scm_ctx_release_scratch(scm_ctx* ctx);
 
 int scm_dev_alloc(scm_ctx* ctx, int64_t bytes, void** d_ptr);
 int scm_dev_free(scm_ctx* ctx, void* d_ptr);

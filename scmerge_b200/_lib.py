@@ -31,6 +31,7 @@ SIGNATURES = {
     "scm_ctx_set_conv_ranks": [_vp, _vp, _i32],
     "scm_ctx_sync": [_vp],
     "scm_ctx_launch_count": [_vp, C.POINTER(_i64)],
+    "scm_ctx_release_scratch": [_vp],
     "scm_dev_alloc": [_vp, _i64, _pp],
     "scm_dev_free": [_vp, _vp],
     "scm_host_alloc_pinned": [_i64, _pp],

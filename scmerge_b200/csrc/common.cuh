@@ -57,7 +57,7 @@ struct scm_ctx {
     scm_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     int world = 1;
-    cudaEvent_t ev0[scm::ST_COUNT], ev1[scm::ST_COUNT];
+    cudaEvent_t ev0[scm::ST_COUNT] = {}, ev1[scm::ST_COUNT] = {};
     bool ev_used[scm::ST_COUNT];
     bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
     bool gram_preshift = true;   // fits run the Gram on a pre-shifted copy of the cells when there is room (env SCM_GRAM_PRESHIFT=0: off)

@@ -225,7 +225,11 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     cudaDeviceProp prop;
     SCM_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(SCM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
-    scm_ctx* c = new scm_ctx();
+    struct Guard {  // the half-built context must not leak when one of the CUDA calls below fails
+        scm_ctx* c;
+        ~Guard() { if (c) scm_ctx_destroy(c); }
+    } guard{new scm_ctx()};
+    scm_ctx* c = guard.c;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
@@ -245,6 +249,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
+    guard.c = nullptr;
     *out = c;
     return 0;
 }
@@ -252,9 +257,12 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
 int scm_ctx_destroy(scm_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < ST_COUNT; i++) { cudaEventDestroy(ctx->ev0[i]); cudaEventDestroy(ctx->ev1[i]); }
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < ST_COUNT; i++) {
+        if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+        if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_stream_d2h) cudaStreamDestroy(ctx->copy_stream_d2h);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -278,6 +286,15 @@ int scm_ctx_set_conv_ranks(scm_ctx* ctx, const int32_t* ks, int32_t nk) {
 int scm_ctx_sync(scm_ctx* ctx) {
     SCM_REQUIRE_CTX(ctx);
     SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scm_ctx_release_scratch(scm_ctx* ctx) {
+    SCM_REQUIRE_CTX(ctx);
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    SCM_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    SCM_CUDA(cudaMemPoolTrimTo(pool, 0));
     return 0;
 }
 

@@ -37,6 +37,10 @@ class Context:
     def sync(self):
         L.check(L.lib().scm_ctx_sync(self._h))
 
+    def release_scratch(self):
+        """Hand the library's cached scratch (e.g. the m x n pre-shifted copy a fit leaves in the pool) back to the driver."""
+        L.check(L.lib().scm_ctx_release_scratch(self._h))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         L.check(L.lib().scm_ctx_launch_count(self._h, C.byref(n)))
