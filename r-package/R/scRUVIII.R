@@ -1,0 +1,114 @@
+## Drop-in bodies for the remaining RUV-III closures of scMerge (same signatures as R/scRUVIII.R:41-44,
+## R/scMerge2_utilis.R:17-26, R/scMerge2.R:368-372).  As in fastRUVIII.R only argument resolution lives in R; the
+## arithmetic is behind the .Call entry points of src/rshim.c.  NOT executed in this repository (no R in the image): the
+## tested twin of every function below is scmerge_b200/ruv.py, which drives the same C ABI in the same order.
+##
+## Helpers shared with fastRUVIII.R: .keys() (replicate structure -> 0-based int keys), .rows_cap().
+
+.ctl_mask <- function(ctl, n) { out <- rep(FALSE, n); out[ctl] <- TRUE; out }   # tological(), R/fastRUVIII.R:113-117
+
+## scRUVIII: standardize2 + fastRUVIII per k + de-standardise + choice of ruvK (R/scRUVIII.R:41-137).
+## Y is genes x cells, which is byte-identical to the device layout (row-major cells x genes): uploaded once, never rewritten.
+## The standardisation is folded into the fit (batch keys) and into the adjust coefficients (center / pre / post).
+scRUVIII <- function(Y = Y, M = M, ctl = ctl, fullalpha = NULL, k = k, cell_type = NULL, batch = NULL,
+                     return_all_RUV = TRUE, BPPARAM = SerialParam(), BSPARAM = ExactParam(), svd_k = 50) {
+  n <- nrow(Y); m <- ncol(Y)
+  g <- .keys(M); b <- .keys(batch); ctl2 <- .ctl_mask(ctl, n)
+  exact <- inherits(BSPARAM, "ExactParam")
+  s <- if (exact) min(m - g$G, sum(ctl2), svd_k, na.rm = TRUE) else min(m - g$G, sum(ctl2), na.rm = TRUE)
+  if (g$G >= m | k[1] == 0) {                          # fastRUVIII's early-out, then mean and sd are added back: the input
+    res <- lapply(k, function(kk) list(newY = t(as.matrix(Y)), M = M, fullalpha = NULL))
+    names(res) <- k
+    if (return_all_RUV) { res$optimal_ruvK <- k[1]; return(res) }
+    one <- res[[1]]; one$optimal_ruvK <- k[1]; return(one)
+  }
+  dY <- .Call("scm_upload", as.matrix(Y), 0L)
+  cap <- .rows_cap(s, max(k), exact)
+  select <- length(k) > 1
+  ## one fit serves every k (R/scRUVIII.R:64-75); scm_fit_gram also keeps the centred Gram for the silhouette PCA
+  mode <- if (cap$exact) 0L else 1L
+  fit <- if (select) .Call("scm_fit_gram", dY, g$key, g$G, b$key, b$G, cap$s, min(k[1], cap$s), mode, as.integer(sort(unique(k[-1]))))
+         else .Call("scm_fit", dY, g$key, g$G, b$key, b$G, cap$s, min(k[1], cap$s), mode)
+  if (is.null(fullalpha)) { fullalpha <- t(fit[[1]]); colnames(fullalpha) <- rownames(Y) }
+  stand_mean <- fit[[3]]; stand_sd <- fit[[4]]
+  adjust_one <- function(kk) {
+    kk <- min(kk, nrow(fullalpha))
+    out <- .Call("scm_adjust_", dY, t(fullalpha[seq_len(kk), , drop = FALSE]), kk, ctl2, stand_mean, 1 / stand_sd, stand_sd, NULL)
+    newY <- t(out); dimnames(newY) <- rev(dimnames(Y))  # cells x genes, like the reference's t(t(newY) * sd + mean)
+    list(newY = newY, M = M, fullalpha = fullalpha)
+  }
+  f_score <- 1; names(f_score) <- k[1]
+  if (select) {
+    if (is.null(cell_type)) ct <- g else ct <- .keys(cell_type)          # R/scRUVIII.R:89-92
+    sil <- vapply(k, function(kk) {
+      kk <- min(kk, nrow(fullalpha))
+      .Call("scm_sil", dY, fit$gram, fit$colmean, t(fullalpha[seq_len(kk), , drop = FALSE]), kk, ctl2, stand_mean, 1 / stand_sd,
+            stand_sd, ct$key, ct$G, b$key, b$G, 10L)
+    }, numeric(2))
+    zo <- (sil + 1) / 2                                                   # zeroOneScale, R/scRUVIII.R:186-190
+    f_score <- 2 * zo[1, ] * (1 - zo[2, ]) / (zo[1, ] + (1 - zo[2, ]))    # f_measure, R/scRUVIII.R:177-180
+    names(f_score) <- k
+    message("optimal ruvK:", k[which.max(f_score)])
+  }
+  best <- which.max(f_score)
+  if (return_all_RUV) {
+    res <- lapply(k, adjust_one); names(res) <- k
+    res$optimal_ruvK <- k[best]
+    return(res)
+  }
+  one <- adjust_one(k[best]); one$optimal_ruvK <- k[best]
+  one
+}
+
+## pseudoRUVIII: fit on the pseudobulk matrix, adjust every cell (R/scMerge2_utilis.R:17-150).  Y / Y_pseudo are cells x genes.
+## byChunk / chunkSize / BPPARAM are accepted and unused: the fused adjust kernel streams all cells in one launch.
+pseudoRUVIII <- function(Y, Y_pseudo, M, ctl, k = NULL, eta = NULL, include.intercept = TRUE, inputcheck = TRUE,
+                         fullalpha = NULL, return.info = FALSE, subset = NULL, BPPARAM = BiocParallel::SerialParam(),
+                         BSPARAM = BiocSingular::ExactParam(), normalised = TRUE, verbose = TRUE, byChunk = TRUE,
+                         chunkSize = 50000) {
+  if (!is.null(eta)) stop("eta is not supported on the device path")
+  n <- ncol(Y); P <- nrow(Y_pseudo)
+  g <- .keys(M); ctl2 <- .ctl_mask(ctl, n)
+  exact <- inherits(BSPARAM, "ExactParam")
+  s <- if (exact) min(P - g$G, sum(ctl2), k, na.rm = TRUE) else min(P - g$G, sum(ctl2), na.rm = TRUE)   # :60-65 (cap is k here)
+  if (g$G >= P | k == 0) return(Y_pseudo)                                                                 # :72-76
+  if (is.null(fullalpha)) {
+    dP <- .Call("scm_upload", as.matrix(Y_pseudo), 1L)
+    cap <- .rows_cap(s, k, exact)
+    fit <- .Call("scm_fit", dP, g$key, g$G, NULL, 0L, cap$s, min(k, cap$s), if (cap$exact) 0L else 1L)
+    fullalpha <- t(fit[[1]]); colnames(fullalpha) <- colnames(Y)
+  }
+  if (!normalised) return(list(M = M, fullalpha = fullalpha))
+  ## a dgCMatrix goes up as its three slots (genes x cells expected by scm_upload_sparse: pass t(Y) when Y is cells x genes)
+  dY <- if (methods::is(Y, "dgCMatrix")) { Yt <- Matrix::t(Y); .Call("scm_upload_sparse", Yt@p, Yt@i, Yt@x, dim(Yt), FALSE) }
+        else .Call("scm_upload", as.matrix(Y), 1L)
+  means <- .Call("scm_segmean", dY, integer(nrow(Y)), 1L)[[1]][, 1]       # adjusted_means <- colMeans(Y), :97
+  kk <- min(k, nrow(fullalpha))
+  sub <- if (is.null(subset)) NULL else as.integer(which(.ctl_mask(subset, n)) - 1L)
+  out <- .Call("scm_adjust_", dY, t(fullalpha[seq_len(kk), , drop = FALSE]), kk, ctl2, means, NULL, NULL, sub)
+  newY <- DelayedArray::DelayedArray(t(out))
+  rownames(newY) <- rownames(Y); colnames(newY) <- if (is.null(sub)) colnames(Y) else colnames(Y)[sub + 1L]
+  if (!return.info) newY else list(newY = newY, M = M, fullalpha = fullalpha)
+}
+
+## getAdjustedMat: adjust-only from a stored fullalpha (R/scMerge2.R:368-410).  exprsMat is genes x cells; ctl and
+## return_subset_genes are matched by NAME and keep the matrix order, like the reference's intersect(rownames(.), .).
+getAdjustedMat <- function(exprsMat, fullalpha, ctl = rownames(exprsMat), adjusted_means = NULL, ruvK = 20,
+                           return_subset_genes = NULL) {
+  ctl2 <- rownames(exprsMat) %in% ctl
+  if (!any(ctl2)) stop("No provided ctl genes in the data")
+  sub <- NULL
+  if (!is.null(return_subset_genes)) {
+    sub <- which(rownames(exprsMat) %in% return_subset_genes)
+    if (length(sub) == 0) stop("No provided return_subset_genes genes in the data")
+  }
+  dY <- if (methods::is(exprsMat, "dgCMatrix")) .Call("scm_upload_sparse", exprsMat@p, exprsMat@i, exprsMat@x, dim(exprsMat), FALSE)
+        else .Call("scm_upload", as.matrix(exprsMat), 0L)
+  if (is.null(adjusted_means)) adjusted_means <- .Call("scm_segmean", dY, integer(ncol(exprsMat)), 1L)[[1]][, 1]
+  kk <- min(ruvK, nrow(fullalpha))
+  fa <- fullalpha[seq_len(kk), rownames(exprsMat), drop = FALSE]         # name indexing, R/scMerge2.R:399-405
+  out <- .Call("scm_adjust_", dY, t(fa), kk, ctl2, adjusted_means, NULL, NULL, if (is.null(sub)) NULL else as.integer(sub - 1L))
+  rownames(out) <- if (is.null(sub)) rownames(exprsMat) else rownames(exprsMat)[sub]
+  colnames(out) <- colnames(exprsMat)
+  out
+}

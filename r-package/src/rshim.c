@@ -9,8 +9,7 @@
  *   create_pseudoBulk / aggregate.Matrix (R/scMerge2_utilis.R:325-346,461-486)       -> scm_segmean()
  *   as(., "CsparseMatrix") + batchelor::cosineNorm (R/scMerge2.R:164-166,193-198)     -> scm_upload_sparse()
  *   scRUVg (R/scRUVg.R:30-85)                                                         -> scm_ruvg()
- *   calculateSil / kBET_batch_sil (R/scRUVIII.R:182-199)                              -> scm_sil()   (scm_fit_gram, the scm_fit
- *     variant that also keeps the centred Gram and the column means on the device via scm_ruv3_fit_gram, is analogous to scm_fit)
+ *   calculateSil / kBET_batch_sil (R/scRUVIII.R:182-199)                              -> scm_fit_gram() + scm_sil()
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -51,19 +50,35 @@ SEXP scm_upload(SEXP Y, SEXP layout) {
 
 static void* to_dev(const void* h, int64_t bytes) { void* d; CHECK(scm_dev_alloc(ctx(), bytes, &d)); CHECK(scm_h2d(ctx(), d, h, bytes)); return d; }
 
-/* fit: group (int, 0-based), G, batch (int or NULL), Bt, s, kconv, mode -> list(fullalpha s x n [row-major], sigma, mean, sd) */
-SEXP scm_fit(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kconv, SEXP mode) {
+/* plain device buffer held by R (centred Gram, column means); freed by the finalizer */
+static void dbuf_fin(SEXP x) { void* p = R_ExternalPtrAddr(x); if (p) { scm_dev_free(ctx(), p); R_ClearExternalPtr(x); } }
+static SEXP wrap_dbuf(void* p) {
+    SEXP out = PROTECT(R_MakeExternalPtr(p, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(out, dbuf_fin, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+
+/* fit: group (int, 0-based), G, batch (int or NULL), Bt, s, kconv, mode
+ *   -> list(fullalpha s x n [row-major], sigma, mean, sd[, gram = <n x n on the device>, colmean = <n on the device>])
+ * keep_gram: scm_ruv3_fit_gram keeps the centred Gram of all cells and their column means on the device for scm_sil();
+ * more_k (int vector or NULL): further ruvK values the same fullalpha has to serve (scm_ctx_set_conv_ranks, R/scRUVIII.R:64-75). */
+static SEXP fit_impl(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kconv, SEXP mode, int keep_gram, SEXP more_k) {
     dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
     int s = Rf_asInteger(s_), has_b = !Rf_isNull(batch);
     int32_t* dg = (int32_t*)to_dev(INTEGER(group), d->m * 4);
     int32_t* db = has_b ? (int32_t*)to_dev(INTEGER(batch), d->m * 4) : NULL;
-    double *dfa, *dsig, *dmean = NULL, *dsd = NULL;
+    double *dfa, *dsig, *dmean = NULL, *dsd = NULL, *dgram = NULL, *dcm = NULL;
     CHECK(scm_dev_alloc(ctx(), (int64_t)s * d->n * 8, (void**)&dfa)); CHECK(scm_dev_alloc(ctx(), s * 8, (void**)&dsig));
     if (has_b) { CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dmean)); CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dsd)); }
+    if (keep_gram) { CHECK(scm_dev_alloc(ctx(), d->n * d->n * 8, (void**)&dgram)); CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dcm)); }
+    if (!Rf_isNull(more_k)) CHECK(scm_ctx_set_conv_ranks(ctx(), INTEGER(more_k), Rf_length(more_k)));
     int32_t iters; double resid;
-    CHECK(scm_ruv3_fit(ctx(), d->p, d->m, d->n, d->ld, dg, Rf_asInteger(G), db, has_b ? Rf_asInteger(Bt) : 0, s, Rf_asInteger(kconv),
-                       Rf_asInteger(mode), 1e-10, 300, 1, dfa, dsig, dmean, dsd, &iters, &resid));
-    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    int rc = scm_ruv3_fit_gram(ctx(), d->p, d->m, d->n, d->ld, dg, Rf_asInteger(G), db, has_b ? Rf_asInteger(Bt) : 0, s, Rf_asInteger(kconv),
+                               Rf_asInteger(mode), 1e-10, 300, 1, dfa, dsig, dmean, dsd, &iters, &resid, dgram, dcm);
+    scm_ctx_set_conv_ranks(ctx(), NULL, 0);
+    CHECK(rc);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, keep_gram ? 6 : 4));
     SEXP fa = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, s));          /* n x s column-major == s x n row-major; R side t()s it */
     CHECK(scm_d2h(ctx(), REAL(fa), dfa, (int64_t)s * d->n * 8)); SET_VECTOR_ELT(out, 0, fa);
     SEXP sg = PROTECT(Rf_allocVector(REALSXP, s)); CHECK(scm_d2h(ctx(), REAL(sg), dsig, s * 8)); SET_VECTOR_ELT(out, 1, sg);
@@ -72,11 +87,28 @@ SEXP scm_fit(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kco
         SEXP sd = PROTECT(Rf_allocVector(REALSXP, d->n)); CHECK(scm_d2h(ctx(), REAL(sd), dsd, d->n * 8)); SET_VECTOR_ELT(out, 3, sd);
         UNPROTECT(2);
     }
+    if (keep_gram) {
+        SEXP nm = PROTECT(Rf_allocVector(STRSXP, 6));
+        const char* names[6] = {"fullalpha", "sigma", "mean", "sd", "gram", "colmean"};
+        for (int i = 0; i < 6; i++) SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+        Rf_setAttrib(out, R_NamesSymbol, nm);
+        SET_VECTOR_ELT(out, 4, wrap_dbuf(dgram)); SET_VECTOR_ELT(out, 5, wrap_dbuf(dcm));
+        UNPROTECT(1);
+    }
     scm_dev_free(ctx(), dg); scm_dev_free(ctx(), db); scm_dev_free(ctx(), dfa); scm_dev_free(ctx(), dsig);
     scm_dev_free(ctx(), dmean); scm_dev_free(ctx(), dsd);
     UNPROTECT(3);
     return out;
 }
+SEXP scm_fit(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kconv, SEXP mode) {
+    return fit_impl(Yp, group, G, batch, Bt, s_, kconv, mode, 0, R_NilValue);
+}
+SEXP scm_fit_gram(SEXP Yp, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP s_, SEXP kconv, SEXP mode, SEXP more_k) {
+    return fit_impl(Yp, group, G, batch, Bt, s_, kconv, mode, 1, more_k);
+}
+
+/* hands the library's cached scratch back to the driver (scm_ctx_release_scratch), e.g. from gc() hooks */
+SEXP scm_release_scratch(void) { CHECK(scm_ctx_release_scratch(ctx())); return R_NilValue; }
 
 /* adjust: alpha (n x k column-major == k x n row-major), ctl (logical n), center/pre/post (numeric n or NULL), subset (int 0-based or NULL)
  * returns an R matrix genes(or subset) x cells, i.e. the byte image of the device result */
@@ -197,7 +229,8 @@ SEXP scm_sil(SEXP Yp, SEXP gram, SEXP colmean, SEXP alpha, SEXP k_, SEXP ctl, SE
 }
 
 static const R_CallMethodDef calls[] = {
-    {"scm_upload", (DL_FUNC)&scm_upload, 2}, {"scm_fit", (DL_FUNC)&scm_fit, 8},
+    {"scm_upload", (DL_FUNC)&scm_upload, 2}, {"scm_fit", (DL_FUNC)&scm_fit, 8}, {"scm_fit_gram", (DL_FUNC)&scm_fit_gram, 9},
+    {"scm_release_scratch", (DL_FUNC)&scm_release_scratch, 0},
     {"scm_adjust_", (DL_FUNC)&scm_adjust_, 8}, {"scm_segmean", (DL_FUNC)&scm_segmean, 3},
     {"scm_upload_sparse", (DL_FUNC)&scm_upload_sparse, 5}, {"scm_ruvg", (DL_FUNC)&scm_ruvg, 3}, {"scm_sil", (DL_FUNC)&scm_sil, 14},
     {NULL, NULL, 0}};

@@ -140,6 +140,51 @@ def test_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def _call_sites(text):
+    """(.Call name, number of arguments) for every `.Call("name", ...)` in R source (comments stripped)."""
+    text = "\n".join(ln.split("#")[0] for ln in text.splitlines())
+    out = []
+    for mt in re.finditer(r'\.Call\(\s*"([A-Za-z0-9_]+)"', text):
+        i, depth, nargs = mt.end(), 1, 0
+        while depth:
+            ch = text[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                nargs += 1
+            i += 1
+        out.append((mt.group(1), nargs))
+    return out
+
+
+def test_r_shim_typechecks_and_matches_the_r_closures():
+    """The R side cannot be built or run here (no R).  What CAN be checked on CPU: (1) r-package/src/rshim.c compiles
+    (syntax + types) against include/scmerge_b200.h and a stand-in for R's C API (tests/r_stub), so every C-ABI call in it has
+    the declared arity and pointer types; (2) every `.Call("name", ...)` in r-package/R/*.R is registered in the shim's
+    R_CallMethodDef table with that number of arguments."""
+    import glob
+    import shutil
+    import subprocess
+    shim = os.path.join(ROOT, "r-package", "src", "rshim.c")
+    if shutil.which("gcc"):
+        r = subprocess.run(["gcc", "-fsyntax-only", "-std=c11", "-Wall", "-Werror=implicit-function-declaration",
+                            "-Werror=incompatible-pointer-types", "-Werror=int-conversion", "-Wno-cast-function-type",
+                            "-I" + os.path.join(ROOT, "tests", "r_stub"), "-I" + os.path.join(ROOT, "include"), shim],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    table = dict((nm, int(na)) for nm, na in re.findall(r'\{"([a-z_]+)",\s*\(DL_FUNC\)&[a-z_]+,\s*(\d+)\}', open(shim).read()))
+    assert table, "no R_CallMethodDef entries found"
+    sites = []
+    for path in glob.glob(os.path.join(ROOT, "r-package", "R", "*.R")):
+        sites += _call_sites(open(path).read())
+    assert len(sites) >= 10
+    for name, nargs in sites:
+        assert name in table, f'.Call("{name}") is not registered in rshim.c'
+        assert table[name] == nargs, f'.Call("{name}") passes {nargs} arguments, the shim registers {table[name]}'
+
+
 def test_shard_rows_partition():
     from scmerge_b200.dist import shard_rows
     for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
