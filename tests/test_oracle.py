@@ -78,6 +78,33 @@ def test_residop_is_group_mean_subtraction(sim):
         assert np.allclose(Y0[g == j], sim["Y"][g == j] - sim["Y"][g == j].mean(axis=0), atol=1e-12)
 
 
+def test_gram_identity_holds_for_any_shift_and_centred_gram_is_recoverable(sim):
+    """The algebra the device fit relies on.  For ANY fixed vector a
+        Y0'Y0 = sum_i (y_i - a)(y_i - a)' - sum_g n_g (mu_g - a)(mu_g - a)'
+    (the fit uses the mean of a strided sample of cells as `a`, so that the Gram kernel can read a pre-shifted copy), and the
+    centred Gram of all cells, needed by the ruvK selection, is the same correction with ONE group:
+        sum_i (y_i - ybar)(y_i - ybar)' = sum_i (y_i - a)(y_i - a)' - m (ybar - a)(ybar - a)'."""
+    Y, M = sim["Y"], orc.replicate_matrix(sim["M"])
+    m, n = Y.shape
+    g = orc.group_ids(M)
+    Y0 = orc.my_residop(Y, M)                       # literal dense projector (R/fastRUVIII.R:121-129)
+    G0 = Y0.T @ Y0
+    ybar = Y.mean(axis=0)
+    Gc = (Y - ybar).T @ (Y - ybar)
+    rng = np.random.default_rng(5)
+    stride = max(1, m // 64)
+    for a in (np.zeros(n), ybar, Y[::stride].mean(axis=0), ybar + rng.normal(size=n)):
+        Ga = (Y - a).T @ (Y - a)
+        corr = np.zeros((n, n))
+        for grp in range(M.shape[1]):
+            rows = g == grp
+            d = Y[rows].mean(axis=0) - a
+            corr += rows.sum() * np.outer(d, d)
+        scale = np.abs(G0).max()
+        assert np.abs(Ga - corr - G0).max() / scale < 1e-12
+        assert np.abs(Ga - m * np.outer(ybar - a, ybar - a) - Gc).max() / np.abs(Gc).max() < 1e-12
+
+
 def test_standardize2_plain_formulas():
     rng = np.random.default_rng(0)
     Y = rng.normal(size=(30, 50)) + 3
