@@ -185,6 +185,46 @@ def test_r_shim_typechecks_and_matches_the_r_closures():
         assert table[name] == nargs, f'.Call("{name}") passes {nargs} arguments, the shim registers {table[name]}'
 
 
+def test_pseudobulk_keys_match_the_oracle_bit_exactly():
+    """Host logic only (no device): the composite (batch, fold, cluster) key of every cell reproduces the row order, the
+    names and the group membership of the reference's `bulkExprs` (create_pseudoBulk batch by batch,
+    R/scMerge2_utilis.R:259-263,461-486), including droplevels() of empty combinations and ragged batches (a batch with
+    fewer cells than k_fold, a cluster missing from a batch)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ruv_oracle as orc
+    from scmerge_b200.scmerge2 import pseudobulk_keys
+    rng = np.random.default_rng(11)
+    m, n, K = 137, 9, 6
+    batch = np.array(["b2"] * 70 + ["b10"] * 63 + ["b3"] * 4)            # "b10" < "b2" < "b3": sorted LEVEL order, 4 cells < K
+    clust = rng.choice(["T", "B", "NK"], size=m)
+    clust[batch == "b3"] = "T"                                          # clusters B / NK are missing from batch b3
+    X = rng.normal(size=(n, m))                                         # genes x cells
+    which = np.empty(m, dtype=np.int64)
+    for b in np.unique(batch):
+        idx = np.nonzero(batch == b)[0]
+        Kb = min(idx.shape[0], K)
+        which[idx[rng.permutation(idx.shape[0])]] = (np.arange(idx.shape[0]) % Kb) + 1   # cvFolds: rep(1:K, length.out) over a random order
+    keys, P, names, pb_t, pb_b = pseudobulk_keys(batch, clust, K, which=which)
+    bulks, ref_names = [], []
+    for b in np.unique(batch):
+        sel = batch == b
+        bulk, nm = orc.create_pseudobulk(X[:, sel], clust[sel], which[sel], k_fold=min(int(sel.sum()), K))
+        bulks.append(bulk)
+        ref_names += [f"{b}_{x}" for x in nm]
+    ref = np.concatenate(bulks)
+    assert names == ref_names and P == ref.shape[0] == len(set(names))
+    assert keys.dtype == np.int32 and keys.min() == 0 and keys.max() == P - 1
+    for p in range(P):                                                  # same cells in every pseudobulk (bit-exact indices)
+        cells = np.nonzero(keys == p)[0]
+        np.testing.assert_array_equal(X[:, cells].sum(axis=1) / cells.shape[0], ref[p])
+    tlev, blev = np.unique(clust), np.unique(batch)
+    assert [f"{blev[b]}_{tlev[t]}" for b, t in zip(pb_b, pb_t)] == [x.rsplit("_", 1)[0] for x in names]
+    # a seeded draw has the cvFolds structure: fold sizes within a batch differ by at most one
+    k2, P2, *_ = pseudobulk_keys(batch, clust, K, seed=1)
+    assert k2.shape == (m,) and 0 < P2 <= 3 * 3 * K
+
+
 def test_shard_rows_partition():
     from scmerge_b200.dist import shard_rows
     for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
