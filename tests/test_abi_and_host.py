@@ -225,6 +225,32 @@ def test_pseudobulk_keys_match_the_oracle_bit_exactly():
     assert k2.shape == (m,) and 0 < P2 <= 3 * 3 * K
 
 
+def test_create_chunk_and_replicate_keys_against_independent_restatements():
+    """Two independently written versions of the same reference logic must agree everywhere: createChunk
+    (R/scMerge2_utilis.R:153-170) of the host mirror vs the oracle, and replicate_keys vs the oracle's one-hot
+    ruv::replicate.matrix for label vectors, data-frame-like labels and one-hot matrices."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ruv_oracle as orc
+    from scmerge_b200.ruv import createChunk, replicate_keys, replicate_matrix
+    for n in list(range(1, 60)) + [999, 1000, 1001, 1499, 1500, 1501, 50_000, 74_999, 75_000, 125_001]:
+        for cs in (1, 2, 7, 10, 1000, 50_000):
+            assert createChunk(n, cs) == orc.create_chunk(n, cs), (n, cs)
+    rng = np.random.default_rng(2)
+    for labels in (rng.integers(0, 5, 40), rng.integers(3, 90, 200) * 7, np.array(list("abcabcddz")), rng.normal(size=12).round(1),
+                   np.stack([rng.integers(0, 3, 30), rng.integers(0, 2, 30)], axis=1).astype(str)):
+        keys, G = replicate_keys(labels)
+        M_ref = orc.replicate_matrix(labels)
+        assert M_ref.shape == (len(labels), G)
+        np.testing.assert_array_equal(np.argmax(M_ref, axis=1), keys)
+        np.testing.assert_array_equal(replicate_matrix(labels), M_ref)
+        k2, G2 = replicate_keys(M_ref)                       # a one-hot matrix passes through with its column order
+        assert G2 == G
+        np.testing.assert_array_equal(k2, keys)
+    with pytest.raises(ValueError, match="one-hot"):
+        replicate_keys(np.array([[1.0, 1.0], [0.0, 1.0]]))
+
+
 def test_shard_rows_partition():
     from scmerge_b200.dist import shard_rows
     for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
