@@ -51,8 +51,8 @@ def parse():
     p.add_argument("--types", type=int, default=20)
     p.add_argument("--batches", type=int, default=4)
     p.add_argument("--cpu-cells", type=int, default=None,
-                   help="cells in the bounded CPU-baseline sample (default 20000; 50000 for the scmerge2 workload, whose fit cost "
-                        "does not depend on the number of cells)")
+                   help="cells in the bounded CPU-baseline sample (default 50000 = BASELINE.json configs[1]; the exact path is linear in "
+                        "the number of cells)")
     p.add_argument("--workload", default="fastruviii", choices=["fastruviii", "scmerge2"],
                    help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] (cosine norm, "
                         "pseudobulk fit, adjust all cells; not the headline line)")
