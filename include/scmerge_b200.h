@@ -17,6 +17,9 @@
  *   - all arithmetic is IEEE float64; replicate / batch / pseudobulk keys are int32, 0-based, -1 = "skip row".
  *   - all work is enqueued on the context's stream; functions with host outputs synchronise that stream.
  *   - there is no CPU fallback: every entry point fails with SCM_ERR_CUDA if no sm_100 device is usable.
+ *   - process model: ONE process per GPU (R's single thread, one torchrun rank per device).  Contexts of one process must all be
+ *     on the same device: the kernels' dynamic shared-memory attributes are set once per process, for the device of the first
+ *     launch.  Calls on one context must not overlap (no internal locking); different contexts may be used from different threads.
  */
 #ifndef SCMERGE_B200_H
 #define SCMERGE_B200_H
