@@ -4,8 +4,11 @@ What is rank-local and what crosses ranks in scm_ruv3_fit is mirrored here with 
 device stages (the oracle's arithmetic), driven through the SAME all-reduce hook and row sharding the GPU
 path uses.  The test proves the decomposition
 
-    group sums / counts  -> all-reduce -> shift a = global column mean
+    group sums / counts  -> all-reduce -> global column mean (stand_mean / the PCA centre)
+    sums of a strided sample of <= 4096 local cells -> all-reduce -> shift a (the same vector on every rank; the Gram kernel
+        reads the pre-shifted copy Y - a, scm_api.cu ruv3_fit_impl)
     local Gram of (Y - a) -> all-reduce -> minus sum_g n_g (mu_g - a)(mu_g - a)'  == Gram of the residual Y0
+                                        -> minus m (ybar - a)(ybar - a)'          == centred Gram of all cells (ruvK selection)
 
 gives every rank the single-process result, and that the hook sums raw buffers in place.
 """
@@ -51,18 +54,28 @@ def _worker(rank, world, port, q):
         counts = np.bincount(gl, minlength=G).astype(np.int64)
         meta = np.array([0, hi - lo], dtype=np.int64)
         allreduce(sums); allreduce(counts); allreduce(meta)
-        a = sums.sum(axis=0) / meta[1]
+        ybar = sums.sum(axis=0) / meta[1]
+        ms = min(Yl.shape[0], 64)                      # the library samples <= 4096 cells; 64 keeps the sample a strict subset here
+        stride = Yl.shape[0] // ms if ms else 1
+        psum = Yl[: ms * stride : stride].sum(axis=0) if ms else np.zeros(Y.shape[1])
+        pcount = np.array([ms], dtype=np.int64)
+        allreduce(psum); allreduce(pcount)
+        a = psum / pcount[0]
+        assert np.abs(a - ybar).max() > 1e-6            # really a different vector than the global mean
         gram = (Yl - a).T @ (Yl - a)
         allreduce(gram)
         mu = sums / counts[:, None]
         C = np.sqrt(counts)[:, None] * (mu - a)
         G0 = gram - C.T @ C
+        Gc = gram - meta[1] * np.outer(ybar - a, ybar - a)
         # single-process truth
         full_sums = np.zeros((G, Y.shape[1]))
         np.add.at(full_sums, g, Y)
         Y0 = Y - (full_sums / np.bincount(g, minlength=G)[:, None])[g]
         ref = Y0.T @ Y0
-        q.put((rank, int(meta[1]), float(np.linalg.norm(G0 - ref) / np.linalg.norm(ref)), float(np.abs(G0).sum())))
+        refc = (Y - Y.mean(axis=0)).T @ (Y - Y.mean(axis=0))
+        q.put((rank, int(meta[1]), float(np.linalg.norm(G0 - ref) / np.linalg.norm(ref)), float(np.abs(G0).sum()),
+               float(np.linalg.norm(Gc - refc) / np.linalg.norm(refc)), float(np.abs(a).sum())))
     finally:
         dist.destroy_process_group()
 
@@ -83,3 +96,5 @@ def test_two_rank_fit_decomposition_gloo():
     assert [r[1] for r in res] == [1500, 1500]           # the row counts were summed across ranks
     assert all(r[2] < 1e-12 for r in res)                  # sharded Gram of the residual == single process
     assert res[0][3] == res[1][3]                          # bit-identical on both ranks (no broadcast needed)
+    assert all(r[4] < 1e-12 for r in res)                  # centred Gram of all cells recovered from the shifted one
+    assert res[0][5] == res[1][5]                          # every rank agreed on the same shift vector
