@@ -251,6 +251,33 @@ def test_create_chunk_and_replicate_keys_against_independent_restatements():
         replicate_keys(np.array([[1.0, 1.0], [0.0, 1.0]]))
 
 
+def test_every_entry_point_rejects_null_arguments_without_crashing():
+    """No exception or signal may cross the C ABI: every exported function called with a NULL context / NULL pointers / zero
+    sizes returns a negative status (scm_ctx_destroy(NULL) is a no-op) and leaves a message in scm_last_error().  Run in a
+    subprocess so that a segfault would be reported as a failure instead of killing the test session."""
+    import subprocess
+    import sys
+    code = """
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from scmerge_b200 import _lib as L
+lib = L.lib()
+for name, args in L.SIGNATURES.items():
+    vals = [L.ALLREDUCE_FN(0) if a is L.ALLREDUCE_FN else 0.0 if a is C.c_double else None if (a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents")) else 0
+            for a in args]
+    rc = getattr(lib, name)(*vals)
+    if name in ("scm_last_error", "scm_version"):
+        continue
+    ok = rc == 0 if name == "scm_ctx_destroy" else rc < 0
+    assert ok, (name, rc)
+    if rc < 0:
+        assert lib.scm_last_error(), name
+print("OK")
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_shard_rows_partition():
     from scmerge_b200.dist import shard_rows
     for m, w in [(10, 3), (7, 8), (1_000_000, 8), (0, 2)]:
