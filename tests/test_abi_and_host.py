@@ -268,7 +268,7 @@ for name, args in L.SIGNATURES.items():
     rc = getattr(lib, name)(*vals)
     if name in ("scm_last_error", "scm_version"):
         continue
-    ok = rc == 0 if name == "scm_ctx_destroy" else rc < 0
+    ok = rc == 0 if name == "scm_ctx_destroy" else rc <= 0 if name == "scm_host_free_pinned" else rc < 0  # cudaFreeHost(NULL) succeeds on a GPU box
     assert ok, (name, rc)
     if rc < 0:
         assert lib.scm_last_error(), name
