@@ -17,9 +17,11 @@
  *   - all arithmetic is IEEE float64; replicate / batch / pseudobulk keys are int32, 0-based, -1 = "skip row".
  *   - all work is enqueued on the context's stream; functions with host outputs synchronise that stream.
  *   - there is no CPU fallback: every entry point fails with SCM_ERR_CUDA if no sm_100 device is usable.
- *   - process model: ONE process per GPU (R's single thread, one torchrun rank per device).  Contexts of one process must all be
- *     on the same device: the kernels' dynamic shared-memory attributes are set once per process, for the device of the first
- *     launch.  Calls on one context must not overlap (no internal locking); different contexts may be used from different threads.
+ *   - process model: either ONE process per GPU (one torchrun rank per device; cross-rank sums through the built-in NCCL
+ *     communicator, scm_ctx_comm_init_nccl, or a host-supplied hook, scm_ctx_set_allreduce), or ONE process driving several GPUs
+ *     (R's single thread: scm_multi_create + scm_multi_ruv3_host; ncclCommInitAll and one host thread per device inside the
+ *     library).  A context belongs to one device; contexts on different devices may live in one process.  Calls on one context
+ *     must not overlap (no internal locking); different contexts may be used from different threads.
  */
 #ifndef SCMERGE_B200_H
 #define SCMERGE_B200_H
@@ -47,6 +49,7 @@ extern "C" {
 
 typedef struct scm_ctx scm_ctx;
 typedef struct scm_coef scm_coef;
+typedef struct scm_multi scm_multi;
 
 /* Host-supplied in-place sum all-reduce over the ranks that share the cells (one process per GPU).
  * `dtype`: 0 = float64, 1 = int64.  Must be enqueued on (or ordered after) `stream`.  Return 0 on success. */
@@ -62,6 +65,41 @@ int scm_device_pci_bus_id(int device, char* buf, int len);
 int scm_ctx_create(int device, void* cuda_stream /* NULL = own stream */, scm_ctx** out);
 int scm_ctx_destroy(scm_ctx* ctx);
 int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size);
+/* Built-in communicator: NCCL, resolved with dlopen("libnccl.so.2") at first use (no link-time dependency; SCM_ERR_COMM when it
+ * cannot be loaded).  One process per GPU: rank 0 obtains the 128-byte unique id (scm_nccl_unique_id), the host hands it to the
+ * other ranks by any means (a file, MPI, torch.distributed, ...), and every rank calls scm_ctx_comm_init_nccl (collective).  The
+ * communicator takes precedence over a hook and is destroyed with the context.  world_size == 1 resets to "no communication".
+ * These replace the BiocParallel process pool of the reference's chunked adjust (R/scMerge2_utilis.R:104-124) as the way the
+ * cells are spread over workers; the reference has no collective of its own. */
+int scm_nccl_unique_id(void* id128 /* 128 bytes */);
+int scm_ctx_comm_init_nccl(scm_ctx* ctx, const void* id128, int rank, int world_size);
+/* transport: 0 none (single rank), 1 built-in NCCL, 2 host hook */
+int scm_ctx_comm_info(scm_ctx* ctx, int* rank, int* world_size, int* transport);
+/* In-place sum of a device buffer over the ranks through whichever transport the context has (dtype 0 = float64, 1 = int64);
+ * enqueued on the context's stream.  The host-side gathers of the ruvK selection use it. */
+int scm_allreduce_sum(scm_ctx* ctx, void* d_buf, int64_t count, int dtype);
+/* Facts about the last eigen-solve on this context: Rayleigh-Ritz steps, the subspace-angle estimate it stopped at, `conv_rank`
+ * = the largest r such that the first r rows of the returned fullalpha span a converged invariant subspace (angle estimate
+ * <= 1e-8): re-using fullalpha with a ruvK above it (fullalpha= of R/fastRUVIII.R:83, getAdjustedMat R/scMerge2.R:399) is not
+ * backed by the fit; `products` = Gram x block products after the first Rayleigh-Ritz step. */
+int scm_ctx_fit_info(scm_ctx* ctx, int32_t* iters, double* resid, int32_t* conv_rank, int32_t* products);
+
+/* ---- one process, several GPUs (what a single R process needs) ---------------------------------------
+ * scm_multi_create: a context + stream per listed device (devices == NULL: 0 .. ndev-1) and one NCCL rank per device
+ * (ncclCommInitAll).  scm_multi_ruv3_host: scm_ruv3_host with the cells split into contiguous, balanced row blocks, one host
+ * thread per device, every block streamed over its own PCIe link; fit results are reported by device 0 (after the Gram
+ * all-reduce they are bit-identical on all devices).  Same arguments and error behaviour as scm_ruv3_host.
+ * scm_multi_ctx hands out the per-device context (device-resident calls on one shard; owned by the handle). */
+int scm_multi_create(const int* devices, int ndev, scm_multi** out);
+int scm_multi_destroy(scm_multi* mg);
+int scm_multi_size(const scm_multi* mg);
+scm_ctx* scm_multi_ctx(scm_multi* mg, int i);
+int scm_multi_ruv3_host(scm_multi* mg, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,
+                        const int32_t* h_batch, int32_t Bt, const uint8_t* h_ctl, int32_t k, int32_t s, int mode, double tol,
+                        int32_t maxit, uint64_t seed, const double* h_fullalpha_in, int32_t s_in, int center_mode,
+                        const double* h_center, double* h_out, int64_t ldo, double* h_fullalpha, double* h_sigma, double* h_mean,
+                        double* h_sd, int32_t* iters_out, double* resid_out);
+
 /* Additional subspace dimensions the EXACT eigensolver has to converge in the following fits (besides `kconv`): scRUVIII with
  * several ruvK (R/scRUVIII.R:64-75) re-uses ONE fullalpha for every k, so the top-k subspace must be accurate for each of
  * them.  nk = 0 resets. */
@@ -213,7 +251,9 @@ int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld
  *   batch : NULL for fastRUVIII / pseudoRUVIII; batch id per cell (Bt batches) for scRUVIII, which adds
  *           standardize2 (R/scRUVIII.R:158-175): stand_mean / stand_sd are returned in d_mean / d_sd (n each)
  *   s     : rows of fullalpha to return (host applies the svd_k rule R/fastRUVIII.R:66-70), kconv = min(k, s)
- * Cross-rank state (group sums, batch sums, the n x n Gram) is summed through the all-reduce hook.
+ * Every local cell must carry a key in [0, G) (M assigns each cell to a replicate group; SCM_ERR_INVALID otherwise).
+ * Cross-rank state is summed with TWO all-reduces per fit: [group sums | batch sums | counts | NA flag, rows] and
+ * [n x n centred Gram | within-batch squared deviations] (built-in NCCL communicator or the hook).
  * Outputs: d_fullalpha (s x n), d_sigma (s singular values of Y0). */
 int scm_ruv3_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld,
                  const int32_t* d_group, int32_t G, const int32_t* d_batch, int32_t Bt,
@@ -282,9 +322,10 @@ int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t
 int scm_adjust_to_host(scm_ctx* ctx, double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out, int64_t ldo);
 
 /* Stage timers (ms, CUDA events on the context stream) of the last scm_ruv3_fit / scm_adjust:
- * 0 seg_colsum, 1 gram (SYRK + split reduce), 2 allreduce, 3 eig, 4 coef, 5 adjust, 6 standardise,
- * 7 the gram_syrk kernel alone, 8 ingest (scm_csc_to_dense / scm_cosine_rows), 9 the pre-shifted copy of the cells the fit's Gram
- * reads (part of 1; 0 when that path is off). */
+ * 0 seg_colsum (the summing pass; it also writes the pre-shifted copy of the cells the fit's Gram reads), 1 gram (SYRK + split
+ * reduce + re-centring), 2 allreduce (the LAST collective), 3 eig, 4 coef, 5 adjust, 6 standardise (last pass), 7 the gram_syrk
+ * kernel alone, 8 ingest (scm_csc_to_dense / scm_cosine_rows), 9 the pre-shifted copy as a separate pass (only with
+ * SCM_K1_FUSED_COPY=0; part of 1). */
 int scm_timers(scm_ctx* ctx, double* ms, int n);
 
 #ifdef __cplusplus

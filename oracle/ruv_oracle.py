@@ -498,11 +498,11 @@ def scmerge2_core(exprs_genes_x_cells, batch, clust, which, ctl=None, ruvK=20, k
     n = X.shape[0]
     ctl = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
     bulks, names, rep = [], [], []
-    for b in np.unique(batch):
+    for i, b in enumerate(np.unique(batch), start=1):  # batch_list <- sort(unique(batch)) (R/scMerge2.R:139)
         sel = batch == b
         bulk, nm = create_pseudobulk(X[:, sel], clust[sel], which[sel], k_fold=k_fold)
         bulks.append(bulk)
-        names += [f"{b}_{x}" for x in nm]
+        names += [f"{i}_{x}" for x in nm]  # rownames(res) <- paste(i, rownames(res), sep = "_"): the batch INDEX (R/scMerge2_utilis.R:266)
         rep += [x.rsplit("_", 1)[0] for x in nm]
     Yp = np.concatenate(bulks)
     res = pseudoRUVIII(X.T, Yp, np.array(rep), ctl, ruvK, exact=exact, rng=rng)

@@ -4,7 +4,7 @@ The arithmetic lives in `libscmerge_b200.so` (hand-written sm_100a CUDA, C ABI i
 this package is the host-side mirror of the R closures.  There is no CPU fallback.
 """
 from ._lib import LIB_PATH, NonFiniteError, NotConvergedWarning, ScmError, SingularError, lib  # noqa: F401
-from .device import Context, DeviceArray, DeviceMatrix, bind_host_to_gpu, default_context, pinned_empty  # noqa: F401
+from .device import Context, DeviceArray, DeviceMatrix, MultiContext, bind_host_to_gpu, default_context, pinned_empty  # noqa: F401
 from .ruv import (ExactParam, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
                   create_pseudoBulk, fastRUVIII, genes_by_name, getAdjustedMat, pseudoRUVIII, replicate_keys, replicate_matrix,
                   scRUVg, scRUVIII, tological)

@@ -28,6 +28,17 @@ SIGNATURES = {
     "scm_ctx_create": [_int, _vp, _pp],
     "scm_ctx_destroy": [_vp],
     "scm_ctx_set_allreduce": [_vp, ALLREDUCE_FN, _vp, _int],
+    "scm_nccl_unique_id": [_vp],
+    "scm_ctx_comm_init_nccl": [_vp, _vp, _int, _int],
+    "scm_ctx_comm_info": [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)],
+    "scm_allreduce_sum": [_vp, _vp, _i64, _int],
+    "scm_ctx_fit_info": [_vp, C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_i32), C.POINTER(_i32)],
+    "scm_multi_create": [C.POINTER(_int), _int, _pp],
+    "scm_multi_destroy": [_vp],
+    "scm_multi_size": [_vp],
+    "scm_multi_ctx": [_vp, _int],
+    "scm_multi_ruv3_host": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _int, _dbl, _i32, _u64, _vp, _i32, _int,
+                            _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
     "scm_ctx_set_conv_ranks": [_vp, _vp, _i32],
     "scm_ctx_sync": [_vp],
     "scm_ctx_launch_count": [_vp, C.POINTER(_i64)],
@@ -71,7 +82,7 @@ SIGNATURES = {
                       _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
     "scm_timers": [_vp, C.POINTER(_dbl), _int],
 }
-_RESTYPES = {"scm_last_error": C.c_char_p}
+_RESTYPES = {"scm_last_error": C.c_char_p, "scm_multi_ctx": C.c_void_p}
 
 
 class ScmError(RuntimeError):

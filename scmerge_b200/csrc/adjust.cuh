@@ -207,13 +207,7 @@ inline int coef_create(scm_ctx* ctx, const double* d_alpha, int64_t n, int32_t k
     SCM_LAUNCH_CHECK(ctx);
     // N = ac ac'  (k x k), Cholesky, N^-1 = Linv' Linv, B = ac' N^-1
     SCM_TRY(gemm(ctx, k, k, (int)n, 1.0, rowmajor(ACU, n), transposed(ACU, n), 0.0, N, k));
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
-    chol_inv_kernel<<<1, 1024, sizeof(double) * 2 * k * (k + 1), st>>>(N, k, 0.0, Linv, flag);
-    SCM_LAUNCH_CHECK(ctx);
+    SCM_TRY(chol_inv_launch(ctx, N, k, 0.0, Linv, flag));
     SCM_TRY(gemm(ctx, k, k, k, 1.0, transposed(Linv, k), rowmajor(Linv, k), 0.0, Ninv, k));
     SCM_TRY(gemm(ctx, (int)n, k, k, 1.0, transposed(ACU, n), rowmajor(Ninv, k), 0.0, c->Bmat, k));
     coef_scale_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(c->Bmat, c->Amat, AU, n, k, d_pre, d_post);

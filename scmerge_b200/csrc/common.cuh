@@ -62,9 +62,18 @@ struct scm_ctx {
     bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
     bool gram_preshift = true;   // fits run the Gram on a pre-shifted copy of the cells when there is room (env SCM_GRAM_PRESHIFT=0: off)
     int gram_lean = 3;           // Gram TMA kernel: bit 0 thin last tile row, bit 1 triangular diagonal units (env SCM_GRAM_LEAN)
+    bool k1_fused_copy = true;   // the pre-shifted copy is written by K1's summing pass (env SCM_K1_FUSED_COPY=0: separate copy kernel)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
     int conv_ranks[16];          // additional subspace dimensions the EXACT eigensolver must converge (scm_ctx_set_conv_ranks)
     int n_conv_ranks = 0;
+    // built-in communicator (comm.cuh): NCCL resolved with dlopen at run time, one rank per context.  Takes precedence over the
+    // host-supplied hook.  `comm_owned` = created by scm_ctx_comm_init_nccl (destroyed with the context); a scm_multi owns its own.
+    void* nccl_comm = nullptr;
+    bool comm_owned = false;
+    int rank = 0;
+    // facts about the last fit on this context (scm_ctx_fit_info)
+    int32_t fit_iters = 0, fit_conv_rank = 0, fit_products = 0;
+    double fit_resid = 0.0;
 };
 
 namespace scm {

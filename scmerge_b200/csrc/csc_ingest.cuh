@@ -190,11 +190,7 @@ inline int csc_to_dense(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_
     if (n <= 6144 && canonical && !getenv("SCM_CSC_GENERIC")) {
         const int slab = (int)((n + 1) & ~(int64_t)1);
         const int smem = (2 * slab + 16) * (int)sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            SCM_CUDA(cudaFuncSetAttribute(csc_densify_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 6144 + 16) * 8));
-            attr_set = true;
-        }
+        SCM_CUDA(cudaFuncSetAttribute(csc_densify_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 6144 + 16) * 8));  // per device
         int per_sm = (int)((220 * 1024) / (smem + 1024));
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;

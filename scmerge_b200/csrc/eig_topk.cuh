@@ -1,17 +1,44 @@
 // K4: top-s eigenpairs of the n x n symmetric PSD Gram by block subspace iteration.
 //
 //   X <- orth(random n x l)                                   l = s + oversampling (<= SCM_MAX_BLOCK)
+//   X <- orth(G X)                                            one product before the first Rayleigh-Ritz step (EXACT), two (RANDOMIZED)
 //   repeat:  Z = G X ; H = X'Z ; (Q, theta) = eig(H)          Rayleigh-Ritz, single-CTA one-sided Jacobi
 //            W = Z Q ; V = X Q ; r_i = ||W_i - theta_i V_i||   true residuals of the Ritz pairs
 //            stop when ||R_kconv||_F / (theta_kconv - theta_kconv+1) <= tol (EXACT; Davis-Kahan bound on the
-//            subspace angle) or after q+1 = 3 products (RANDOMIZED)
-//            X <- CholeskyQR2(W diag(1/theta))                 columns ~ orthonormal already => well conditioned
+//            subspace angle); RANDOMIZED stops after its q + 1 = 3 products (rsvd: p = 10, q = 2)
+//            W <- (G Theta^-1)^(pw-1) W Theta^-1 ; X <- CholeskyQR2(W)
 // All n-sized products run on the DMMA GEMM; the l x l factorizations are single-CTA shared-memory kernels.
+//
+// Control flow lives on the DEVICE: a one-thread kernel (eig_check_kernel) evaluates the stopping rule and the number of extra
+// products of the next iteration into a control block, and every later kernel returns at once when the block says "done" (or
+// "this extra product is not needed").  The host therefore enqueues iterations blindly, two at a time, and reads the control
+// block back once per batch: a converged fit costs ONE host synchronisation instead of one per iteration, and a skipped
+// iteration costs a few microseconds of empty launches (strong scaling: this loop is replicated on every rank).
 #pragma once
 #include "common.cuh"
 #include "gemm_f64.cuh"
 
 namespace scm {
+
+struct EigCtl {
+    int done;       // 0 running, 1 converged, 2 stagnated, 3 non-finite input, 4 iteration limit      (first two ints = the skip
+    int pw;         // products of the current outer iteration (1..4)                                    words of gemm_f64.cuh)
+    int it;         // Rayleigh-Ritz steps finished
+    int conv_rank;  // largest r <= s whose top-r subspace passed the rank test (set when done)
+    int jac_sweeps;
+    int chol_flag;  // a Cholesky pivot was not positive
+    int products;   // G * block products so far
+    int pad;
+    double worst, gap, rmax, top;
+    double hist[16];
+};
+
+struct EigRanks {
+    int n;
+    int k[17];
+};
+
+__device__ __forceinline__ bool eig_skip(const int* skip, int need) { return skip && (skip[0] != 0 || skip[1] < need); }
 
 // ---- random start block ---------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -32,52 +59,64 @@ __global__ void randn_kernel(double* __restrict__ X, int64_t count, uint64_t see
 // ---- single-CTA Cholesky + inverse of the factor ----------------------------------------------------
 // S (l x l, symmetric, row-major ld = l) -> Linv = inverse of the lower Cholesky factor of S + shift*maxdiag*I.
 // A non-positive pivot is replaced by tiny*maxdiag and reported through `flag`.
-__global__ void __launch_bounds__(1024)
-chol_inv_kernel(const double* __restrict__ S, int l, double shift_rel, double* __restrict__ Linv, int* __restrict__ flag) {
+// Right-looking elimination WITHOUT scaling the pivot column (A[i][k] -= A[i][j] A[k][j] / d_j; L[i][j] = A[i][j] / sqrt(d_j) is
+// applied once at the end): column j and d_j are read-only during step j, so a step needs ONE barrier (the scaled form needs
+// three and a serial sqrt on one thread).  16 x 16 threads tile the trailing block, no index divisions.
+// 120 us -> see DESIGN.md K4 table for the measured time at l = 80.
+constexpr int CHOL_THREADS = 256;
+__global__ void __launch_bounds__(CHOL_THREADS)
+chol_inv_kernel(const double* __restrict__ S, int l, double shift_rel, double* __restrict__ Linv, int* __restrict__ flag,
+                const int* __restrict__ skip, int need) {
+    if (eig_skip(skip, need)) return;
     extern __shared__ double sm[];
     const int ld = l + 1;
     double* A = sm;            // l x ld   (becomes L, lower)
     double* X = sm + l * ld;   // l x ld   (L^-1, lower)
     __shared__ double s_maxdiag;
+    __shared__ double s_rd[SCM_MAX_BLOCK + 2];  // 1 / sqrt(d_j)
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tx = tid & 15, ty = tid >> 4;
     for (int idx = tid; idx < l * l; idx += nt) {
         const int i = idx / l, j = idx % l;
         A[i * ld + j] = 0.5 * (S[i * l + j] + S[j * l + i]);
         X[i * ld + j] = 0.0;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
         double md = 0.0;
-        for (int i = 0; i < l; i++) md = fmax(md, A[i * ld + i]);
-        s_maxdiag = md;
+        for (int i = tid; i < l; i += 32) md = fmax(md, A[i * ld + i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        if (tid == 0) s_maxdiag = md;
     }
     __syncthreads();
     const double maxdiag = s_maxdiag;
+    const double floor_d = 1e-280 + 1e-30 * maxdiag;
     for (int i = tid; i < l; i += nt) A[i * ld + i] += shift_rel * maxdiag;
-    __syncthreads();
     for (int j = 0; j < l; j++) {
-        if (tid == 0) {
-            double d = A[j * ld + j];
-            if (!(d > 1e-280 + 1e-30 * maxdiag)) { d = 1e-30 * maxdiag + 1e-280; if (flag) *flag = 1; }
-            A[j * ld + j] = sqrt(d);
+        __syncthreads();
+        double d = A[j * ld + j];
+        if (!(d > floor_d)) { d = floor_d; if (tid == 0 && flag) *flag = 1; }
+        if (tid == 0) s_rd[j] = rsqrt(d);
+        const double inv_d = 1.0 / d;
+        for (int i = j + 1 + ty; i < l; i += 16) {
+            const double aij = A[i * ld + j] * inv_d;
+            for (int k = j + 1 + tx; k <= i; k += 16) A[i * ld + k] -= aij * A[k * ld + j];
         }
-        __syncthreads();
-        const double djj = A[j * ld + j];
-        for (int i = j + 1 + tid; i < l; i += nt) A[i * ld + j] /= djj;
-        __syncthreads();
-        const int rem = l - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += nt) {
-            const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
-            if (k <= i) A[i * ld + k] -= A[i * ld + j] * A[k * ld + j];
-        }
-        __syncthreads();
     }
-    // forward substitution, thread c owns column c of L^-1
+    __syncthreads();
+    // L[i][j] = A[i][j] / sqrt(d_j);  L[j][j] = sqrt(d_j) = d_j * rd_j (the diagonal entry may have been floored: use 1 / rd_j)
+    for (int idx = tid; idx < l * l; idx += nt) {
+        const int i = idx / l, j = idx % l;
+        if (j < i) A[i * ld + j] *= s_rd[j];
+    }
+    __syncthreads();
+    // forward substitution, thread c owns column c of L^-1: X[i][c] = (delta_ic - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i],
+    // 1 / L[i][i] = rd_i
     for (int i = 0; i < l; i++) {
         if (tid < l && tid <= i) {
             const int c = tid;
-            // X[k][c] = 0 for k < c; four independent partial sums break the FMA dependency chain
-            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four partial sums break the FMA dependency chain
             int k = c;
             for (; k + 3 < i; k += 4) {
                 s0 -= A[i * ld + k] * X[k * ld + c];
@@ -86,7 +125,7 @@ chol_inv_kernel(const double* __restrict__ S, int l, double shift_rel, double* _
                 s3 -= A[i * ld + k + 3] * X[(k + 3) * ld + c];
             }
             for (; k < i; k++) s0 -= A[i * ld + k] * X[k * ld + c];
-            X[i * ld + c] = ((s0 + s1) + (s2 + s3)) / A[i * ld + i];
+            X[i * ld + c] = ((s0 + s1) + (s2 + s3)) * s_rd[i];
         }
         __syncthreads();
     }
@@ -96,14 +135,25 @@ chol_inv_kernel(const double* __restrict__ S, int l, double shift_rel, double* _
     }
 }
 
+inline int chol_inv_launch(scm_ctx* ctx, const double* S, int l, double shift_rel, double* Linv, int* flag, const int* skip = nullptr,
+                           int need = 0) {
+    if (l > SCM_MAX_BLOCK) return fail(SCM_ERR_UNSUPPORTED, "chol_inv: l=%d > %d", l, SCM_MAX_BLOCK);
+    const size_t smem = sizeof(double) * 2 * l * (l + 1);
+    SCM_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // per device, cheap
+    chol_inv_kernel<<<1, CHOL_THREADS, smem, ctx->stream>>>(S, l, shift_rel, Linv, flag, skip, need);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 // ---- single-CTA symmetric eigensolver: one-sided (Hestenes) Jacobi ---------------------------------
 // H (l x l symmetric PSD, row-major) -> theta (descending), Q (row-major l x l, column j = eigenvector j).
 __global__ void __launch_bounds__(1024)
 jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, double* __restrict__ theta,
-                  int max_sweeps, double jtol, int* __restrict__ sweeps_out) {
+                  int max_sweeps, double jtol, int* __restrict__ sweeps_out, const int* __restrict__ skip) {
+    if (eig_skip(skip, 0)) return;
     extern __shared__ double sm[];
     const int lp = (l + 1) & ~1;  // even number of columns (a zero column pads odd l)
-    double* A = sm;               // column-major: column j at A + j*lp
+    double* A = sm;               // column-major: column j at A + j*cs
     const int cs = lp + 1;        // column stride: odd, so the two half-warps of a warp hit different banks
     double* V = sm + lp * cs;
     __shared__ int s_rot;
@@ -145,19 +195,24 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
             const double al = nrm2[p], be = nrm2[q];  // read before the shuffles: they order it against lane 0's update
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);  // all lanes: warp stays converged
-            // The rotation parameters (two FP64 divisions, a sqrt and an rsqrt: ~150 FP64 pipe slots) are computed by
-            // ONE lane per pair and broadcast; doing it redundantly in all 16 lanes made this scalar math the bulk of a round.
+            // Rotation parameters by ONE lane per pair, broadcast.  The scalar chain is the critical path of a round, so it is
+            // written with two reciprocal square roots and no division / sqrt:
+            //   rho = sqrt(tau^2 + 4 ga^2), cos 2x = |tau| / rho, cos^2 x = (1 + cos 2x) / 2 =: u, z = rsqrt(u)
+            //   c = cos x = u z,  1 / c = z,  |s| = sin 2x / (2 c) = |ga| z / rho,  t = tan x = s z
+            // (the small rotation angle |x| <= pi/4, sign as in t = sign(tau) 2 ga / (|tau| + rho)); c^2 + s^2 = u z^2 = 1.
             double c = 1.0, s = 0.0;
             if (act && hl == 0) {
                 // rotate unless the columns are orthogonal to the requested level (jtol >= l * eps ~ 2e-14: a tighter
                 // threshold is below the rounding noise of the dot product and never lets a sweep come out clean)
                 if (ga * ga > jtol * jtol * al * be && fabs(ga) > 1e-300) {
-                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), with the inner division folded
-                    // away: one sqrt + one division + one rsqrt on the critical path of a round instead of 2 + 2 + 1
                     const double tau = be - al;
-                    const double t = (tau < 0.0 ? -2.0 * ga : 2.0 * ga) / (fabs(tau) + sqrt(tau * tau + 4.0 * ga * ga));
-                    c = rsqrt(1.0 + t * t);
-                    s = c * t;
+                    const double y = rsqrt(tau * tau + 4.0 * ga * ga);
+                    const double u = 0.5 + 0.5 * fabs(tau) * y;
+                    const double z = rsqrt(u);
+                    c = u * z;
+                    const double sa = fabs(ga) * y * z;
+                    s = ((tau < 0.0) != (ga < 0.0)) ? -sa : sa;
+                    const double t = s * z;
                     nrm2[p] = al - t * ga; nrm2[q] = be + t * ga; s_rot = 1;
                 }
             }
@@ -204,7 +259,8 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
 // res[j] = || W[:, j] - theta[j] V[:, j] ||  (n x l row-major, ld = l); one CTA per column
 __global__ void __launch_bounds__(256)
 resid_kernel(const double* __restrict__ W, const double* __restrict__ V, const double* __restrict__ theta, int64_t n,
-             int l, double* __restrict__ res) {
+             int l, double* __restrict__ res, const int* __restrict__ skip) {
+    if (eig_skip(skip, 0)) return;
     __shared__ double red[8];
     const int j = blockIdx.x;
     const double th = theta[j];
@@ -216,13 +272,77 @@ resid_kernel(const double* __restrict__ W, const double* __restrict__ V, const d
     if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; w++) t += red[w]; res[j] = sqrt(t); }
 }
 
-// W[:, j] *= 1 / max(theta[j], tiny * theta[0])
-__global__ void colscale_kernel(double* __restrict__ W, const double* __restrict__ theta, int64_t n, int l) {
+// dst[:, j] = src[:, j] / max(theta[j], tiny * theta[0])   (dst may alias src)
+__global__ void colscale_kernel(double* dst, const double* src, const double* __restrict__ theta, int64_t n, int l,
+                                const int* __restrict__ skip, int need) {
+    if (eig_skip(skip, need)) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * l) return;
     const int j = (int)(idx % l);
     const double th = fmax(theta[j], 1e-14 * theta[0] + 1e-300);
-    W[idx] /= th;
+    dst[idx] = src[idx] / th;
+}
+
+// The stopping rule, evaluated by one thread after every Rayleigh-Ritz step (see the header comment).
+//   EXACT: Davis-Kahan estimate of the angle between span(V[:, :kq]) and the true invariant subspace, ||R_kq||_F /
+//   (theta_kq - theta_kq+1), for the requested rank and every additional one (scRUVIII with several ruvK re-uses one fit); a
+//   residual at rounding level also counts as converged.  Hopeless case (theta_k ~ theta_k+1: the k-th factor is not separated,
+//   the reference's own answer is ill-conditioned): stop when 15 more iterations gained less than a factor 2.
+//   `nonfinite` (optional): the NA / Inf flag of the fit's first pass over the cells -- a poisoned Gram never converges, so the
+//   loop is cut at once and the host reports the reference's stop() (R/fastRUVIII.R:52-60).
+__global__ void eig_check_kernel(EigCtl* __restrict__ ctl, const double* __restrict__ res, const double* __restrict__ theta, int l, int s,
+                                 EigRanks ranks, double tol, int maxit, int fixed_iters, const int* __restrict__ jac_sweeps,
+                                 const int* __restrict__ chol_flag, const int64_t* __restrict__ nonfinite) {
+    if (threadIdx.x != 0 || ctl->done) return;
+    const int it = ++ctl->it;
+    ctl->products += 1 + (ctl->pw > 1 ? ctl->pw - 1 : 0);  // this step's product + the extra ones of the previous step
+    ctl->jac_sweeps = jac_sweeps ? *jac_sweeps : 0;
+    ctl->chol_flag = chol_flag ? *chol_flag : 0;
+    if (nonfinite && nonfinite[0] != 0) { ctl->done = 3; return; }
+    const double top = theta[0] > 0 ? theta[0] : 1.0;
+    double worst = 0.0, gap = 0.0, rmax = 0.0;
+    auto estimate = [&](int kq, double& g_out, double& rm_out) -> double {
+        double r2 = 0.0, rm = 0.0;
+        for (int i = 0; i < kq; i++) { r2 += res[i] * res[i]; rm = rm > res[i] ? rm : res[i]; }
+        double g = (kq < l) ? theta[kq - 1] - theta[kq] : theta[kq - 1];
+        if (!(g > 1e-300)) g = 1e-300;
+        g_out = g; rm_out = rm;
+        return rm <= 1e-14 * top ? 0.0 : sqrt(r2) / g;
+    };
+    for (int q = 0; q < ranks.n; q++) {
+        const int kq = ranks.k[q] < s ? ranks.k[q] : s;
+        if (kq <= 0) continue;
+        double g, rm;
+        const double est = estimate(kq, g, rm);
+        if (q == 0 || !(est <= worst)) { worst = est; gap = g; }
+        rmax = rmax > rm ? rmax : rm;
+    }
+    ctl->worst = worst; ctl->gap = gap; ctl->rmax = rmax; ctl->top = top;
+    if (!(worst == worst) || !(top == top)) ctl->done = 3;  // NaN
+    else if (fixed_iters) { if (it >= fixed_iters) ctl->done = 1; }
+    else if (worst <= tol) ctl->done = 1;
+    else {
+        ctl->hist[it % 16] = worst;
+        if (it > 40 && worst > 0.5 * ctl->hist[(it + 1) % 16]) ctl->done = 2;
+        else if (it >= maxit) ctl->done = 4;
+    }
+    if (ctl->done) {
+        // how far down the returned rows are trustworthy as a BASIS: the largest r whose top-r subspace passes a 1e-8 angle test
+        // (fullalpha re-used with a larger ruvK than it was fitted for, R/fastRUVIII.R:83 / R/scMerge2.R:399)
+        int cr = 0;
+        for (int r = 1; r <= s; r++) {
+            double g, rm;
+            if (estimate(r, g, rm) <= (tol > 1e-8 ? tol : 1e-8)) cr = r;
+        }
+        ctl->conv_rank = cr;
+        return;
+    }
+    // Extra products of the next outer iteration: W <- G (W Theta^-1) costs one skinny GEMM (~40 us) while a Rayleigh-Ritz
+    // step costs ~1 ms, so the convergence factor per outer iteration becomes rho^pw.  pw is limited by the spread of the Ritz
+    // values inside the block: the scaled columns stay well conditioned for CholeskyQR2 as long as (theta_1 / theta_l)^(pw-1) <= ~1e5.
+    const double spread = (theta[0] > 0 && theta[l - 1] > 0) ? theta[0] / theta[l - 1] : 1e300;
+    int pw = spread > 1.0 ? (int)(log(1e5) / log(spread)) + 1 : 4;
+    ctl->pw = fixed_iters ? 1 : (pw < 1 ? 1 : (pw > 4 ? 4 : pw));
 }
 
 // vecs[r, :] = sign * V[:, r] with the largest-|.| entry made positive; vals[r] = theta[r].  One CTA per row r.
@@ -248,23 +368,22 @@ eig_output_kernel(const double* __restrict__ V, const double* __restrict__ theta
     if (threadIdx.x == 0) vals[r] = theta[r];
 }
 
-// X <- orthonormal basis of span(X) by CholeskyQR2 (X: n x l row-major, T: n x l scratch).
-inline int cholqr2(scm_ctx* ctx, double* X, double* T, int64_t n, int l, double* S, double* Linv, int* flag) {
-    cudaStream_t st = ctx->stream;
-    const size_t smem = sizeof(double) * 2 * l * (l + 1);
-    double* src = X; double* dst = T;
-    for (int pass = 0; pass < 2; pass++) {
-        SCM_TRY(gemm(ctx, l, l, (int)n, 1.0, transposed(src, l), rowmajor(src, l), 0.0, S, l));
-        chol_inv_kernel<<<1, 1024, smem, st>>>(S, l, pass == 0 ? 1e-14 : 0.0, Linv, flag);
-        SCM_LAUNCH_CHECK(ctx);
-        SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(src, l), transposed(Linv, l), 0.0, dst, l));
-        double* t = src; src = dst; dst = t;
-    }
-    return 0;  // two passes: the result is back in X
+// dst <- orthonormal basis of span(src) by CholeskyQR2 (n x l row-major; tmp: n x l scratch; dst may be src, not tmp).
+inline int cholqr2(scm_ctx* ctx, const double* src, double* dst, double* tmp, int64_t n, int l, double* S, double* Linv, int* flag,
+                   const int* skip = nullptr) {
+    SCM_TRY(gemm(ctx, l, l, (int)n, 1.0, transposed(src, l), rowmajor(src, l), 0.0, S, l, skip));
+    SCM_TRY(chol_inv_launch(ctx, S, l, 1e-14, Linv, flag, skip));
+    SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(src, l), transposed(Linv, l), 0.0, tmp, l, skip));
+    SCM_TRY(gemm(ctx, l, l, (int)n, 1.0, transposed(tmp, l), rowmajor(tmp, l), 0.0, S, l, skip));
+    SCM_TRY(chol_inv_launch(ctx, S, l, 0.0, Linv, flag, skip));
+    SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(tmp, l), transposed(Linv, l), 0.0, dst, l, skip));
+    return 0;
 }
 
+// d_nonfinite (optional, device int64): see eig_check_kernel.  Results: ctx->fit_iters / fit_resid / fit_conv_rank / fit_products.
 inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, int32_t kconv, int mode, double tol,
-                    int32_t maxit, uint64_t seed, double* d_vals, double* d_vecs, int32_t* iters_out, double* resid_out) {
+                    int32_t maxit, uint64_t seed, double* d_vals, double* d_vecs, int32_t* iters_out, double* resid_out,
+                    const int64_t* d_nonfinite = nullptr) {
     if (n <= 0 || s <= 0 || s > n) return fail(SCM_ERR_INVALID, "eig_topk: bad n=%lld s=%d", (long long)n, s);
     if (n >= (int64_t)1 << 30) return fail(SCM_ERR_UNSUPPORTED, "eig_topk: n too large");
     int l;
@@ -280,112 +399,97 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
     if (tol <= 0) tol = 1e-10;
     if (maxit <= 0) maxit = 300;
     cudaStream_t st = ctx->stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        SCM_CUDA(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    SCM_CUDA(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // per device, cheap
     Scratch ws(ctx);
     double *X, *Z, *W, *V, *H, *Q, *theta, *S, *Linv, *res;
     int* flag;
+    EigCtl* ctl;
     const int64_t nl = n * l;
     SCM_TRY(ws.alloc(&X, nl)); SCM_TRY(ws.alloc(&Z, nl)); SCM_TRY(ws.alloc(&W, nl)); SCM_TRY(ws.alloc(&V, nl));
     SCM_TRY(ws.alloc(&H, (int64_t)l * l)); SCM_TRY(ws.alloc(&Q, (int64_t)l * l)); SCM_TRY(ws.alloc(&S, (int64_t)l * l));
     SCM_TRY(ws.alloc(&Linv, (int64_t)l * l)); SCM_TRY(ws.alloc(&theta, l)); SCM_TRY(ws.alloc(&res, l));
-    SCM_TRY(ws.alloc(&flag, 4));
-    SCM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, st));
-    randn_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(X, nl, seed * 0x9E3779B97F4A7C15ull + 12345);
-    SCM_LAUNCH_CHECK(ctx);
-    SCM_TRY(cholqr2(ctx, X, Z, n, l, S, Linv, flag));
-    const size_t jsmem = sizeof(double) * 2 * ((l + 1) & ~1) * (((l + 1) & ~1) + 1);
-    const int fixed_iters = (mode == SCM_MODE_RANDOMIZED) ? 3 : 0;  // q = 2 power iterations + the final product
-    double* h = ctx->h_pinned;
-    int it = 0;
-    double worst = 0.0;
-    double hist[16];
-    for (int i = 0; i < 16; i++) hist[i] = 1e300;
-    bool converged = false;
-
-    for (it = 1; it <= maxit; it++) {
-        SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l));
-        SCM_TRY(gemm(ctx, l, l, (int)n, 1.0, transposed(X, l), rowmajor(Z, l), 0.0, H, l));
-        // The first Rayleigh-Ritz problem (random start block) only needs to rotate the basis roughly: a loose Jacobi
-        // tolerance saves ~8 of its 13 sweeps.  Later ones are solved to rounding level, otherwise the residual test below
-        // measures the Jacobi tolerance instead of the subspace error (it stays rigorous for any orthonormal Q).
-        const double jtol = (!fixed_iters && it == 1) ? 1e-6 : 2e-14;
-
-        // one half-warp per column pair: l / 2 pairs need 8 l threads; idle warps would only lengthen every barrier
-        const int jthreads = ((((l + 1) / 2) * 16 + 31) / 32 * 32) < 256 ? 256 : ((((l + 1) / 2) * 16 + 31) / 32 * 32);
-        jacobi_eig_kernel<<<1, jthreads, jsmem, st>>>(H, l, Q, theta, 40, jtol, flag + 1);
-        SCM_LAUNCH_CHECK(ctx);
-        SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(Z, l), rowmajor(Q, l), 0.0, W, l));
-        SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(X, l), rowmajor(Q, l), 0.0, V, l));
-        const bool check = fixed_iters ? (it == fixed_iters) : true;
-        if (check) {
-            resid_kernel<<<l, 256, 0, st>>>(W, V, theta, n, l, res);
-            SCM_LAUNCH_CHECK(ctx);
-            SCM_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
-            SCM_CUDA(cudaMemcpyAsync(h + l, theta, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
-            SCM_CUDA(cudaMemcpyAsync(h + 2 * l, flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-            SCM_CUDA(cudaStreamSynchronize(st));
-            if (getenv("SCM_DEBUG_EIG")) fprintf(stderr, "[eig] it %d l %d jacobi sweeps %d\n", it, l, reinterpret_cast<int*>(h + 2 * l)[1]);
-            // Davis-Kahan estimate of the angle between span(V[:, :kconv]) and the true invariant subspace:
-            // ||R_k||_F / (theta_k - theta_{k+1}); a residual at rounding level also counts as converged.
-            const double* th = h + l;
-            const double top = th[0] > 0 ? th[0] : 1.0;
-            double rmax = 0.0, gap = 0.0;
-            worst = 0.0;
-            // the requested rank and every additional one (scRUVIII with several ruvK re-uses one fit for all of them)
-            for (int q = -1; q < ctx->n_conv_ranks; q++) {
-                const int kq = q < 0 ? kconv : (ctx->conv_ranks[q] < s ? ctx->conv_ranks[q] : s);
-                if (kq <= 0 || (q >= 0 && kq == kconv)) continue;
-                double r2 = 0.0, rm = 0.0;
-                for (int i = 0; i < kq; i++) { r2 += h[i] * h[i]; rm = rm > h[i] ? rm : h[i]; }
-                double g = (kq < l) ? th[kq - 1] - th[kq] : th[kq - 1];
-                if (!(g > 1e-300)) g = 1e-300;
-                const double est = rm <= 1e-14 * top ? 0.0 : sqrt(r2) / g;  // a residual at rounding level counts as converged
-                if (q < 0 || est > worst) { if (est >= worst) { worst = est; gap = g; } }
-                rmax = rmax > rm ? rmax : rm;
-            }
-            if (getenv("SCM_DEBUG_EIG"))
-                fprintf(stderr, "[eig] it %d angle_est %.3e rmax/top %.3e gap/top %.3e theta1 %.3e theta_k %.3e theta_l %.3e\n", it, worst,
-                        rmax / top, gap / top, th[0], th[kconv - 1], th[l - 1]);
-            if (fixed_iters || worst <= tol) { converged = true; break; }
-
-            hist[it % 16] = worst;
-            // hopeless case (theta_k ~ theta_{k+1}: the k-th factor is not separated, the reference's own answer
-            // is ill-conditioned): stop when 15 more iterations gained less than a factor 2
-            if (it > 40 && worst > 0.5 * hist[(it + 1) % 16]) break;
-        }
-        if (it == maxit) break;
-        colscale_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(W, theta, n, l);
-        SCM_LAUNCH_CHECK(ctx);
-        if (!fixed_iters) {
-            // Extra products per outer iteration: W <- G (W Theta^-1) costs one skinny GEMM (~40 us) while a Rayleigh-Ritz
-            // step costs ~1 ms, so the convergence factor per outer iteration becomes rho^p.  p is limited by the spread
-            // of the Ritz values inside the block: the scaled columns stay well conditioned for CholeskyQR2 as long as
-            // (theta_1 / theta_l)^(p-1) <= ~1e5.
-            const double spread = (h[l] > 0 && h[2 * l - 1] > 0) ? h[l] / h[2 * l - 1] : 1e300;
-            int pw = spread > 1.0 ? (int)(log(1e5) / log(spread)) + 1 : 4;
-            pw = pw < 1 ? 1 : (pw > 4 ? 4 : pw);
-            for (int j = 1; j < pw; j++) {
-                SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(W, l), 0.0, Z, l));
-                colscale_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(Z, theta, n, l);
-                SCM_LAUNCH_CHECK(ctx);
-                double* t2 = W; W = Z; Z = t2;
-            }
-        }
-        SCM_TRY(cholqr2(ctx, W, Z, n, l, S, Linv, flag));
-        double* t = X; X = W; W = t;
+    SCM_TRY(ws.alloc(&flag, 4)); SCM_TRY(ws.alloc(&ctl, 1));
+    EigRanks ranks;
+    ranks.n = 1; ranks.k[0] = kconv;
+    for (int q = 0; q < ctx->n_conv_ranks && ranks.n < 17; q++) {
+        const int kq = ctx->conv_ranks[q] < s ? ctx->conv_ranks[q] : s;
+        if (kq > 0 && kq != kconv) ranks.k[ranks.n++] = kq;
     }
+    const int fixed_iters = (mode == SCM_MODE_RANDOMIZED) ? 1 : 0;  // rsvd: the three products are done before the single Rayleigh-Ritz step
+    const int* skip = reinterpret_cast<const int*>(ctl);
+    const size_t jsmem = sizeof(double) * 2 * ((l + 1) & ~1) * (((l + 1) & ~1) + 1);
+    // one half-warp per column pair: l / 2 pairs need 8 l threads; idle warps would only lengthen every barrier
+    const int jthreads = ((((l + 1) / 2) * 16 + 31) / 32 * 32) < 256 ? 256 : ((((l + 1) / 2) * 16 + 31) / 32 * 32);
+    EigCtl* h = reinterpret_cast<EigCtl*>(ctx->h_pinned);
+    static_assert(sizeof(EigCtl) <= sizeof(double) * 4096, "control block must fit the pinned staging area");
+    const bool debug = getenv("SCM_DEBUG_EIG") != nullptr;
+
+    // `safe`: no product before the first Rayleigh-Ritz step.  G X for a random X has the condition number of the block's
+    // spectrum (theta_1 / theta_l); CholeskyQR2 takes ~1e7 of it.  Beyond that the first attempt reports a failed pivot and the
+    // solve is repeated the careful way (Ritz scaling before every orthonormalisation).
+    for (int safe = 0; safe < 2; safe++) {
+        SCM_TRY(zero_async(ctx, flag, sizeof(int) * 4));
+        SCM_TRY(zero_async(ctx, ctl, sizeof(EigCtl)));
+        randn_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(X, nl, seed * 0x9E3779B97F4A7C15ull + 12345);
+        SCM_LAUNCH_CHECK(ctx);
+        SCM_TRY(cholqr2(ctx, X, X, Z, n, l, S, Linv, flag));
+        int pre = safe ? 0 : (mode == SCM_MODE_RANDOMIZED ? 2 : 1);
+        if (mode == SCM_MODE_RANDOMIZED && safe) pre = 2;  // rsvd's semantics are three products, whatever the conditioning
+        for (int j = 0; j < pre; j++) {
+            SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l));
+            SCM_TRY(cholqr2(ctx, Z, X, W, n, l, S, Linv, flag));
+        }
+        int enq = 0;       // Rayleigh-Ritz steps enqueued so far
+        bool finished = false;
+        while (!finished) {
+            const int batch = fixed_iters ? 1 : 2;
+            for (int b = 0; b < batch && enq < maxit; b++, enq++) {
+                SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l, skip));
+                SCM_TRY(gemm(ctx, l, l, (int)n, 1.0, transposed(X, l), rowmajor(Z, l), 0.0, H, l, skip));
+                // The first Rayleigh-Ritz problem only has to rotate the basis roughly and to provide the Ritz scaling: a loose
+                // Jacobi tolerance saves about half of its sweeps.  Later ones are solved to rounding level, otherwise the
+                // residual test measures the Jacobi tolerance instead of the subspace error (the test itself is rigorous for any
+                // orthonormal Q).
+                const double jtol = (!fixed_iters && enq == 0) ? 1e-6 : 2e-14;
+                jacobi_eig_kernel<<<1, jthreads, jsmem, st>>>(H, l, Q, theta, 40, jtol, flag + 1, skip);
+                SCM_LAUNCH_CHECK(ctx);
+                SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(Z, l), rowmajor(Q, l), 0.0, W, l, skip));
+                SCM_TRY(gemm(ctx, (int)n, l, l, 1.0, rowmajor(X, l), rowmajor(Q, l), 0.0, V, l, skip));
+                resid_kernel<<<l, 256, 0, st>>>(W, V, theta, n, l, res, skip);
+                SCM_LAUNCH_CHECK(ctx);
+                eig_check_kernel<<<1, 32, 0, st>>>(ctl, res, theta, l, s, ranks, tol, maxit, fixed_iters, flag + 1, flag, d_nonfinite);
+                SCM_LAUNCH_CHECK(ctx);
+                if (fixed_iters) break;
+                colscale_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(W, W, theta, n, l, skip, 0);
+                SCM_LAUNCH_CHECK(ctx);
+                for (int j = 2; j <= 4; j++) {  // extra products, each skipped on the device unless ctl->pw >= j
+                    SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(W, l), 0.0, Z, l, skip, j));
+                    colscale_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(W, Z, theta, n, l, skip, j);
+                    SCM_LAUNCH_CHECK(ctx);
+                }
+                SCM_TRY(cholqr2(ctx, W, X, Z, n, l, S, Linv, flag, skip));
+            }
+            SCM_CUDA(cudaMemcpyAsync(h, ctl, sizeof(EigCtl), cudaMemcpyDeviceToHost, st));
+            SCM_CUDA(cudaStreamSynchronize(st));
+            if (debug)
+                fprintf(stderr, "[eig] safe %d l %d it %d done %d pw %d products %d jacobi sweeps %d chol_flag %d angle_est %.3e rmax/top %.3e gap/top %.3e\n",
+                        safe, l, h->it, h->done, h->pw, h->products, h->jac_sweeps, h->chol_flag, h->worst, h->rmax / h->top, h->gap / h->top);
+            finished = h->done != 0 || enq >= maxit;
+        }
+        if (h->done == 1 || h->done == 3 || safe == 1 || !(h->chol_flag)) break;
+    }
+    const int done = h->done;
+    const double worst = h->worst;
+    const int it = h->it;
+    ctx->fit_iters = it; ctx->fit_resid = worst; ctx->fit_conv_rank = h->conv_rank; ctx->fit_products = h->products;  // excluding the products before the first Rayleigh-Ritz step
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = worst;
+    if (done == 3) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
     eig_output_kernel<<<s, 256, 0, st>>>(V, theta, n, l, d_vecs, d_vals);
     SCM_LAUNCH_CHECK(ctx);
-    if (iters_out) *iters_out = it > maxit ? maxit : it;
-    if (resid_out) *resid_out = worst;
-    if (!converged)
+    if (done != 1)
         return fail(SCM_ERR_NOCONV, "eig_topk: subspace angle estimate %.3e > tol %.3e after %d iterations "
-                    "(factor %d is not separated from factor %d)", worst, tol, it > maxit ? maxit : it, kconv, kconv + 1);
+                    "(factor %d is not separated from factor %d)", worst, tol, it, kconv, kconv + 1);
     return 0;
 }
 

@@ -18,7 +18,8 @@ constexpr int GM_BT = 64, GM_KC = 16, GM_LDS = GM_BT + 4, GM_THREADS = 128;
 
 __global__ void __launch_bounds__(GM_THREADS)
 gemm_kernel(int M, int N, int K, MatView A, MatView B, double* __restrict__ out, int64_t ldo, int64_t split_stride,
-            int kchunks_per_split, double alpha, double beta, int direct) {
+            int kchunks_per_split, double alpha, double beta, int direct, const int* __restrict__ skip, int need) {
+    if (skip && (skip[0] != 0 || skip[1] < need)) return;  // device-side control flow of the eigensolver (eig_topk.cuh)
     __shared__ double As[2][GM_KC][GM_LDS];
     __shared__ double Bs[2][GM_KC][GM_LDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,7 +108,9 @@ gemm_kernel(int M, int N, int K, MatView A, MatView B, double* __restrict__ out,
 }
 
 __global__ void gemm_splitk_reduce_kernel(const double* __restrict__ part, int splits, int64_t split_stride, int M, int N,
-                                          double alpha, double beta, double* __restrict__ C, int64_t ldc) {
+                                          double alpha, double beta, double* __restrict__ C, int64_t ldc,
+                                          const int* __restrict__ skip, int need) {
+    if (skip && (skip[0] != 0 || skip[1] < need)) return;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * N) return;
     const int i = (int)(idx / N), j = (int)(idx % N);
@@ -118,7 +121,9 @@ __global__ void gemm_splitk_reduce_kernel(const double* __restrict__ part, int s
     C[(int64_t)i * ldc + j] = v;
 }
 
-inline int gemm(scm_ctx* ctx, int M, int N, int K, double alpha, MatView A, MatView B, double beta, double* C, int64_t ldc) {
+// `skip` (optional, device): the launch returns at once when skip[0] != 0 or skip[1] < need (see EigCtl in eig_topk.cuh).
+inline int gemm(scm_ctx* ctx, int M, int N, int K, double alpha, MatView A, MatView B, double beta, double* C, int64_t ldc,
+                const int* skip = nullptr, int need = 0) {
     if (M <= 0 || N <= 0) return 0;
     cudaStream_t st = ctx->stream;
     const int tiles = (int)(ceil_div(M, GM_BT) * ceil_div(N, GM_BT));
@@ -134,7 +139,7 @@ inline int gemm(scm_ctx* ctx, int M, int N, int K, double alpha, MatView A, MatV
     splits = (int)ceil_div(kc_total, per);
     dim3 grid((unsigned)ceil_div(N, GM_BT), (unsigned)ceil_div(M, GM_BT), (unsigned)splits);
     if (splits == 1) {
-        gemm_kernel<<<grid, GM_THREADS, 0, st>>>(M, N, K, A, B, C, ldc, 0, per, alpha, beta, 1);
+        gemm_kernel<<<grid, GM_THREADS, 0, st>>>(M, N, K, A, B, C, ldc, 0, per, alpha, beta, 1, skip, need);
         SCM_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -142,9 +147,9 @@ inline int gemm(scm_ctx* ctx, int M, int N, int K, double alpha, MatView A, MatV
     double* part;
     const int64_t stride = (int64_t)M * N;
     SCM_TRY(ws.alloc(&part, stride * splits));
-    gemm_kernel<<<grid, GM_THREADS, 0, st>>>(M, N, K, A, B, part, N, stride, per, 1.0, 0.0, 0);
+    gemm_kernel<<<grid, GM_THREADS, 0, st>>>(M, N, K, A, B, part, N, stride, per, 1.0, 0.0, 0, skip, need);
     SCM_LAUNCH_CHECK(ctx);
-    gemm_splitk_reduce_kernel<<<(unsigned)ceil_div(stride, 256), 256, 0, st>>>(part, splits, stride, M, N, alpha, beta, C, ldc);
+    gemm_splitk_reduce_kernel<<<(unsigned)ceil_div(stride, 256), 256, 0, st>>>(part, splits, stride, M, N, alpha, beta, C, ldc, skip, need);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -269,12 +269,9 @@ inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t l
         if (!accumulate) SCM_TRY(zero_async(ctx, d_gram, sizeof(double) * n * n));
         return 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(gram_syrk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
-        SCM_CUDA(cudaFuncSetAttribute(gram_syrk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
-        attr_set = true;
-    }
+    // function attributes are per device: set on every call (microseconds), never cached in a process-wide flag
+    SCM_CUDA(cudaFuncSetAttribute(gram_syrk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
+    SCM_CUDA(cudaFuncSetAttribute(gram_syrk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
     const GramPlan p = gram_plan(m, n, ctx->num_sms);
     Scratch ws(ctx);
     double* partial;

@@ -340,15 +340,13 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline PFN_tmapEncodeTiled tmap_encoder() {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const PFN_tmapEncodeTiled fn = [] {  // C++11 static initialisation: safe when several device threads race here
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (PFN_tmapEncodeTiled)p;
-    }
+            return (PFN_tmapEncodeTiled)p;
+        return (PFN_tmapEncodeTiled) nullptr;
+    }();
     return fn;
 }
 
@@ -366,12 +364,8 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)d_Y, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
-        SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
-        attr_set = true;
-    }
+    SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));   // per device
+    SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
     const int valid_last = (int)(n - (int64_t)(p.ntile - 1) * GR_BT);
     if (d_shift)
         gram_tma_kernel<true><<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial,

@@ -20,6 +20,7 @@
 #include "adjust.cuh"
 #include "common.cuh"
 #include "eig_topk.cuh"
+#include "fit_core.cuh"
 #include "gram_tma.cuh"
 #include "seg_colsum.cuh"
 
@@ -33,10 +34,13 @@ __global__ void add_i64_kernel(int64_t* __restrict__ dst, const int64_t* __restr
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) dst[i] += src[i];
 }
-// meta[0] |= flag, meta[1] += rows
-__global__ void meta_acc_kernel(const int32_t* __restrict__ flag, int64_t rows, int64_t* __restrict__ meta) {
-    if (flag[0]) meta[0] = 1;
-    meta[1] += rows;
+// shift[j] = sum_g sums[g, j] / rows: column mean of the first chunk (every cell of a fit carries a group key)
+__global__ void first_chunk_mean_kernel(const double* __restrict__ sums, int32_t G, int64_t n, double rows, double* __restrict__ shift) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int g = 0; g < G; g++) s += sums[(int64_t)g * n + j];
+    shift[j] = rows > 0 ? s / rows : 0.0;
 }
 
 // Rows per PCIe chunk: ~512 MB, a multiple of 1024 rows (test hook SCM_HOST_CHUNK_ROWS forces several chunks on small inputs).
@@ -156,36 +160,49 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     } guard{ev};
 
     Scratch ws(ctx);
+    // declared after `ws`, so destroyed before it: on EVERY exit path (errors included) the bulk copies still queued on the copy
+    // streams have finished before Scratch hands dY back to the pool
+    struct CopyFence {
+        scm_ctx* c;
+        ~CopyFence() { if (c->copy_stream) cudaStreamSynchronize(c->copy_stream); if (c->copy_stream_d2h) cudaStreamSynchronize(c->copy_stream_d2h); }
+    } fence{ctx};
     double *dY, *gsums = nullptr, *tsums = nullptr, *shift = nullptr, *Gm = nullptr, *vals = nullptr, *vecs = nullptr, *fa = nullptr;
     double *bsums = nullptr, *ssq = nullptr, *sd = nullptr, *inv_sd = nullptr, *center = nullptr, *sig = nullptr;
-    int64_t *gcounts = nullptr, *tcounts = nullptr, *bcounts = nullptr, *meta = nullptr;
+    double *buf1 = nullptr, *buf2 = nullptr, *cnt_f64 = nullptr, *uvec = nullptr, *dvec = nullptr;
+    int64_t *gcounts = nullptr, *gcnt_local = nullptr, *tcounts = nullptr, *bcounts = nullptr, *bcnt_local = nullptr, *meta = nullptr;
     int32_t *dgroup = nullptr, *dbatch = nullptr, *flag = nullptr;
     uint8_t* dctl;
     const int32_t s = do_fit ? a.s : a.s_in;
+    const int32_t Gk = do_fit ? a.G : 1;  // adjust-only runs use one group (column means)
+    const int32_t Btk = sc ? a.Bt : 0;
+    // the two all-reduce buffers of fit_core.cuh: [gsums | bsums | counts | flag, rows] and [Gm | ssq]
+    const int64_t len1 = (int64_t)(Gk + Btk) * n + Gk + Btk + 2, len2 = (do_fit ? n * n : 0) + (int64_t)Btk * n;
     SCM_TRY(ws.alloc(&dY, m * ld));
     SCM_TRY(ws.alloc(&dctl, n));
     SCM_TRY(ws.alloc(&fa, (int64_t)s * n));
-    SCM_TRY(ws.alloc(&meta, 2)); SCM_TRY(ws.alloc(&flag, 1));
-    SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&center, n));
-    SCM_CUDA(cudaMemsetAsync(meta, 0, 16, st));
+    SCM_TRY(ws.alloc(&meta, 4)); SCM_TRY(ws.alloc(&flag, 1));
+    SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&center, n)); SCM_TRY(ws.alloc(&uvec, n)); SCM_TRY(ws.alloc(&dvec, n));
+    SCM_TRY(ws.alloc(&buf1, len1)); SCM_TRY(ws.alloc(&buf2, len2 > 0 ? len2 : 1));
+    gsums = buf1; bsums = buf1 + (int64_t)Gk * n; cnt_f64 = buf1 + (int64_t)(Gk + Btk) * n;
+    Gm = buf2; ssq = buf2 + (do_fit ? n * n : 0);
     SCM_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    SCM_CUDA(cudaMemsetAsync(shift, 0, sizeof(double) * n, st));
     SCM_CUDA(cudaMemcpyAsync(dctl, a.h_ctl, n, cudaMemcpyHostToDevice, st));
-    const int32_t Gk = do_fit ? a.G : 1;  // adjust-only runs use one group (column means)
-    SCM_TRY(ws.alloc(&gsums, (int64_t)Gk * n)); SCM_TRY(ws.alloc(&tsums, (int64_t)Gk * n));
-    SCM_TRY(ws.alloc(&gcounts, Gk)); SCM_TRY(ws.alloc(&tcounts, Gk));
+    SCM_TRY(ws.alloc(&tsums, (int64_t)Gk * n));
+    SCM_TRY(ws.alloc(&gcounts, Gk)); SCM_TRY(ws.alloc(&gcnt_local, Gk)); SCM_TRY(ws.alloc(&tcounts, Gk));
+    SCM_TRY(ws.alloc(&bcounts, Btk > 0 ? Btk : 1)); SCM_TRY(ws.alloc(&bcnt_local, Btk > 0 ? Btk : 1));
     SCM_TRY(ws.alloc(&dgroup, m));
     SCM_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * Gk * n, st));
-    SCM_CUDA(cudaMemsetAsync(gcounts, 0, sizeof(int64_t) * Gk, st));
+    SCM_CUDA(cudaMemsetAsync(gcnt_local, 0, sizeof(int64_t) * Gk, st));
     if (do_fit) {
-        SCM_TRY(ws.alloc(&Gm, n * n)); SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n)); SCM_TRY(ws.alloc(&sig, s));
+        SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n)); SCM_TRY(ws.alloc(&sig, s));
         SCM_CUDA(cudaMemcpyAsync(dgroup, a.h_group, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
     } else {
         SCM_CUDA(cudaMemsetAsync(dgroup, 0, sizeof(int32_t) * m, st));
         SCM_CUDA(cudaMemcpyAsync(fa, a.h_fullalpha_in, sizeof(double) * s * n, cudaMemcpyHostToDevice, st));
     }
     if (sc) {
-        SCM_TRY(ws.alloc(&dbatch, m)); SCM_TRY(ws.alloc(&bsums, (int64_t)a.Bt * n)); SCM_TRY(ws.alloc(&ssq, (int64_t)a.Bt * n));
-        SCM_TRY(ws.alloc(&bcounts, a.Bt)); SCM_TRY(ws.alloc(&sd, n)); SCM_TRY(ws.alloc(&inv_sd, n));
+        SCM_TRY(ws.alloc(&dbatch, m)); SCM_TRY(ws.alloc(&sd, n)); SCM_TRY(ws.alloc(&inv_sd, n));
         SCM_CUDA(cudaMemcpyAsync(dbatch, a.h_batch, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
     }
     // The small uploads / memsets above are copy-engine work of the COMPUTE stream.  While its channel still targets the copy
@@ -234,21 +251,14 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
             if (trace.on) cudaEventRecord(tl_seg[c], st);
             add_f64_kernel<<<(unsigned)ceil_div((int64_t)Gk * n, 256), 256, 0, st>>>(gsums, tsums, (int64_t)Gk * n);
             SCM_LAUNCH_CHECK(ctx);
-            add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcounts, tcounts, Gk);
-            SCM_LAUNCH_CHECK(ctx);
-            meta_acc_kernel<<<1, 1, 0, st>>>(flag, rows, meta);
+            add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcnt_local, tcounts, Gk);
             SCM_LAUNCH_CHECK(ctx);
         }
         if (!do_fit) continue;
         if (c == 0) {
-            // shift = column mean of the first chunk (summed over ranks so that every rank uses the same vector)
-            int64_t* m0;
-            SCM_TRY(ws.alloc(&m0, 2));
-            SCM_TRY(copy_async(ctx, m0, meta, 16));  // kernels, not cudaMemcpyAsync: see common.cuh (copy-engine queueing)
-            SCM_TRY(copy_async(ctx, tsums, gsums, sizeof(double) * Gk * n));
-            SCM_TRY(allreduce(ctx, tsums, (int64_t)Gk * n, 0));
-            SCM_TRY(allreduce(ctx, m0, 2, 1));
-            colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, m0, shift);
+            // Gram shift = column mean of this rank's FIRST chunk: known before the second chunk lands, no agreement between
+            // ranks needed (the local Gram is moved to the global mean by a rank-2 update before its all-reduce, fit_core.cuh)
+            first_chunk_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, (double)rows, shift);
             SCM_LAUNCH_CHECK(ctx);
         }
         StageTimer t(ctx, ST_GRAM);
@@ -273,35 +283,42 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     }
     int rc = 0;
     scm_coef* coef = nullptr;
-    if (do_fit) {
-        SCM_TRY(allreduce(ctx, gsums, (int64_t)Gk * n, 0));
-        SCM_TRY(allreduce(ctx, gcounts, Gk, 1));
-        SCM_TRY(allreduce(ctx, meta, 2, 1));
-        SCM_TRY(allreduce(ctx, Gm, n * n, 0));
-        colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, Gk, n, meta, center);  // global mean (stand_mean)
-        SCM_LAUNCH_CHECK(ctx);
-        if (sc) {  // standardize2: pooled within-batch sd needs the batch means first -> one more pass over the resident Y
+    if (need_sums) {
+        // all-reduce 1 (one float64 buffer): group sums, batch sums, counts, NA/Inf flag, rows -> global column means
+        if (sc) {  // standardize2, pass 1 over the resident cells (R/scRUVIII.R:163-166)
             StageTimer t(ctx, ST_STD);
-            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, a.Bt, nullptr, bsums, bcounts, nullptr));
-            SCM_TRY(allreduce(ctx, bsums, (int64_t)a.Bt * n, 0));
-            SCM_TRY(allreduce(ctx, bcounts, a.Bt, 1));
-            groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, a.Bt, n);
+            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, Btk, nullptr, bsums, bcnt_local, nullptr));
+        }
+        const int64_t span = n > Gk + Btk ? n : Gk + Btk;
+        fit_pack_kernel<<<(unsigned)ceil_div(span, 256), 256, 0, st>>>(gsums, Gk, n, gcnt_local, bcnt_local, Btk, flag, m, shift, cnt_f64, uvec);
+        SCM_LAUNCH_CHECK(ctx);
+        SCM_TRY(allreduce(ctx, buf1, len1, 0));
+        fit_unpack_kernel<<<(unsigned)ceil_div(span, 256), 256, 0, st>>>(gsums, Gk, n, cnt_f64, Btk, gcounts, bcounts, meta, shift, center, dvec);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    if (do_fit) {
+        if (sc) {  // standardize2, pass 2: squared deviations from the global batch means (R/scRUVIII.R:167-170)
+            StageTimer t(ctx, ST_STD);
+            groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, Btk, n);
             SCM_LAUNCH_CHECK(ctx);
-            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, a.Bt, bsums, ssq, nullptr, nullptr));
-            SCM_TRY(allreduce(ctx, ssq, (int64_t)a.Bt * n, 0));
-            pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bcounts, a.Bt, n, meta, sd, inv_sd);
+            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, Btk, bsums, ssq, nullptr, nullptr));
+        }
+        gram_recentre_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)n), 256, 0, st>>>(Gm, n, uvec, dvec, (double)m);
+        SCM_LAUNCH_CHECK(ctx);
+        SCM_TRY(allreduce(ctx, buf2, len2, 0));  // all-reduce 2: [centred Gram | ssq]
+        if (sc) {
+            pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bcounts, Btk, n, meta, sd, inv_sd);
             SCM_LAUNCH_CHECK(ctx);
         }
-        SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, a.G, shift, inv_sd));
-        int64_t hmeta[2];
-        SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
-        SCM_CUDA(cudaStreamSynchronize(st));
-        if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
-        trace.mark("Gram residual done (sync)");
+        SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, a.G, center, inv_sd));
+        int64_t* hmeta = reinterpret_cast<int64_t*>(ctx->h_pinned + 2048);
+        SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, st));  // lands with the eigensolver's first read-back
+        trace.mark("Gram residual enqueued");
         {
             StageTimer t(ctx, ST_EIG);
             const int32_t kconv = a.k < s ? a.k : s;
-            rc = eig_topk(ctx, Gm, n, s, kconv, a.mode, a.tol, a.maxit, a.seed, vals, vecs, a.iters_out, a.resid_out);
+            rc = eig_topk(ctx, Gm, n, s, kconv, a.mode, a.tol, a.maxit, a.seed, vals, vecs, a.iters_out, a.resid_out, meta);
+            if (rc == SCM_ERR_NONFINITE || rc == 0 || rc == SCM_ERR_NOCONV) SCM_TRY(fit_meta_check(hmeta));
             if (rc != 0 && rc != SCM_ERR_NOCONV) return rc;
             dim3 grid((unsigned)ceil_div(n, 256), (unsigned)s);
             fullalpha_kernel<<<grid, 256, 0, st>>>(vals, vecs, s, n, fa, sig);
@@ -312,10 +329,6 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         if (sc && a.h_mean) SCM_CUDA(cudaMemcpyAsync(a.h_mean, center, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
         if (sc && a.h_sd) SCM_CUDA(cudaMemcpyAsync(a.h_sd, sd, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     } else if (a.center_mode == 1) {
-        SCM_TRY(allreduce(ctx, gsums, n, 0));
-        SCM_TRY(allreduce(ctx, meta, 2, 1));
-        colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, 1, n, meta, center);
-        SCM_LAUNCH_CHECK(ctx);
         if (a.h_mean) SCM_CUDA(cudaMemcpyAsync(a.h_mean, center, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     } else if (a.center_mode == 2) {
         if (!a.h_center) return fail(SCM_ERR_INVALID, "scm_ruv3_host: center_mode 2 without h_center");

@@ -10,11 +10,13 @@
 //     W = Y0c V diag(1/sigma),   alpha = diag(1/sigma) V' G[ctl, :],   sigma_a = sqrt(lambda_a),
 // i.e. newY = Y - ((Y - mean) B) A with B = 1[ctl] V diag(1/sigma) (n x k) and A = alpha (k x n): the fused rank-k update
 // (K6) does the rest and also emits W.  The m x m cross product of the reference's >= 5:1 aspect-ratio branch is never
-// formed.  Cross-rank state (column sums, Gram) goes through the all-reduce hook like in scm_ruv3_fit.
+// formed.  Cross-rank state (column sums, Gram) is summed exactly like in scm_ruv3_fit (fit_core.cuh: the Gram runs on the
+// pre-shifted copy of the cells, SHIFT = false kernel).
 #pragma once
 #include "adjust.cuh"
 #include "common.cuh"
 #include "eig_topk.cuh"
+#include "fit_core.cuh"
 #include "gemm_f64.cuh"
 #include "gram_tma.cuh"
 #include "seg_colsum.cuh"
@@ -76,37 +78,25 @@ inline int ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n,
     if (k > SCM_MAX_K) return fail(SCM_ERR_UNSUPPORTED, "scm_ruvg_fit: k=%d > %d", k, SCM_MAX_K);
     cudaStream_t st = ctx->stream;
     Scratch ws(ctx);
-    double *csum, *Gm, *Gc, *Gcc, *vals, *vecs, *Bm, *Vs;
-    int64_t *ccount, *meta;
+    double *Gc, *Gcc, *vals, *vecs, *Bm, *Vs;
     int32_t *key, *flag, *cidx, *ccnt;
-    SCM_TRY(ws.alloc(&csum, n)); SCM_TRY(ws.alloc(&ccount, 1)); SCM_TRY(ws.alloc(&meta, 2)); SCM_TRY(ws.alloc(&flag, 2));
-    SCM_TRY(ws.alloc(&key, m_local > 0 ? m_local : 1)); SCM_TRY(ws.alloc(&Gm, n * n));
+    SCM_TRY(ws.alloc(&flag, 2)); SCM_TRY(ws.alloc(&key, m_local > 0 ? m_local : 1));
     SCM_TRY(ws.alloc(&cidx, n)); SCM_TRY(ws.alloc(&ccnt, 1));
-    SCM_CUDA(cudaMemsetAsync(flag, 0, 2 * sizeof(int32_t), st));
-    SCM_CUDA(cudaMemsetAsync(key, 0, sizeof(int32_t) * (m_local > 0 ? m_local : 1), st));
-    {   // column means (my_residop with Z = 1) + NA/Inf scan
-        StageTimer t(ctx, ST_SEG);
-        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, key, 1, nullptr, csum, ccount, flag));
-        meta_kernel<<<1, 1, 0, st>>>(flag, m_local, meta);
-        SCM_LAUNCH_CHECK(ctx);
-    }
-    SCM_TRY(allreduce(ctx, csum, n, 0));
-    SCM_TRY(allreduce(ctx, meta, 2, 1));
-    colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(csum, 1, n, meta, d_center);
-    SCM_LAUNCH_CHECK(ctx);
-    {
-        StageTimer t(ctx, ST_GRAM);
-        SCM_TRY(gram(ctx, d_Y, m_local, n, ld, d_center, Gm, true));
-    }
-    SCM_TRY(allreduce(ctx, Gm, n * n, 0));
+    SCM_TRY(zero_async(ctx, flag, 2 * sizeof(int32_t)));
+    SCM_TRY(zero_async(ctx, key, sizeof(int32_t) * (m_local > 0 ? m_local : 1)));
+    // column means (my_residop with Z = 1) + NA/Inf scan + centred Gram: the fit's cell passes with ONE replicate group
+    FitState fs;
+    SCM_TRY(fit_state(ctx, ws, d_Y, m_local, n, ld, key, 1, nullptr, 0, fs));
+    double* Gm = fs.Gm;
+    SCM_TRY(copy_async(ctx, d_center, fs.ybar, sizeof(double) * n));
     ctl_index_kernel<<<1, 1024, 0, st>>>(d_ctl, n, cidx, ccnt);
     SCM_LAUNCH_CHECK(ctx);
-    int64_t hmeta[2];
+    int64_t* hmeta;
+    SCM_TRY(fit_meta_to_host(ctx, fs, &hmeta));
     int32_t c = 0;
-    SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
     SCM_CUDA(cudaMemcpyAsync(&c, ccnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SCM_CUDA(cudaStreamSynchronize(st));
-    if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+    SCM_TRY(fit_meta_check(hmeta));
     if (k > c) return fail(SCM_ERR_INVALID, "k must not be larger than the number of controls");  // R/scRUVg.R:56-58
     SCM_TRY(ws.alloc(&Gc, (int64_t)c * n)); SCM_TRY(ws.alloc(&Gcc, (int64_t)c * c));
     SCM_TRY(ws.alloc(&vals, k)); SCM_TRY(ws.alloc(&vecs, (int64_t)k * c));

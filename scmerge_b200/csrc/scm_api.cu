@@ -1,9 +1,11 @@
 // C ABI of libscmerge_b200 (see include/scmerge_b200.h).  Single translation unit: all kernels are header-only.
 #include "adjust.cuh"
 #include "adjust_tma.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "csc_ingest.cuh"
 #include "eig_topk.cuh"
+#include "fit_core.cuh"
 #include "gemm_f64.cuh"
 #include "gram_syrk.cuh"
 #include "gram_tma.cuh"
@@ -42,12 +44,6 @@ __global__ void colmean_kernel(const double* __restrict__ sums, int32_t G, int64
     mean[j] = s / (double)meta[1];
 }
 
-// out[j] = sums[j] / count[0]  (0 when there are no rows)
-__global__ void vec_mean_kernel(const double* __restrict__ sums, const int64_t* __restrict__ count, int64_t n, double* __restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = count[0] > 0 ? sums[j] / (double)count[0] : 0.0;
-}
-
 // tot[j] = sum_g sums[g, j]
 __global__ void group_total_kernel(const double* __restrict__ sums, int32_t G, int64_t n, double* __restrict__ tot) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,31 +51,6 @@ __global__ void group_total_kernel(const double* __restrict__ sums, int32_t G, i
     double s = 0.0;
     for (int g = 0; g < G; g++) s += sums[(int64_t)g * n + j];
     tot[j] = s;
-}
-
-// out[i, j] = Y[i, j] - shift[j]: the pre-shifted copy of the cells the Gram kernel reads (HBM-bound: 8 m n read + 8 m n written).
-// One CTA per 8-row group (grid-stride), 16-byte accesses when both leading dimensions are even and the bases aligned.
-template <int VEC>
-__global__ void __launch_bounds__(256)
-shift_copy_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, const double* __restrict__ shift,
-                  double* __restrict__ out, int64_t ldo) {
-    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < m; r0 += (int64_t)gridDim.x * 8) {
-        const int nr = (int)min((int64_t)8, m - r0);
-        for (int64_t j = (int64_t)threadIdx.x * VEC; j < n; j += 256 * VEC) {
-            if (VEC == 2 && j + 1 < n) {
-                const double2 s = *reinterpret_cast<const double2*>(shift + j);
-                double2 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (u < nr) v[u] = ldg_stream2(Y + (r0 + u) * ld + j);
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (u < nr) *reinterpret_cast<double2*>(out + (r0 + u) * ldo + j) = make_double2(v[u].x - s.x, v[u].y - s.y);
-            } else {
-                for (int u = 0; u < nr; u++) out[(r0 + u) * ldo + j] = Y[(r0 + u) * ld + j] - shift[j];
-            }
-        }
-    }
 }
 
 // out[j] = sum_g counts[g] * means[g, j] / sum_g counts[g]: the column means of all cells from the group means
@@ -91,16 +62,6 @@ __global__ void weighted_colmean_kernel(const double* __restrict__ means, const 
     int64_t tot = 0;
     for (int g = 0; g < G; g++) { const int64_t c = counts[g]; tot += c; s += (double)c * means[(int64_t)g * ldm + j]; }
     out[j] = tot > 0 ? s / (double)tot : 0.0;
-}
-
-// sums[g, :] /= counts[g]  (empty groups -> 0)
-__global__ void groupmean_kernel(double* __restrict__ sums, const int64_t* __restrict__ counts, int32_t G, int64_t n) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    for (int g = 0; g < G; g++) {
-        const int64_t c = counts[g];
-        sums[(int64_t)g * n + j] = c > 0 ? sums[(int64_t)g * n + j] / (double)c : 0.0;
-    }
 }
 
 // pooled within-batch sd (R/scRUVIII.R:170): sd[j] = sqrt( sum_b ssq[b, j] / (m - #non-empty batches) )
@@ -180,14 +141,6 @@ inline int cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, in
     return 0;
 }
 
-inline int allreduce(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
-    if (ctx->world <= 1 || !ctx->allreduce) return 0;
-    StageTimer t(ctx, ST_COMM);
-    const int rc = ctx->allreduce(d_buf, count, dtype, (void*)ctx->stream, ctx->allreduce_user);
-    if (rc != 0) return fail(SCM_ERR_COMM, "all-reduce hook returned %d", rc);
-    return 0;
-}
-
 }  // namespace scm
 
 #include "host_pipeline.cuh"
@@ -235,6 +188,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_LEAN")) c->gram_lean = atoi(e) & 3;
     if (const char* e = getenv("SCM_GRAM_PRESHIFT")) c->gram_preshift = (e[0] != '0');
+    if (const char* e = getenv("SCM_K1_FUSED_COPY")) c->k1_fused_copy = (e[0] != '0');
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
     else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < ST_COUNT; i++) {
@@ -258,6 +212,7 @@ int scm_ctx_destroy(scm_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
     for (int i = 0; i < ST_COUNT; i++) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
@@ -275,6 +230,101 @@ int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int wor
     ctx->allreduce = fn; ctx->allreduce_user = user; ctx->world = world_size;
     return 0;
 }
+
+int scm_nccl_unique_id(void* id128) {
+    if (!id128) return fail(SCM_ERR_INVALID, "scm_nccl_unique_id: null buffer");
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return fail(SCM_ERR_COMM, "NCCL is not available: %s", api.why.c_str());
+    nccl_unique_id id;
+    SCM_NCCL(api.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int scm_ctx_comm_init_nccl(scm_ctx* ctx, const void* id128, int rank, int world_size) {
+    SCM_REQUIRE_CTX(ctx);
+    if (world_size < 1 || rank < 0 || rank >= world_size || (world_size > 1 && !id128))
+        return fail(SCM_ERR_INVALID, "scm_ctx_comm_init_nccl: bad rank %d / world %d", rank, world_size);
+    comm_release(ctx);
+    ctx->world = world_size; ctx->rank = rank;
+    if (world_size == 1) return 0;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return fail(SCM_ERR_COMM, "NCCL is not available: %s", api.why.c_str());
+    nccl_unique_id id;
+    memcpy(id.internal, id128, 128);
+    nccl_comm_t comm = nullptr;
+    SCM_NCCL(api.CommInitRank(&comm, world_size, id, rank));
+    ctx->nccl_comm = comm; ctx->comm_owned = true;
+    return 0;
+}
+
+int scm_ctx_comm_info(scm_ctx* ctx, int* rank, int* world_size, int* transport) {
+    if (!ctx) return fail(SCM_ERR_INVALID, "null context");
+    if (rank) *rank = ctx->rank;
+    if (world_size) *world_size = ctx->world;
+    if (transport) *transport = ctx->world <= 1 ? 0 : (ctx->nccl_comm ? 1 : (ctx->allreduce ? 2 : 0));
+    return 0;
+}
+
+int scm_allreduce_sum(scm_ctx* ctx, void* d_buf, int64_t count, int dtype) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!d_buf || count < 0 || (dtype != 0 && dtype != 1)) return fail(SCM_ERR_INVALID, "scm_allreduce_sum: bad arguments");
+    return allreduce(ctx, d_buf, count, dtype);
+}
+
+int scm_ctx_fit_info(scm_ctx* ctx, int32_t* iters, double* resid, int32_t* conv_rank, int32_t* products) {
+    if (!ctx) return fail(SCM_ERR_INVALID, "null context");
+    if (iters) *iters = ctx->fit_iters;
+    if (resid) *resid = ctx->fit_resid;
+    if (conv_rank) *conv_rank = ctx->fit_conv_rank;
+    if (products) *products = ctx->fit_products;
+    return 0;
+}
+
+// ---- one process, several GPUs -------------------------------------------------------------------------------------
+int scm_multi_create(const int* devices, int ndev, scm_multi** out) {
+    if (!out || ndev < 1 || ndev > 64) return fail(SCM_ERR_INVALID, "scm_multi_create: bad arguments");
+    std::vector<int> dev(ndev);
+    for (int i = 0; i < ndev; i++) dev[i] = devices ? devices[i] : i;
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (dev[i] == dev[j]) return fail(SCM_ERR_INVALID, "scm_multi_create: device %d listed twice", dev[i]);
+    scm_multi* mg = new scm_multi();
+    struct Guard { scm_multi* m; bool ok; ~Guard() { if (!ok) scm_multi_destroy(m); } } guard{mg, false};
+    for (int i = 0; i < ndev; i++) {
+        scm_ctx* c = nullptr;
+        SCM_TRY(scm_ctx_create(dev[i], nullptr, &c));
+        c->rank = i; c->world = ndev;
+        mg->ctx.push_back(c);
+    }
+    if (ndev > 1) {
+        const NcclApi& api = nccl_api();
+        if (!api.ok) return fail(SCM_ERR_COMM, "NCCL is not available: %s", api.why.c_str());
+        mg->comms.assign(ndev, nullptr);
+        SCM_NCCL(api.CommInitAll(mg->comms.data(), ndev, dev.data()));
+        for (int i = 0; i < ndev; i++) { mg->ctx[i]->nccl_comm = mg->comms[i]; mg->ctx[i]->comm_owned = false; }
+    }
+    guard.ok = true;
+    *out = mg;
+    return 0;
+}
+
+int scm_multi_destroy(scm_multi* mg) {
+    if (!mg) return 0;
+    for (scm_ctx* c : mg->ctx) {
+        if (!c) continue;
+        cudaSetDevice(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+    }
+    for (auto comm : mg->comms) if (comm) nccl_api().CommDestroy(comm);
+    for (scm_ctx* c : mg->ctx) { if (c) { c->nccl_comm = nullptr; scm_ctx_destroy(c); } }
+    delete mg;
+    return 0;
+}
+
+int scm_multi_size(const scm_multi* mg) { return mg ? (int)mg->ctx.size() : 0; }
+
+scm_ctx* scm_multi_ctx(scm_multi* mg, int i) { return (mg && i >= 0 && i < (int)mg->ctx.size()) ? mg->ctx[i] : nullptr; }
 
 int scm_ctx_set_conv_ranks(scm_ctx* ctx, const int32_t* ks, int32_t nk) {
     if (!ctx || nk < 0 || nk > 16 || (nk > 0 && !ks)) return fail(SCM_ERR_INVALID, "scm_ctx_set_conv_ranks: bad arguments (at most 16 ranks)");
@@ -528,125 +578,36 @@ static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64
     if (d_batch && (Bt <= 0 || !d_mean || !d_sd)) return fail(SCM_ERR_INVALID, "scm_ruv3_fit: batch given without Bt / d_mean / d_sd");
     cudaStream_t st = ctx->stream;
     Scratch ws(ctx);
-    double *gsums, *shift, *Gm, *vals, *vecs, *inv_sd = nullptr;
-    int64_t *gcounts, *meta;
-    int32_t* flag;
-    SCM_TRY(ws.alloc(&gsums, (int64_t)G * n)); SCM_TRY(ws.alloc(&gcounts, G)); SCM_TRY(ws.alloc(&meta, 2));
-    SCM_TRY(ws.alloc(&flag, 1)); SCM_TRY(ws.alloc(&shift, n)); SCM_TRY(ws.alloc(&Gm, n * n));
+    double *vals, *vecs, *inv_sd = nullptr;
     SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n));
-    SCM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
-    ctx->ev_used[ST_PRESHIFT] = false;
-    {   // residual operator, part 1: replicate-group sums (my_residop, R/fastRUVIII.R:121-129) + NA/Inf scan (:52-60)
-        StageTimer t(ctx, ST_SEG);
-        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_group, G, nullptr, gsums, gcounts, flag));
-        meta_kernel<<<1, 1, 0, st>>>(flag, m_local, meta);
-        SCM_LAUNCH_CHECK(ctx);
-    }
-    SCM_TRY(allreduce(ctx, gsums, (int64_t)G * n, 0));
-    SCM_TRY(allreduce(ctx, gcounts, G, 1));
-    SCM_TRY(allreduce(ctx, meta, 2, 1));
-    colmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, G, n, meta, shift);
-    SCM_LAUNCH_CHECK(ctx);
-    if (d_batch) {  // standardize2 (R/scRUVIII.R:158-175): global mean, pooled within-batch variance
+    // One summing pass + one Gram pass over the local cells, two all-reduces (fit_core.cuh): replicate-group sums (my_residop,
+    // R/fastRUVIII.R:121-129), NA/Inf scan (:52-60), standardize2's statistics (R/scRUVIII.R:158-175) and the centred Gram.
+    FitState fs;
+    SCM_TRY(fit_state(ctx, ws, d_Y, m_local, n, ld, d_group, G, d_batch, Bt, fs));
+    if (d_batch) {  // global mean + pooled within-batch sd
         StageTimer t(ctx, ST_STD);
-        double *bsums, *ssq;
-        int64_t* bcounts;
-        SCM_TRY(ws.alloc(&bsums, (int64_t)Bt * n)); SCM_TRY(ws.alloc(&ssq, (int64_t)Bt * n)); SCM_TRY(ws.alloc(&bcounts, Bt));
         SCM_TRY(ws.alloc(&inv_sd, n));
-        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_batch, Bt, nullptr, bsums, bcounts, nullptr));
-        SCM_TRY(allreduce(ctx, bsums, (int64_t)Bt * n, 0));
-        SCM_TRY(allreduce(ctx, bcounts, Bt, 1));
-        groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, Bt, n);
+        pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(fs.ssq, fs.bcounts, Bt, n, fs.meta, d_sd, inv_sd);
         SCM_LAUNCH_CHECK(ctx);
-        SCM_TRY(seg_colsum(ctx, d_Y, m_local, n, ld, d_batch, Bt, bsums, ssq, nullptr, nullptr));
-        SCM_TRY(allreduce(ctx, ssq, (int64_t)Bt * n, 0));
-        pooled_sd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bcounts, Bt, n, meta, d_sd, inv_sd);
-        SCM_LAUNCH_CHECK(ctx);
-        SCM_CUDA(cudaMemcpyAsync(d_mean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        SCM_TRY(copy_async(ctx, d_mean, fs.ybar, sizeof(double) * n));
     }
-    // Gram of the shifted cells (local), summed over ranks, then corrected to the Gram of the residual Y0.  The Gram kernel
-    // without a shift vector has no DADD in its DMMA stream and is 10 % faster (gram_tma.cuh), so it reads a PRE-SHIFTED copy
-    // of the cells.  The identity of DESIGN.md section 2 holds for ANY fixed shift: `pre` is the column mean of a strided sample
-    // of <= 4096 cells per rank (summed over the ranks: the same vector everywhere), close enough to the mean that nothing
-    // cancels, and available before the first full pass.  Without room for the copy (or with SCM_GRAM_PRESHIFT=0) the Gram
-    // kernel subtracts the exact column mean from its fragments as before.
-    struct AsyncBuf {  // stream-ordered buffer that may fail to allocate (freed on every exit path)
-        double* p = nullptr;
-        cudaStream_t st;
-        ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
-    } ypre;
-    ypre.st = st;
-    double*& Ypre = ypre.p;
-    const double* gshift = shift;
-    const int64_t ldp = (n + 1) & ~(int64_t)1;
-    if (ctx->gram_preshift && ctx->use_tma) {
-        double *pre, *psum;
-        int64_t* pcount;
-        int32_t* zkey;
-        const int64_t ms = m_local < 4096 ? m_local : 4096, stride = ms > 0 ? m_local / ms : 1;
-        SCM_TRY(ws.alloc(&pre, n)); SCM_TRY(ws.alloc(&psum, n)); SCM_TRY(ws.alloc(&pcount, 1)); SCM_TRY(ws.alloc(&zkey, ms));
-        SCM_TRY(zero_async(ctx, zkey, sizeof(int32_t) * ms));
-        SCM_TRY(seg_colsum(ctx, d_Y, ms, n, ld * stride, zkey, 1, nullptr, psum, pcount, nullptr));
-        SCM_TRY(allreduce(ctx, psum, n, 0));
-        SCM_TRY(allreduce(ctx, pcount, 1, 1));
-        vec_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(psum, pcount, n, pre);
-        SCM_LAUNCH_CHECK(ctx);
-        gshift = pre;
-        if (m_local > 0) {
-            if (cudaMallocAsync((void**)&Ypre, sizeof(double) * (size_t)m_local * (size_t)ldp, st) != cudaSuccess) {
-                cudaGetLastError();  // no room for the copy: in-kernel shift (by `pre`, which every rank already agreed on)
-                Ypre = nullptr;
-            }
-        }
-    }
-    {
-        StageTimer t(ctx, ST_GRAM);
-        int grc;
-        if (Ypre) {
-            const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
-            const int64_t groups = ceil_div(m_local, 8);
-            const unsigned grid = (unsigned)(groups < (int64_t)ctx->num_sms * 16 ? groups : (int64_t)ctx->num_sms * 16);
-            {
-                StageTimer tc(ctx, ST_PRESHIFT);
-                if (vec2) shift_copy_kernel<2><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
-                else shift_copy_kernel<1><<<grid, 256, 0, st>>>(d_Y, m_local, n, ld, gshift, Ypre, ldp);
-            }
-            SCM_LAUNCH_CHECK(ctx);
-            grc = gram(ctx, Ypre, m_local, n, ldp, nullptr, Gm, true);
-        } else {
-            grc = gram(ctx, d_Y, m_local, n, ld, gshift, Gm, true);
-        }
-        SCM_TRY(grc);
-    }
-    SCM_TRY(allreduce(ctx, Gm, n * n, 0));
-    if (d_gram_centred) {
-        // centred Gram of ALL cells (PCA of Y / of any newY): Gm - m (ybar - gshift)(ybar - gshift)', i.e. the residual
-        // correction for ONE group holding every cell (exactly Gm when the shift is the global mean)
-        SCM_CUDA(cudaMemcpyAsync(d_gram_centred, Gm, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
-        if (gshift != shift) {
-            double* tot;
-            SCM_TRY(ws.alloc(&tot, n));
-            group_total_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(gsums, G, n, tot);
-            SCM_LAUNCH_CHECK(ctx);
-            SCM_TRY(gram_residual(ctx, d_gram_centred, n, tot, meta + 1, 1, gshift, nullptr));
-        }
-    }
-    if (d_colmean) SCM_CUDA(cudaMemcpyAsync(d_colmean, shift, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    SCM_TRY(gram_residual(ctx, Gm, n, gsums, gcounts, G, gshift, inv_sd));
-    int64_t hmeta[2];
-    SCM_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, st));
-    SCM_CUDA(cudaStreamSynchronize(st));
-    if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+    // centred Gram of ALL cells (PCA of Y / of any newY, the ruvK selection) and their column means
+    if (d_gram_centred) SCM_TRY(copy_async(ctx, d_gram_centred, fs.Gm, sizeof(double) * n * n));
+    if (d_colmean) SCM_TRY(copy_async(ctx, d_colmean, fs.ybar, sizeof(double) * n));
+    // residual operator, part 2: Gram of Y0 = centred Gram - sum_g n_g (mu_g - ybar)(mu_g - ybar)', standardised when scRUVIII
+    SCM_TRY(gram_residual(ctx, fs.Gm, n, fs.gsums, fs.gcounts, G, fs.ybar, inv_sd));
+    int64_t* hmeta;
+    SCM_TRY(fit_meta_to_host(ctx, fs, &hmeta));  // lands with the eigensolver's first read-back: no synchronisation of its own
     int rc;
     {   // runSVD (R/fastRUVIII.R:91) + t(u) %*% Y (:93) == sqrt(lambda) v'
         StageTimer t(ctx, ST_EIG);
-        rc = eig_topk(ctx, Gm, n, s, kconv, mode, tol, maxit, seed, vals, vecs, iters_out, resid_out);
+        rc = eig_topk(ctx, fs.Gm, n, s, kconv, mode, tol, maxit, seed, vals, vecs, iters_out, resid_out, fs.meta);
+        if (rc == SCM_ERR_NONFINITE || rc == 0 || rc == SCM_ERR_NOCONV) SCM_TRY(fit_meta_check(hmeta));
         if (rc != 0 && rc != SCM_ERR_NOCONV) return rc;
         dim3 grid((unsigned)ceil_div(n, 256), (unsigned)s);
         fullalpha_kernel<<<grid, 256, 0, st>>>(vals, vecs, s, n, d_fullalpha, d_sigma);
         SCM_LAUNCH_CHECK(ctx);
     }
-    SCM_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
 
@@ -687,6 +648,28 @@ int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t
     HostArgs a{h_Y, m, n, ldh, h_group, G, h_batch, Bt, h_ctl, k, s, mode, tol, maxit, seed, h_fullalpha_in, s_in, center_mode,
                h_center, h_out, ldo, h_fullalpha, h_sigma, h_mean, h_sd, iters_out, resid_out};
     return ruv3_host(ctx, a);
+}
+
+int scm_multi_ruv3_host(scm_multi* mg, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,
+                        const int32_t* h_batch, int32_t Bt, const uint8_t* h_ctl, int32_t k, int32_t s, int mode, double tol, int32_t maxit,
+                        uint64_t seed, const double* h_fullalpha_in, int32_t s_in, int center_mode, const double* h_center, double* h_out,
+                        int64_t ldo, double* h_fullalpha, double* h_sigma, double* h_mean, double* h_sd, int32_t* iters_out,
+                        double* resid_out) {
+    if (!mg || mg->ctx.empty()) return fail(SCM_ERR_INVALID, "scm_multi_ruv3_host: null handle");
+    const int nd = (int)mg->ctx.size();
+    if (m < nd) return fail(SCM_ERR_INVALID, "scm_multi_ruv3_host: fewer cells (%lld) than devices (%d)", (long long)m, nd);
+    const int64_t base = m / nd, rem = m % nd;
+    return multi_run(mg, [&](int r) -> int {
+        scm_ctx* ctx = mg->ctx[r];
+        SCM_CUDA(cudaSetDevice(ctx->device));
+        const int64_t r0 = r * base + (r < rem ? r : rem), rows = base + (r < rem ? 1 : 0);  // contiguous, balanced, never empty
+        const bool lead = r == 0;  // after the Gram all-reduce every device holds bit-identical fit results: device 0 reports them
+        HostArgs a{h_Y + r0 * ldh, rows, n, ldh, h_group ? h_group + r0 : nullptr, G, h_batch ? h_batch + r0 : nullptr, Bt, h_ctl, k, s, mode,
+                   tol, maxit, seed, h_fullalpha_in, s_in, center_mode, h_center, h_out + r0 * ldo, ldo, lead ? h_fullalpha : nullptr,
+                   lead ? h_sigma : nullptr, lead ? h_mean : nullptr, lead ? h_sd : nullptr, lead ? iters_out : nullptr,
+                   lead ? resid_out : nullptr};
+        return ruv3_host(ctx, a);
+    });
 }
 
 int scm_timers(scm_ctx* ctx, double* ms, int n) {

@@ -84,16 +84,24 @@ __global__ void seg_scan_kernel(const int* __restrict__ cnt, int32_t G, int64_t*
     if (threadIdx.x == 0) { seg_start[G] = base_start; chunk_off[G] = base_chunk; pslot_off[G] = base_slot; }
 }
 
-template <int VEC, bool SQUARE>
+// COPY: every visited element is also written, shifted, to copy_out[row, col] = Y[row, col] - copy_shift[col] (the pre-shifted
+// copy of the cells the fit's Gram reads): the stream that is being summed anyway pays for the copy's read.
+template <int VEC, bool SQUARE, bool COPY = false>
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const int32_t* __restrict__ perm,
                    const int64_t* __restrict__ seg_start, const int* __restrict__ chunk_off,
                    const int* __restrict__ pslot_off, int32_t G, const double* __restrict__ center,
-                   double* __restrict__ partial, double* __restrict__ sums, int* __restrict__ flag) {
+                   double* __restrict__ partial, double* __restrict__ sums, int* __restrict__ flag,
+                   const double* __restrict__ copy_shift = nullptr, double* __restrict__ copy_out = nullptr, int64_t ldc = 0) {
     const int nchunks = chunk_off[G];
     const int64_t col = ((int64_t)blockIdx.x * SEG_THREADS + threadIdx.x) * VEC;
     const bool v0 = col < n, v1 = (VEC == 2) && (col + 1 < n);
     bool bad = false;
+    double h0 = 0.0, h1 = 0.0;
+    if (COPY) {
+        if (v0) h0 = copy_shift[col];
+        if (v1) h1 = copy_shift[col + 1];
+    }
     for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
         int lo = 0, hi = G;  // largest g with chunk_off[g] <= chunk (empty groups share offsets: take the last)
         while (hi - lo > 1) {
@@ -113,10 +121,12 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
         if (v0) {
             for (int r = 0; r < len; r += 8) {
                 double x0[8], x1[8];
+                int rows[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const bool ok = r + u < len;
                     const int64_t row = ok ? (int64_t)perm[start + r + u] : 0;
+                    rows[u] = (int)row;
                     const double* p = Y + row * ld + col;
                     x0[u] = 0.0; x1[u] = 0.0;
                     if (ok) {
@@ -130,6 +140,11 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
                         bad |= nonfinite(x0[u]) | nonfinite(x1[u]);
                         if (SQUARE) { double d0 = x0[u] - c0, d1 = x1[u] - c1; a0 += d0 * d0; a1 += d1 * d1; }
                         else { a0 += x0[u]; a1 += x1[u]; }
+                        if (COPY) {
+                            double* q = copy_out + (int64_t)rows[u] * ldc + col;
+                            if (VEC == 2 && v1) __stcs(reinterpret_cast<double2*>(q), make_double2(x0[u] - h0, x1[u] - h1));
+                            else __stcs(q, x0[u] - h0);
+                        }
                     }
                 }
             }
@@ -140,6 +155,17 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
         }
     }
     if (bad && flag) *flag = 1;
+}
+
+// Rows whose key is outside [0, G) are not visited by seg_partial_kernel: they sit behind seg_start[G] in the sorted order and
+// still belong in the shifted copy (the Gram is over ALL cells).
+__global__ void seg_copy_skipped_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, const int32_t* __restrict__ perm,
+                                        const int64_t* __restrict__ seg_start, int32_t G, const double* __restrict__ shift,
+                                        double* __restrict__ out, int64_t ldo) {
+    for (int64_t pos = seg_start[G] + blockIdx.x; pos < m; pos += gridDim.x) {
+        const int64_t row = perm[pos];
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) out[row * ldo + j] = Y[row * ld + j] - shift[j];
+    }
 }
 
 // sums[g, col] = sum of the group's chunk partials in chunk order (groups with 0 rows -> 0, 1 chunk -> already written)
@@ -189,13 +215,17 @@ inline int seg_plan_build(scm_ctx* ctx, Scratch& ws, const int32_t* d_key, int64
     char* tmp;
     SCM_TRY(ws.alloc(&tmp, (int64_t)tmp_bytes));
     SCM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, skey_in, skey_out, sval_in, perm, (int)m, 0, end_bit, st));
-    ctx->launches += 3;
+    // CUB's launches are counted from its documented structure, not observed: histogram + exclusive sum + one onesweep pass per
+    // 8 key bits (the launch lists under profiles/ show exactly these three kernels for G < 256)
+    ctx->launches += 2 + (end_bit + 7) / 8;
     sp.perm = perm; sp.seg_start = seg_start; sp.chunk_off = chunk_off; sp.pslot_off = pslot_off;
     return 0;
 }
 
+// d_copy_out (optional, m x ldc, ldc even when ld is): receives Y - d_copy_shift (n) for EVERY row, written from the summing pass.
 inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_key,
-                      int32_t G, const double* d_center, double* d_sums, int64_t* d_counts, int32_t* d_nonfinite) {
+                      int32_t G, const double* d_center, double* d_sums, int64_t* d_counts, int32_t* d_nonfinite,
+                      const double* d_copy_shift = nullptr, double* d_copy_out = nullptr, int64_t ldc = 0) {
     if (m < 0 || n <= 0 || G <= 0 || ld < n) return fail(SCM_ERR_INVALID, "seg_colsum: bad shape m=%lld n=%lld ld=%lld G=%d", (long long)m, (long long)n, (long long)ld, G);
     if (m >= (int64_t)1 << 31) return fail(SCM_ERR_UNSUPPORTED, "seg_colsum: m >= 2^31 rows per rank");
     cudaStream_t st = ctx->stream;
@@ -226,7 +256,18 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     grid.y = (unsigned)gy;
     const bool sq = d_center != nullptr;
 #define SEG_LAUNCH(V, S) seg_partial_kernel<V, S><<<grid, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, d_center, partial, d_sums, d_nonfinite)
-    if (vec2) { if (sq) SEG_LAUNCH(2, true); else SEG_LAUNCH(2, false); }
+    if (d_copy_out) {
+        if (sq || !d_copy_shift || ldc < n) return fail(SCM_ERR_INVALID, "seg_colsum: the shifted copy needs a shift vector, ldc >= n and the plain-sum mode");
+        const bool vec2c = vec2 && (ldc % 2 == 0) && (((uintptr_t)d_copy_out) % 16 == 0);
+        if (vec2c) seg_partial_kernel<2, false, true><<<grid, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, nullptr, partial, d_sums, d_nonfinite, d_copy_shift, d_copy_out, ldc);
+        else {
+            dim3 grid1((unsigned)ceil_div(n, (int64_t)SEG_THREADS), grid.y);
+            seg_partial_kernel<1, false, true><<<grid1, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, nullptr, partial, d_sums, d_nonfinite, d_copy_shift, d_copy_out, ldc);
+        }
+        SCM_LAUNCH_CHECK(ctx);
+        seg_copy_skipped_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(d_Y, m, n, ld, perm, seg_start, G, d_copy_shift, d_copy_out, ldc);
+    }
+    else if (vec2) { if (sq) SEG_LAUNCH(2, true); else SEG_LAUNCH(2, false); }
     else      { if (sq) SEG_LAUNCH(1, true); else SEG_LAUNCH(1, false); }
 #undef SEG_LAUNCH
     SCM_LAUNCH_CHECK(ctx);

@@ -18,16 +18,23 @@ class Context:
     """Owns a `scm_ctx` (one GPU, one stream).  `stream` may be a raw cudaStream_t (int), e.g.
     `torch.cuda.current_stream().cuda_stream`, so that torch events and NCCL order with our kernels."""
 
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, _borrowed=None):
         self._h = C.c_void_p()
-        # stream=None: the library creates its own non-blocking stream.  stream=0 is torch's default stream, i.e. the
-        # legacy NULL stream, which must be passed as the cudaStreamLegacy handle (1) because NULL means "own stream".
-        handle = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
-        L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(handle), C.byref(self._h)))
         self.device = int(device)
         self.stream = stream
         self._cb = None  # keep the ctypes callback alive
         self.world, self.rank, self._ar_fn = 1, None, None
+        if _borrowed is not None:  # a context owned by a MultiContext (scm_multi_ctx)
+            self._h = C.c_void_p(_borrowed)
+            self._fin = None
+            r, w = C.c_int(0), C.c_int(1)
+            L.check(L.lib().scm_ctx_comm_info(self._h, C.byref(r), C.byref(w), None))
+            self.rank, self.world = r.value, w.value
+            return
+        # stream=None: the library creates its own non-blocking stream.  stream=0 is torch's default stream, i.e. the
+        # legacy NULL stream, which must be passed as the cudaStreamLegacy handle (1) because NULL means "own stream".
+        handle = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
+        L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(handle), C.byref(self._h)))
         self._fin = weakref.finalize(self, L.lib().scm_ctx_destroy, self._h)
 
     @property
@@ -69,15 +76,61 @@ class Context:
         self._cb = L.ALLREDUCE_FN(_cb)
         L.check(L.lib().scm_ctx_set_allreduce(self._h, self._cb, None, int(world_size)))
 
+    def init_nccl(self, rank: int, world_size: int, bcast):
+        """Built-in NCCL communicator, one rank per context (scm_ctx_comm_init_nccl; collective).  `bcast(b: bytes | None) ->
+        bytes` must return rank 0's argument on every rank (any transport: torch.distributed, MPI, a shared file):
+        it carries the 128-byte NCCL unique id.  After this the library's collectives never leave C."""
+        uid = C.create_string_buffer(128)
+        if rank == 0 and world_size > 1:
+            L.check(L.lib().scm_nccl_unique_id(uid))
+        if world_size > 1:
+            got = bcast(bytes(uid.raw) if rank == 0 else None)
+            uid = C.create_string_buffer(bytes(got), 128)
+        L.check(L.lib().scm_ctx_comm_init_nccl(self._h, uid, int(rank), int(world_size)))
+        self.world, self.rank, self._ar_fn, self._cb = int(world_size), int(rank), None, None
+
+    def transport(self) -> str:
+        t = C.c_int(0)
+        L.check(L.lib().scm_ctx_comm_info(self._h, None, None, C.byref(t)))
+        return ("none", "nccl", "hook")[t.value]
+
+    def fit_info(self) -> dict:
+        """Rayleigh-Ritz steps, final subspace-angle estimate, converged rank and extra products of the last eigen-solve."""
+        it, cr, pr, rs = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        L.check(L.lib().scm_ctx_fit_info(self._h, C.byref(it), C.byref(rs), C.byref(cr), C.byref(pr)))
+        return {"iters": it.value, "resid": rs.value, "conv_rank": cr.value, "products": pr.value}
+
     def allreduce(self, arr: "DeviceArray"):
         """Sum a float64 / int64 device array in place over the ranks (no-op for a single rank)."""
-        if self.world <= 1 or self._ar_fn is None:
+        if self.world <= 1:
             return
         if arr.dtype not in (np.dtype(np.float64), np.dtype(np.int64)):
             raise TypeError("all-reduce supports float64 and int64")
+        L.check(L.lib().scm_allreduce_sum(self._h, arr.ptr, int(np.prod(arr.shape, dtype=np.int64)),
+                                          0 if arr.dtype == np.dtype(np.float64) else 1))
         self.sync()
-        self._ar_fn(arr.address, int(np.prod(arr.shape, dtype=np.int64)), 0 if arr.dtype == np.dtype(np.float64) else 1, 0)
-        self.sync()
+
+    def allgather_bytes(self, payload: bytes) -> list:
+        """Every rank's byte string, in rank order, through the sum all-reduce (one-hot slices of a zero buffer).  Small
+        payloads only (label tables): each byte travels as an int64."""
+        if self.world <= 1:
+            return [payload]
+        if self.rank is None:
+            raise ValueError("multi-rank host logic needs the rank: Context.set_allreduce(fn, world_size, rank) or init_nccl")
+        sizes = np.zeros(self.world, dtype=np.int64)
+        sizes[self.rank] = len(payload)
+        d = self.to_device(sizes)
+        self.allreduce(d)
+        sizes = d.to_host()
+        d.free()
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        buf = np.zeros(int(off[-1]) + 1, dtype=np.int64)
+        buf[off[self.rank]:off[self.rank + 1]] = np.frombuffer(payload, dtype=np.uint8)
+        d = self.to_device(buf)
+        self.allreduce(d)
+        buf = d.to_host()
+        d.free()
+        return [buf[off[r]:off[r + 1]].astype(np.uint8).tobytes() for r in range(self.world)]
 
     # ---- memory -------------------------------------------------------------------------------
     def empty(self, shape, dtype=np.float64) -> "DeviceArray":
@@ -90,6 +143,36 @@ class Context:
             L.check(L.lib().scm_h2d(self._h, d.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
             self.sync()  # `host` may be a temporary
         return d
+
+
+class MultiContext:
+    """One process, several GPUs (scm_multi_create): a context + NCCL rank per device inside the library, one host thread per
+    device per call.  This is the handle a single R process would hold; `ruv3_host` is scm_multi_ruv3_host."""
+
+    def __init__(self, devices=None, ndev: int | None = None):
+        self._h = C.c_void_p()
+        if devices is None:
+            n = int(ndev if ndev is not None else 1)
+            arr = None
+        else:
+            devices = [int(d) for d in devices]
+            n = len(devices)
+            arr = (C.c_int * n)(*devices)
+        L.check(L.lib().scm_multi_create(arr, n, C.byref(self._h)))
+        self.size = n
+        self._fin = weakref.finalize(self, L.lib().scm_multi_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def ctx(self, i: int) -> Context:
+        p = L.lib().scm_multi_ctx(self._h, int(i))
+        if not p:
+            raise IndexError(i)
+        c = Context(_borrowed=p)
+        c._owner = self  # keep the handle alive while the borrowed context is in use
+        return c
 
 
 def bind_host_to_gpu(device: int = 0):

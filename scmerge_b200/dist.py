@@ -2,9 +2,12 @@
 NVLink) for the only cross-rank state of the RUV-III fit: replicate-group sums + counts, batch sums, the
 NA/Inf flag and the n x n Gram partial.  Everything else is rank-local.
 
-The C library never links NCCL itself: it calls back into the host-supplied sum all-reduce
-(`scm_ctx_set_allreduce`) with a raw buffer pointer, which this module wraps zero-copy as a torch tensor.
-The same hook works on host memory with the `gloo` backend, which is how the CPU tests exercise it.
+Two transports for those sums:
+  * `init_builtin_nccl(ctx)`: the library's own NCCL communicator (dlopen'd libnccl, scm_ctx_comm_init_nccl); torch.distributed
+    is only used once, to hand rank 0's 128-byte unique id to the other ranks.  This is what bench.py runs.
+  * `torch_allreduce_hook`: the host-supplied sum all-reduce (`scm_ctx_set_allreduce`) with a raw buffer pointer, wrapped
+    zero-copy as a torch tensor.  The same hook works on host memory with the `gloo` backend, which is how the CPU tests
+    exercise the host-side logic.
 """
 from __future__ import annotations
 
@@ -45,3 +48,18 @@ def torch_allreduce_hook(device: int | None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     return fn
+
+
+def init_builtin_nccl(ctx, rank: int | None = None, world: int | None = None):
+    """Create the library's own NCCL communicator for `ctx` over the default torch.distributed process group."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+
+    def bcast(b):
+        box = [b]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    ctx.init_nccl(rank, world, bcast)
+    return ctx

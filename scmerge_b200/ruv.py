@@ -19,9 +19,9 @@ import warnings
 import numpy as np
 
 from . import _lib as L
-from .device import Context, DeviceArray, DeviceMatrix, default_context
+from .device import Context, DeviceArray, DeviceMatrix, MultiContext, default_context
 
-__all__ = ["fastRUVIII", "scRUVIII", "scRUVg", "genes_by_name", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
+__all__ = ["FullAlpha", "fastRUVIII", "scRUVIII", "scRUVg", "genes_by_name", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
            "replicate_matrix", "replicate_keys", "tological", "createChunk", "RUVFit", "ExactParam", "RandomParam",
            "IrlbaParam"]
 
@@ -57,8 +57,42 @@ def replicate_matrix(a) -> np.ndarray:
     return M
 
 
-def replicate_keys(M, spare: int | None = None):
-    """Replicate structure -> (int32 group id per cell, number of groups).  A numeric matrix must be a one-hot
+def _active_ctx(Y, ctx):
+    """The context a call will run on, if one already exists (never creates one: the early-outs stay device-free)."""
+    if isinstance(ctx, MultiContext):
+        return None  # one process holds ALL the cells: labels and m are global already
+    if ctx is not None:
+        return ctx
+    return Y.ctx if isinstance(Y, DeviceMatrix) else None
+
+
+def _total_cells(ctx, m_local: int) -> int:
+    """Cells over ALL ranks that share them (the m of the reference's formulas: svd_k rule, early-out, PCA rank)."""
+    if ctx is None or ctx.world <= 1:
+        return int(m_local)
+    d = ctx.to_device(np.array([m_local], dtype=np.int64))
+    ctx.allreduce(d)
+    tot = int(d.to_host()[0])
+    d.free()
+    return tot
+
+
+def _global_levels(ctx, levels: np.ndarray) -> np.ndarray:
+    """Sorted union of the label levels seen by any rank.  Shards are contiguous row blocks and data usually arrives ordered
+    by batch, so a rank routinely lacks some batch / cell type: coding labels per rank would give every rank its own
+    key -> group mapping (and its own G, Bt, s), and the all-reduced sums would mix different groups."""
+    import pickle
+    parts = ctx.allgather_bytes(pickle.dumps(np.asarray(levels)))
+    got = [pickle.loads(p) for p in parts]
+    got = [g for g in got if g.shape[0] > 0]
+    if not got:
+        return np.asarray(levels)
+    return np.unique(np.concatenate(got))
+
+
+def replicate_keys(M, spare: int | None = None, ctx=None):
+    """Replicate structure -> (int32 group id per cell, number of groups).
+    `ctx` with several ranks: the level table is built over ALL ranks (see _global_levels), so ids and G are global.  A numeric matrix must be a one-hot
     partition (every row exactly one 1): the device path implements the residual operator as a segmented
     mean, which is what my_residop (R/fastRUVIII.R:121-129) computes for such M; a general M is rejected.
     `spare`: for non-negative integer labels with m - (max + 1) >= spare the O(m) histogram that drops unused label
@@ -79,6 +113,9 @@ def replicate_keys(M, spare: int | None = None):
         a = np.array(["_".join(str(x) for x in row) for row in a])
     if a.ndim != 1:
         raise ValueError("M must be a replicate matrix or a label vector")
+    if ctx is not None and ctx.world > 1:
+        levels = _global_levels(ctx, np.unique(a))
+        return np.searchsorted(levels, a).astype(np.int32), int(levels.shape[0])
     if np.issubdtype(a.dtype, np.integer) and a.shape[0] > 0:
         lo, hi = int(a.min()), int(a.max())
         if spare is not None and lo >= 0 and a.shape[0] - (hi + 1) >= spare:
@@ -147,6 +184,41 @@ def _dptr(a):
     return a.ptr if a is not None else None
 
 
+class FullAlpha(np.ndarray):
+    """fullalpha (s x n) as returned by a device fit: a plain float64 array that also remembers `conv_rank`, the number of
+    leading rows the eigensolver converged as an invariant subspace (scm_ctx_fit_info).  The reference's exact SVD makes every
+    row valid; here the rows beyond the ranks a fit was asked for are Ritz vectors of a subspace iteration that stopped once
+    the requested ranks had converged.  Re-using the array with a larger k (fastRUVIII(fullalpha=), getAdjustedMat(ruvK=))
+    than `conv_rank` raises a warning instead of silently differing from a direct fit."""
+
+    conv_rank = None
+
+    def __new__(cls, arr, conv_rank=None):
+        obj = np.asarray(arr, dtype=np.float64).view(cls)
+        obj.conv_rank = conv_rank
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self.conv_rank = getattr(obj, "conv_rank", None)
+
+    def __reduce__(self):  # pickling keeps the rank (the fit/adjust split is the reference's checkpoint, SURVEY.md section 5)
+        fn, args, state = super().__reduce__()
+        return fn, args, (state, self.conv_rank)
+
+    def __setstate__(self, state):
+        super().__setstate__(state[0])
+        self.conv_rank = state[1]
+
+
+def _check_conv_rank(fullalpha, k: int):
+    cr = getattr(fullalpha, "conv_rank", None)
+    if cr is not None and k > cr and k <= np.shape(fullalpha)[0]:
+        warnings.warn(f"ruvK = {k} exceeds the rank this fullalpha was converged for ({cr}): rows {cr + 1}..{k} are unconverged Ritz "
+                      "vectors, the result will differ from a direct fit with this k.  Fit with the largest k you intend to use "
+                      "(or list every k in scRUVIII).", L.NotConvergedWarning, stacklevel=4)
+
+
 class RUVFit:
     """Result of the fit half of RUV-III: the small, host-side 'checkpoint' (fullalpha and, for scRUVIII, the
     standardisation vectors).  `fullalpha` is s x n like the reference's (R/fastRUVIII.R:93)."""
@@ -181,7 +253,8 @@ def _fit(ctx: Context, dY: DeviceMatrix, keys: np.ndarray, G: int, s: int, k: in
         warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
     else:
         L.check(rc)
-    fit = RUVFit(d_fa.to_host(), d_sig.to_host(), d_mean.to_host() if d_mean is not None else None,
+    info = ctx.fit_info()
+    fit = RUVFit(FullAlpha(d_fa.to_host(), info["conv_rank"]), d_sig.to_host(), d_mean.to_host() if d_mean is not None else None,
                  d_sd.to_host() if d_sd is not None else None, iters.value, resid.value)
     for a in (d_keys, d_batch, d_fa, d_sig, d_mean, d_sd):
         if a is not None:
@@ -197,6 +270,7 @@ class _Coef:
     def __init__(self, ctx: Context, n: int, fullalpha: np.ndarray, k: int, ctl: np.ndarray, center=None, pre=None, post=None):
         self.ctx, self.n = ctx, n
         self.k = int(min(k, fullalpha.shape[0]))
+        _check_conv_rank(fullalpha, self.k)
         if self.k > L.MAX_K:
             raise L.ScmError(L.ERR_UNSUPPORTED, f"ruvK = {self.k} > {L.MAX_K} is not supported by the fused adjust kernel")
         self._args = (np.ascontiguousarray(fullalpha[:self.k], dtype=np.float64), np.ascontiguousarray(ctl, dtype=np.uint8),
@@ -348,14 +422,23 @@ def _host_pipeline(ctx: Context, Y: np.ndarray, ctl: np.ndarray, k: int, keys=No
     sd = np.empty(n) if b32 is not None else None
     cen = np.ascontiguousarray(center, dtype=np.float64) if center is not None else None
     iters, resid = C.c_int32(0), C.c_double(0.0)
-    rc = lib.scm_ruv3_host(ctx.handle, vp(Y), m, n, n, vp(keys32), G, vp(b32), Bt, vp(ctl8), int(k), int(s_out),
-                           L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, vp(fa_in), 0 if do_fit else s_out,
-                           center_mode, vp(cen), vp(out), n, vp(fa) if do_fit else None, vp(sig), vp(mean), vp(sd),
-                           C.byref(iters), C.byref(resid))
+    # a MultiContext (one process, several GPUs) takes the same arguments: the library splits the cells over its devices
+    multi = isinstance(ctx, MultiContext)
+    call = lib.scm_multi_ruv3_host if multi else lib.scm_ruv3_host
+    rc = call(ctx.handle, vp(Y), m, n, n, vp(keys32), G, vp(b32), Bt, vp(ctl8), int(k), int(s_out),
+              L.MODE_EXACT if exact else L.MODE_RANDOMIZED, tol, maxit, seed, vp(fa_in), 0 if do_fit else s_out,
+              center_mode, vp(cen), vp(out), n, vp(fa) if do_fit else None, vp(sig), vp(mean), vp(sd),
+              C.byref(iters), C.byref(resid))
+    if multi:
+        ctx = ctx.ctx(0)  # fit facts are identical on every device; device 0 reports them
     if rc == L.ERR_NOCONV:
         warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=3)
     else:
         L.check(rc)
+    if do_fit:
+        fa = FullAlpha(fa, ctx.fit_info()["conv_rank"])
+    else:
+        _check_conv_rank(fullalpha_in, int(min(k, s_out)))
     return out, RUVFit(fa, sig, mean, sd, iters.value, resid.value)
 
 
@@ -396,15 +479,19 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if k is None:
         raise TypeError("k must be given (the reference fails on k = NULL, R/fastRUVIII.R:78)")
     m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
-    keys, G = replicate_keys(M, spare=n)
+    actx = _active_ctx(Y, ctx)
+    keys, G = replicate_keys(M, spare=n, ctx=actx)
     if keys.shape[0] != m:
         raise ValueError("M must have one row per row of Y")
     ctl = tological(ctl, n)
     exact = _is_exact(BSPARAM)
-    s = _svd_k(m, G, int(ctl.sum()), exact, svd_k)
-    if G >= m or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input
+    m_total = _total_cells(actx, m)  # several ranks: the reference's m is the number of cells over all of them
+    s = _svd_k(m_total, G, int(ctl.sum()), exact, svd_k)
+    if G >= m_total or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input
         newY, fa = Y, None
         return {"newY": newY, "M": M, "fullalpha": fa} if return_info else newY
+    if isinstance(ctx, MultiContext) and not (_is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray))):
+        raise TypeError("a MultiContext drives HOST matrices (C-contiguous float64 cells x genes); device-resident shards use MultiContext.ctx(i)")
     ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
     if _is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray)):
         # host matrix: one pipelined call (H2D / fit / adjust / D2H overlapped)
@@ -413,7 +500,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
             newY, fit = _host_pipeline(ctx, Y, ctl, int(k), keys=keys, G=G, s=s_dev, exact=exact_dev, out=out)
             fullalpha = fit.fullalpha
         else:
-            fullalpha = np.asarray(fullalpha, dtype=np.float64)
+            fullalpha = np.asanyarray(fullalpha, dtype=np.float64)
             newY, _ = _host_pipeline(ctx, Y, ctl, int(k), fullalpha_in=fullalpha, center_mode=0, out=out)
         return {"newY": newY, "M": M, "fullalpha": fullalpha} if return_info else newY
     dY, copied = _as_device(ctx, Y)
@@ -423,7 +510,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
         s_dev, exact_dev = _device_rows_cap(s, k, exact)
         fit = _fit(ctx, dY, keys, G, s_dev, int(k), exact_dev)
         fullalpha = fit.fullalpha
-    fullalpha = np.asarray(fullalpha, dtype=np.float64)
+    fullalpha = np.asanyarray(fullalpha, dtype=np.float64)
     dout, _ = _adjust(ctx, dY, fullalpha, int(k), ctl, out=out if isinstance(out, DeviceMatrix) else None)
     newY = _finish(dout, copied, out if isinstance(out, np.ndarray) else None)
     if copied:
@@ -445,21 +532,25 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     if batch is None:
         raise ValueError("batch is required")
     ks = [int(k)] if np.isscalar(k) else [int(x) for x in k]
-    keys, G = replicate_keys(M)
+    actx = _active_ctx(Y, ctx)
+    keys, G = replicate_keys(M, ctx=actx)
     m = Y.m if isinstance(Y, DeviceMatrix) else np.shape(Y)[1]
     if keys.shape[0] != m:
         raise ValueError("M must have one row per cell (column of Y)")
-    if G >= m or ks[0] == 0:  # fastRUVIII's early-out (R/fastRUVIII.R:78-80): resolved before touching the device
+    m_total = _total_cells(actx, m)
+    if G >= m_total or ks[0] == 0:  # fastRUVIII's early-out (R/fastRUVIII.R:78-80): resolved before touching the device
         return _scruviii_degenerate(Y, M, ks, return_all_RUV)
     ctx = ctx or default_context()
+    if isinstance(ctx, MultiContext) and not (isinstance(Y, np.ndarray) and _is_host_matrix(Y.T) and len(ks) == 1 and fullalpha is None):
+        raise TypeError("a MultiContext drives HOST matrices with a single ruvK (genes x cells in column-major order)")
     if isinstance(Y, np.ndarray) and _is_host_matrix(Y.T) and len(ks) == 1 and fullalpha is None:
         # genes x cells in column-major order (R's layout) is cells x genes row-major: pipelined host path
         Yt = Y.T
         m, n = Yt.shape
-        bkeys, Bt = replicate_keys(np.asarray(batch))
+        bkeys, Bt = replicate_keys(np.asarray(batch), ctx=actx)
         ctlm = tological(ctl, n)
         exact = _is_exact(BSPARAM)
-        s = _svd_k(m, G, int(ctlm.sum()), exact, svd_k)
+        s = _svd_k(m_total, G, int(ctlm.sum()), exact, svd_k)
         s_dev, exact_dev = _device_rows_cap(s, ks[0], exact)
         newY, fit = _host_pipeline(ctx, Yt, ctlm, ks[0], keys=keys, G=G, s=s_dev, exact=exact_dev, batch_keys=bkeys, Bt=Bt)
         res = {ks[0]: {"newY": newY, "M": M, "fullalpha": fit.fullalpha}, "optimal_ruvK": ks[0],
@@ -476,10 +567,10 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
         # genes x cells: C-order needs a transpose on the device, Fortran order is already cells x genes row-major
         dY, copied = DeviceMatrix.from_host(ctx, Y.T), True
     m, n = dY.m, dY.n
-    bkeys, Bt = replicate_keys(np.asarray(batch))
+    bkeys, Bt = replicate_keys(np.asarray(batch), ctx=ctx)
     ctl = tological(ctl, n)
     exact = _is_exact(BSPARAM)
-    s = _svd_k(m, G, int(ctl.sum()), exact, svd_k)
+    s = _svd_k(m_total, G, int(ctl.sum()), exact, svd_k)
     results = {}
     s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
     select = len(ks) > 1
@@ -493,13 +584,13 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
             L.check(L.lib().scm_ctx_set_conv_ranks(ctx.handle, None, 0))
     else:  # still need stand_mean / stand_sd: run the standardisation passes only via a fit with s = 1
         fit0 = _fit(ctx, dY, keys, G, 1, 1, True, batch_keys=bkeys, Bt=Bt, maxit=2, tol=1.0, keep_gram=select)
-        fit = RUVFit(np.asarray(fullalpha, dtype=np.float64), None, fit0.stand_mean, fit0.stand_sd)
+        fit = RUVFit(np.asanyarray(fullalpha, dtype=np.float64), None, fit0.stand_mean, fit0.stand_sd)
         fit.d_gram, fit.d_colmean = fit0.d_gram, fit0.d_colmean
     f_score, sil = np.ones(1), None
     if select:
         # R/scRUVIII.R:83-105: silhouette of the cell types (the replicate structure when cell_type is NULL, :89-92) and of
         # the batches in the first 10 PCs of every candidate's adjusted matrix, F-score of the two, which.max
-        ct_keys, n_ct = (keys, G) if cell_type is None else replicate_keys(np.asarray(cell_type))
+        ct_keys, n_ct = (keys, G) if cell_type is None else replicate_keys(np.asarray(cell_type), ctx=ctx)
         sil = np.empty((2, len(ks)))
         for i, kk in enumerate(ks):
             with _Coef(ctx, n, fit.fullalpha, kk, ctl, fit.stand_mean, 1.0 / fit.stand_sd, fit.stand_sd) as coef:
@@ -602,7 +693,7 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
         if pcopied:
             dP.free()
         fullalpha = fit.fullalpha
-    fullalpha = np.asarray(fullalpha, dtype=np.float64)
+    fullalpha = np.asanyarray(fullalpha, dtype=np.float64)
     if not normalised:
         return {"M": M, "fullalpha": fullalpha}
     if _is_host_matrix(Y) and subset is None:
@@ -656,13 +747,18 @@ def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, 
         if sub.shape[0] == 0:
             raise ValueError("No provided return_subset_genes genes in the data")
     means = column_means(dY) if adjusted_means is None else np.asarray(adjusted_means, dtype=np.float64)
-    dout, _ = _adjust(ctx, dY, np.asarray(fullalpha, dtype=np.float64), int(ruvK), ctl_mask, center=means, subset=sub)
+    dout, _ = _adjust(ctx, dY, np.asanyarray(fullalpha, dtype=np.float64), int(ruvK), ctl_mask, center=means, subset=sub)
     if copied:
         dY.free()
         res = dout.to_host().T
         dout.free()
         return res
     return dout
+
+
+def multi_fastRUVIII(mg: MultiContext, Y, M, ctl, k, **kw):
+    """fastRUVIII of a host matrix on ALL the devices of a MultiContext (scm_multi_ruv3_host): the call a single R process makes."""
+    return fastRUVIII(Y, M, ctl, k=k, ctx=mg, **kw)
 
 
 # ---- K1 front-ends ----------------------------------------------------------------------------------------

@@ -128,7 +128,7 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
     to a random order of the cells (`which = rep(1:K, length.out = n_b)`); the pseudobulk of (b, f, t) is the mean of the
     cells of cluster t in that fold.  Keys are ordered batch-major, then fold, then cluster level, which is the row
     order of the reference's `bulkExprs`.  `which` (fold id per cell, 1-based) may be passed to reproduce an R draw.
-    Returns (keys int32, P, names 'b_t_f', cluster level index per pseudobulk, batch index per pseudobulk)."""
+    Returns (keys int32, P, names 'i_t_f' (i = 1-based batch index), cluster level index per pseudobulk, batch index per pseudobulk)."""
     blev, b = np.unique(np.asarray(batch), return_inverse=True)
     tlev, t = np.unique(np.asarray(clust), return_inverse=True)
     m, T = b.shape[0], tlev.shape[0]
@@ -150,7 +150,9 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
     keys = remap[raw].astype(np.int32)
     ids = np.nonzero(present)[0]
     pb_t, pb_f, pb_b = ids % T, (ids // T) % K, ids // (T * K)
-    names = [f"{blev[bb]}_{tlev[tt]}_{ff + 1}" for bb, tt, ff in zip(pb_b, pb_t, pb_f)]
+    # rownames(res) <- paste(i, rownames(res), sep = "_") with i the 1-based position in sort(unique(batch))
+    # (R/scMerge2_utilis.R:266, R/scMerge2.R:139): the batch INDEX, not its label
+    names = [f"{bb + 1}_{tlev[tt]}_{ff + 1}" for bb, tt, ff in zip(pb_b, pb_t, pb_f)]
     return keys, int(ids.shape[0]), names, pb_t.astype(np.int32), pb_b.astype(np.int32)
 
 

@@ -1,5 +1,7 @@
-"""torchrun worker for the multi-GPU parity test: every rank holds a contiguous block of cells, the fit runs with
-the NCCL all-reduce hook, rank-local adjust, and each rank checks its rows against the single-process oracle."""
+"""torchrun worker for the multi-GPU parity test: every rank holds a contiguous block of cells, the fit runs with the library's
+own NCCL communicator (SCM_TEST_TRANSPORT=hook: the torch.distributed hook instead), rank-local adjust, and each rank checks its
+rows against the single-process oracle.  The cells are ORDERED BY BATCH and one cell type only occurs in the last rows, so the
+shards do not see every label: the level tables must be built over all ranks (scmerge_b200.ruv._global_levels)."""
 import os
 import sys
 
@@ -17,45 +19,60 @@ def main():
 
     import scmerge_b200 as sm
     from oracle import ruv_oracle as orc
-    from scmerge_b200.dist import shard_rows, torch_allreduce_hook
+    from scmerge_b200.dist import init_builtin_nccl, shard_rows, torch_allreduce_hook
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = sm.Context(local, stream=torch.cuda.current_stream().cuda_stream)
-    ctx.set_allreduce(torch_allreduce_hook(local), world, rank)
+    transport = os.environ.get("SCM_TEST_TRANSPORT", "nccl")
+    if transport == "hook":
+        ctx = sm.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+        ctx.set_allreduce(torch_allreduce_hook(local), world, rank)
+    else:
+        ctx = init_builtin_nccl(sm.Context(local), rank, world)
+    assert ctx.transport() == transport
     P = orc.planted_factors(9000, 384, 128, 10, n_types=6, n_batch=3, seed=31)
+    # batch-ordered cells (stable), labels as strings; cell type "t5" is moved to the very end: rank 0 never sees it
+    order = np.argsort(P["batch"], kind="stable")
+    order = np.concatenate([order[P["types"][order] != 5], order[P["types"][order] == 5]])
+    Yall, types_all = P["Y"][order], np.array([f"t{t}" for t in P["types"][order]])
+    batch_all = np.array([f"b{b}" for b in P["batch"][order]])
     lo, hi = shard_rows(9000, world, rank)
-    ok = True
+    assert len(set(batch_all[lo:hi])) < 3 or world == 1, "the shards are supposed to miss batches"
     # fastRUVIII path
-    out = sm.fastRUVIII(P["Y"][lo:hi], P["types"][lo:hi], P["ctl"], k=10, return_info=True, ctx=ctx)
-    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 10, return_info=True)
+    out = sm.fastRUVIII(Yall[lo:hi], types_all[lo:hi], P["ctl"], k=10, return_info=True, ctx=ctx)
+    ref = orc.fastRUVIII(Yall, types_all, P["ctl"], 10, return_info=True)
     e1 = orc.rel_frobenius(out["newY"], ref["newY"][lo:hi])
     a1 = float(orc.principal_angles(out["fullalpha"][:10], ref["fullalpha"][:10]).max())
+    # device-resident shard (scm_ruv3_fit + scm_adjust instead of the host pipeline)
+    dY = sm.DeviceMatrix.from_host(ctx, Yall[lo:hi])
+    outd = sm.fastRUVIII(dY, types_all[lo:hi], P["ctl"], k=10, return_info=True, ctx=ctx)
+    e1d = orc.rel_frobenius(outd["newY"].to_host(), ref["newY"][lo:hi])
+    dY.free()
     # scRUVIII path (standardisation statistics also cross ranks)
-    batch = np.array([f"b{b}" for b in P["batch"]])
-    res = sm.scRUVIII(P["Y"][lo:hi].T, P["types"][lo:hi], P["ctl"], k=10, batch=batch[lo:hi], ctx=ctx)
-    ref2 = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 10, batch)
+    res = sm.scRUVIII(Yall[lo:hi].T, types_all[lo:hi], P["ctl"], k=10, batch=batch_all[lo:hi], ctx=ctx)
+    ref2 = orc.scRUVIII(Yall.T, types_all, P["ctl"], 10, batch_all)
     e2 = orc.rel_frobenius(res[10]["newY"], ref2[10]["newY"][lo:hi])
     # ruvK selection across ranks (scores and labels gathered, distance pass split over the ranks) and scRUVg
-    sel = sm.scRUVIII(P["Y"][lo:hi].T, P["types"][lo:hi], P["ctl"], k=[4, 10], batch=batch[lo:hi], cell_type=P["types"][lo:hi], ctx=ctx)
-    rsel = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], [4, 10], batch, cell_type=P["types"])
+    sel = sm.scRUVIII(Yall[lo:hi].T, types_all[lo:hi], P["ctl"], k=[4, 10], batch=batch_all[lo:hi], cell_type=types_all[lo:hi], ctx=ctx)
+    rsel = orc.scRUVIII(Yall.T, types_all, P["ctl"], [4, 10], batch_all, cell_type=types_all)
     e3 = float(np.abs(sel["sil"] - rsel["sil"]).max())
     same_k = sel["optimal_ruvK"] == rsel["optimal_ruvK"]
     e4 = orc.rel_frobenius(sel[4]["newY"], rsel[4]["newY"][lo:hi])
-    rg = sm.scRUVg(P["Y"][lo:hi], P["ctl"], 8, ctx=ctx)
+    rg = sm.scRUVg(Yall[lo:hi], P["ctl"], 8, ctx=ctx)
     # reference: the definition (first k left singular vectors of the centred control block, alpha = W'Y0) without the
     # oracle's literal m x m cross product of the >= 5:1 branch (9000 x 9000 here; equality of the two is a CPU test)
-    Y0 = P["Y"] - P["Y"].mean(axis=0)
+    Y0 = Yall - Yall.mean(axis=0)
     U = np.linalg.svd(Y0[:, orc.tological(P["ctl"], 384)], full_matrices=False)[0][:, :8]
-    e5 = orc.rel_frobenius(rg["newY"], (P["Y"] - U @ (U.T @ Y0))[lo:hi])
+    e5 = orc.rel_frobenius(rg["newY"], (Yall - U @ (U.T @ Y0))[lo:hi])
     # every rank must hold bit-identical fullalpha (no broadcast in the design)
-    fa = torch.from_numpy(out["fullalpha"].copy()).cuda()
+    fa = torch.from_numpy(np.array(out["fullalpha"])).cuda()
     lst = [torch.empty_like(fa) for _ in range(world)]
     dist.all_gather(lst, fa)
     same = all(torch.equal(lst[0], t) for t in lst)
-    ok = e1 < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8
-    print(f"rank {rank}/{world}: rows [{lo},{hi}) fast err {e1:.2e} angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same} "
-          f"selection sil err {e3:.2e} same_k {same_k} newY err {e4:.2e} scRUVg err {e5:.2e}", flush=True)
+    ok = (e1 < 1e-8 and e1d < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8)
+    print(f"rank {rank}/{world} [{transport}]: rows [{lo},{hi}) batches here {sorted(set(batch_all[lo:hi]))} fast err {e1:.2e} (device {e1d:.2e}) "
+          f"angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same} selection sil err {e3:.2e} same_k {same_k} newY err {e4:.2e} "
+          f"scRUVg err {e5:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -207,11 +207,11 @@ def test_pseudobulk_keys_match_the_oracle_bit_exactly():
         which[idx[rng.permutation(idx.shape[0])]] = (np.arange(idx.shape[0]) % Kb) + 1   # cvFolds: rep(1:K, length.out) over a random order
     keys, P, names, pb_t, pb_b = pseudobulk_keys(batch, clust, K, which=which)
     bulks, ref_names = [], []
-    for b in np.unique(batch):
+    for i, b in enumerate(np.unique(batch), start=1):
         sel = batch == b
         bulk, nm = orc.create_pseudobulk(X[:, sel], clust[sel], which[sel], k_fold=min(int(sel.sum()), K))
         bulks.append(bulk)
-        ref_names += [f"{b}_{x}" for x in nm]
+        ref_names += [f"{i}_{x}" for x in nm]                         # paste(i, rownames(res)): the batch INDEX (R/scMerge2_utilis.R:266)
     ref = np.concatenate(bulks)
     assert names == ref_names and P == ref.shape[0] == len(set(names))
     assert keys.dtype == np.int32 and keys.min() == 0 and keys.max() == P - 1
@@ -219,7 +219,8 @@ def test_pseudobulk_keys_match_the_oracle_bit_exactly():
         cells = np.nonzero(keys == p)[0]
         np.testing.assert_array_equal(X[:, cells].sum(axis=1) / cells.shape[0], ref[p])
     tlev, blev = np.unique(clust), np.unique(batch)
-    assert [f"{blev[b]}_{tlev[t]}" for b, t in zip(pb_b, pb_t)] == [x.rsplit("_", 1)[0] for x in names]
+    assert [f"{b + 1}_{tlev[t]}" for b, t in zip(pb_b, pb_t)] == [x.rsplit("_", 1)[0] for x in names]
+    assert names[0].split("_")[0] == "1" and list(blev) == ["b10", "b2", "b3"]          # index 1 = first SORTED level ("b10")
     # a seeded draw has the cvFolds structure: fold sizes within a batch differ by at most one
     k2, P2, *_ = pseudobulk_keys(batch, clust, K, seed=1)
     assert k2.shape == (m,) and 0 < P2 <= 3 * 3 * K
@@ -268,7 +269,10 @@ for name, args in L.SIGNATURES.items():
     rc = getattr(lib, name)(*vals)
     if name in ("scm_last_error", "scm_version"):
         continue
-    ok = rc == 0 if name == "scm_ctx_destroy" else rc <= 0 if name == "scm_host_free_pinned" else rc < 0  # cudaFreeHost(NULL) succeeds on a GPU box
+    if name == "scm_multi_ctx":  # returns a pointer: NULL for a NULL handle
+        assert rc is None, rc
+        continue
+    ok = rc == 0 if name in ("scm_ctx_destroy", "scm_multi_destroy", "scm_multi_size") else rc <= 0 if name == "scm_host_free_pinned" else rc < 0  # cudaFreeHost(NULL) succeeds on a GPU box
     assert ok, (name, rc)
     if rc < 0:
         assert lib.scm_last_error(), name

@@ -737,3 +737,112 @@ def test_scruviii_reference_test_shape(sm):
     assert np.allclose(res["f_score"], ref["f_score"], rtol=0, atol=1e-7)
     assert res["optimal_ruvK"] == ref["optimal_ruvK"]
     assert set(res.keys()) >= set(ks) | {"optimal_ruvK"}       # list named by k + $optimal_ruvK (R/scRUVIII.R:77,126-136)
+
+
+# ---- round 2: one summing pass writes the shifted copy, device-side eigensolver control, converged rank -----------------
+def test_k1_fused_shifted_copy_is_bit_identical(sm, monkeypatch):
+    """The pre-shifted copy of the cells written from K1's summing pass (SCM_K1_FUSED_COPY=1) must give the same bits as the
+    separate copy kernel (SCM_K1_FUSED_COPY=0): same shift vector, same subtraction, only the kernel that stores it differs.
+    Odd gene count (scalar tail column, padded leading dimension)."""
+    P = orc.planted_factors(5000, 257, 96, 6, n_types=4, n_batch=3, seed=7)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SCM_K1_FUSED_COPY", flag)
+        ctx = sm.Context(0)
+        dY = sm.DeviceMatrix.from_host(ctx, P["Y"])
+        res = sm.fastRUVIII(dY, P["types"], P["ctl"], k=6, return_info=True, ctx=ctx)
+        outs.append((res["newY"].to_host(), np.asarray(res["fullalpha"])))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 6)
+    assert orc.rel_frobenius(outs[0][0], ref) < TOL_NEWY
+
+
+def test_gram_shift_paths_agree(sm, monkeypatch):
+    """The centred Gram does not depend on HOW the local shift is applied: pre-shifted copy + SHIFT=false kernel (default),
+    shift subtracted at fragment load (SCM_GRAM_PRESHIFT=0) and the cp.async kernel (SCM_GRAM_TMA=0) must all reproduce the
+    oracle; means far from zero (offset 50) make a wrong re-centring visible."""
+    P = orc.planted_factors(6000, 320, 100, 8, n_types=5, n_batch=3, seed=17)
+    Y = P["Y"] + 50.0
+    ref = orc.fastRUVIII(Y, P["types"], P["ctl"], 8, return_info=True)
+    for env in ({}, {"SCM_GRAM_PRESHIFT": "0"}, {"SCM_GRAM_TMA": "0"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        ctx = sm.Context(0)
+        out = sm.fastRUVIII(Y, P["types"], P["ctl"], k=8, return_info=True, ctx=ctx)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY, env
+        assert orc.principal_angles(out["fullalpha"][:8], ref["fullalpha"][:8]).max() < 1e-6, env
+
+
+def test_every_cell_needs_a_replicate_key(sm, ctx):
+    """M assigns every cell to a group (ruv::replicate.matrix): a key outside [0, G) in a FIT is rejected (the Gram is over all
+    cells, the group sums would silently miss the row)."""
+    P = orc.planted_factors(800, 64, 32, 3, n_types=3, n_batch=2, seed=3)
+    from scmerge_b200.ruv import _fit
+    dY = sm.DeviceMatrix.from_host(ctx, P["Y"])
+    keys = P["types"].astype(np.int32).copy()
+    keys[5] = -1
+    with pytest.raises(sm.ScmError, match="replicate key"):
+        _fit(ctx, dY, keys, 3, 10, 3, True)
+    dY.free()
+
+
+def test_converged_rank_is_reported_and_guards_reuse(sm, ctx):
+    """fullalpha is the reference's checkpoint (R/fastRUVIII.R:83, R/scMerge2.R:399).  The device fit converges the ranks it
+    was asked for; the returned array carries `conv_rank`, re-use within it matches a direct fit, re-use beyond it warns."""
+    import warnings
+    P = orc.planted_factors(4000, 200, 80, 12, n_types=4, n_batch=3, seed=23)
+    dY = sm.DeviceMatrix.from_host(ctx, P["Y"])
+    r12 = sm.fastRUVIII(dY, P["types"], P["ctl"], k=12, return_info=True, ctx=ctx)
+    fa = r12["fullalpha"]
+    assert isinstance(fa, sm.FullAlpha) and fa.conv_rank is not None and fa.conv_rank >= 12
+    ref5 = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # no warning: 5 <= conv_rank
+        got5 = sm.fastRUVIII(dY, P["types"], P["ctl"], k=5, fullalpha=fa, ctx=ctx).to_host()
+    assert orc.rel_frobenius(got5, ref5) < TOL_NEWY
+    r3 = sm.fastRUVIII(dY, P["types"], P["ctl"], k=3, return_info=True, ctx=ctx)
+    fa3 = r3["fullalpha"]
+    if fa3.conv_rank < 40:
+        with pytest.warns(sm.NotConvergedWarning, match="exceeds the rank"):
+            sm.fastRUVIII(dY, P["types"], P["ctl"], k=40, fullalpha=fa3, ctx=ctx)
+    info = ctx.fit_info()
+    assert info["iters"] >= 1 and info["conv_rank"] == fa3.conv_rank
+    dY.free()
+
+
+def test_chol_inv_and_eig_small_blocks(sm, ctx):
+    """The single-CTA Cholesky / Jacobi kernels behind K4 and K5 at block sizes from 1 to the limit: eigenvalues against LAPACK
+    (relative 1e-12), eigenvectors as invariant subspaces."""
+    rng = np.random.default_rng(5)
+    lib = sm.lib()
+    for n, s in [(40, 1), (64, 7), (150, 33), (300, 64), (513, 96)]:
+        A = rng.normal(size=(n + 20, n)) * np.linspace(1, 6, n)[None, :] ** 2
+        Gm = A.T @ A
+        d_G = ctx.to_device(Gm)
+        d_vals, d_vecs = ctx.empty((s,)), ctx.empty((s, n))
+        it, rs = C.c_int32(0), C.c_double(0.0)
+        rc = lib.scm_eig_topk(ctx.handle, d_G.ptr, n, s, s, 0, 1e-10, 500, 1, d_vals.ptr, d_vecs.ptr, C.byref(it), C.byref(rs))
+        assert rc in (0, -6), lib.scm_last_error()
+        w, V = np.linalg.eigh(Gm)
+        w, V = w[::-1], V[:, ::-1]
+        vals, vecs = d_vals.to_host(), d_vecs.to_host()
+        assert np.allclose(vals, w[:s], rtol=1e-9), (n, s)
+        if rc == 0:
+            assert orc.principal_angles(vecs, V[:, :s].T).max() < 1e-6, (n, s)
+        for a in (d_G, d_vals, d_vecs):
+            a.free()
+
+
+def test_single_process_multi_context_same_device(sm):
+    """scm_multi_create with ONE device: the single-process driver (what an R session holds) must give exactly the per-context
+    result; with more devices it is covered by tests/test_gpu_multi.py."""
+    P = orc.planted_factors(3000, 128, 64, 5, n_types=4, n_batch=2, seed=2)
+    mg = sm.MultiContext(devices=[0])
+    from scmerge_b200.ruv import multi_fastRUVIII
+    out = multi_fastRUVIII(mg, P["Y"], P["types"], P["ctl"], k=5, return_info=True)
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5, return_info=True)
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(out["fullalpha"][:5], ref["fullalpha"][:5]).max() < 1e-6
