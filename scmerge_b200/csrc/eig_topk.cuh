@@ -238,7 +238,8 @@ jacobi_eig_kernel(const double* __restrict__ H, int l, double* __restrict__ Q, d
         double a = 0.0;
         for (int i = lane; i < lp; i += 32) a += A[j * cs + i] * A[j * cs + i];
         a = warp_sum(a);
-        if (lane == 0) s_norm[j] = (j < l) ? sqrt(a) : -1.0;
+        // NaN-safe: the ranking below indexes shared memory with its result, a NaN norm (poisoned input) must still get a rank
+        if (lane == 0) s_norm[j] = (j < l) ? ((a == a) ? sqrt(a) : 0.0) : -1.0;
     }
     __syncthreads();
     for (int j = tid; j < lp; j += nt) {
@@ -325,6 +326,13 @@ __global__ void eig_check_kernel(EigCtl* __restrict__ ctl, const double* __restr
         ctl->hist[it % 16] = worst;
         if (it > 40 && worst > 0.5 * ctl->hist[(it + 1) % 16]) ctl->done = 2;
         else if (it >= maxit) ctl->done = 4;
+        else if (it >= 8) {
+            // rate over the last four steps: stop when, at that rate, the tolerance is out of reach within maxit (flat noise bulk:
+            // k exceeds the number of separated factors; 60 Rayleigh-Ritz steps of stagnation cost 66 ms at l = 80)
+            const double r4 = worst / ctl->hist[(it - 4) % 16];
+            if (!(r4 < 1.0)) { if (it >= 12) ctl->done = 2; }
+            else if (4.0 * log(tol / worst) / log(r4) > (double)(maxit - it)) ctl->done = 2;
+        }
     }
     if (ctl->done) {
         // how far down the returned rows are trustworthy as a BASIS: the largest r whose top-r subspace passes a 1e-8 angle test
@@ -343,6 +351,12 @@ __global__ void eig_check_kernel(EigCtl* __restrict__ ctl, const double* __restr
     const double spread = (theta[0] > 0 && theta[l - 1] > 0) ? theta[0] / theta[l - 1] : 1e300;
     int pw = spread > 1.0 ? (int)(log(1e5) / log(spread)) + 1 : 4;
     ctl->pw = fixed_iters ? 1 : (pw < 1 ? 1 : (pw > 4 ? 4 : pw));
+}
+
+// Arms the control block before the first product: a non-finite input (the NA / Inf flag of the fit's pass over the cells) ends
+// the solve before any kernel touches the poisoned Gram.
+__global__ void eig_prime_kernel(EigCtl* __restrict__ ctl, const int64_t* __restrict__ nonfinite) {
+    if (threadIdx.x == 0 && nonfinite && nonfinite[0] != 0) ctl->done = 3;
 }
 
 // vecs[r, :] = sign * V[:, r] with the largest-|.| entry made positive; vals[r] = theta[r].  One CTA per row r.
@@ -430,14 +444,18 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
     for (int safe = 0; safe < 2; safe++) {
         SCM_TRY(zero_async(ctx, flag, sizeof(int) * 4));
         SCM_TRY(zero_async(ctx, ctl, sizeof(EigCtl)));
+        if (d_nonfinite) {
+            eig_prime_kernel<<<1, 32, 0, st>>>(ctl, d_nonfinite);
+            SCM_LAUNCH_CHECK(ctx);
+        }
         randn_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(X, nl, seed * 0x9E3779B97F4A7C15ull + 12345);
         SCM_LAUNCH_CHECK(ctx);
         SCM_TRY(cholqr2(ctx, X, X, Z, n, l, S, Linv, flag));
         int pre = safe ? 0 : (mode == SCM_MODE_RANDOMIZED ? 2 : 1);
         if (mode == SCM_MODE_RANDOMIZED && safe) pre = 2;  // rsvd's semantics are three products, whatever the conditioning
         for (int j = 0; j < pre; j++) {
-            SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l));
-            SCM_TRY(cholqr2(ctx, Z, X, W, n, l, S, Linv, flag));
+            SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l, skip));
+            SCM_TRY(cholqr2(ctx, Z, X, W, n, l, S, Linv, flag, skip));
         }
         int enq = 0;       // Rayleigh-Ritz steps enqueued so far
         bool finished = false;

@@ -102,8 +102,11 @@ __global__ void gram_recentre_kernel(double* __restrict__ gram, int64_t n, const
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = blockIdx.y;
     if (j >= n) return;
+    // explicit roundings, no FMA contraction: every term is symmetric in (i, j) bit for bit, so the centred Gram stays EXACTLY
+    // symmetric (fma(u_i, d_j, d_i u_j) would round one product and not the other)
     const double di = d[i], dj = d[j];
-    gram[i * n + j] += u[i] * dj + di * u[j] + m_local * di * dj;
+    const double t = __dadd_rn(__dadd_rn(__dmul_rn(u[i], dj), __dmul_rn(di, u[j])), __dmul_rn(m_local, __dmul_rn(di, dj)));
+    gram[i * n + j] = __dadd_rn(gram[i * n + j], t);
 }
 
 // sums[g, :] /= counts[g]  (empty groups -> 0)
