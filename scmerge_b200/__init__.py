@@ -5,8 +5,8 @@ this package is the host-side mirror of the R closures.  There is no CPU fallbac
 """
 from ._lib import LIB_PATH, NonFiniteError, NotConvergedWarning, ScmError, SingularError, lib  # noqa: F401
 from .device import Context, DeviceArray, DeviceMatrix, MultiContext, bind_host_to_gpu, default_context, pinned_empty  # noqa: F401
-from .ruv import (ExactParam, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
-                  create_pseudoBulk, fastRUVIII, genes_by_name, getAdjustedMat, pseudoRUVIII, replicate_keys, replicate_matrix,
+from .ruv import (ExactParam, FullAlpha, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
+                  create_pseudoBulk, fastRUVIII, genes_by_name, getAdjustedMat, multi_fastRUVIII, pseudoRUVIII, replicate_keys, replicate_matrix,
                   scRUVg, scRUVIII, tological)
 
 from .scmerge2 import DeviceCSC, cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402

@@ -400,6 +400,9 @@ adjust_subset_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t
     __syncthreads();
     for (int o = threadIdx.x; o < nsub; o += blockDim.x) {
         const int g = sub[o];
+        // a gene index outside [0, n) never touches memory: the column comes out as NaN (hosts validate the subset before
+        // uploading it; this is the guard for callers that do not)
+        if ((unsigned)g >= (unsigned)n) { out[i * ldo + o] = __longlong_as_double(0x7ff8000000000000LL); continue; }
         double v = Y[i * ld + g];
         for (int a = 0; a < k; a++) v -= sw[a] * Amat[(int64_t)a * n + g];
         out[i * ldo + o] = v;

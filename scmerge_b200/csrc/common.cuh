@@ -64,6 +64,10 @@ struct scm_ctx {
     int gram_lean = 3;           // Gram TMA kernel: bit 0 thin last tile row, bit 1 triangular diagonal units (env SCM_GRAM_LEAN)
     bool k1_fused_copy = true;   // the pre-shifted copy is written by K1's summing pass (env SCM_K1_FUSED_COPY=0: separate copy kernel)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
+    // page-locked bounce buffers of the host drivers for callers whose matrices are ordinary pageable memory (R's REAL(),
+    // plain numpy): allocated on first use, one PCIe chunk each, kept until the context dies (host_pipeline.cuh)
+    void* stage_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
     int conv_ranks[16];          // additional subspace dimensions the EXACT eigensolver must converge (scm_ctx_set_conv_ranks)
     int n_conv_ranks = 0;
     // built-in communicator (comm.cuh): NCCL resolved with dlopen at run time, one rank per context.  Takes precedence over the

@@ -15,7 +15,11 @@
 //     two bulk copies queued.
 // Included by scm_api.cu after the small helper kernels (meta_kernel, colmean_kernel, ...).
 #pragma once
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "adjust.cuh"
 #include "common.cuh"
@@ -55,6 +59,91 @@ inline int64_t host_chunk_rows(int64_t ld) {
     return rows_per_chunk;
 }
 
+// ---- pageable host matrices ------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from / to ordinary (pageable) memory is staged by the driver through ONE internal buffer, synchronously and
+// single-threaded: 7-12 GB/s instead of the 55 GB/s of the link, and nothing overlaps (measured: 2.2 s instead of 0.58 s per
+// 1M x 2000 fastRUVIII call).  An R session's REAL(Y) is such memory.  The host drivers therefore detect pageable arguments and
+// stage them themselves: a helper thread copies chunk c + 1 into a page-locked bounce buffer with several memcpy threads while
+// chunk c crosses PCIe and chunk c - 1 is being summed; downloads mirror that.  Page-locked callers take the direct path.
+constexpr int STAGE_NB = 4;  // bounce buffers: 2 for the upload ring + 2 for the download ring (used one direction at a time: all 4)
+
+inline bool host_is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+inline int stage_reserve(scm_ctx* ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return 0;
+    for (void*& b : ctx->stage_buf) { if (b) cudaFreeHost(b); b = nullptr; }
+    ctx->stage_bytes = 0;
+    for (void*& b : ctx->stage_buf) SCM_CUDA(cudaMallocHost(&b, bytes));
+    ctx->stage_bytes = bytes;
+    return 0;
+}
+
+inline int host_copy_threads() {
+    int t = 8;
+    if (const char* e = getenv("SCM_HOST_COPY_THREADS")) t = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && t > hw) t = hw;
+    return t < 1 ? 1 : t;
+}
+
+// rows x row_bytes strided host copy on `nt` threads (memcpy saturates one core long before it saturates the memory system)
+inline void parallel_copy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, int64_t rows, int nt) {
+    if (rows <= 0) return;
+    auto body = [=](int64_t r0, int64_t r1) {
+        if (dst_pitch == row_bytes && src_pitch == row_bytes) {
+            memcpy((char*)dst + r0 * row_bytes, (const char*)src + r0 * row_bytes, (size_t)(r1 - r0) * row_bytes);
+        } else {
+            for (int64_t r = r0; r < r1; r++) memcpy((char*)dst + r * dst_pitch, (const char*)src + r * src_pitch, row_bytes);
+        }
+    };
+    if (nt <= 1 || rows < 64) { body(0, rows); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (rows + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const int64_t r0 = t * per, r1 = r0 + per < rows ? r0 + per : rows;
+        if (r0 >= r1) break;
+        th.emplace_back(body, r0, r1);
+    }
+    for (auto& x : th) x.join();
+}
+
+// Hand-over counter between the staging helper thread and the driver (chunks published in order).
+struct ChunkGate {
+    std::mutex mu;
+    std::condition_variable cv;
+    int ready = 0;
+    int error = 0;
+    char msg[256] = "";
+    void publish(int upto) { { std::lock_guard<std::mutex> g(mu); ready = upto; } cv.notify_all(); }
+    void fail_with(int rc, const char* why) {
+        { std::lock_guard<std::mutex> g(mu); if (!error) { error = rc; snprintf(msg, sizeof(msg), "%s", why); } }
+        cv.notify_all();
+    }
+    int wait_for(int c) {  // returns 0 once chunk c has been published, the helper's status if it died
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return ready > c || error != 0; });
+        return error;
+    }
+};
+// joins the helper on every exit path; `gate` is failed first so that a helper blocked on it wakes up and leaves
+struct HelperJoin {
+    std::thread& t;
+    ChunkGate* wake;
+    ~HelperJoin() {
+        if (wake) wake->fail_with(SCM_ERR_INVALID, "driver left early");
+        if (t.joinable()) t.join();
+    }
+};
+#define SCM_HELPER_CUDA(expr, gate)                                                                    \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) { (gate).fail_with(SCM_ERR_CUDA, cudaGetErrorString(_e)); return; }     \
+    } while (0)
+
 // The download half of the host drivers: the fused adjust kernel (K6) runs chunk by chunk IN PLACE on the device-resident
 // matrix and every finished chunk goes back over PCIe (copy stream) while the next one is being adjusted.  d_Y holds newY
 // afterwards.  Returns after the last byte has landed in h_out.
@@ -81,6 +170,33 @@ inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64
         cudaEventCreate(&tl_zero);
         cudaEventRecord(tl_zero, st);
     }
+    // pageable destination: D2H lands in page-locked bounce buffers, a helper thread copies them out with several memcpy threads
+    const bool staged = host_is_pageable(h_out);
+    ChunkGate issued, drained;
+    std::thread drainer;
+    HelperJoin joiner{drainer, staged ? &issued : nullptr};
+    std::vector<cudaEvent_t> evd;
+    struct EvGuard2 {
+        std::vector<cudaEvent_t>& v;
+        ~EvGuard2() { for (auto e : v) cudaEventDestroy(e); }
+    } guard2{evd};
+    if (staged) {
+        SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
+        evd.resize(nchunks);
+        for (auto& e : evd) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const int nt = host_copy_threads();
+        const int dev = ctx->device;
+        drainer = std::thread([&, nt, dev] {
+            cudaSetDevice(dev);
+            for (int c = 0; c < nchunks; c++) {
+                if (issued.wait_for(c) != 0) return;
+                SCM_HELPER_CUDA(cudaEventSynchronize(evd[c]), drained);
+                const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+                parallel_copy2d(h_out + r0 * ldo, (size_t)ldo * 8, ctx->stage_buf[c % STAGE_NB], (size_t)n * 8, (size_t)n * 8, rows, nt);
+                drained.publish(c + 1);
+            }
+        });
+    }
     for (int c = 0; c < nchunks; c++) {
         const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
         {
@@ -90,11 +206,23 @@ inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64
         if (trace) cudaEventRecord(tl_adj[c], st);
         SCM_CUDA(cudaEventRecord(ev[c], st));
         SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
-        if (ldo == n && ld == n)
+        if (staged) {
+            if (c >= STAGE_NB && drained.wait_for(c - STAGE_NB) != 0) return fail(drained.error, "download helper: %s", drained.msg);
+            double* sb = (double*)ctx->stage_buf[c % STAGE_NB];
+            if (ld == n) SCM_CUDA(cudaMemcpyAsync(sb, dY + r0 * ld, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
+            else SCM_CUDA(cudaMemcpy2DAsync(sb, n * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+            SCM_CUDA(cudaEventRecord(evd[c], cs));
+            issued.publish(c + 1);
+        } else if (ldo == n && ld == n)
             SCM_CUDA(cudaMemcpyAsync(h_out + r0 * ldo, dY + r0 * ld, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
         else
             SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
         if (trace) cudaEventRecord(tl_copy[c], cs);
+    }
+    if (staged) {
+        if (drained.wait_for(nchunks - 1) != 0) return fail(drained.error, "download helper: %s", drained.msg);
+        joiner.wake = nullptr;  // finished normally
+        drainer.join();
     }
     if (trace) {
         cudaStreamSynchronize(cs);
@@ -234,15 +362,42 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         SCM_CUDA(cudaEventRecord(ev[c], cs));
         return 0;
     };
-    SCM_TRY(issue_copy(0));
-    if (nchunks > 1) SCM_TRY(issue_copy(1));
+    // pageable source: a helper thread stages chunk by chunk through the page-locked bounce buffers (see above)
+    const bool staged_in = host_is_pageable(a.h_Y);
+    ChunkGate fed;
+    std::thread feeder;
+    HelperJoin feeder_join{feeder, nullptr};
+    if (staged_in) {
+        SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
+        const int nt = host_copy_threads();
+        const int dev = ctx->device;
+        feeder = std::thread([&, nt, dev] {
+            cudaSetDevice(dev);
+            for (int c = 0; c < nchunks; c++) {
+                if (fed.error) return;
+                if (c >= STAGE_NB) SCM_HELPER_CUDA(cudaEventSynchronize(ev[c - STAGE_NB]), fed);  // the slot's previous H2D has finished
+                const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+                double* sb = (double*)ctx->stage_buf[c % STAGE_NB];
+                parallel_copy2d(sb, (size_t)n * 8, a.h_Y + r0 * a.ldh, (size_t)a.ldh * 8, (size_t)n * 8, rows, nt);
+                if (ld == n) SCM_HELPER_CUDA(cudaMemcpyAsync(dY + r0 * ld, sb, (size_t)rows * n * 8, cudaMemcpyHostToDevice, cs), fed);
+                else SCM_HELPER_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, sb, n * 8, n * 8, rows, cudaMemcpyHostToDevice, cs), fed);
+                SCM_HELPER_CUDA(cudaEventRecord(ev[c], cs), fed);
+                fed.publish(c + 1);
+            }
+        });
+        feeder_join.wake = &fed;
+    } else {
+        SCM_TRY(issue_copy(0));
+        if (nchunks > 1) SCM_TRY(issue_copy(1));
+    }
     for (int c = 0; c < nchunks; c++) {
         const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
         if (trace.on && c > 0) cudaEventRecord(tl_comp[c - 1], st);
         // host-mediated hand-over with two bulk copies in flight: chunk c is in HBM when the event has fired, its fit work
         // is enqueued right away and copy c + 2 joins the queue (the copy engine never idles, the queue never grows)
+        if (staged_in && fed.wait_for(c) != 0) return fail(fed.error, "upload helper: %s", fed.msg);
         SCM_CUDA(cudaEventSynchronize(ev[c]));
-        if (c + 2 < nchunks) SCM_TRY(issue_copy(c + 2));
+        if (!staged_in && c + 2 < nchunks) SCM_TRY(issue_copy(c + 2));
         if (trace.on) cudaEventRecord(tl_wait[c], st);
         if (!need_sums) continue;
         {
@@ -263,6 +418,10 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         }
         StageTimer t(ctx, ST_GRAM);
         SCM_TRY(gram(ctx, dY + r0 * ld, rows, n, ld, shift, Gm, c == nchunks - 1, c > 0));
+    }
+    if (staged_in) {  // every chunk has been published: the helper is done
+        feeder_join.wake = nullptr;
+        feeder.join();
     }
     trace.mark("upload + fit chunks enqueued");
     if (trace.on) {

@@ -221,6 +221,7 @@ int scm_ctx_destroy(scm_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_stream_d2h) cudaStreamDestroy(ctx->copy_stream_d2h);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (void* b : ctx->stage_buf) if (b) cudaFreeHost(b);
     delete ctx;
     return 0;
 }

@@ -66,15 +66,27 @@ def _active_ctx(Y, ctx):
     return Y.ctx if isinstance(Y, DeviceMatrix) else None
 
 
+def _rank_table(ctx, row) -> np.ndarray:
+    """world x len(row) int64 table holding every rank's `row` (one sum all-reduce of one-hot rows)."""
+    row = np.asarray(row, dtype=np.int64)
+    if ctx is None or ctx.world <= 1:
+        return row[None, :]
+    if ctx.rank is None:
+        raise ValueError("multi-rank host logic needs the rank: Context.set_allreduce(fn, world_size, rank) or init_nccl")
+    tab = np.zeros((ctx.world, row.shape[0]), dtype=np.int64)
+    tab[ctx.rank] = row
+    d = ctx.to_device(tab)
+    ctx.allreduce(d)
+    tab = d.to_host()
+    d.free()
+    return tab
+
+
 def _total_cells(ctx, m_local: int) -> int:
     """Cells over ALL ranks that share them (the m of the reference's formulas: svd_k rule, early-out, PCA rank)."""
     if ctx is None or ctx.world <= 1:
         return int(m_local)
-    d = ctx.to_device(np.array([m_local], dtype=np.int64))
-    ctx.allreduce(d)
-    tot = int(d.to_host()[0])
-    d.free()
-    return tot
+    return int(_rank_table(ctx, [m_local])[:, 0].sum())
 
 
 def _global_levels(ctx, levels: np.ndarray) -> np.ndarray:
@@ -88,6 +100,31 @@ def _global_levels(ctx, levels: np.ndarray) -> np.ndarray:
     if not got:
         return np.asarray(levels)
     return np.unique(np.concatenate(got))
+
+
+def _global_int_keys(ctx, a: np.ndarray, spare):
+    """Integer labels on several ranks without sorting a million of them per call: min / max / row count of every rank in one
+    small all-reduce; with enough slack (see replicate_keys: `spare`) the labels ARE the keys, otherwise a presence histogram
+    (O(m), summed over the ranks) gives the global level table.  Returns None when the labels are too sparse for that."""
+    m = a.shape[0]
+    lo, hi = (int(a.min()), int(a.max())) if m else (2 ** 62, -1)
+    tab = _rank_table(ctx, [m, lo, hi])
+    m_tot, lo, hi = int(tab[:, 0].sum()), int(tab[:, 1].min()), int(tab[:, 2].max())
+    if hi < 0:
+        return a.astype(np.int32, copy=False), 0
+    if lo < 0 or hi >= 4 * m_tot + 1024:
+        return None
+    if spare is not None and m_tot - (hi + 1) >= spare:
+        return a.astype(np.int32, copy=False), hi + 1
+    present = np.bincount(a, minlength=hi + 1).astype(np.int64)
+    d = ctx.to_device(present)
+    ctx.allreduce(d)
+    present = d.to_host() > 0
+    d.free()
+    if present.all():
+        return a.astype(np.int32, copy=False), hi + 1
+    remap = np.cumsum(present) - 1
+    return remap[a].astype(np.int32), int(present.sum())
 
 
 def replicate_keys(M, spare: int | None = None, ctx=None):
@@ -114,6 +151,10 @@ def replicate_keys(M, spare: int | None = None, ctx=None):
     if a.ndim != 1:
         raise ValueError("M must be a replicate matrix or a label vector")
     if ctx is not None and ctx.world > 1:
+        if np.issubdtype(a.dtype, np.integer):
+            got = _global_int_keys(ctx, a, spare)
+            if got is not None:
+                return got
         levels = _global_levels(ctx, np.unique(a))
         return np.searchsorted(levels, a).astype(np.int32), int(levels.shape[0])
     if np.issubdtype(a.dtype, np.integer) and a.shape[0] > 0:
@@ -312,6 +353,8 @@ def _adjust(ctx: Context, dY: DeviceMatrix, fullalpha: np.ndarray, k: int, ctl: 
         d_sub, nsub = None, 0
         if subset is not None:
             sub = np.ascontiguousarray(subset, dtype=np.int32)
+            if sub.ndim != 1 or (sub.size and (sub.min() < 0 or sub.max() >= n)):
+                raise IndexError(f"gene subset outside [0, {n})")  # the device kernel indexes Y and A with it
             d_sub, nsub = ctx.to_device(sub), int(sub.shape[0])
         n_out = nsub if d_sub is not None else n
         if out is None:
@@ -667,7 +710,7 @@ def scRUVg(Y, ctl, k, Z=1, eta=None, include_intercept=True, fullW=None, svdyc=N
 
 def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, inputcheck=True, fullalpha=None,
                  return_info=False, subset=None, BPPARAM=None, BSPARAM=None, normalised=True, verbose=True, byChunk=True,
-                 chunkSize=50000, ctx: Context | None = None):
+                 chunkSize=50000, ctx: Context | None = None, gene_names=None):
     """R/scMerge2_utilis.R:17-150.  Fit on the pseudobulk matrix (P x n), adjust every cell of Y (m x n).
     byChunk / chunkSize / BPPARAM are accepted for parity; the fused kernel streams all cells in one launch."""
     del BPPARAM, include_intercept, verbose, byChunk, chunkSize, inputcheck
@@ -704,7 +747,7 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
         return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": st.stand_mean}
     dY, copied = _as_device(ctx, Y)
     means = column_means(dY)  # adjusted_means <- colMeans(Y) over ALL cells (R/scMerge2_utilis.R:97)
-    sub = None if subset is None else np.nonzero(tological(subset, n))[0] if np.asarray(subset).dtype == bool else np.asarray(subset)
+    sub = _resolve_subset(subset, n, gene_names)
     dout, _ = _adjust(ctx, dY, fullalpha, int(k), ctl, center=means, subset=sub)
     newY = _finish(dout, copied)
     if copied:
@@ -712,6 +755,29 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
     if not return_info:
         return newY
     return {"newY": newY, "M": M, "fullalpha": fullalpha, "adjusted_means": means}
+
+
+def _resolve_subset(subset, n: int, gene_names=None):
+    """`Y[, subset]` of pseudoRUVIII (R/scMerge2_utilis.R:117-121,131-136) -> 0-based column indices IN THE GIVEN ORDER.
+    Logical mask: which(); integers: as they are (order and repeats kept); names (scMerge2 passes `chosen.hvg`,
+    R/scMerge2.R:283,305): match(subset, colnames(Y)), and like R's subscript an unknown name is an error."""
+    if subset is None:
+        return None
+    a = np.asarray(subset)
+    if a.dtype == bool:
+        return np.nonzero(tological(a, n))[0]
+    if a.dtype.kind in ("U", "S", "O"):
+        if gene_names is None:
+            raise ValueError("gene names given as `subset` but no gene_names (colnames of Y)")
+        pos = {g: i for i, g in enumerate(np.asarray(gene_names).tolist())}
+        missing = [g for g in a.tolist() if g not in pos]
+        if missing:
+            raise IndexError(f"subscript out of bounds: {missing[:3]} not in colnames(Y)")
+        return np.array([pos[g] for g in a.tolist()], dtype=np.int64)
+    a = a.astype(np.int64)
+    if a.size and (a.min() < 0 or a.max() >= n):
+        raise IndexError(f"subscript out of bounds: gene subset outside [0, {n})")
+    return a
 
 
 def genes_by_name(sel, n: int, gene_names=None) -> np.ndarray:

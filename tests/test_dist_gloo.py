@@ -98,3 +98,86 @@ def test_two_rank_fit_decomposition_gloo():
     assert res[0][3] == res[1][3]                          # bit-identical on both ranks (no broadcast needed)
     assert all(r[4] < 1e-12 for r in res)                  # centred Gram of all cells recovered from the shifted one
     assert res[0][5] == res[1][5]                          # every rank agreed on the same shift vector
+
+
+# ---- label tables across ranks (shards ordered by batch do not see every level) -------------------------------
+class _FakeDev:
+    def __init__(self, arr):
+        self.arr = np.array(arr, copy=True)
+
+    def to_host(self):
+        return self.arr
+
+    def free(self):
+        pass
+
+
+class _GlooCtx:
+    """Stand-in for scmerge_b200.Context on CPU: same host-side protocol (to_device / allreduce / allgather_bytes), the sum
+    all-reduce runs over gloo on host memory instead of NCCL on a device buffer."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def to_device(self, arr):
+        return _FakeDev(arr)
+
+    def allreduce(self, d):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(d.arr)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def allgather_bytes(self, payload):
+        from scmerge_b200.device import Context
+        return Context.allgather_bytes(self, payload)
+
+
+def _label_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    from scmerge_b200.dist import shard_rows
+    from scmerge_b200.ruv import _total_cells, replicate_keys
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = _GlooCtx(rank, world)
+        rng = np.random.default_rng(4)
+        m = 1001
+        batch = np.sort(rng.choice(["b1", "b2", "b3"], size=m))                  # ordered by batch: rank 0 never sees "b3"
+        types = rng.integers(0, 7, size=m) * 3                                     # integer labels with holes (0, 3, .., 18)
+        types[:500][types[:500] == 18] = 0                                        # level 18 only occurs on the last rank
+        pairs = np.stack([batch, types.astype(str)], axis=1)                      # data.frame-like labels
+        lo, hi = shard_rows(m, world, rank)
+        out = {}
+        for name, lab, spare in (("batch", batch, None), ("types", types, None), ("types_spare", types, 10), ("pairs", pairs, None)):
+            keys, G = replicate_keys(lab[lo:hi], spare=spare, ctx=ctx)
+            ref_keys, ref_G = replicate_keys(lab, spare=spare)                     # single-process truth on ALL cells
+            out[name] = (bool(np.array_equal(keys, ref_keys[lo:hi])), int(G), int(ref_G), int(len(set(lab[lo:hi].ravel().tolist()))))
+        out["m_total"] = _total_cells(ctx, hi - lo)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_label_tables_are_global_across_ranks_gloo():
+    import torch.multiprocessing as mp
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = _free_port()
+    procs = [mpctx.Process(target=_label_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        out = res[rank]
+        assert out["m_total"] == 1001
+        for name in ("batch", "types", "types_spare", "pairs"):
+            same, G, ref_G, _seen = out[name]
+            assert same and G == ref_G, (rank, name, out[name])                   # global ids and global G on every rank
+    assert res[0]["batch"][1] == 3 and res[0]["batch"][3] < 3                      # rank 0 saw fewer batches than exist

@@ -846,3 +846,26 @@ def test_single_process_multi_context_same_device(sm):
     ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5, return_info=True)
     assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
     assert orc.principal_angles(out["fullalpha"][:5], ref["fullalpha"][:5]).max() < 1e-6
+
+
+def test_pageable_and_pinned_host_matrices_give_identical_bits(sm, monkeypatch):
+    """scm_ruv3_host stages ordinary (pageable) host memory -- what an R session's REAL(Y) is -- through page-locked bounce
+    buffers with helper threads; page-locked callers take the direct copies.  Same chunks, same kernels: the results must agree
+    bit for bit.  SCM_HOST_CHUNK_ROWS forces 11 chunks (ragged last one), i.e. several trips around the 4-buffer ring."""
+    monkeypatch.setenv("SCM_HOST_CHUNK_ROWS", "1000")
+    P = orc.planted_factors(10_500, 130, 60, 5, n_types=4, n_batch=3, seed=12)
+    ctx = sm.Context(0)
+    Yp = sm.pinned_empty((10_500, 130))
+    Yp[:] = P["Y"]
+    outp = sm.pinned_empty((10_500, 130))
+    r_pin = sm.fastRUVIII(Yp, P["types"], P["ctl"], k=5, return_info=True, ctx=ctx, out=outp)
+    r_pag = sm.fastRUVIII(np.array(P["Y"]), P["types"], P["ctl"], k=5, return_info=True, ctx=ctx)
+    np.testing.assert_array_equal(np.asarray(r_pin["newY"]), r_pag["newY"])
+    np.testing.assert_array_equal(np.asarray(r_pin["fullalpha"]), np.asarray(r_pag["fullalpha"]))
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5)
+    assert orc.rel_frobenius(r_pag["newY"], ref) < TOL_NEWY
+    # scRUVIII (batch statistics) and the adjust-only entry (pseudoRUVIII with column means) through the staged path
+    batch = np.array([f"b{b}" for b in P["batch"]])
+    s = sm.scRUVIII(np.asfortranarray(P["Y"].T), P["types"], P["ctl"], k=5, batch=batch, ctx=ctx)
+    refs = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 5, batch)
+    assert orc.rel_frobenius(s[5]["newY"], refs[5]["newY"]) < TOL_NEWY
