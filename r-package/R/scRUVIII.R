@@ -22,9 +22,19 @@ scRUVIII <- function(Y = Y, M = M, ctl = ctl, fullalpha = NULL, k = k, cell_type
     if (return_all_RUV) { res$optimal_ruvK <- k[1]; return(res) }
     one <- res[[1]]; one$optimal_ruvK <- k[1]; return(one)
   }
-  dY <- .Call("scm_upload", as.matrix(Y), 0L)
   cap <- .rows_cap(s, max(k), exact)
   select <- length(k) > 1
+  if (!select && is.null(fullalpha) && is.matrix(Y) && is.double(Y)) {
+    ## a plain R matrix and one ruvK: the whole closure in ONE call on REAL(Y) itself (scm_ruv3_host / scm_multi_ruv3_host:
+    ## upload, fit, adjust and download overlapped; all GPUs of useGPUs()).  genes x cells column-major IS the device layout.
+    r <- .Call("scm_host", Y, g$key, g$G, b$key, b$G, ctl2, as.integer(k[1]), cap$s, if (cap$exact) 0L else 1L, NULL, 0L, NULL)
+    fa <- t(r[[2]]); colnames(fa) <- rownames(Y); attr(fa, "conv_rank") <- r[[6]]
+    newY <- t(r[[1]]); dimnames(newY) <- rev(dimnames(Y))
+    one <- list(newY = newY, M = M, fullalpha = fa)
+    if (return_all_RUV) { res <- list(one); names(res) <- k[1]; res$optimal_ruvK <- k[1]; return(res) }
+    one$optimal_ruvK <- k[1]; return(one)
+  }
+  dY <- .Call("scm_upload", as.matrix(Y), 0L)
   ## one fit serves every k (R/scRUVIII.R:64-75); scm_fit_gram also keeps the centred Gram for the silhouette PCA
   mode <- if (cap$exact) 0L else 1L
   fit <- if (select) .Call("scm_fit_gram", dY, g$key, g$G, b$key, b$G, cap$s, min(k[1], cap$s), mode, as.integer(sort(unique(k[-1]))))
@@ -79,12 +89,29 @@ pseudoRUVIII <- function(Y, Y_pseudo, M, ctl, k = NULL, eta = NULL, include.inte
     fullalpha <- t(fit[[1]]); colnames(fullalpha) <- colnames(Y)
   }
   if (!normalised) return(list(M = M, fullalpha = fullalpha))
+  if (is.null(sub) && methods::is(Y, "dgCMatrix")) {
+    ## sparse-native: the three slots of t(Y) (genes x cells, compressed by cell) are the only copy of the cells on the device;
+    ## column means come from one pseudobulk pass with a single key, newY is streamed straight into the R matrix
+    Yt <- Matrix::t(Y)
+    cs <- .Call("scm_upload_csc", Yt@p, Yt@i, Yt@x, dim(Yt), FALSE)
+    means <- .Call("scm_csc_pseudobulk", cs, integer(nrow(Y)), 1L)[[3]]
+    kk <- min(k, nrow(fullalpha))
+    out <- .Call("scm_csc_adjust_", cs, t(fullalpha[seq_len(kk), , drop = FALSE]), kk, ctl2, means)
+    newY <- DelayedArray::DelayedArray(t(out)); dimnames(newY) <- dimnames(Y)
+    return(if (!return.info) newY else list(newY = newY, M = M, fullalpha = fullalpha))
+  }
   ## a dgCMatrix goes up as its three slots (genes x cells expected by scm_upload_sparse: pass t(Y) when Y is cells x genes)
   dY <- if (methods::is(Y, "dgCMatrix")) { Yt <- Matrix::t(Y); .Call("scm_upload_sparse", Yt@p, Yt@i, Yt@x, dim(Yt), FALSE) }
         else .Call("scm_upload", as.matrix(Y), 1L)
   means <- .Call("scm_segmean", dY, integer(nrow(Y)), 1L)[[1]][, 1]       # adjusted_means <- colMeans(Y), :97
   kk <- min(k, nrow(fullalpha))
-  sub <- if (is.null(subset)) NULL else as.integer(which(.ctl_mask(subset, n)) - 1L)
+  ## Y[, subset] of the reference (R/scMerge2_utilis.R:117-121): names are matched against colnames(Y) IN THE GIVEN ORDER
+  ## (scMerge2 passes chosen.hvg), integers are positions, a logical vector is a mask; anything not in Y is an error as in R
+  sub <- if (is.null(subset)) NULL else {
+    pos <- if (is.character(subset)) match(subset, colnames(Y)) else if (is.logical(subset)) which(subset) else as.integer(subset)
+    if (anyNA(pos) || any(pos < 1L) || any(pos > n)) stop("subscript out of bounds: `subset` names genes that are not columns of Y")
+    as.integer(pos - 1L)
+  }
   out <- .Call("scm_adjust_", dY, t(fullalpha[seq_len(kk), , drop = FALSE]), kk, ctl2, means, NULL, NULL, sub)
   newY <- DelayedArray::DelayedArray(t(out))
   rownames(newY) <- rownames(Y); colnames(newY) <- if (is.null(sub)) colnames(Y) else colnames(Y)[sub + 1L]
@@ -102,10 +129,19 @@ getAdjustedMat <- function(exprsMat, fullalpha, ctl = rownames(exprsMat), adjust
     sub <- which(rownames(exprsMat) %in% return_subset_genes)
     if (length(sub) == 0) stop("No provided return_subset_genes genes in the data")
   }
+  kk <- min(ruvK, nrow(fullalpha))
+  cr <- attr(fullalpha, "conv_rank")
+  if (!is.null(cr) && !is.na(cr) && kk > cr) warning("ruvK = ", kk, " exceeds the rank this fullalpha was converged for (", cr, ")")
+  if (is.null(sub) && is.matrix(exprsMat) && is.double(exprsMat)) {
+    ## plain matrix, all genes: ONE call on REAL(exprsMat) (column means accumulate during the chunked upload)
+    fa <- fullalpha[seq_len(kk), rownames(exprsMat), drop = FALSE]
+    r <- .Call("scm_host", exprsMat, NULL, 0L, NULL, 0L, ctl2, kk, 0L, 0L, t(fa), if (is.null(adjusted_means)) 1L else 2L, adjusted_means)
+    out <- r[[1]]; dimnames(out) <- dimnames(exprsMat)
+    return(out)
+  }
   dY <- if (methods::is(exprsMat, "dgCMatrix")) .Call("scm_upload_sparse", exprsMat@p, exprsMat@i, exprsMat@x, dim(exprsMat), FALSE)
         else .Call("scm_upload", as.matrix(exprsMat), 0L)
   if (is.null(adjusted_means)) adjusted_means <- .Call("scm_segmean", dY, integer(ncol(exprsMat)), 1L)[[1]][, 1]
-  kk <- min(ruvK, nrow(fullalpha))
   fa <- fullalpha[seq_len(kk), rownames(exprsMat), drop = FALSE]         # name indexing, R/scMerge2.R:399-405
   out <- .Call("scm_adjust_", dY, t(fa), kk, ctl2, adjusted_means, NULL, NULL, if (is.null(sub)) NULL else as.integer(sub - 1L))
   rownames(out) <- if (is.null(sub)) rownames(exprsMat) else rownames(exprsMat)[sub]

@@ -1,6 +1,6 @@
 /* .Call shim between R and libscmerge_b200 (include/scmerge_b200.h).  Logic-free by design: it unpacks
  * SEXPs, forwards to the C ABI and turns non-zero status codes into R errors.  NOT compiled in this
- * repository's environment (no R headers here); see INTEGRATION.md for the build line.
+ * repository's environment (no R headers here; type-checked against tests/r_stub); see INTEGRATION.md for the build line.
  *
  * Replaces, inside scMerge's own closures, the arithmetic of
  *   fastRUVIII  (R/fastRUVIII.R:41-111)      -> scm_fit(), scm_adjust_()
@@ -20,7 +20,28 @@
                          if (rc_ == SCM_ERR_NOCONV) Rf_warning("%s", scm_last_error()); } while (0)
 
 static scm_ctx* g_ctx = NULL;
-static scm_ctx* ctx(void) { if (!g_ctx) CHECK(scm_ctx_create(0, NULL, &g_ctx)); return g_ctx; }
+static scm_multi* g_multi = NULL;   /* set by scm_use_gpus(): ONE R process driving several GPUs (scm_multi_create) */
+static scm_ctx* ctx(void) {
+    if (g_multi) return scm_multi_ctx(g_multi, 0);
+    if (!g_ctx) CHECK(scm_ctx_create(0, NULL, &g_ctx));
+    return g_ctx;
+}
+
+/* scm_use_gpus(n): n > 1 creates one context + NCCL rank per device inside the library (ncclCommInitAll); the host-matrix
+ * closures (scm_host) then split the cells over all of them.  n <= 1 goes back to a single device.  Device-resident objects
+ * created before the switch belong to the old context: call it first, before anything is uploaded. */
+SEXP scm_use_gpus(SEXP n_) {
+    int n = Rf_asInteger(n_);
+    if (g_multi) { scm_multi_destroy(g_multi); g_multi = NULL; }
+    if (n > 1) {
+        if (g_ctx) { scm_ctx_destroy(g_ctx); g_ctx = NULL; }
+        CHECK(scm_multi_create(NULL, n, &g_multi));
+    }
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, 1));
+    INTEGER(out)[0] = g_multi ? scm_multi_size(g_multi) : 1;
+    UNPROTECT(1);
+    return out;
+}
 
 /* device matrix held by R as an external pointer {ptr, m, n, ld}; freed by the finalizer */
 typedef struct { double* p; int64_t m, n, ld; } dmat;
@@ -228,7 +249,126 @@ SEXP scm_sil(SEXP Yp, SEXP gram, SEXP colmean, SEXP alpha, SEXP k_, SEXP ctl, SE
     return out;
 }
 
+/* The whole closure on the R matrix itself, PCIe overlapped with the kernels (scm_ruv3_host / scm_multi_ruv3_host): upload in
+ * chunks with the fit streaming behind, adjust + download chunk by chunk.  REAL(Y) is ordinary pageable memory; the library
+ * stages it through its own page-locked bounce buffers with helper threads, so no pinning is needed on the R side.
+ *   Y      : genes x cells numeric matrix (column-major == row-major cells x genes; the layout scMerge()/scMerge2() hold)
+ *   group  : int 0-based replicate keys or NULL (adjust only);  batch: int keys or NULL (non-NULL: scRUVIII)
+ *   alpha_in: NULL = fit, else s_in x n fullalpha (as n x s_in column-major) for adjust-only;  center_mode 0 none, 1 colMeans, 2 center
+ * returns list(newY genes x cells, fullalpha (n x s image) | NULL, sigma | NULL, mean | NULL, sd | NULL, conv_rank) */
+SEXP scm_host(SEXP Y, SEXP group, SEXP G, SEXP batch, SEXP Bt, SEXP ctl, SEXP k_, SEXP s_, SEXP mode, SEXP alpha_in, SEXP center_mode,
+              SEXP center) {
+    SEXP dim = Rf_getAttrib(Y, R_DimSymbol);
+    int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+    int k = Rf_asInteger(k_), fit = Rf_isNull(alpha_in), has_b = !Rf_isNull(batch);
+    int s = fit ? Rf_asInteger(s_) : (int)(Rf_xlength(alpha_in) / n);
+    uint8_t* hc = (uint8_t*)R_alloc(n, 1); for (int64_t j = 0; j < n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 6));
+    SEXP newY = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)m)); SET_VECTOR_ELT(out, 0, newY);
+    SEXP fa = R_NilValue, sg = R_NilValue, mu = R_NilValue, sd = R_NilValue;
+    int np = 2;
+    if (fit) {
+        fa = PROTECT(Rf_allocMatrix(REALSXP, (int)n, s)); SET_VECTOR_ELT(out, 1, fa);
+        sg = PROTECT(Rf_allocVector(REALSXP, s)); SET_VECTOR_ELT(out, 2, sg); np += 2;
+    }
+    if (has_b || Rf_asInteger(center_mode) == 1) { mu = PROTECT(Rf_allocVector(REALSXP, n)); SET_VECTOR_ELT(out, 3, mu); np++; }
+    if (has_b) { sd = PROTECT(Rf_allocVector(REALSXP, n)); SET_VECTOR_ELT(out, 4, sd); np++; }
+    int32_t iters = 0, conv = 0; double resid = 0.0;
+    const int32_t* hg = Rf_isNull(group) ? NULL : (const int32_t*)INTEGER(group);
+    const int32_t* hb = has_b ? (const int32_t*)INTEGER(batch) : NULL;
+    const double* hin = fit ? NULL : REAL(alpha_in);
+    const double* hcen = Rf_isNull(center) ? NULL : REAL(center);
+    int rc;
+    if (g_multi)
+        rc = scm_multi_ruv3_host(g_multi, REAL(Y), m, n, n, hg, Rf_asInteger(G), hb, has_b ? Rf_asInteger(Bt) : 0, hc, k, s, Rf_asInteger(mode),
+                                 1e-10, 500, 1, hin, fit ? 0 : s, Rf_asInteger(center_mode), hcen, REAL(newY), n,
+                                 fit ? REAL(fa) : NULL, fit ? REAL(sg) : NULL, mu == R_NilValue ? NULL : REAL(mu),
+                                 sd == R_NilValue ? NULL : REAL(sd), &iters, &resid);
+    else
+        rc = scm_ruv3_host(ctx(), REAL(Y), m, n, n, hg, Rf_asInteger(G), hb, has_b ? Rf_asInteger(Bt) : 0, hc, k, s, Rf_asInteger(mode),
+                           1e-10, 500, 1, hin, fit ? 0 : s, Rf_asInteger(center_mode), hcen, REAL(newY), n,
+                           fit ? REAL(fa) : NULL, fit ? REAL(sg) : NULL, mu == R_NilValue ? NULL : REAL(mu),
+                           sd == R_NilValue ? NULL : REAL(sd), &iters, &resid);
+    CHECK(rc);
+    CHECK(scm_ctx_fit_info(ctx(), NULL, NULL, &conv, NULL));
+    SEXP cr = PROTECT(Rf_allocVector(INTSXP, 1)); INTEGER(cr)[0] = fit ? conv : NA_INTEGER; SET_VECTOR_ELT(out, 5, cr); np++;
+    UNPROTECT(np);
+    return out;
+}
+
+/* ---- sparse-native scMerge2 passes: the dgCMatrix slots stay the only copy of the cells on the device ---------------------
+ * scm_upload_csc: (@p, @i, @x, @Dim of a genes x cells dgCMatrix, cosineNorm) -> external pointer {indptr, idx, val, inv_norm}
+ * (validated with scm_csc_check; un-canonical input is an error here: use scm_upload_sparse for the dense path). */
+typedef struct { int64_t* p; int32_t* i; double* x; double* inv; int64_t m, n, nnz; } dcsc;
+static void dcsc_fin(SEXP e) {
+    dcsc* d = (dcsc*)R_ExternalPtrAddr(e);
+    if (d) { scm_dev_free(ctx(), d->p); scm_dev_free(ctx(), d->i); scm_dev_free(ctx(), d->x); scm_dev_free(ctx(), d->inv); R_Free(d); R_ClearExternalPtr(e); }
+}
+SEXP scm_upload_csc(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP cosine) {
+    int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1], nnz = Rf_xlength(x);
+    int64_t* hp = (int64_t*)R_alloc(m + 1, 8);
+    for (int64_t c = 0; c <= m; c++) hp[c] = INTEGER(p)[c];
+    dcsc* d = R_Calloc(1, dcsc);
+    d->m = m; d->n = n; d->nnz = nnz;
+    d->p = (int64_t*)to_dev(hp, (m + 1) * 8); d->i = (int32_t*)to_dev(INTEGER(i), nnz * 4); d->x = (double*)to_dev(REAL(x), nnz * 8);
+    int32_t canonical = 0, hflag = 0, *dflag = (int32_t*)to_dev(&hflag, 4);
+    CHECK(scm_csc_check(ctx(), d->p, d->i, m, n, nnz, &canonical));
+    if (!canonical) Rf_error("cells with unsorted or duplicate gene indices: not a canonical dgCMatrix");
+    CHECK(scm_dev_alloc(ctx(), m * 8, (void**)&d->inv));
+    CHECK(scm_csc_rownorm(ctx(), d->p, d->x, m, Rf_asLogical(cosine), 1e-8, d->inv, dflag));
+    CHECK(scm_d2h(ctx(), &hflag, dflag, 4));
+    scm_dev_free(ctx(), dflag);
+    if (hflag) Rf_warning("Y contains missing values or infinities.");
+    SEXP out = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(out, dcsc_fin, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+/* pseudobulk means by int key (create_pseudoBulk, R/scMerge2_utilis.R:461-486) + colMeans of all cells (:97):
+ * list(means n x P image, counts P, colmeans n) */
+SEXP scm_csc_pseudobulk(SEXP cp, SEXP key, SEXP P_) {
+    dcsc* d = (dcsc*)R_ExternalPtrAddr(cp);
+    int P = Rf_asInteger(P_);
+    int64_t ldn = (d->n + 1) / 2 * 2;
+    int32_t* dk = (int32_t*)to_dev(INTEGER(key), d->m * 4);
+    double *dm, *dmean; int64_t* dc;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)P * ldn * 8, (void**)&dm)); CHECK(scm_dev_alloc(ctx(), P * 8, (void**)&dc));
+    CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dmean));
+    CHECK(scm_csc_seg_colmean(ctx(), d->p, d->i, d->x, d->inv, d->m, d->n, dk, P, dm, ldn, dc));
+    CHECK(scm_group_colmean(ctx(), dm, dc, P, d->n, ldn, dmean));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP mm = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, P));
+    CHECK(scm_copy2d(ctx(), REAL(mm), d->n * 8, dm, ldn * 8, d->n * 8, P, 1));
+    int64_t* hcn = (int64_t*)R_alloc(P, 8); CHECK(scm_d2h(ctx(), hcn, dc, (int64_t)P * 8));
+    SEXP cc = PROTECT(Rf_allocVector(REALSXP, P)); for (int g = 0; g < P; g++) REAL(cc)[g] = (double)hcn[g];
+    SEXP cm = PROTECT(Rf_allocVector(REALSXP, d->n)); CHECK(scm_d2h(ctx(), REAL(cm), dmean, d->n * 8));
+    SET_VECTOR_ELT(out, 0, mm); SET_VECTOR_ELT(out, 1, cc); SET_VECTOR_ELT(out, 2, cm);
+    scm_dev_free(ctx(), dk); scm_dev_free(ctx(), dm); scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dmean);
+    UNPROTECT(4);
+    return out;
+}
+/* newY (genes x cells) = adjust of every cell from the sparse rows, result streamed to the R matrix chunk by chunk
+ * (scm_csc_adjust_to_host: the dense matrix never exists on the device).  alpha: n x k image, ctl logical n, center numeric n. */
+SEXP scm_csc_adjust_(SEXP cp, SEXP alpha, SEXP k_, SEXP ctl, SEXP center) {
+    dcsc* d = (dcsc*)R_ExternalPtrAddr(cp);
+    int k = Rf_asInteger(k_);
+    double* da = (double*)to_dev(REAL(alpha), (int64_t)k * d->n * 8);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    double* dce = Rf_isNull(center) ? NULL : (double*)to_dev(REAL(center), d->n * 8);
+    scm_coef* coef; CHECK(scm_coef_create(ctx(), da, d->n, k, dc, dce, NULL, NULL, &coef));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, (int)d->m));
+    CHECK(scm_csc_adjust_to_host(ctx(), d->p, d->i, d->x, d->inv, d->m, d->n, coef, REAL(out), d->n));
+    scm_coef_destroy(ctx(), coef);
+    scm_dev_free(ctx(), da); scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dce);
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
+    {"scm_use_gpus", (DL_FUNC)&scm_use_gpus, 1}, {"scm_host", (DL_FUNC)&scm_host, 12},
+    {"scm_upload_csc", (DL_FUNC)&scm_upload_csc, 5}, {"scm_csc_pseudobulk", (DL_FUNC)&scm_csc_pseudobulk, 3},
+    {"scm_csc_adjust_", (DL_FUNC)&scm_csc_adjust_, 5},
     {"scm_upload", (DL_FUNC)&scm_upload, 2}, {"scm_fit", (DL_FUNC)&scm_fit, 8}, {"scm_fit_gram", (DL_FUNC)&scm_fit_gram, 9},
     {"scm_release_scratch", (DL_FUNC)&scm_release_scratch, 0},
     {"scm_adjust_", (DL_FUNC)&scm_adjust_, 8}, {"scm_segmean", (DL_FUNC)&scm_segmean, 3},

@@ -11,6 +11,8 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define STRSXP 16
 #define VECSXP 19
 extern SEXP R_NilValue, R_DimSymbol, R_NamesSymbol;
+extern int R_NaInt;
+#define NA_INTEGER R_NaInt
 int* INTEGER(SEXP x);
 int* LOGICAL(SEXP x);
 double* REAL(SEXP x);
