@@ -7,6 +7,7 @@
 //   solve   : Gram correction, top-s eigenpairs, coefficients (small, latency bound),
 //   download: the fused adjust kernel (K6) runs chunk by chunk IN PLACE and each finished chunk goes back over
 //             PCIe while the next one is being adjusted.
+//   A matrix that does not fit the device is streamed TWICE through three chunk buffers instead (out-of-core, see ruv3_host).
 // Two things keep the overlap real (both found with SCM_HOST_TRACE=1, which prints the per-chunk device timeline):
 //   * nothing that a copy engine might execute (cudaMemsetAsync, small cudaMemcpyAsync) is issued on the compute stream
 //     while bulk copies are in flight, and the compute stream is moved back to the compute engine by a trivial kernel
@@ -120,7 +121,7 @@ struct ChunkGate {
     char msg[256] = "";
     void publish(int upto) { { std::lock_guard<std::mutex> g(mu); ready = upto; } cv.notify_all(); }
     void fail_with(int rc, const char* why) {
-        { std::lock_guard<std::mutex> g(mu); if (!error) { error = rc; snprintf(msg, sizeof(msg), "%s", why); } }
+        { std::lock_guard<std::mutex> g(mu); if (!error) { error = rc; snprintf(msg, sizeof(msg), "%.250s", why); } }
         cv.notify_all();
     }
     int wait_for(int c) {  // returns 0 once chunk c has been published, the helper's status if it died
@@ -144,100 +145,202 @@ struct HelperJoin {
         if (_e != cudaSuccess) { (gate).fail_with(SCM_ERR_CUDA, cudaGetErrorString(_e)); return; }     \
     } while (0)
 
-// The download half of the host drivers: the fused adjust kernel (K6) runs chunk by chunk IN PLACE on the device-resident
-// matrix and every finished chunk goes back over PCIe (copy stream) while the next one is being adjusted.  d_Y holds newY
-// afterwards.  Returns after the last byte has landed in h_out.
+// ---- chunk movers ---------------------------------------------------------------------------------------------------------
+// Both directions exist in a direct form (page-locked host memory: cudaMemcpyAsync straight from / to the caller's buffer, issued by
+// the driver thread) and a staged form (pageable memory: a helper thread + memcpy threads + the bounce buffers).  A "slot" is
+// where a chunk lives on the device: its own place inside the resident matrix (in-core) or one of a small ring of chunk buffers
+// that are re-used (out-of-core); a re-used slot is guarded by the event the driver records when its previous tenant is done.
+struct ChunkPlan {
+    int64_t m, n, ld, rows_per_chunk;
+    int nchunks;
+    int64_t row0(int c) const { return (int64_t)c * rows_per_chunk; }
+    int64_t rows(int c) const { return row0(c) + rows_per_chunk <= m ? rows_per_chunk : m - row0(c); }
+};
+
+struct Uploader {
+    scm_ctx* ctx;
+    ChunkPlan pl;
+    const double* h_src;
+    int64_t ldh;
+    cudaStream_t cs;
+    bool staged;
+    int slots_in_flight;            // ring size of the device slots (0: every chunk has its own place)
+    int stage_lo, stage_n;          // bounce buffers this direction may use: stage_buf[stage_lo .. stage_lo + stage_n)
+    std::vector<double*> dst;       // device address of chunk c
+    std::vector<cudaEvent_t> ev;    // chunk c has landed
+    std::vector<cudaEvent_t> freed; // recorded by the driver when the tenant of chunk c's slot is done (out-of-core only)
+    ChunkGate fed, released;        // staged: chunks published by the helper / slots released by the driver
+    std::thread feeder;
+    int issued = 0;                 // direct mode: copies issued so far
+
+    ~Uploader() {
+        fed.fail_with(SCM_ERR_INVALID, "driver left early");
+        released.fail_with(SCM_ERR_INVALID, "driver left early");
+        if (feeder.joinable()) feeder.join();
+        cudaStreamSynchronize(cs);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto e : freed) if (e) cudaEventDestroy(e);
+    }
+    int init() {
+        ev.assign(pl.nchunks, nullptr);
+        for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (slots_in_flight > 0) {
+            freed.assign(pl.nchunks, nullptr);
+            for (auto& e : freed) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    int copy_chunk(int c, const double* src, int64_t src_ld, cudaStream_t stream) {
+        const int64_t rows = pl.rows(c), n = pl.n, ld = pl.ld;
+        if (slots_in_flight > 0 && c >= slots_in_flight) SCM_CUDA(cudaStreamWaitEvent(stream, freed[c - slots_in_flight], 0));
+        if (src_ld == n && ld == n) SCM_CUDA(cudaMemcpyAsync(dst[c], src, (size_t)rows * n * 8, cudaMemcpyHostToDevice, stream));
+        else SCM_CUDA(cudaMemcpy2DAsync(dst[c], ld * 8, src, src_ld * 8, n * 8, rows, cudaMemcpyHostToDevice, stream));
+        SCM_CUDA(cudaEventRecord(ev[c], stream));
+        return 0;
+    }
+    // direct mode: chunk c may be issued once the driver has recorded the release of chunk c - slots_in_flight
+    int issue_direct_upto(int last) {
+        for (; issued <= last && issued < pl.nchunks; issued++)
+            SCM_TRY(copy_chunk(issued, h_src + pl.row0(issued) * ldh, ldh, cs));
+        return 0;
+    }
+    int start() {
+        if (!staged) return issue_direct_upto(slots_in_flight > 0 ? (slots_in_flight < 2 ? slots_in_flight : 2) - 1 : 1);
+        const int nt = host_copy_threads();
+        const int dev = ctx->device;
+        feeder = std::thread([this, nt, dev] {
+            cudaSetDevice(dev);
+            for (int c = 0; c < pl.nchunks; c++) {
+                if (fed.error) return;
+                if (c >= stage_n) SCM_HELPER_CUDA(cudaEventSynchronize(ev[c - stage_n]), fed);  // the bounce buffer's previous H2D has finished
+                double* sb = (double*)ctx->stage_buf[stage_lo + c % stage_n];
+                parallel_copy2d(sb, (size_t)pl.n * 8, h_src + pl.row0(c) * ldh, (size_t)ldh * 8, (size_t)pl.n * 8, pl.rows(c), nt);
+                if (slots_in_flight > 0 && c >= slots_in_flight && released.wait_for(c - slots_in_flight) != 0) return;  // event recorded?
+                if (copy_chunk(c, sb, pl.n, cs) != 0) { fed.fail_with(SCM_ERR_CUDA, g_err); return; }
+                fed.publish(c + 1);
+            }
+        });
+        return 0;
+    }
+    // Returns when chunk c is in HBM.  Direct mode keeps two copies queued behind it.
+    int wait(int c) {
+        if (staged && fed.wait_for(c) != 0) return fail(fed.error, "upload helper: %s", fed.msg);
+        SCM_CUDA(cudaEventSynchronize(ev[c]));
+        return 0;
+    }
+    // The driver is done with the device slot of chunk c (everything that reads or writes it has been enqueued on `stream`).
+    int release(int c, cudaStream_t stream) {
+        if (slots_in_flight > 0) {
+            SCM_CUDA(cudaEventRecord(freed[c], stream));
+            if (staged) released.publish(c + 1);
+        }
+        if (!staged) SCM_TRY(issue_direct_upto(c + (slots_in_flight > 0 ? slots_in_flight : 2)));
+        return 0;
+    }
+    int finish() {
+        if (staged && feeder.joinable()) {
+            if (fed.wait_for(pl.nchunks - 1) != 0) return fail(fed.error, "upload helper: %s", fed.msg);
+            feeder.join();
+        }
+        return 0;
+    }
+};
+
+struct Downloader {
+    scm_ctx* ctx;
+    ChunkPlan pl;
+    double* h_dst;
+    int64_t ldo;
+    cudaStream_t cs;
+    bool staged;
+    int stage_lo, stage_n;
+    std::vector<cudaEvent_t> evd;   // chunk c has left the device
+    ChunkGate issued, drained;
+    std::thread drainer;
+
+    ~Downloader() {
+        issued.fail_with(SCM_ERR_INVALID, "driver left early");
+        if (drainer.joinable()) drainer.join();
+        cudaStreamSynchronize(cs);
+        for (auto e : evd) if (e) cudaEventDestroy(e);
+    }
+    int init() {
+        evd.assign(pl.nchunks, nullptr);
+        for (auto& e : evd) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!staged) return 0;
+        const int nt = host_copy_threads();
+        const int dev = ctx->device;
+        drainer = std::thread([this, nt, dev] {
+            cudaSetDevice(dev);
+            for (int c = 0; c < pl.nchunks; c++) {
+                if (issued.wait_for(c) != 0) return;
+                SCM_HELPER_CUDA(cudaEventSynchronize(evd[c]), drained);
+                parallel_copy2d(h_dst + pl.row0(c) * ldo, (size_t)ldo * 8, ctx->stage_buf[stage_lo + c % stage_n], (size_t)pl.n * 8,
+                                (size_t)pl.n * 8, pl.rows(c), nt);
+                drained.publish(c + 1);
+            }
+        });
+        return 0;
+    }
+    // Chunk c (at d_src, leading dimension ld) goes home once `ready` (recorded on the compute stream) has fired.
+    int push(int c, const double* d_src, cudaEvent_t ready) {
+        const int64_t rows = pl.rows(c), n = pl.n, ld = pl.ld;
+        SCM_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+        if (staged) {
+            if (c >= stage_n && drained.wait_for(c - stage_n) != 0) return fail(drained.error, "download helper: %s", drained.msg);
+            double* sb = (double*)ctx->stage_buf[stage_lo + c % stage_n];
+            if (ld == n) SCM_CUDA(cudaMemcpyAsync(sb, d_src, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
+            else SCM_CUDA(cudaMemcpy2DAsync(sb, n * 8, d_src, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+        } else if (ldo == n && ld == n) {
+            SCM_CUDA(cudaMemcpyAsync(h_dst + pl.row0(c) * ldo, d_src, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
+        } else {
+            SCM_CUDA(cudaMemcpy2DAsync(h_dst + pl.row0(c) * ldo, ldo * 8, d_src, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
+        }
+        SCM_CUDA(cudaEventRecord(evd[c], cs));
+        if (staged) issued.publish(c + 1);
+        return 0;
+    }
+    int finish() {
+        if (staged) {
+            if (drained.wait_for(pl.nchunks - 1) != 0) return fail(drained.error, "download helper: %s", drained.msg);
+            drainer.join();
+        }
+        SCM_CUDA(cudaStreamSynchronize(cs));
+        return 0;
+    }
+};
+
+// The download half of the host drivers for a RESIDENT matrix: the fused adjust kernel (K6) runs chunk by chunk IN PLACE and every
+// finished chunk goes back over PCIe (copy stream) while the next one is being adjusted.  d_Y holds newY afterwards.  Returns
+// after the last byte has landed in h_out.
 inline int adjust_download(scm_ctx* ctx, double* dY, int64_t m, int64_t n, int64_t ld, const scm_coef* coef, double* h_out,
                            int64_t ldo, int64_t rows_per_chunk) {
     if (!dY || !h_out || !coef || ldo < n) return fail(SCM_ERR_INVALID, "adjust_download: bad arguments");
     cudaStream_t st = ctx->stream;
     if (!ctx->copy_stream_d2h) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream_d2h, cudaStreamNonBlocking));
-    cudaStream_t cs = ctx->copy_stream_d2h;
     if (rows_per_chunk <= 0) rows_per_chunk = host_chunk_rows(ld);
-    const int nchunks = (int)ceil_div(m, rows_per_chunk);
-    std::vector<cudaEvent_t> ev(nchunks + 1);
+    ChunkPlan pl{m, n, ld, rows_per_chunk, (int)ceil_div(m, rows_per_chunk)};
+    const bool staged = host_is_pageable(h_out);
+    if (staged) SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
+    std::vector<cudaEvent_t> ev(pl.nchunks);
     for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     struct EvGuard {
         std::vector<cudaEvent_t>& v;
         ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
     } guard{ev};
-    const bool trace = getenv("SCM_HOST_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tl_adj, tl_copy;
-    cudaEvent_t tl_zero = nullptr;
-    if (trace) {
-        tl_adj.resize(nchunks); tl_copy.resize(nchunks);
-        for (int c = 0; c < nchunks; c++) { cudaEventCreate(&tl_adj[c]); cudaEventCreate(&tl_copy[c]); }
-        cudaEventCreate(&tl_zero);
-        cudaEventRecord(tl_zero, st);
-    }
-    // pageable destination: D2H lands in page-locked bounce buffers, a helper thread copies them out with several memcpy threads
-    const bool staged = host_is_pageable(h_out);
-    ChunkGate issued, drained;
-    std::thread drainer;
-    HelperJoin joiner{drainer, staged ? &issued : nullptr};
-    std::vector<cudaEvent_t> evd;
-    struct EvGuard2 {
-        std::vector<cudaEvent_t>& v;
-        ~EvGuard2() { for (auto e : v) cudaEventDestroy(e); }
-    } guard2{evd};
-    if (staged) {
-        SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
-        evd.resize(nchunks);
-        for (auto& e : evd) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        const int nt = host_copy_threads();
-        const int dev = ctx->device;
-        drainer = std::thread([&, nt, dev] {
-            cudaSetDevice(dev);
-            for (int c = 0; c < nchunks; c++) {
-                if (issued.wait_for(c) != 0) return;
-                SCM_HELPER_CUDA(cudaEventSynchronize(evd[c]), drained);
-                const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-                parallel_copy2d(h_out + r0 * ldo, (size_t)ldo * 8, ctx->stage_buf[c % STAGE_NB], (size_t)n * 8, (size_t)n * 8, rows, nt);
-                drained.publish(c + 1);
-            }
-        });
-    }
-    for (int c = 0; c < nchunks; c++) {
-        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
+    Downloader down{ctx, pl, h_out, ldo, ctx->copy_stream_d2h, staged, 0, STAGE_NB};
+    SCM_TRY(down.init());
+    for (int c = 0; c < pl.nchunks; c++) {
+        double* dc = dY + pl.row0(c) * ld;
         {
             StageTimer t(ctx, ST_ADJUST);
-            SCM_TRY(adjust(ctx, dY + r0 * ld, rows, n, ld, coef, nullptr, 0, dY + r0 * ld, ld, nullptr));
+            SCM_TRY(adjust(ctx, dc, pl.rows(c), n, ld, coef, nullptr, 0, dc, ld, nullptr));
         }
-        if (trace) cudaEventRecord(tl_adj[c], st);
         SCM_CUDA(cudaEventRecord(ev[c], st));
-        SCM_CUDA(cudaStreamWaitEvent(cs, ev[c], 0));
-        if (staged) {
-            if (c >= STAGE_NB && drained.wait_for(c - STAGE_NB) != 0) return fail(drained.error, "download helper: %s", drained.msg);
-            double* sb = (double*)ctx->stage_buf[c % STAGE_NB];
-            if (ld == n) SCM_CUDA(cudaMemcpyAsync(sb, dY + r0 * ld, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
-            else SCM_CUDA(cudaMemcpy2DAsync(sb, n * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
-            SCM_CUDA(cudaEventRecord(evd[c], cs));
-            issued.publish(c + 1);
-        } else if (ldo == n && ld == n)
-            SCM_CUDA(cudaMemcpyAsync(h_out + r0 * ldo, dY + r0 * ld, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, cs));
-        else
-            SCM_CUDA(cudaMemcpy2DAsync(h_out + r0 * ldo, ldo * 8, dY + r0 * ld, ld * 8, n * 8, rows, cudaMemcpyDeviceToHost, cs));
-        if (trace) cudaEventRecord(tl_copy[c], cs);
-    }
-    if (staged) {
-        if (drained.wait_for(nchunks - 1) != 0) return fail(drained.error, "download helper: %s", drained.msg);
-        joiner.wake = nullptr;  // finished normally
-        drainer.join();
-    }
-    if (trace) {
-        cudaStreamSynchronize(cs);
-        cudaStreamSynchronize(st);
-        for (int c = 0; c < nchunks; c++) {
-            float ta = 0.f, tc = 0.f;
-            cudaEventElapsedTime(&ta, tl_zero, tl_adj[c]);
-            cudaEventElapsedTime(&tc, tl_zero, tl_copy[c]);
-            if (c < 4 || c >= nchunks - 2) fprintf(stderr, "[adjust_download]   chunk %2d: adjusted %8.2f ms, D2H landed %8.2f ms\n", c, ta, tc);
-            cudaEventDestroy(tl_adj[c]); cudaEventDestroy(tl_copy[c]);
-        }
-        cudaEventDestroy(tl_zero);
+        SCM_TRY(down.push(c, dc, ev[c]));
     }
     // the host waits for the downloads: stream-ordered frees of d_Y issued after this function returns are safe
-    SCM_CUDA(cudaStreamSynchronize(cs));
+    SCM_TRY(down.finish());
     SCM_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -267,6 +370,45 @@ struct HostTrace {
     }
 };
 
+// Out-of-core standardize2: the squared deviations have to be summed in the same pass that sums the batch totals, i.e. before the
+// (global) batch means mu_b exist, so they are taken about the rank's shift a and moved afterwards.  For the LOCAL cells of batch b,
+//     sum (y - mu_b)^2 = sum (y - a)^2 - 2 (mu_b - a) (s_loc - n_loc a) + n_loc (mu_b - a)^2,
+// s_loc / n_loc the local batch sum / size (copies taken before the all-reduce).  |mu_b - a| is a batch effect, not a mean: nothing
+// cancels beyond the ratio of between-batch to within-batch variance.
+__global__ void ssq_finish_kernel(double* __restrict__ ssq, const double* __restrict__ bmeans, const double* __restrict__ s_loc,
+                                  const int64_t* __restrict__ n_loc, int32_t Bt, int64_t n, const double* __restrict__ a) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int b = 0; b < Bt; b++) {
+        const double nl = (double)n_loc[b], dlt = bmeans[(int64_t)b * n + j] - a[j];
+        ssq[(int64_t)b * n + j] += -2.0 * dlt * (s_loc[(int64_t)b * n + j] - nl * a[j]) + nl * dlt * dlt;
+    }
+}
+// dst[b, :] = a for every batch b (the per-group centre argument of the squared-deviation K1 pass)
+__global__ void tile_rows_kernel(double* __restrict__ dst, const double* __restrict__ a, int32_t Bt, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int b = 0; b < Bt; b++) dst[(int64_t)b * n + j] = a[j];
+}
+
+// Device memory the resident (in-core) form may take: SCM_HOST_DEVICE_BUDGET bytes, else 85 % of what is free right now.
+inline int64_t host_device_budget() {
+    if (const char* e = getenv("SCM_HOST_DEVICE_BUDGET")) return atoll(e);
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return (int64_t)1 << 62; }
+    return (int64_t)((double)fr * 0.85);
+}
+
+// The whole closure on a host matrix.  Two forms, same kernels and the same results up to summation order:
+//   in-core     : Y is uploaded once into a resident device matrix (chunks arrive on a copy stream while the fit accumulates behind
+//                 them), adjusted in place and downloaded chunk by chunk.  PCIe: 8 m n up + 8 m n down, one after the other
+//                 (the fit needs every cell before the first adjusted byte exists).
+//   out-of-core : when the matrix does not fit the device budget, Y is STREAMED TWICE through a ring of three chunk buffers:
+//                 pass 1 sums and accumulates the Gram, pass 2 re-uploads every chunk, adjusts it and sends it home, upload and
+//                 download running concurrently (full duplex).  PCIe: 16 m n up + 8 m n down, but the second upload hides
+//                 under the download, so the wall time matches the in-core form; device memory: 3 chunks (1.5 GB) + n^2.
+//                 This is the chunked `bplapply` adjust of pseudoRUVIII (R/scMerge2_utilis.R:104-124) and the HDF5 / DelayedArray
+//                 use case of the reference's vignette (vignettes/scMerge.Rmd:401-441) for a matrix that lives in host memory.
 inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     const HostTrace trace;
     const int64_t m = a.m, n = a.n;
@@ -276,27 +418,28 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     if (do_fit && (!a.h_group || a.G <= 0 || a.s <= 0)) return fail(SCM_ERR_INVALID, "scm_ruv3_host: fit requested without groups / s");
     cudaStream_t st = ctx->stream;
     if (!ctx->copy_stream) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    cudaStream_t cs = ctx->copy_stream;
+    if (!ctx->copy_stream_d2h) SCM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream_d2h, cudaStreamNonBlocking));
     const int64_t ld = (n + 1) & ~(int64_t)1;
     const int64_t rows_per_chunk = host_chunk_rows(ld);
-    const int nchunks = (int)ceil_div(m, rows_per_chunk);
-    std::vector<cudaEvent_t> ev(nchunks);
-    for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    struct EvGuard {
-        std::vector<cudaEvent_t>& v;
-        ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
-    } guard{ev};
+    ChunkPlan pl{m, n, ld, rows_per_chunk, (int)ceil_div(m, rows_per_chunk)};
+    const int nchunks = pl.nchunks;
+    const bool need_sums = do_fit || a.center_mode == 1;
+    constexpr int RING = 3;
+    const bool stream_mode = nchunks > RING && (getenv("SCM_HOST_STREAM") ? atoi(getenv("SCM_HOST_STREAM")) != 0
+                                                                           : m * ld * 8 + n * n * 32 > host_device_budget());
+    const bool staged_in = host_is_pageable(a.h_Y), staged_out = host_is_pageable(a.h_out);
+    if (staged_in || staged_out) SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
 
     Scratch ws(ctx);
     // declared after `ws`, so destroyed before it: on EVERY exit path (errors included) the bulk copies still queued on the copy
-    // streams have finished before Scratch hands dY back to the pool
+    // streams have finished before Scratch hands the device matrix back to the pool
     struct CopyFence {
         scm_ctx* c;
         ~CopyFence() { if (c->copy_stream) cudaStreamSynchronize(c->copy_stream); if (c->copy_stream_d2h) cudaStreamSynchronize(c->copy_stream_d2h); }
     } fence{ctx};
     double *dY, *gsums = nullptr, *tsums = nullptr, *shift = nullptr, *Gm = nullptr, *vals = nullptr, *vecs = nullptr, *fa = nullptr;
     double *bsums = nullptr, *ssq = nullptr, *sd = nullptr, *inv_sd = nullptr, *center = nullptr, *sig = nullptr;
-    double *buf1 = nullptr, *buf2 = nullptr, *cnt_f64 = nullptr, *uvec = nullptr, *dvec = nullptr;
+    double *buf1 = nullptr, *buf2 = nullptr, *cnt_f64 = nullptr, *uvec = nullptr, *dvec = nullptr, *tb = nullptr, *atile = nullptr;
     int64_t *gcounts = nullptr, *gcnt_local = nullptr, *tcounts = nullptr, *bcounts = nullptr, *bcnt_local = nullptr, *meta = nullptr;
     int32_t *dgroup = nullptr, *dbatch = nullptr, *flag = nullptr;
     uint8_t* dctl;
@@ -305,7 +448,7 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     const int32_t Btk = sc ? a.Bt : 0;
     // the two all-reduce buffers of fit_core.cuh: [gsums | bsums | counts | flag, rows] and [Gm | ssq]
     const int64_t len1 = (int64_t)(Gk + Btk) * n + Gk + Btk + 2, len2 = (do_fit ? n * n : 0) + (int64_t)Btk * n;
-    SCM_TRY(ws.alloc(&dY, m * ld));
+    SCM_TRY(ws.alloc(&dY, stream_mode ? (int64_t)RING * rows_per_chunk * ld : m * ld));
     SCM_TRY(ws.alloc(&dctl, n));
     SCM_TRY(ws.alloc(&fa, (int64_t)s * n));
     SCM_TRY(ws.alloc(&meta, 4)); SCM_TRY(ws.alloc(&flag, 1));
@@ -315,13 +458,15 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     Gm = buf2; ssq = buf2 + (do_fit ? n * n : 0);
     SCM_CUDA(cudaMemsetAsync(flag, 0, 4, st));
     SCM_CUDA(cudaMemsetAsync(shift, 0, sizeof(double) * n, st));
+    SCM_CUDA(cudaMemsetAsync(buf1, 0, sizeof(double) * len1, st));
+    if (len2 > 0 && stream_mode) SCM_CUDA(cudaMemsetAsync(buf2, 0, sizeof(double) * len2, st));
     SCM_CUDA(cudaMemcpyAsync(dctl, a.h_ctl, n, cudaMemcpyHostToDevice, st));
-    SCM_TRY(ws.alloc(&tsums, (int64_t)Gk * n));
-    SCM_TRY(ws.alloc(&gcounts, Gk)); SCM_TRY(ws.alloc(&gcnt_local, Gk)); SCM_TRY(ws.alloc(&tcounts, Gk));
+    SCM_TRY(ws.alloc(&tsums, (int64_t)(Gk > Btk ? Gk : Btk) * n));
+    SCM_TRY(ws.alloc(&gcounts, Gk)); SCM_TRY(ws.alloc(&gcnt_local, Gk)); SCM_TRY(ws.alloc(&tcounts, Gk > Btk ? Gk : Btk));
     SCM_TRY(ws.alloc(&bcounts, Btk > 0 ? Btk : 1)); SCM_TRY(ws.alloc(&bcnt_local, Btk > 0 ? Btk : 1));
     SCM_TRY(ws.alloc(&dgroup, m));
-    SCM_CUDA(cudaMemsetAsync(gsums, 0, sizeof(double) * Gk * n, st));
     SCM_CUDA(cudaMemsetAsync(gcnt_local, 0, sizeof(int64_t) * Gk, st));
+    SCM_CUDA(cudaMemsetAsync(bcnt_local, 0, sizeof(int64_t) * (Btk > 0 ? Btk : 1), st));
     if (do_fit) {
         SCM_TRY(ws.alloc(&vals, s)); SCM_TRY(ws.alloc(&vecs, (int64_t)s * n)); SCM_TRY(ws.alloc(&sig, s));
         SCM_CUDA(cudaMemcpyAsync(dgroup, a.h_group, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
@@ -332,6 +477,7 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     if (sc) {
         SCM_TRY(ws.alloc(&dbatch, m)); SCM_TRY(ws.alloc(&sd, n)); SCM_TRY(ws.alloc(&inv_sd, n));
         SCM_CUDA(cudaMemcpyAsync(dbatch, a.h_batch, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+        if (stream_mode) { SCM_TRY(ws.alloc(&tb, (int64_t)Btk * n)); SCM_TRY(ws.alloc(&atile, (int64_t)Btk * n)); }
     }
     // The small uploads / memsets above are copy-engine work of the COMPUTE stream.  While its channel still targets the copy
     // engine, its next operation (even an event record) is arbitrated behind every bulk copy of the copy stream: measured with
@@ -340,114 +486,71 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     // (this also makes the pool allocations visible to the copy stream).
     SCM_TRY(zero_async(ctx, flag, 4));
     SCM_CUDA(cudaStreamSynchronize(st));
+    trace.mark(stream_mode ? "allocated (out-of-core: ring of 3 chunk buffers, two passes)" : "allocated (in-core)");
 
-    trace.mark("allocated");
-    // trace mode: device timeline of every chunk (H2D landed / fit work done), relative to the first enqueue
-    std::vector<cudaEvent_t> tl_copy, tl_comp, tl_wait, tl_seg;
-    cudaEvent_t tl_zero = nullptr;
-    if (trace.on) {
-        tl_copy.resize(nchunks); tl_comp.resize(nchunks); tl_wait.resize(nchunks); tl_seg.resize(nchunks);
-        for (int c = 0; c < nchunks; c++) { cudaEventCreate(&tl_copy[c]); cudaEventCreate(&tl_comp[c]); cudaEventCreate(&tl_wait[c]); cudaEventCreate(&tl_seg[c]); }
-        cudaEventCreate(&tl_zero);
-        cudaEventRecord(tl_zero, st);
-    }
-    // ---- upload, with the fit accumulating behind it
-    const bool need_sums = do_fit || a.center_mode == 1;
-    const bool copy_1d = a.ldh == n && ld == n;
-    auto issue_copy = [&](int c) -> int {
-        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-        if (copy_1d) SCM_CUDA(cudaMemcpyAsync(dY + r0 * ld, a.h_Y + r0 * a.ldh, (size_t)rows * n * 8, cudaMemcpyHostToDevice, cs));
-        else SCM_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, a.h_Y + r0 * a.ldh, a.ldh * 8, n * 8, rows, cudaMemcpyHostToDevice, cs));
-        if (trace.on) cudaEventRecord(tl_copy[c], cs);
-        SCM_CUDA(cudaEventRecord(ev[c], cs));
-        return 0;
-    };
-    // pageable source: a helper thread stages chunk by chunk through the page-locked bounce buffers (see above)
-    const bool staged_in = host_is_pageable(a.h_Y);
-    ChunkGate fed;
-    std::thread feeder;
-    HelperJoin feeder_join{feeder, nullptr};
-    if (staged_in) {
-        SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
-        const int nt = host_copy_threads();
-        const int dev = ctx->device;
-        feeder = std::thread([&, nt, dev] {
-            cudaSetDevice(dev);
-            for (int c = 0; c < nchunks; c++) {
-                if (fed.error) return;
-                if (c >= STAGE_NB) SCM_HELPER_CUDA(cudaEventSynchronize(ev[c - STAGE_NB]), fed);  // the slot's previous H2D has finished
-                const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-                double* sb = (double*)ctx->stage_buf[c % STAGE_NB];
-                parallel_copy2d(sb, (size_t)n * 8, a.h_Y + r0 * a.ldh, (size_t)a.ldh * 8, (size_t)n * 8, rows, nt);
-                if (ld == n) SCM_HELPER_CUDA(cudaMemcpyAsync(dY + r0 * ld, sb, (size_t)rows * n * 8, cudaMemcpyHostToDevice, cs), fed);
-                else SCM_HELPER_CUDA(cudaMemcpy2DAsync(dY + r0 * ld, ld * 8, sb, n * 8, n * 8, rows, cudaMemcpyHostToDevice, cs), fed);
-                SCM_HELPER_CUDA(cudaEventRecord(ev[c], cs), fed);
-                fed.publish(c + 1);
-            }
-        });
-        feeder_join.wake = &fed;
-    } else {
-        SCM_TRY(issue_copy(0));
-        if (nchunks > 1) SCM_TRY(issue_copy(1));
-    }
-    for (int c = 0; c < nchunks; c++) {
-        const int64_t r0 = (int64_t)c * rows_per_chunk, rows = (r0 + rows_per_chunk <= m ? rows_per_chunk : m - r0);
-        if (trace.on && c > 0) cudaEventRecord(tl_comp[c - 1], st);
-        // host-mediated hand-over with two bulk copies in flight: chunk c is in HBM when the event has fired, its fit work
-        // is enqueued right away and copy c + 2 joins the queue (the copy engine never idles, the queue never grows)
-        if (staged_in && fed.wait_for(c) != 0) return fail(fed.error, "upload helper: %s", fed.msg);
-        SCM_CUDA(cudaEventSynchronize(ev[c]));
-        if (!staged_in && c + 2 < nchunks) SCM_TRY(issue_copy(c + 2));
-        if (trace.on) cudaEventRecord(tl_wait[c], st);
-        if (!need_sums) continue;
-        {
-            StageTimer t(ctx, ST_SEG);
-            SCM_TRY(seg_colsum(ctx, dY + r0 * ld, rows, n, ld, dgroup + r0, Gk, nullptr, tsums, tcounts, flag));
-            if (trace.on) cudaEventRecord(tl_seg[c], st);
-            add_f64_kernel<<<(unsigned)ceil_div((int64_t)Gk * n, 256), 256, 0, st>>>(gsums, tsums, (int64_t)Gk * n);
-            SCM_LAUNCH_CHECK(ctx);
-            add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcnt_local, tcounts, Gk);
-            SCM_LAUNCH_CHECK(ctx);
-        }
-        if (!do_fit) continue;
-        if (c == 0) {
-            // Gram shift = column mean of this rank's FIRST chunk: known before the second chunk lands, no agreement between
-            // ranks needed (the local Gram is moved to the global mean by a rank-2 update before its all-reduce, fit_core.cuh)
-            first_chunk_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, (double)rows, shift);
-            SCM_LAUNCH_CHECK(ctx);
-        }
-        StageTimer t(ctx, ST_GRAM);
-        SCM_TRY(gram(ctx, dY + r0 * ld, rows, n, ld, shift, Gm, c == nchunks - 1, c > 0));
-    }
-    if (staged_in) {  // every chunk has been published: the helper is done
-        feeder_join.wake = nullptr;
-        feeder.join();
-    }
-    trace.mark("upload + fit chunks enqueued");
-    if (trace.on) {
-        cudaEventRecord(tl_comp[nchunks - 1], st);
-        cudaStreamSynchronize(cs); trace.mark("H2D done"); cudaStreamSynchronize(st); trace.mark("chunk Gram / sums done");
+    auto slot = [&](int c) -> double* { return stream_mode ? dY + (int64_t)(c % RING) * rows_per_chunk * ld : dY + pl.row0(c) * ld; };
+    // ---- pass 1: upload, with the sums and the Gram accumulating behind it
+    if (need_sums || !stream_mode) {
+        Uploader up{ctx, pl, a.h_Y, a.ldh, ctx->copy_stream, staged_in, stream_mode ? RING : 0, 0, STAGE_NB};
+        up.dst.resize(nchunks);
+        for (int c = 0; c < nchunks; c++) up.dst[c] = slot(c);
+        SCM_TRY(up.init());
+        SCM_TRY(up.start());
         for (int c = 0; c < nchunks; c++) {
-            float t_copy = 0.f, t_comp = 0.f, t_wait = 0.f, t_seg = 0.f;
-            cudaEventElapsedTime(&t_copy, tl_zero, tl_copy[c]);
-            cudaEventElapsedTime(&t_comp, tl_zero, tl_comp[c]);
-            cudaEventElapsedTime(&t_wait, tl_zero, tl_wait[c]);
-            if (need_sums) cudaEventElapsedTime(&t_seg, tl_zero, tl_seg[c]);
-            if (c < 6 || c >= nchunks - 3)
-                fprintf(stderr, "[scm_ruv3_host]   chunk %2d: H2D landed %8.2f ms, wait released %8.2f, sums done %8.2f, fit work done %8.2f ms\n", c,
-                        t_copy, t_wait, t_seg, t_comp);
-            cudaEventDestroy(tl_copy[c]); cudaEventDestroy(tl_comp[c]); cudaEventDestroy(tl_wait[c]); cudaEventDestroy(tl_seg[c]);
+            const int64_t r0 = pl.row0(c), rows = pl.rows(c);
+            double* dc = slot(c);
+            // host-mediated hand-over: chunk c is in HBM when wait() returns, its fit work is enqueued right away and the next
+            // copies join the queue (the copy engine never idles, the queue never grows)
+            SCM_TRY(up.wait(c));
+            if (need_sums) {
+                StageTimer t(ctx, ST_SEG);
+                SCM_TRY(seg_colsum(ctx, dc, rows, n, ld, dgroup + r0, Gk, nullptr, tsums, tcounts, flag));
+                add_f64_kernel<<<(unsigned)ceil_div((int64_t)Gk * n, 256), 256, 0, st>>>(gsums, tsums, (int64_t)Gk * n);
+                SCM_LAUNCH_CHECK(ctx);
+                add_i64_kernel<<<(unsigned)ceil_div(Gk, 256), 256, 0, st>>>(gcnt_local, tcounts, Gk);
+                SCM_LAUNCH_CHECK(ctx);
+            }
+            if (do_fit) {
+                if (c == 0) {
+                    // Gram shift = column mean of this rank's FIRST chunk: known before the second chunk lands, no agreement
+                    // between ranks needed (the local Gram is moved to the global mean by a rank-2 update before its all-reduce)
+                    first_chunk_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tsums, Gk, n, (double)rows, shift);
+                    SCM_LAUNCH_CHECK(ctx);
+                    if (sc && stream_mode) {
+                        tile_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(atile, shift, Btk, n);
+                        SCM_LAUNCH_CHECK(ctx);
+                    }
+                }
+                if (sc && stream_mode) {
+                    // standardize2 out of core: batch sums AND squared deviations about the shift in this one pass (the batch means
+                    // they should be taken about do not exist yet; ssq_recentre_kernel moves them afterwards)
+                    StageTimer t(ctx, ST_STD);
+                    SCM_TRY(seg_colsum(ctx, dc, rows, n, ld, dbatch + r0, Btk, nullptr, tb, tcounts, nullptr));
+                    add_f64_kernel<<<(unsigned)ceil_div((int64_t)Btk * n, 256), 256, 0, st>>>(bsums, tb, (int64_t)Btk * n);
+                    SCM_LAUNCH_CHECK(ctx);
+                    add_i64_kernel<<<(unsigned)ceil_div(Btk, 256), 256, 0, st>>>(bcnt_local, tcounts, Btk);
+                    SCM_LAUNCH_CHECK(ctx);
+                    SCM_TRY(seg_colsum(ctx, dc, rows, n, ld, dbatch + r0, Btk, atile, tb, nullptr, nullptr));
+                    add_f64_kernel<<<(unsigned)ceil_div((int64_t)Btk * n, 256), 256, 0, st>>>(ssq, tb, (int64_t)Btk * n);
+                    SCM_LAUNCH_CHECK(ctx);
+                }
+                StageTimer t(ctx, ST_GRAM);
+                SCM_TRY(gram(ctx, dc, rows, n, ld, shift, Gm, c == nchunks - 1, c > 0));
+            }
+            SCM_TRY(up.release(c, st));
         }
-        cudaEventDestroy(tl_zero);
+        SCM_TRY(up.finish());
     }
+    trace.mark("pass 1 enqueued (upload + sums + Gram)");
     int rc = 0;
     scm_coef* coef = nullptr;
     if (need_sums) {
         // all-reduce 1 (one float64 buffer): group sums, batch sums, counts, NA/Inf flag, rows -> global column means
-        if (sc) {  // standardize2, pass 1 over the resident cells (R/scRUVIII.R:163-166)
+        if (sc && !stream_mode) {  // standardize2, pass 1 over the resident cells (R/scRUVIII.R:163-166)
             StageTimer t(ctx, ST_STD);
             SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, Btk, nullptr, bsums, bcnt_local, nullptr));
         }
+        if (sc && stream_mode) SCM_TRY(copy_async(ctx, tb, bsums, sizeof(double) * Btk * n));  // local batch sums, for ssq_finish_kernel
         const int64_t span = n > Gk + Btk ? n : Gk + Btk;
         fit_pack_kernel<<<(unsigned)ceil_div(span, 256), 256, 0, st>>>(gsums, Gk, n, gcnt_local, bcnt_local, Btk, flag, m, shift, cnt_f64, uvec);
         SCM_LAUNCH_CHECK(ctx);
@@ -460,7 +563,12 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
             StageTimer t(ctx, ST_STD);
             groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bsums, bcounts, Btk, n);
             SCM_LAUNCH_CHECK(ctx);
-            SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, Btk, bsums, ssq, nullptr, nullptr));
+            if (stream_mode) {
+                ssq_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ssq, bsums, tb, bcnt_local, Btk, n, shift);
+                SCM_LAUNCH_CHECK(ctx);
+            } else {
+                SCM_TRY(seg_colsum(ctx, dY, m, n, ld, dbatch, Btk, bsums, ssq, nullptr, nullptr));
+            }
         }
         gram_recentre_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)n), 256, 0, st>>>(Gm, n, uvec, dvec, (double)m);
         SCM_LAUNCH_CHECK(ctx);
@@ -500,14 +608,46 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
         int crc = coef_create(ctx, fa, n, kk, dctl, c_center, sc ? inv_sd : nullptr, sc ? sd : nullptr, &coef);
         if (crc != 0) return crc;
     }
+    struct CoefGuard { scm_ctx* c; scm_coef* k; ~CoefGuard() { if (k) coef_destroy(c, k); } } coef_guard{ctx, coef};
     trace.mark("eig + coefficients done");
-    // ---- adjust in place chunk by chunk, each finished chunk goes back to the host while the next is computed
-    {
-        const int arc = adjust_download(ctx, dY, m, n, ld, coef, a.h_out, a.ldo, rows_per_chunk);
-        coef_destroy(ctx, coef);
-        if (arc != 0) return arc;
+    if (!stream_mode) {
+        // ---- in-core: adjust in place chunk by chunk, each finished chunk goes back to the host while the next is computed
+        SCM_TRY(adjust_download(ctx, dY, m, n, ld, coef, a.h_out, a.ldo, rows_per_chunk));
+        trace.mark("adjust + D2H done");
+        return rc;
     }
-    trace.mark("adjust + D2H done");
+    // ---- out-of-core, pass 2: every chunk comes up again, is adjusted in its ring slot and goes home; uploads and downloads run
+    // concurrently on their own streams (and, for pageable buffers, their own halves of the bounce buffers)
+    {
+        Uploader up{ctx, pl, a.h_Y, a.ldh, ctx->copy_stream, staged_in, RING, 0, STAGE_NB / 2};
+        up.dst.resize(nchunks);
+        for (int c = 0; c < nchunks; c++) up.dst[c] = slot(c);
+        Downloader down{ctx, pl, a.h_out, a.ldo, ctx->copy_stream_d2h, staged_out, STAGE_NB / 2, STAGE_NB / 2};
+        std::vector<cudaEvent_t> ev(nchunks);
+        for (auto& e : ev) SCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        struct EvGuard {
+            std::vector<cudaEvent_t>& v;
+            ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
+        } guard{ev};
+        SCM_TRY(up.init());
+        SCM_TRY(down.init());
+        SCM_TRY(up.start());
+        for (int c = 0; c < nchunks; c++) {
+            double* dc = slot(c);
+            SCM_TRY(up.wait(c));
+            {
+                StageTimer t(ctx, ST_ADJUST);
+                SCM_TRY(adjust(ctx, dc, pl.rows(c), n, ld, coef, nullptr, 0, dc, ld, nullptr));
+            }
+            SCM_CUDA(cudaEventRecord(ev[c], st));
+            SCM_TRY(down.push(c, dc, ev[c]));
+            SCM_TRY(up.release(c, ctx->copy_stream_d2h));  // the slot is free once its chunk has left the device
+        }
+        SCM_TRY(up.finish());
+        SCM_TRY(down.finish());
+        SCM_CUDA(cudaStreamSynchronize(st));
+    }
+    trace.mark("pass 2 done (upload + adjust + download)");
     return rc;
 }
 

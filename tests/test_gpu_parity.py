@@ -869,3 +869,51 @@ def test_pageable_and_pinned_host_matrices_give_identical_bits(sm, monkeypatch):
     s = sm.scRUVIII(np.asfortranarray(P["Y"].T), P["types"], P["ctl"], k=5, batch=batch, ctx=ctx)
     refs = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 5, batch)
     assert orc.rel_frobenius(s[5]["newY"], refs[5]["newY"]) < TOL_NEWY
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_out_of_core_host_path_matches_in_core(sm, monkeypatch, pinned):
+    """A host matrix that does not fit the device is streamed twice through three chunk buffers (scm_ruv3_host, out-of-core form:
+    the chunked adjust of R/scMerge2_utilis.R:104-124 for a matrix that lives in host memory).  Forced here with
+    SCM_HOST_STREAM=1 and 13 ragged chunks.  fastRUVIII runs the same kernels on the same chunks in both forms: bit-identical.
+    scRUVIII sums its squared deviations about the shift and re-centres them (no second pass over the cells): oracle parity.
+    Pageable and page-locked buffers (staged / direct copies), in-place host result, adjust-only entry with column means."""
+    monkeypatch.setenv("SCM_HOST_CHUNK_ROWS", "800")
+    P = orc.planted_factors(10_100, 120, 50, 5, n_types=4, n_batch=3, seed=21)
+    ctx = sm.Context(0)
+
+    def buf(a):
+        if not pinned:
+            return np.array(a)
+        b = sm.pinned_empty(a.shape)
+        b[:] = a
+        return b
+    Y = buf(P["Y"])
+    monkeypatch.setenv("SCM_HOST_STREAM", "0")
+    r_in = sm.fastRUVIII(Y, P["types"], P["ctl"], k=5, return_info=True, ctx=ctx, out=buf(np.zeros_like(P["Y"])))
+    monkeypatch.setenv("SCM_HOST_STREAM", "1")
+    r_oc = sm.fastRUVIII(Y, P["types"], P["ctl"], k=5, return_info=True, ctx=ctx, out=buf(np.zeros_like(P["Y"])))
+    np.testing.assert_array_equal(np.asarray(r_in["newY"]), np.asarray(r_oc["newY"]))
+    np.testing.assert_array_equal(np.asarray(r_in["fullalpha"]), np.asarray(r_oc["fullalpha"]))
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 5)
+    assert orc.rel_frobenius(np.asarray(r_oc["newY"]), ref) < TOL_NEWY
+    # in place on the host: the result overwrites the input buffer
+    Yio = buf(P["Y"])
+    sm.fastRUVIII(Yio, P["types"], P["ctl"], k=5, ctx=ctx, out=Yio)
+    np.testing.assert_array_equal(np.asarray(Yio), np.asarray(r_oc["newY"]))
+    # scRUVIII (genes x cells, column-major == cells x genes row-major) with batch statistics taken in the single pass
+    batch = np.array([f"b{b}" for b in P["batch"]])
+    Yt = np.asfortranarray(P["Y"].T) if not pinned else buf(P["Y"]).T
+    s_oc = sm.scRUVIII(Yt, P["types"], P["ctl"], k=5, batch=batch, ctx=ctx)
+    refs = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 5, batch)
+    assert orc.rel_frobenius(s_oc[5]["newY"], refs[5]["newY"]) < TOL_NEWY
+    st = orc.standardize2(P["Y"].T, batch)
+    assert np.allclose(s_oc["stand_mean"], st["stand_mean"], rtol=1e-12, atol=1e-13)
+    assert np.allclose(s_oc["stand_sd"], np.sqrt(st["stand_var"]), rtol=1e-10)
+    # adjust-only with column means accumulated during pass 1 (pseudoRUVIII / getAdjustedMat) and without any sums (fullalpha re-use)
+    fa = np.asarray(r_oc["fullalpha"])
+    a1 = sm.pseudoRUVIII(Y, P["Y"][:40], P["types"][:40], P["ctl"], k=5, fullalpha=fa, ctx=ctx)
+    ref1 = orc.pseudoRUVIII(P["Y"], P["Y"][:40], P["types"][:40], orc.tological(P["ctl"], 120), 5, fullalpha=fa)
+    assert orc.rel_frobenius(a1, ref1["newY"]) < TOL_NEWY
+    a0 = sm.fastRUVIII(Y, P["types"], P["ctl"], k=5, fullalpha=fa, ctx=ctx)
+    np.testing.assert_array_equal(np.asarray(a0), np.asarray(r_oc["newY"]))
