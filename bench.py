@@ -69,14 +69,15 @@ def parse():
                    help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] as the headline of this run")
     p.add_argument("--density", type=float, default=0.1, help="scmerge2: fraction of non-zero entries of the sparse expression matrix")
     p.add_argument("--dense-input", action="store_true", help="scmerge2 workload: dense device matrix instead of the sparse one")
-    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k | all | none")
+    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k,out_of_core | all | none")
+    p.add_argument("--ooc-cells", type=int, default=2_000_000, help="out_of_core extra: cells of the host matrix (x 3000 genes; 4000000 = BASELINE configs[3] on ONE GPU, needs ~100 GB of host RAM)")
     p.add_argument("--transport", default="nccl", choices=["nccl", "hook"], help="cross-rank sums: the library's NCCL communicator or the torch hook")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-parity", action="store_true")
     a = p.parse_args()
     ex = a.extras.lower()
-    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k"} if ex == "all" else set(ex.split(",")))
+    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k", "out_of_core"} if ex == "all" else set(ex.split(",")))
     return a
 
 
@@ -679,6 +680,46 @@ def run_ours(a):
                     "adjust_hbm_frac": by / (adj * 1e-3) * 1e-9 / hbm if adj > 0 else None, "adjust_algorithmic": "12*nnz read + 8*m*n written"}
         if world == 1:
             guarded("scmerge2", x_scm2)
+
+        def x_ooc():
+            """BASELINE configs[3]'s shape on ONE GPU through the host call: the matrix lives in (pageable) host memory, is
+            streamed twice through three chunk buffers and adjusted in place on the host."""
+            mo, go, co = a.ooc_cells, 3000, 500
+            need = mo * go * 8
+            avail = 0
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) * 1024
+            if avail < 1.6 * need + (8 << 30):
+                return {"skipped": f"host has {avail / 2**30:.0f} GiB available, the {need / 2**30:.0f} GiB matrix needs head-room"}
+            Yh = np.empty((mo, go))
+            keys_o = np.empty(mo, dtype=np.int32)
+            ctl_o = None
+            step_rows = 200_000
+            for r0 in range(0, mo, step_rows):  # generated on the device block by block (same generator, block index as the "rank")
+                r1 = min(mo, r0 + step_rows)
+                dYb, kb, ctl_o, _ = make_data(a, ctx, 1000 + r0 // step_rows, torch, r1 - r0, n=go, c=co)
+                dYb.to_host(Yh[r0:r1])
+                keys_o[r0:r1] = kb
+                dYb.free()
+            ctx.release_scratch()
+            os.environ["SCM_HOST_STREAM"] = "1"
+            try:
+                t0 = time.perf_counter()
+                res = sm.fastRUVIII(Yh, keys_o, ctl_o, k=20, return_info=True, ctx=ctx, out=Yh)
+                t1 = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                sm.fastRUVIII(Yh, keys_o, ctl_o, k=20, ctx=ctx, out=Yh, fullalpha=res["fullalpha"])  # second call: warm bounce buffers
+                t2 = time.perf_counter() - t0
+            finally:
+                os.environ.pop("SCM_HOST_STREAM", None)
+            return {"workload": f"fastRUVIII {mo} cells x {go} genes ({need / 1e9:.0f} GB) held in PAGEABLE host memory, one B200, out-of-core form "
+                                f"(3 chunk buffers on the device, matrix streamed twice, result written in place on the host)",
+                    "fit_and_adjust_s": t1, "cells_per_s": mo / t1, "pcie_bytes": 3 * need, "effective_gb_s": 3 * need / t1 * 1e-9,
+                    "adjust_only_s": t2, "adjust_only_effective_gb_s": 2 * need / t2 * 1e-9, "fit": ctx.fit_info(),
+                    "conv_rank": int(res["fullalpha"].conv_rank), "device_bytes_for_cells": 3 * 512 * 2**20}
+        if world == 1:
+            guarded("out_of_core", x_ooc)
 
     if rank == 0:
         m = m_local
