@@ -239,16 +239,20 @@ inline int coef_from_factors(scm_ctx* ctx, const double* d_B, const double* d_A,
 }
 
 // ---- K6 ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load4(const double* __restrict__ rowp, int64_t g0, int64_t n, bool vec, bool rowok, double (&v)[4]) {
+// `nc`: the matrix is not written by this kernel, so it may be read through the non-coherent path (ld.global.nc, streaming).  An
+// IN-PLACE adjust (out == Y) must use ordinary loads: PTX leaves ld.global.nc undefined for locations the kernel also writes.
+__device__ __forceinline__ void load4(const double* rowp, int64_t g0, int64_t n, bool vec, bool rowok, bool nc, double (&v)[4]) {
     if (rowok && vec && g0 + 3 < n) {
-        const double2 a = ldg_stream2(rowp + g0), b = ldg_stream2(rowp + g0 + 2);
+        double2 a, b;
+        if (nc) { a = ldg_stream2(rowp + g0); b = ldg_stream2(rowp + g0 + 2); }
+        else { a = *reinterpret_cast<const double2*>(rowp + g0); b = *reinterpret_cast<const double2*>(rowp + g0 + 2); }
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (rowok && g0 + j < n) ? __ldg(rowp + g0 + j) : 0.0;
+        for (int j = 0; j < 4; j++) v[j] = (rowok && g0 + j < n) ? (nc ? __ldg(rowp + g0 + j) : rowp[g0 + j]) : 0.0;
     }
 }
-__device__ __forceinline__ void store4(double* __restrict__ rowp, int64_t g0, int64_t n, bool vec, bool rowok, const double (&v)[4]) {
+__device__ __forceinline__ void store4(double* rowp, int64_t g0, int64_t n, bool vec, bool rowok, const double (&v)[4]) {
     if (!rowok) return;
     if (vec && g0 + 3 < n) {
         stg_stream2(rowp + g0, make_double2(v[0], v[1]));
@@ -267,9 +271,9 @@ constexpr int ADJ_WARPS = 4;
 // loads in flight while it computes on the previous one (explicit double buffering: ya / yb).
 template <int KT, int MT, bool PASS_B>
 __global__ void __launch_bounds__(ADJ_WARPS * 32, (KT <= 3) ? 3 : 2)
-adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, const double* __restrict__ Bfrag,
+adjust_kernel(const double* Y /* may alias out */, int64_t m, int64_t n, int64_t ld, const double* __restrict__ Bfrag,
               const double* __restrict__ Afrag, const double* __restrict__ w0, const int32_t* __restrict__ ctl_blocks,
-              int nblk_ctl, int nblk, int k, double* __restrict__ out, int64_t ldo, double* __restrict__ Wout, int vec_in, int vec_out) {
+              int nblk_ctl, int nblk, int k, double* out, int64_t ldo, double* __restrict__ Wout, int vec_in, int vec_out, int nc) {
     __shared__ double s_part[ADJ_WARPS][MT * KT * 2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
@@ -285,7 +289,7 @@ adjust_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t ld, co
     auto load_block = [&](double (&y)[MT][4], int gb) {
         const int64_t g0 = (int64_t)gb * 16 + 4 * tig;
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) load4(rowp[mt], g0, n, vec_in, rowok[mt], y[mt]);
+        for (int mt = 0; mt < MT; mt++) load4(rowp[mt], g0, n, vec_in, rowok[mt], nc != 0, y[mt]);
     };
     // ---- pass A: partial W over this warp's control-gene blocks
     double w[MT][KT][2];
@@ -416,12 +420,13 @@ inline int adjust_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, 
     const int vec_out = pass_b ? ((ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0)) : 0;
     const int64_t rows_per_cta = 8 * MT;
     const unsigned grid = (unsigned)ceil_div(m, rows_per_cta);
+    const int nc = (d_out == nullptr || (const double*)d_out != d_Y) ? 1 : 0;  // in place: ordinary loads (see load4)
     if (pass_b)
         adjust_kernel<KT, MT, true><<<grid, ADJ_WARPS * 32, 0, ctx->stream>>>(d_Y, m, n, ld, c->Bfrag, c->Afrag, c->w0, c->ctl_blocks,
-                                                                             c->nblk_ctl, c->nblk, c->k, d_out, ldo, d_W, vec_in, vec_out);
+                                                                             c->nblk_ctl, c->nblk, c->k, d_out, ldo, d_W, vec_in, vec_out, nc);
     else
         adjust_kernel<KT, MT, false><<<grid, ADJ_WARPS * 32, 0, ctx->stream>>>(d_Y, m, n, ld, c->Bfrag, c->Afrag, c->w0, c->ctl_blocks,
-                                                                              c->nblk_ctl, c->nblk, c->k, d_out, ldo, d_W, vec_in, vec_out);
+                                                                              c->nblk_ctl, c->nblk, c->k, d_out, ldo, d_W, vec_in, vec_out, nc);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -62,6 +62,7 @@ struct scm_ctx {
     bool use_tma = true;         // Gram: TMA + mbarrier kernel (false: cp.async kernel; env SCM_GRAM_TMA=0)
     bool gram_preshift = true;   // fits run the Gram on a pre-shifted copy of the cells when there is room (env SCM_GRAM_PRESHIFT=0: off)
     int gram_lean = 3;           // Gram TMA kernel: bit 0 thin last tile row, bit 1 triangular diagonal units (env SCM_GRAM_LEAN)
+    bool gram_class_order = true;  // Gram TMA kernel: class-ordered unit list (env SCM_GRAM_ORDER=0: split-major list)
     bool k1_fused_copy = true;   // the pre-shifted copy is written by K1's summing pass (env SCM_K1_FUSED_COPY=0: separate copy kernel)
     double* h_pinned = nullptr;  // small pinned staging area (scalars read back by the eigensolver)
     // page-locked bounce buffers of the host drivers for callers whose matrices are ordinary pageable memory (R's REAL(),

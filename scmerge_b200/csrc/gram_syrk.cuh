@@ -258,7 +258,7 @@ __global__ void group_dev_kernel(const double* __restrict__ sums, const int64_t*
 }
 
 // TMA + mbarrier variant (gram_tma.cuh): returns 1 when not applicable
-inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift,
+inline int gram_tma_launch(scm_ctx* ctx, Scratch& ws, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift,
                            const GramPlan& p, double* partial);
 
 inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift, double* d_gram,
@@ -278,7 +278,7 @@ inline int gram(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t l
     SCM_TRY(ws.alloc(&partial, (int64_t)p.S * p.T * GR_BT * GR_BT));
     const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
     if (timed) cudaEventRecord(ctx->ev0[ST_SYRK], st);
-    const int tma_rc = ctx->use_tma ? gram_tma_launch(ctx, d_Y, m, n, ld, d_shift, p, partial) : 1;
+    const int tma_rc = ctx->use_tma ? gram_tma_launch(ctx, ws, d_Y, m, n, ld, d_shift, p, partial) : 1;
     if (tma_rc < 0) return tma_rc;
     if (tma_rc == 0) { /* launched on the TMA path */ }
     else if (vec2)

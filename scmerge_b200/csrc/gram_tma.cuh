@@ -162,21 +162,54 @@ __device__ __forceinline__ void gram_chunk_diag(const uint8_t* __restrict__ sa, 
     }
 }
 
-// Unit order: CTA c executes units c, c + grid, ... of the split-major list (tiles of a split in triangular order), so the
-// unit classes (full / thin / diagonal) are interleaved.  With the lean units CTAs drift up to ~1.5 units apart, the cells of a
-// split are no longer shared through L2 and the DRAM traffic of the kernel is 155 GB at 1M x 2000 (10x the algorithmic 16 GB,
-// 14 % of the HBM bandwidth; 50 GB with full units only).  A class-ordered list ([all full] ++ [thin] ++ [diagonal], each
-// split-major: nobody drifts) brought the traffic back to 61 GB (ncu r01g) but was 1.4 % slower; that build also carried 60
-// bytes of register spills from the extra decode state (the consumer warps already fill their 232 registers: 128
-// accumulators + fragments + shifts + addressing), so the comparison is not clean and the simpler order stays.
+// Unit order.  CTA c executes units c, c + grid, ... of a unit LIST.  With the split-major list (tiles of a split in triangular
+// order) the unit classes (full / thin / diagonal) are interleaved: the lean units are cheaper than the full ones, CTAs drift
+// up to ~1.5 units apart, the cells of a split are no longer shared through L2 and the DRAM traffic of the kernel is 165 GB at
+// 1M x 2000 (10x the algorithmic 16 GB; 50 GB with full units only).  The list is therefore CLASS-ORDERED: [all full units]
+// ++ [all thin] ++ [all diagonal], each split-major, so that the CTAs of a wave run units of equal cost on (nearly) the same
+// cells and stay in step.  The list is a TABLE in global memory (gram_units_kernel, (split, tile) per entry): producer and
+// consumers read their entry with one load where they used to divide by T, so the order costs no registers (round 1 computed
+// the class-ordered mapping arithmetically in the consumer warps, which already fill their 232 registers, and spilled 60 bytes).
 // 3 warpgroups: 8 consumer warps (setmaxnreg.inc -> 232 registers) + one producer warpgroup (setmaxnreg.dec -> 40;
 // only its first lane works).  232 * 256 + 40 * 128 = 64512 <= 65536 registers.
 constexpr int GT_THREADS = 384;
 
+// Builds the class-ordered unit list (see "Unit order" above).  One CTA: tiles are classified once, then every thread fills its
+// share of the S * T entries.  `lean` as in the kernel: bit 0 thin last tile row, bit 1 triangular diagonal units.
+__global__ void __launch_bounds__(256)
+gram_units_kernel(int ntile, int T, int S, int na_last, int lean, int2* __restrict__ list) {
+    __shared__ int s_tile[3][1024];  // tiles of class 0 full / 1 thin / 2 diagonal, in triangular order
+    __shared__ int s_cnt[3];
+    if (threadIdx.x == 0) {
+        int c[3] = {0, 0, 0};
+        for (int t = 0; t < T && t < 1024; t++) {
+            int ti, tj;
+            tri_decode(t, ti, tj);
+            int cls = 0;
+            if ((lean & 2) && ti == tj) cls = 2;
+            else if ((lean & 1) && ti != tj && ti == ntile - 1 && na_last <= GT_THIN_NA) cls = 1;
+            s_tile[cls][c[cls]++] = t;
+        }
+        s_cnt[0] = c[0]; s_cnt[1] = c[1]; s_cnt[2] = c[2];
+    }
+    __syncthreads();
+    const int n0 = s_cnt[0], n1 = s_cnt[1], n2 = s_cnt[2];
+    const int64_t total = (int64_t)S * T;
+    for (int64_t p = threadIdx.x; p < total; p += blockDim.x) {
+        int cls, off;
+        if (p < (int64_t)S * n0) { cls = 0; off = (int)p; }
+        else if (p < (int64_t)S * (n0 + n1)) { cls = 1; off = (int)(p - (int64_t)S * n0); }
+        else { cls = 2; off = (int)(p - (int64_t)S * (n0 + n1)); }
+        const int nc = cls == 0 ? n0 : (cls == 1 ? n1 : n2);
+        list[p] = make_int2(off / nc, s_tile[cls][off % nc]);
+    }
+}
+
 template <bool SHIFT>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, const double* __restrict__ shift, int T, int S,
-                int64_t rows_per_split, double* __restrict__ partial, int ntile, int na_last, int lean) {
+                int64_t rows_per_split, double* __restrict__ partial, int ntile, int na_last, int lean,
+                const int2* __restrict__ unit_list) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment.  By pointer arithmetic the compiler keeps the shared address space and emits LDS; through uintptr_t it
     // emits generic LD.E.  Measured on the SHIFT = true variant: generic 130.9 ms, LDS 132.6 ms (different instruction
@@ -209,9 +242,10 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
         if (tid != 256) return;
         uint32_t gl = 0;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int split = (int)(u / T);
+            const int2 ud = unit_list ? unit_list[u] : make_int2((int)(u / T), (int)(u % T));  // (split, tile): see gram_units_kernel
+            const int split = ud.x;
             int ti, tj;
-            tri_decode((int)(u % T), ti, tj);
+            tri_decode(ud.y, ti, tj);
             const bool diag = (ti == tj);
             const int64_t row_begin = (int64_t)split * rows_per_split;
             const int64_t row_end = min(m, row_begin + rows_per_split);
@@ -238,15 +272,16 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t m, int64_t n, 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     uint32_t gu = 0;  // chunks consumed so far by this CTA
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const int split = (int)(u / T);
+        const int2 ud = unit_list ? unit_list[u] : make_int2((int)(u / T), (int)(u % T));
+        const int split = ud.x;
         int ti, tj;
-        tri_decode((int)(u % T), ti, tj);
+        tri_decode(ud.y, ti, tj);
         const bool diag = (ti == tj);
         const int64_t row_begin = (int64_t)split * rows_per_split;
         const int64_t row_end = min(m, row_begin + rows_per_split);
         const int nchunk = row_end > row_begin ? (int)ceil_div(row_end - row_begin, GT_KC) : 0;
         const int colA0 = ti * GR_BT, colB0 = tj * GR_BT;
-        double* out = partial + ((int64_t)split * T + (u % T)) * (GR_BT * GR_BT);
+        double* out = partial + ((int64_t)split * T + ud.y) * (GR_BT * GR_BT);
         const bool last_row = ti == ntile - 1;
         auto shift_at = [&](int64_t g) -> double { return (SHIFT && shift && g < n) ? shift[g] : 0.0; };
         if ((lean & 2) && diag) {
@@ -351,7 +386,7 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // Returns 1 when the TMA path is not applicable (caller falls back to the cp.async kernel), 0 on success, <0 on error.
-inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift,
+inline int gram_tma_launch(scm_ctx* ctx, Scratch& ws, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_shift,
                            const GramPlan& p, double* partial) {
     if (ld % 2 != 0 || ((uintptr_t)d_Y) % 16 != 0 || m >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31)) return 1;
     PFN_tmapEncodeTiled enc = tmap_encoder();
@@ -367,12 +402,19 @@ inline int gram_tma_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n
     SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));   // per device
     SCM_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
     const int valid_last = (int)(n - (int64_t)(p.ntile - 1) * GR_BT);
+    const int na_last = (valid_last + 7) / 8;
+    int2* units = nullptr;
+    if (ctx->gram_class_order && ctx->gram_lean && p.T <= 1024 && p.S > 1) {
+        SCM_TRY(ws.alloc(&units, (int64_t)p.S * p.T));
+        gram_units_kernel<<<1, 256, 0, ctx->stream>>>(p.ntile, p.T, p.S, na_last, ctx->gram_lean, units);
+        SCM_LAUNCH_CHECK(ctx);
+    }
     if (d_shift)
         gram_tma_kernel<true><<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, d_shift, p.T, p.S, p.rows_per_split, partial,
-                                                                                  p.ntile, (valid_last + 7) / 8, ctx->gram_lean);
+                                                                                  p.ntile, na_last, ctx->gram_lean, units);
     else
         gram_tma_kernel<false><<<p.grid, GT_THREADS, GT_SMEM_BYTES, ctx->stream>>>(tmap, m, n, nullptr, p.T, p.S, p.rows_per_split, partial,
-                                                                                   p.ntile, (valid_last + 7) / 8, ctx->gram_lean);
+                                                                                   p.ntile, na_last, ctx->gram_lean, units);
     return 0;
 }
 

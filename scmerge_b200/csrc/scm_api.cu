@@ -187,6 +187,7 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SCM_GRAM_TMA")) c->use_tma = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_LEAN")) c->gram_lean = atoi(e) & 3;
+    if (const char* e = getenv("SCM_GRAM_ORDER")) c->gram_class_order = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_PRESHIFT")) c->gram_preshift = (e[0] != '0');
     if (const char* e = getenv("SCM_K1_FUSED_COPY")) c->k1_fused_copy = (e[0] != '0');
     if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }

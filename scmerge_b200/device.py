@@ -107,8 +107,7 @@ class Context:
         if arr.dtype not in (np.dtype(np.float64), np.dtype(np.int64)):
             raise TypeError("all-reduce supports float64 and int64")
         L.check(L.lib().scm_allreduce_sum(self._h, arr.ptr, int(np.prod(arr.shape, dtype=np.int64)),
-                                          0 if arr.dtype == np.dtype(np.float64) else 1))
-        self.sync()
+                                          0 if arr.dtype == np.dtype(np.float64) else 1))  # enqueued on the context's stream: reads after it are ordered
 
     def allgather_bytes(self, payload: bytes) -> list:
         """Every rank's byte string, in rank order, through the sum all-reduce (one-hot slices of a zero buffer).  Small

@@ -86,6 +86,10 @@ def _total_cells(ctx, m_local: int) -> int:
     """Cells over ALL ranks that share them (the m of the reference's formulas: svd_k rule, early-out, PCA rank)."""
     if ctx is None or ctx.world <= 1:
         return int(m_local)
+    cached = getattr(ctx, "_m_total_once", None)  # left by _global_int_keys of the same call (one-shot: every rank takes the same path)
+    ctx._m_total_once = None
+    if cached is not None and cached[0] == int(m_local):
+        return cached[1]
     return int(_rank_table(ctx, [m_local])[:, 0].sum())
 
 
@@ -110,6 +114,7 @@ def _global_int_keys(ctx, a: np.ndarray, spare):
     lo, hi = (int(a.min()), int(a.max())) if m else (2 ** 62, -1)
     tab = _rank_table(ctx, [m, lo, hi])
     m_tot, lo, hi = int(tab[:, 0].sum()), int(tab[:, 1].min()), int(tab[:, 2].max())
+    ctx._m_total_once = (int(m), m_tot)  # saves _total_cells its own round trip
     if hi < 0:
         return a.astype(np.int32, copy=False), 0
     if lo < 0 or hi >= 4 * m_tot + 1024:
