@@ -1,7 +1,7 @@
 // K4: top-s eigenpairs of the n x n symmetric PSD Gram by block subspace iteration.
 //
 //   X <- orth(random n x l)                                   l = s + oversampling (<= SCM_MAX_BLOCK)
-//   X <- orth(G X)                                            one product before the first Rayleigh-Ritz step (EXACT), two (RANDOMIZED)
+//   X <- orth(G X), twice                                     two products before the first Rayleigh-Ritz step (both modes)
 //   repeat:  Z = G X ; H = X'Z ; (Q, theta) = eig(H)          Rayleigh-Ritz, single-CTA one-sided Jacobi
 //            W = Z Q ; V = X Q ; r_i = ||W_i - theta_i V_i||   true residuals of the Ritz pairs
 //            stop when ||R_kconv||_F / (theta_kconv - theta_kconv+1) <= tol (EXACT; Davis-Kahan bound on the
@@ -642,16 +642,24 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
                     const int64_t* d_nonfinite = nullptr) {
     if (n <= 0 || s <= 0 || s > n) return fail(SCM_ERR_INVALID, "eig_topk: bad n=%lld s=%d", (long long)n, s);
     if (n >= (int64_t)1 << 30) return fail(SCM_ERR_UNSUPPORTED, "eig_topk: n too large");
+    if (kconv <= 0 || kconv > s) kconv = s;
+    int kmax = kconv;  // the largest rank that has to CONVERGE (scRUVIII with several ruvK lists more)
+    for (int q = 0; q < ctx->n_conv_ranks; q++) { const int kq = ctx->conv_ranks[q] < s ? ctx->conv_ranks[q] : s; kmax = kmax > kq ? kmax : kq; }
     int l;
     if (mode == SCM_MODE_RANDOMIZED) l = s + 10;  // rsvd oversampling p = 10
-    else l = s + (s / 2 > 16 ? s / 2 : 16);
+    else {
+        // Oversampling serves the ranks that must converge (rate lambda_{l+1} / lambda_kmax), not the s rows that are returned:
+        // the block is kmax + max(kmax / 2, 16) columns, at least s + 8.  For s = 50, k = 20 that is 64 columns instead of the
+        // 80 of round 1: every l x l kernel of the iteration (Jacobi above all) shrinks with it.
+        const int over = kmax + (kmax / 2 > 16 ? kmax / 2 : 16);
+        l = over > s + 8 ? over : s + 8;
+    }
     l = (l + 7) & ~7;
     if (l > n) l = (int)n;
     if (l > SCM_MAX_BLOCK) {
         if (s + 8 <= SCM_MAX_BLOCK) l = SCM_MAX_BLOCK;
         else return fail(SCM_ERR_UNSUPPORTED, "eig_topk: s=%d needs a subspace block > %d (not implemented on the device path)", s, SCM_MAX_BLOCK);
     }
-    if (kconv <= 0 || kconv > s) kconv = s;
     if (tol <= 0) tol = 1e-10;
     if (maxit <= 0) maxit = 300;
     cudaStream_t st = ctx->stream;
@@ -672,9 +680,7 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
     }
     const int fixed_iters = (mode == SCM_MODE_RANDOMIZED) ? 1 : 0;  // rsvd: the three products are done before the single Rayleigh-Ritz step
     const int* skip = reinterpret_cast<const int*>(ctl);
-    int ktop = 0;  // leading columns the warm-started Jacobi solves to full accuracy: the largest rank to converge + a guard band
-    for (int q = 0; q < ranks.n; q++) ktop = ktop > ranks.k[q] ? ktop : ranks.k[q];
-    ktop = ktop + 8 < l ? ktop + 8 : l;
+    const int ktop = kmax + 8 < l ? kmax + 8 : l;  // leading columns of the experimental bulk tolerance (see jacobi_eig_kernel)
     EigCtl* h = reinterpret_cast<EigCtl*>(ctx->h_pinned);
     static_assert(sizeof(EigCtl) <= sizeof(double) * 4096, "control block must fit the pinned staging area");
     const bool debug = getenv("SCM_DEBUG_EIG") != nullptr;
@@ -696,7 +702,10 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
         randn_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, st>>>(X, nl, seed * 0x9E3779B97F4A7C15ull + 12345);
         SCM_LAUNCH_CHECK(ctx);
         SCM_TRY(cholqr2(ctx, X, X, n, l, S, Linv, flag, nullptr, ctl->skip2, &ctl->pass1_only));
-        int pre = safe ? 0 : (mode == SCM_MODE_RANDOMIZED ? 2 : 1);
+        // products before the first Rayleigh-Ritz step: a product + CholeskyQR2 costs ~0.2 ms at n = 2000, l = 64, a Rayleigh-Ritz
+        // step ~0.65 ms (Jacobi 0.45).  With two of them the 1M x 2000 bench problem converges at the SECOND step (one gave three
+        // steps with the 64-column block; the 80-column block of round 1 needed two steps but pays 25 % more per l x l kernel).
+        int pre = safe ? 0 : 2;
         if (mode == SCM_MODE_RANDOMIZED && safe) pre = 2;  // rsvd's semantics are three products, whatever the conditioning
         for (int j = 0; j < pre; j++) {
             SCM_TRY(gemm(ctx, (int)n, l, (int)n, 1.0, rowmajor(d_gram, n), rowmajor(X, l), 0.0, Z, l, skip));
