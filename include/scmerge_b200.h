@@ -299,6 +299,35 @@ int scm_ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
                  double tol, int32_t maxit, uint64_t seed, double* d_alpha, double* d_center, double* d_sigma, scm_coef** coef_out,
                  int32_t* iters_out, double* resid_out);
 
+/* ---- replicate-finding numerics of scReplicate ----------------------------------------------------
+ * What is arithmetic in R/scReplicate.R once kmeans / igraph (out of scope, they stay R) are taken away.
+ *   scm_gather            out[i, j] = Y[rows[i], cols[j]] (NULL = identity): exprs_mat[HVG_list[[j]], batch == batch_list[j]]
+ *                         (R/scReplicate.R:398-404,808-811)
+ *   scm_group_median      med[g, j] = median over the cells with key g of X[:, j] (G x n; NaN for an empty group, NaNs ignored):
+ *                         DelayedMatrixStats::rowMedians per cluster in centroidDist (R/scReplicate.R:459).  Keys on the host AND
+ *                         on the device (the segment layout is index plumbing built on the host)
+ *   scm_sqdist_to_center  dist[i] = sum_j (X[i, j] - center[key_i, j])^2: colSums((exprs_mat - centroid_batch)^2) (R/scReplicate.R:460)
+ *   scm_pair_dist         D[i, j] = distance between row i of A and row j of B; metric 0 Euclidean (proxyC::dist), 1 one minus
+ *                         cosine, 2 one minus Pearson correlation (proxyC::simil): compute_dist_mat (R/scReplicate.R:470-490,497-505).
+ *                         Inner products on the FP64 DMMA GEMM; a zero / constant row gives NaN like the reference's 0 / 0
+ *   scm_block_median      h_med[bi * K2 + bj] = median(D[rows of cluster bi, columns of cluster bj], na.rm = TRUE) with the rows /
+ *                         columns of D ordered by cluster (offsets on the host): compute_dist_res (R/scReplicate.R:507-513)
+ *   scm_centred_gram      centred Gram sum (y - ybar)(y - ybar)' and column means of ALL cells (cross-rank like scm_ruv3_fit): with
+ *                         scm_pca_scores(coef = NULL) this is BiocSingular::runPCA(x, rank = 10, scale = TRUE, center = TRUE)$x of
+ *                         computePCA_byHVGMarker (R/scReplicate.R:793-819) and of the kmeans input (:392-395) */
+int scm_gather(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_rows, int64_t msub,
+               const int32_t* d_cols, int64_t nsub, double* d_out, int64_t ldo);
+int scm_group_median(scm_ctx* ctx, const double* d_X, int64_t m, int64_t n, int64_t ld, const int32_t* h_key, const int32_t* d_key,
+                     int32_t G, double* d_med);
+int scm_sqdist_to_center(scm_ctx* ctx, const double* d_X, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,
+                         const double* d_center, double* d_dist);
+int scm_pair_dist(scm_ctx* ctx, const double* d_A, int64_t m1, int64_t lda, const double* d_B, int64_t m2, int64_t ldb, int64_t n,
+                  int metric, double* d_D, int64_t ldd);
+int scm_block_median(scm_ctx* ctx, const double* d_D, int64_t ldd, const int64_t* h_row_off, int32_t K1, const int64_t* h_col_off,
+                     int32_t K2, double* h_med);
+int scm_centred_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, double* d_gram, double* d_colmean,
+                     int64_t* m_total_out);
+
 /* scm_ruv3_host: the whole closure on HOST matrices (what `.Call` hands over), with the PCIe copies overlapped with
  * the kernels: Y is uploaded in row chunks on a copy stream while the replicate sums and the Gram accumulate behind
  * it, then the adjust kernel runs chunk by chunk in place and every finished chunk is downloaded while the next is

@@ -508,3 +508,60 @@ def scmerge2_core(exprs_genes_x_cells, batch, clust, which, ctl=None, ruvK=20, k
     res = pseudoRUVIII(X.T, Yp, np.array(rep), ctl, ruvK, exact=exact, rng=rng)
     res["bulkExprs"], res["names"] = Yp, names
     return res
+
+
+# ---- replicate-finding numerics of scReplicate (the clustering / graph logic around them stays R) ------
+def centroid_dist(exprs_mat):
+    """centroidDist, R/scReplicate.R:458-464.  exprs_mat: genes x cells of ONE cluster.  Per-gene median (rowMedians), squared
+    distance of every cell to that centroid, rank(point_dist) / length (rank(): ties get their average rank)."""
+    from scipy.stats import rankdata
+    X = np.asarray(exprs_mat, dtype=np.float64)
+    centroid = np.median(X, axis=1)
+    point_dist = ((X - centroid[:, None]) ** 2).sum(axis=0)
+    point_rank = rankdata(point_dist, method="average")
+    return point_rank / point_rank.shape[0]
+
+
+def pair_dist_mat(mat1, mat2, dist="cor"):
+    """compute_dist_mat, R/scReplicate.R:470-490.  mat1 / mat2: genes x cells.  proxyC (un-vendored) published definitions:
+    simil(method = "cosine" | "correlation") between the cells (rows of t(mat)) -> 1 - similarity; dist() = Euclidean."""
+    A, B = np.asarray(mat1, dtype=np.float64).T, np.asarray(mat2, dtype=np.float64).T
+    if dist in ("cosine", "cor"):
+        if dist == "cor":
+            A, B = A - A.mean(axis=1, keepdims=True), B - B.mean(axis=1, keepdims=True)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            A = A / np.sqrt((A * A).sum(axis=1, keepdims=True))
+            B = B / np.sqrt((B * B).sum(axis=1, keepdims=True))
+        return 1.0 - A @ B.T
+    out = np.empty((A.shape[0], B.shape[0]))
+    for r0 in range(0, A.shape[0], 256):
+        diff = A[r0:r0 + 256, None, :] - B[None, :, :]
+        out[r0:r0 + 256] = np.sqrt((diff * diff).sum(axis=2))
+    return out
+
+
+def compute_dist_res(exprs_mat, cells1, res1, cells2, res2, dist="cor"):
+    """compute_dist_res, R/scReplicate.R:493-520.  cells1 / cells2: column indices of the two batches' cells, res1 / res2: their
+    cluster ids 1..K.  dist_res[i, j] = median(dist_mat[res1 == i, res2 == j], na.rm = TRUE), a max(res1) x max(res2) matrix."""
+    X = np.asarray(exprs_mat, dtype=np.float64)
+    res1, res2 = np.asarray(res1), np.asarray(res2)
+    D = pair_dist_mat(X[:, cells1], X[:, cells2], dist)
+    K1, K2 = int(res1.max()), int(res2.max())
+    out = np.full((K1, K2), np.nan)
+    for i in range(1, K1 + 1):
+        for j in range(1, K2 + 1):
+            blk = D[np.ix_(res1 == i, res2 == j)]
+            blk = blk[~np.isnan(blk)]
+            if blk.size:
+                out[i - 1, j - 1] = np.median(blk)
+    return out
+
+
+def run_pca_scores(x, rank=10):
+    """BiocSingular::runPCA(x, rank, scale = TRUE, center = TRUE, BSPARAM = ExactParam())$x (R/scReplicate.R:813-815): scores U D
+    of the column-centred, unit-variance (n - 1 denominator) cells x genes matrix; columns are defined up to sign."""
+    X = np.asarray(x, dtype=np.float64)
+    Xs = (X - X.mean(axis=0)) / X.std(axis=0, ddof=1)
+    U, S, _ = np.linalg.svd(Xs, full_matrices=False)
+    r = min(rank, S.shape[0])
+    return U[:, :r] * S[:r]

@@ -2,7 +2,8 @@
 ## pseudoRUVIII; getAdjustedMat for return_matrix = FALSE) resolve these closures in scMerge's own namespace, so replacing the
 ## bindings there makes the unmodified drivers run the B200 path.  useB200(FALSE) restores the originals.
 .saved <- new.env(parent = emptyenv())
-.closures <- c("fastRUVIII", "scRUVIII", "pseudoRUVIII", "getAdjustedMat", "scRUVg")
+.closures <- c("fastRUVIII", "scRUVIII", "pseudoRUVIII", "getAdjustedMat", "scRUVg",
+               "centroidDist", "compute_dist_mat", "compute_dist_res", "computePCA_byHVGMarker")   # scReplicate's arithmetic helpers
 
 useB200 <- function(on = TRUE) {
   if (!requireNamespace("scMerge", quietly = TRUE)) stop("scMerge is not installed")

@@ -365,7 +365,70 @@ SEXP scm_csc_adjust_(SEXP cp, SEXP alpha, SEXP k_, SEXP ctl, SEXP center) {
     return out;
 }
 
+/* ---- replicate-finding numerics of scReplicate (R/scReplicate.R:458-520,793-819; include/scmerge_b200.h "replicate-finding") -----
+ * X arguments are genes x cells R matrices (column-major == the device's row-major cells x genes). */
+static dmat up_gc(SEXP X) {   /* temporary upload of a genes x cells matrix; caller frees d.p */
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    dmat d; d.n = INTEGER(dim)[0]; d.m = INTEGER(dim)[1]; d.ld = (d.n + 1) / 2 * 2;
+    CHECK(scm_dev_alloc(ctx(), d.m * d.ld * 8, (void**)&d.p));
+    CHECK(scm_copy2d(ctx(), d.p, d.ld * 8, REAL(X), d.n * 8, d.n * 8, d.m, 0));
+    return d;
+}
+/* squared distance of every cell to the per-gene MEDIAN of its cluster (centroidDist before rank(), R/scReplicate.R:459-460) */
+SEXP scm_centroid_sqdist(SEXP X, SEXP key, SEXP G_) {
+    dmat d = up_gc(X);
+    int G = Rf_asInteger(G_);
+    int32_t* dk = (int32_t*)to_dev(INTEGER(key), d.m * 4);
+    double *dmed, *ddist;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)G * d.n * 8, (void**)&dmed)); CHECK(scm_dev_alloc(ctx(), d.m * 8, (void**)&ddist));
+    CHECK(scm_group_median(ctx(), d.p, d.m, d.n, d.ld, (const int32_t*)INTEGER(key), dk, G, dmed));
+    CHECK(scm_sqdist_to_center(ctx(), d.p, d.m, d.n, d.ld, dk, G, dmed, ddist));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, d.m));
+    CHECK(scm_d2h(ctx(), REAL(out), ddist, d.m * 8));
+    scm_dev_free(ctx(), dk); scm_dev_free(ctx(), dmed); scm_dev_free(ctx(), ddist); scm_dev_free(ctx(), d.p);
+    UNPROTECT(1);
+    return out;
+}
+/* compute_dist_mat (R/scReplicate.R:470-490): returns the m2 x m1 image of the m1 x m2 row-major distance matrix (R side t()s it);
+ * with offsets (numeric vectors K1 + 1 / K2 + 1, cells ordered by cluster) the K2 x K1 image of the block medians of compute_dist_res (:507-513) */
+SEXP scm_dist(SEXP X1, SEXP X2, SEXP metric, SEXP row_off, SEXP col_off) {
+    dmat a = up_gc(X1), b = up_gc(X2);
+    double* dD; CHECK(scm_dev_alloc(ctx(), a.m * b.m * 8, (void**)&dD));
+    CHECK(scm_pair_dist(ctx(), a.p, a.m, a.ld, b.p, b.m, b.ld, a.n, Rf_asInteger(metric), dD, b.m));
+    SEXP out;
+    if (Rf_isNull(row_off)) {
+        out = PROTECT(Rf_allocMatrix(REALSXP, (int)b.m, (int)a.m));
+        CHECK(scm_d2h(ctx(), REAL(out), dD, a.m * b.m * 8));
+    } else {
+        int K1 = Rf_length(row_off) - 1, K2 = Rf_length(col_off) - 1;
+        int64_t* ro = (int64_t*)R_alloc(K1 + 1, 8); int64_t* co = (int64_t*)R_alloc(K2 + 1, 8);
+        for (int i = 0; i <= K1; i++) ro[i] = (int64_t)REAL(row_off)[i];
+        for (int j = 0; j <= K2; j++) co[j] = (int64_t)REAL(col_off)[j];
+        out = PROTECT(Rf_allocMatrix(REALSXP, K2, K1));
+        CHECK(scm_block_median(ctx(), dD, b.m, ro, K1, co, K2, REAL(out)));
+    }
+    scm_dev_free(ctx(), dD); scm_dev_free(ctx(), a.p); scm_dev_free(ctx(), b.p);
+    UNPROTECT(1);
+    return out;
+}
+/* BiocSingular::runPCA(t(X), rank, scale = TRUE, center = TRUE)$x (R/scReplicate.R:813-815): rank x cells image of the score matrix */
+SEXP scm_pca(SEXP X, SEXP rank_) {
+    dmat d = up_gc(X);
+    int rank = Rf_asInteger(rank_);
+    double *dg, *dm_, *dsc; int64_t mt = 0; int32_t iters; double resid;
+    CHECK(scm_dev_alloc(ctx(), d.n * d.n * 8, (void**)&dg)); CHECK(scm_dev_alloc(ctx(), d.n * 8, (void**)&dm_));
+    CHECK(scm_dev_alloc(ctx(), d.m * rank * 8, (void**)&dsc));
+    CHECK(scm_centred_gram(ctx(), d.p, d.m, d.n, d.ld, dg, dm_, &mt));
+    CHECK(scm_pca_scores(ctx(), dg, d.n, mt, NULL, dm_, rank, d.p, d.m, d.ld, dsc, NULL, 1e-9, 500, &iters, &resid));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, rank, (int)d.m));
+    CHECK(scm_d2h(ctx(), REAL(out), dsc, d.m * rank * 8));
+    scm_dev_free(ctx(), dg); scm_dev_free(ctx(), dm_); scm_dev_free(ctx(), dsc); scm_dev_free(ctx(), d.p);
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
+    {"scm_centroid_sqdist", (DL_FUNC)&scm_centroid_sqdist, 3}, {"scm_dist", (DL_FUNC)&scm_dist, 5}, {"scm_pca", (DL_FUNC)&scm_pca, 2},
     {"scm_use_gpus", (DL_FUNC)&scm_use_gpus, 1}, {"scm_host", (DL_FUNC)&scm_host, 12},
     {"scm_upload_csc", (DL_FUNC)&scm_upload_csc, 5}, {"scm_csc_pseudobulk", (DL_FUNC)&scm_csc_pseudobulk, 3},
     {"scm_csc_adjust_", (DL_FUNC)&scm_csc_adjust_, 5},

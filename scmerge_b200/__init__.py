@@ -11,4 +11,7 @@ from .ruv import (ExactParam, FullAlpha, IrlbaParam, RandomParam, RUVFit, aggreg
 
 from .scmerge2 import DeviceCSC, cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402
 
-__version__ = "0.1.0"
+from .replicate import (centroidDist, cluster_centroid_dist, compute_dist_mat, compute_dist_res,  # noqa: F401,E402
+                        computePCA_byHVGMarker, run_pca_scores)
+
+__version__ = "0.2.0"

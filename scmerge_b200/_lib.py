@@ -80,6 +80,12 @@ SIGNATURES = {
     "scm_silhouette": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _i32, _i64, _i64, C.POINTER(_dbl), C.POINTER(_dbl)],
     "scm_ruv3_host": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _int, _dbl, _i32, _u64, _vp, _i32, _int,
                       _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl)],
+    "scm_gather": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64],
+    "scm_group_median": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp],
+    "scm_sqdist_to_center": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp],
+    "scm_pair_dist": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _i64],
+    "scm_block_median": [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp],
+    "scm_centred_gram": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, C.POINTER(_i64)],
     "scm_timers": [_vp, C.POINTER(_dbl), _int],
 }
 _RESTYPES = {"scm_last_error": C.c_char_p, "scm_multi_ctx": C.c_void_p}

@@ -147,6 +147,7 @@ inline int cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, in
 #include "ruvg.cuh"
 #include "select_k.cuh"
 #include "csc_sparse.cuh"
+#include "replicate.cuh"
 
 using namespace scm;
 
@@ -650,6 +651,52 @@ int scm_ruv3_host(scm_ctx* ctx, const double* h_Y, int64_t m, int64_t n, int64_t
     HostArgs a{h_Y, m, n, ldh, h_group, G, h_batch, Bt, h_ctl, k, s, mode, tol, maxit, seed, h_fullalpha_in, s_in, center_mode,
                h_center, h_out, ldo, h_fullalpha, h_sigma, h_mean, h_sd, iters_out, resid_out};
     return ruv3_host(ctx, a);
+}
+
+// ---- replicate-finding numerics ------------------------------------------------------------------
+int scm_gather(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_rows, int64_t msub,
+               const int32_t* d_cols, int64_t nsub, double* d_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    return gather(ctx, d_Y, m, n, ld, d_rows, msub, d_cols, nsub, d_out, ldo);
+}
+int scm_group_median(scm_ctx* ctx, const double* d_X, int64_t m, int64_t n, int64_t ld, const int32_t* h_key, const int32_t* d_key,
+                     int32_t G, double* d_med) {
+    SCM_REQUIRE_CTX(ctx);
+    return group_median(ctx, d_X, m, n, ld, h_key, d_key, G, d_med);
+}
+int scm_sqdist_to_center(scm_ctx* ctx, const double* d_X, int64_t m, int64_t n, int64_t ld, const int32_t* d_key, int32_t G,
+                         const double* d_center, double* d_dist) {
+    SCM_REQUIRE_CTX(ctx);
+    return sqdist_to_center(ctx, d_X, m, n, ld, d_key, G, d_center, d_dist);
+}
+int scm_pair_dist(scm_ctx* ctx, const double* d_A, int64_t m1, int64_t lda, const double* d_B, int64_t m2, int64_t ldb, int64_t n,
+                  int metric, double* d_D, int64_t ldd) {
+    SCM_REQUIRE_CTX(ctx);
+    return pair_dist(ctx, d_A, m1, lda, d_B, m2, ldb, n, metric, d_D, ldd);
+}
+int scm_block_median(scm_ctx* ctx, const double* d_D, int64_t ldd, const int64_t* h_row_off, int32_t K1, const int64_t* h_col_off,
+                     int32_t K2, double* h_med) {
+    SCM_REQUIRE_CTX(ctx);
+    return block_median(ctx, d_D, ldd, h_row_off, K1, h_col_off, K2, h_med);
+}
+int scm_centred_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, double* d_gram, double* d_colmean,
+                     int64_t* m_total_out) {
+    SCM_REQUIRE_CTX(ctx);
+    if (!d_Y || !d_gram || !d_colmean || n <= 0 || m_local < 0 || ld < n) return fail(SCM_ERR_INVALID, "scm_centred_gram: bad arguments");
+    Scratch ws(ctx);
+    int32_t* key;
+    SCM_TRY(ws.alloc(&key, m_local > 0 ? m_local : 1));
+    SCM_TRY(zero_async(ctx, key, sizeof(int32_t) * (m_local > 0 ? m_local : 1)));
+    FitState fs;
+    SCM_TRY(fit_state(ctx, ws, d_Y, m_local, n, ld, key, 1, nullptr, 0, fs));
+    SCM_TRY(copy_async(ctx, d_gram, fs.Gm, sizeof(double) * n * n));
+    SCM_TRY(copy_async(ctx, d_colmean, fs.ybar, sizeof(double) * n));
+    int64_t* hmeta;
+    SCM_TRY(fit_meta_to_host(ctx, fs, &hmeta));
+    SCM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hmeta[0] != 0) return fail(SCM_ERR_NONFINITE, "Y contains missing values or infinities.  This is not supported.");
+    if (m_total_out) *m_total_out = hmeta[1];
+    return 0;
 }
 
 int scm_multi_ruv3_host(scm_multi* mg, const double* h_Y, int64_t m, int64_t n, int64_t ldh, const int32_t* h_group, int32_t G,
