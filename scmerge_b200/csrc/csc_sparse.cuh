@@ -13,12 +13,17 @@
 //                           <= 128 cells, every warp sums ITS cells (fixed order) into a private shared-memory accumulator
 //                           row (no atomics: indices inside a cell are unique), the warp rows are added in warp order and
 //                           the chunk partial goes through the same ordered final reduction: deterministic
-//   csc_adjust_kernel       K6 on sparse rows, 32 cells per CTA: pass A is a sparse gather W_i = s_i sum_nz x_ij B[j, :] - c'B
-//                           (a quad of lanes per non-zero, 16-byte loads of zero-padded B rows, 2 sectors per row and load;
-//                           v1 ran lanes over the k factors with shuffles: 26 ms; v2 one lane per non-zero: L1TEX-bound at
-//                           12 sector look-ups per non-zero, 14 ms), pass B builds 32 x 256 tiles of the
-//                           scaled sparse rows in shared memory (zero fill + scatter through per-cell cursors: indices are
-//                           sorted) and adds (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out.
+//   csc_project_kernel      pass A of K6 on sparse rows, W_i = s_i sum_nz x_ij B[j, :] - c'B, as its own kernel: the rows of B for
+//                           a range of genes stay resident in shared memory for the whole launch (1066 genes at k <= 24, one
+//                           launch per range), a quad of lanes per cell, eight non-zeros per trip.  History of this gather: lanes
+//                           over the k factors with shuffles 26 ms; one lane per non-zero 14 ms; a quad per non-zero through L1TEX
+//                           7.5 ms (6 sector look-ups per non-zero, L1TEX 73 % of peak); B staged per 32-cell tile in 256-gene
+//                           slabs 5.9 ms (eight staging round trips per tile); this form 2.85 ms, within 1.7x of the shared-memory
+//                           bandwidth bound (192 bytes of B per non-zero)
+//   csc_adjust_kernel       pass B, 32 cells per CTA: builds 32 x 256 tiles of the scaled sparse rows in shared memory (zero
+//                           fill + scatter through per-cell cursors, the first 32 candidates of all eight cells of a warp loaded
+//                           before any is used) and adds (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out
+//                           (6.6 ms: zero fill + scatter 1.8, DMMA + store 4.7)
 // All three require canonical cells (indices strictly increasing, what csc_check_kernel verifies); otherwise the caller
 // falls back to densify + the dense kernels.
 #pragma once
@@ -152,14 +157,113 @@ inline int csc_seg_colsum(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* 
     return 0;
 }
 
+// ---- pass A of K6 on sparse rows, as its own kernel: W[cell, :] = s_cell * sum_nz x B[idx, :] -----------------------------
+// The gather of one 8 KT-double row of B per non-zero is what bounded the fused kernel (round 1: through L1TEX, 6 sector look-ups
+// per non-zero, 7.5 of 12.5 ms; staged per 32-cell tile in 256-gene slabs it was still 5.9 ms: eight staging round trips per tile
+// and a global-load latency per pair of non-zeros).  Here the rows of B for a RANGE OF GENES (as many as fit 200 KB of shared
+// memory: 1066 genes at k <= 24) stay resident in shared memory for the whole launch; one launch per gene range.  A quad of
+// lanes owns a cell: lane `sub` holds the 16-byte pieces sub, sub + 4, ... of the row (2 KT accumulators per lane), walks the
+// cell's non-zeros of the range eight at a time (all index / value loads of a trip in flight together), and 32 warps x 8 quads
+// per SM keep 256 cells in flight.  Indices are sorted inside a cell, so a range is a run: the position where it ended is kept
+// in `cursor` for the next range's launch.  W accumulates over the launches in global memory (m x 8 KT doubles).
+constexpr int CSP_THREADS = 1024;
+template <int KT>
+__global__ void __launch_bounds__(CSP_THREADS, 1)
+csc_project_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                   const double* __restrict__ inv, int64_t m, const double* __restrict__ Bpad, int32_t g_lo, int32_t g_hi, int first,
+                   int last, const double* __restrict__ w0, int k, int64_t* __restrict__ cursor, double* __restrict__ W) {
+    extern __shared__ __align__(16) double csp_B[];  // [(g_hi - g_lo)][KP]
+    constexpr int KP = KT * 8;
+    {
+        const double2* src = reinterpret_cast<const double2*>(Bpad + (int64_t)g_lo * KP);
+        double2* dst = reinterpret_cast<double2*>(csp_B);
+        const int cnt = (g_hi - g_lo) * (KP / 2);
+        for (int e = threadIdx.x; e < cnt; e += CSP_THREADS) cp_async16(dst + e, src + e, true);
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int sub = threadIdx.x & 3;
+    const int64_t quad = ((int64_t)blockIdx.x * CSP_THREADS + threadIdx.x) >> 2, nquad = ((int64_t)gridDim.x * CSP_THREADS) >> 2;
+    for (int64_t cell = quad; cell < m; cell += nquad) {
+        int64_t p = first ? indptr[cell] : cursor[cell];
+        const int64_t p1 = indptr[cell + 1];
+        double v[2 * KT];
+#pragma unroll
+        for (int i = 0; i < 2 * KT; i++) v[i] = 0.0;
+        auto add_row = [&](int32_t g, double x) {
+            const double2* r = reinterpret_cast<const double2*>(csp_B + (int64_t)(g - g_lo) * KP) + sub;
+#pragma unroll
+            for (int i = 0; i < KT; i++) { const double2 b = r[4 * i]; v[2 * i] = fma(x, b.x, v[2 * i]); v[2 * i + 1] = fma(x, b.y, v[2 * i + 1]); }
+        };
+        while (p + 7 < p1) {  // eight non-zeros per trip: all sixteen loads are issued before the range test (p + 7 < p1: in bounds)
+            int32_t gg[8];
+            double xx[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { gg[u] = idx[p + u]; xx[u] = val[p + u]; }
+            if (gg[7] >= g_hi) break;  // sorted: all eight are inside the range iff the last one is
+#pragma unroll
+            for (int u = 0; u < 8; u++) add_row(gg[u], xx[u]);
+            p += 8;
+        }
+        while (p + 1 < p1) {  // the rest of the run two at a time
+            const int32_t ga = idx[p], gb = idx[p + 1];
+            const double xa = val[p], xb = val[p + 1];
+            if (gb >= g_hi) break;
+            add_row(ga, xa); add_row(gb, xb);
+            p += 2;
+        }
+        while (p < p1) {
+            const int32_t g = idx[p];
+            if (g >= g_hi) break;
+            add_row(g, val[p]);
+            p++;
+        }
+        if (!last && sub == 0) cursor[cell] = p;
+        const double sq = inv[cell];
+        double* wr = W + cell * KP;
+#pragma unroll
+        for (int i = 0; i < KT; i++) {
+            const int col = 2 * (sub + 4 * i);
+            double2 acc = first ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(wr + col);
+            acc.x += v[2 * i] * sq; acc.y += v[2 * i + 1] * sq;
+            if (last) {  // finished: subtract center' B, zero the padding columns
+                acc.x = col < k ? acc.x - w0[col] : 0.0;
+                acc.y = col + 1 < k ? acc.y - w0[col + 1] : 0.0;
+            }
+            *reinterpret_cast<double2*>(wr + col) = acc;
+        }
+    }
+}
+
+template <int KT>
+inline int csc_project_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
+                              int64_t m, int64_t n, const scm_coef* c, double* W) {
+    constexpr int KP = KT * 8;
+    int64_t per = (200 * 1024) / (KP * 8);  // genes whose rows of B fit the shared memory of one CTA
+    if (per > n) per = n;
+    const int nr = (int)ceil_div(n, per);
+    int64_t* cursor = nullptr;
+    if (nr > 1) SCM_TRY(ws.alloc(&cursor, m));
+    SCM_CUDA(cudaFuncSetAttribute(csc_project_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    for (int r = 0; r < nr; r++) {
+        const int64_t lo = r * per, hi = lo + per < n ? lo + per : n;
+        const size_t smem = (size_t)(hi - lo) * KP * 8;
+        csc_project_kernel<KT><<<ctx->num_sms, CSP_THREADS, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, c->Bpad, (int32_t)lo, (int32_t)hi,
+                                                                              r == 0, r == nr - 1, c->w0, c->k, cursor, W);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
 // ---- K6 on sparse rows ----------------------------------------------------------------------------------------------
 constexpr int CSA_WARPS = 4, CSA_MT = 4, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256;  // 32 cells x 256 genes x 8 B = 64 KB tile
 
 template <int KT>
 __global__ void __launch_bounds__(CSA_WARPS * 32, 3)
 csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                  const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Bpad, const double* __restrict__ Afrag,
-                  const double* __restrict__ w0, int k, int nblk, double* __restrict__ out, int64_t ldo, int vec_out) {
+                  const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Wg, const double* __restrict__ Afrag,
+                  int k, int nblk, double* __restrict__ out, int64_t ldo, int vec_out, int dbg) {
     extern __shared__ __align__(16) uint8_t csa_smem[];
     double* tile = reinterpret_cast<double*>(csa_smem);                       // [32][CSA_SLAB + 2] (padded: conflict-free fragment reads)
     constexpr int TLD = CSA_SLAB + 2;
@@ -181,42 +285,10 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
             sc[tid] = ok ? inv[cell] : 0.0;
         }
         __syncthreads();
-        // ---- pass A: W[cell, a] = s * sum_nz x B[idx, a] - w0[a].  Warp w owns cells 8w .. 8w+7.  A QUAD of lanes shares one
-        // non-zero (8 non-zeros per warp step): lane `sub` of the quad loads the 16-byte pieces sub, sub + 4, ... of the
-        // zero-padded B row, so one warp-wide load touches 2 sectors per row (the minimum: 6 sector look-ups per non-zero; the
-        // kernel is L1TEX-bound, ncu profiles/r01) and accumulates 2 KT private partial sums; three xor-shuffles over the 8 quads
-        // finish the column totals.
-        constexpr int KP = KT * 8;
-        const int sub = lane & 3, grp = lane >> 2;
-        for (int r = 0; r < 8; r++) {
-            const int c = warp * 8 + r;
-            const int64_t p0 = cur[c], p1 = endp[c];
-            double v[2 * KT];
-#pragma unroll
-            for (int i = 0; i < 2 * KT; i++) v[i] = 0.0;
-#pragma unroll 2
-            for (int64_t p = p0 + grp; p < p1; p += 8) {
-                const double x = val[p];  // indices were validated by scm_csc_check (a per-element guard here costs 2 ms of 12.5)
-                const double2* brow = reinterpret_cast<const double2*>(Bpad + (int64_t)idx[p] * KP) + sub;
-                double2 b[KT];
-#pragma unroll
-                for (int i = 0; i < KT; i++) b[i] = __ldg(brow + 4 * i);
-#pragma unroll
-                for (int i = 0; i < KT; i++) { v[2 * i] = fma(x, b[i].x, v[2 * i]); v[2 * i + 1] = fma(x, b[i].y, v[2 * i + 1]); }
-            }
-#pragma unroll
-            for (int off = 4; off <= 16; off <<= 1)
-#pragma unroll
-                for (int i = 0; i < 2 * KT; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
-            if (grp == 0) {
-                const double s = sc[c];
-#pragma unroll
-                for (int i = 0; i < KT; i++) {
-                    const int col = 2 * (sub + 4 * i);
-                    Wsm[c * KP + col] = col < k ? v[2 * i] * s - w0[col] : 0.0;
-                    Wsm[c * KP + col + 1] = col + 1 < k ? v[2 * i + 1] * s - w0[col + 1] : 0.0;
-                }
-            }
+        // ---- W = (s x - center) B comes from csc_project_kernel (global memory, m x 8 KT): this tile's 32 rows into shared memory
+        for (int e = tid; e < CSA_ROWS * KT * 8; e += CSA_WARPS * 32) {
+            const int64_t cell = row0 + e / (KT * 8);
+            Wsm[e] = cell < m ? Wg[cell * (KT * 8) + e % (KT * 8)] : 0.0;
         }
         __syncthreads();
         double w[CSA_MT][KT][2];
@@ -228,33 +300,50 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                 w[mt][nt][0] = -v.x; w[mt][nt][1] = -v.y;  // pass B adds (-W) A
             }
         // ---- pass B, slab by slab
-        for (int64_t g0 = 0; g0 < n; g0 += CSA_SLAB) {
+        for (int64_t g0 = 0; g0 < n && !(dbg & 2); g0 += CSA_SLAB) {
             const int width = (int)min((int64_t)CSA_SLAB, n - g0);
             __syncthreads();  // previous slab consumed
             for (int e = tid; e < CSA_ROWS * (TLD / 2); e += CSA_WARPS * 32) *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(0.0, 0.0);
             __syncthreads();
-            // scatter: warp w walks the cursors of its 8 cells (indices are sorted: the slab's non-zeros are a contiguous run)
-            for (int r = 0; r < 8; r++) {
-                const int c = warp * 8 + r;
-                int64_t p = cur[c];
-                const int64_t p1 = endp[c];
-                const double s = sc[c];
-                while (true) {
-                    const int64_t q = p + lane;
-                    int32_t g = q < p1 ? idx[q] : INT32_MAX;
-                    const bool in = g < g0 + width;
-                    if (in && g >= g0) tile[c * TLD + (g - (int32_t)g0)] = val[q] * s;  // g < g0 only for un-sorted (unsupported) input
-                    const unsigned mask = __ballot_sync(0xffffffffu, in);
-                    p += __popc(mask);
-                    if (mask != 0xffffffffu) break;
+            // scatter: warp w walks the cursors of its 8 cells (indices are sorted: the slab's non-zeros are a contiguous run).  The
+            // first 32 candidates of ALL eight cells are loaded before any of them is used (eight independent loads in flight per
+            // lane instead of a chain of eight); a cell with more than 32 non-zeros in the slab finishes in the loop below.
+            {
+                int32_t gq[8];
+                double xq[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int c = warp * 8 + r;
+                    const int64_t q = cur[c] + lane;
+                    const bool ok = q < endp[c];
+                    gq[r] = ok ? idx[q] : INT32_MAX;
+                    xq[r] = ok ? val[q] : 0.0;
                 }
-                __syncwarp();
-                if (lane == 0) cur[c] = p;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const int c = warp * 8 + r;
+                    const double s = sc[c];
+                    const bool in = gq[r] < g0 + width;
+                    if (in && gq[r] >= g0) tile[c * TLD + (gq[r] - (int32_t)g0)] = xq[r] * s;  // g < g0 only for un-sorted (unsupported) input
+                    unsigned mask = __ballot_sync(0xffffffffu, in);
+                    int64_t p = cur[c] + __popc(mask);
+                    const int64_t p1 = endp[c];
+                    while (mask == 0xffffffffu) {  // rare: more than 32 non-zeros of this cell in the slab
+                        const int64_t q = p + lane;
+                        const int32_t g = q < p1 ? idx[q] : INT32_MAX;
+                        const bool in2 = g < g0 + width;
+                        if (in2 && g >= g0) tile[c * TLD + (g - (int32_t)g0)] = val[q] * s;
+                        mask = __ballot_sync(0xffffffffu, in2);
+                        p += __popc(mask);
+                    }
+                    __syncwarp();
+                    if (lane == 0) cur[c] = p;
+                }
             }
             __syncthreads();
             // DMMA over this slab's 16-gene blocks, warps round-robin
             const int nb_slab = (width + 15) / 16;
-            for (int b = warp; b < nb_slab; b += CSA_WARPS) {
+            for (int b = warp; b < nb_slab && !(dbg & 4); b += CSA_WARPS) {
                 const int gb = (int)(g0 / 16) + b;
                 double y[CSA_MT][4];
 #pragma unroll
@@ -296,8 +385,14 @@ inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_
     int64_t grid = (int64_t)ctx->num_sms * 3;
     if (grid > ntiles) grid = ntiles;
     const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
-    csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, c->Bpad, c->Afrag, c->w0,
-                                                                                c->k, c->nblk, d_out, ldo, vec_out);
+    Scratch ws(ctx);
+    double* W;
+    SCM_TRY(ws.alloc(&W, m * KT * 8));
+    const int dbg = getenv("SCM_CSC_DEBUG") ? atoi(getenv("SCM_CSC_DEBUG")) : 0;  // diagnostics: 1 no projection, 2 no pass B, 4 no DMMA / store
+    if (dbg & 1) SCM_TRY(zero_async(ctx, W, sizeof(double) * m * KT * 8));
+    else SCM_TRY(csc_project_launch<KT>(ctx, ws, d_indptr, d_idx, d_val, d_inv, m, n, c, W));
+    csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, W, c->Afrag, c->k, c->nblk,
+                                                                                d_out, ldo, vec_out, dbg);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }
