@@ -30,6 +30,18 @@ def main():
     else:
         ctx = init_builtin_nccl(sm.Context(local), rank, world)
     assert ctx.transport() == transport
+    if os.environ.get("SCM_TEST_DUMP"):
+        # bit-for-bit twin of tests/test_gpu_multi.py::test_one_process_two_gpus_matches_the_torchrun_path: the same host matrix,
+        # the same balanced row blocks, the per-rank host driver under torchrun; every rank dumps its rows
+        Pd = orc.planted_factors(9001, 384, 128, 10, n_types=6, n_batch=3, seed=31)
+        base, rem = 9001 // world, 9001 % world
+        lo = rank * base + min(rank, rem)
+        hi = lo + base + (1 if rank < rem else 0)
+        out = sm.fastRUVIII(np.ascontiguousarray(Pd["Y"][lo:hi]), Pd["types"][lo:hi], Pd["ctl"], k=10, return_info=True, ctx=ctx)
+        np.savez(os.environ["SCM_TEST_DUMP"] + f".rank{rank}.npz", newY=out["newY"], fullalpha=np.asarray(out["fullalpha"]), lo=lo, hi=hi)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0)
     P = orc.planted_factors(9000, 384, 128, 10, n_types=6, n_batch=3, seed=31)
     # batch-ordered cells (stable), labels as strings; cell type "t5" is moved to the very end: rank 0 never sees it
     order = np.argsort(P["batch"], kind="stable")

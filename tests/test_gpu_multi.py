@@ -48,3 +48,27 @@ def test_one_process_two_gpus_matches_oracle_and_is_deterministic():
     res = sm.scRUVIII(np.asfortranarray(P["Y"].T), P["types"], P["ctl"], k=10, batch=batch, ctx=mg)
     ref2 = orc.scRUVIII(P["Y"].T, P["types"], P["ctl"], 10, batch)
     assert orc.rel_frobenius(res[10]["newY"], ref2[10]["newY"]) < 1e-8
+
+
+def test_one_process_two_gpus_matches_the_torchrun_path(tmp_path):
+    """ONE process driving 2 GPUs (scm_multi_ruv3_host: ncclCommInitAll, a host thread per device) against one process per GPU
+    (torchrun, scm_ctx_comm_init_nccl) on the same host matrix and the same row blocks: same kernels, same collectives, so the
+    adjusted matrix and fullalpha must agree BIT FOR BIT."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import scmerge_b200 as sm
+    from oracle import ruv_oracle as orc
+    dump = str(tmp_path / "torchrun")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SCM_TEST_TRANSPORT="nccl", SCM_TEST_DUMP=dump))
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
+    parts = [np.load(dump + f".rank{i}.npz") for i in range(2)]
+    assert int(parts[0]["lo"]) == 0 and int(parts[0]["hi"]) == int(parts[1]["lo"]) and int(parts[1]["hi"]) == 9001
+    P = orc.planted_factors(9001, 384, 128, 10, n_types=6, n_batch=3, seed=31)
+    mg = sm.MultiContext(devices=[0, 1])
+    out = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=10, return_info=True, ctx=mg)
+    np.testing.assert_array_equal(np.concatenate([parts[0]["newY"], parts[1]["newY"]]), out["newY"])
+    np.testing.assert_array_equal(parts[0]["fullalpha"], np.asarray(out["fullalpha"]))
+    np.testing.assert_array_equal(parts[1]["fullalpha"], np.asarray(out["fullalpha"]))
