@@ -670,13 +670,24 @@ def run_ours(a):
             srcx = sm.DeviceCSC(ctx, Xs.indptr, Xs.indices, Xs.data, 1_000_000, n)
             dOx = sm.DeviceMatrix(ctx, 1_000_000, n)
             ms, st, _ = timed(lambda: sm.scMerge2_core(srcx, None, None, ctl=None, ruvK=a.k, pb=pbx, return_bulk=False, ctx=ctx, out=dOx), 3, 2)
+            fa_rows = int(min(pbx[1] - a.types, n))  # scMerge2's default RandomParam: svd_k = min(P - ncol(M), sum(ctl))
+            # the same call with max(ruvK, 50) converged rows of fullalpha instead of all of them (adjusted cells identical)
+            import scmerge_b200.ruv as ruv_mod
+            ruv_mod.FULLALPHA_ROWS = "truncate"
+            try:
+                ms_t, st_t, _ = timed(lambda: sm.scMerge2_core(srcx, None, None, ctl=None, ruvK=a.k, pb=pbx, return_bulk=False, ctx=ctx, out=dOx), 3, 2)
+            finally:
+                ruv_mod.FULLALPHA_ROWS = "reference"
             adj = st.get("adjust", 0.0)
             by = 12.0 * Xs.nnz + 8.0 * 1_000_000 * n
             srcx.free()
             dOx.free()
             return {"workload": f"BASELINE configs[2]: scMerge2 core, sparse 1M cells x {n} genes (density {a.density}), 8 batches, {a.types} cell types, "
                                 f"{pbx[1]} pseudobulks, ruvK={a.k}, device-resident sparse input", "ms_per_step": ms / 3,
-                    "value": 1_000_000 / (ms / 3 * 1e-3), "unit": "cells/s", "stages_ms": st,
+                    "value": 1_000_000 / (ms / 3 * 1e-3), "unit": "cells/s", "stages_ms": st, "fullalpha_rows": fa_rows,
+                    "fullalpha_rows_note": "all rows the reference's rule asks for (whole spectrum of the Gram, eig_full.cuh)",
+                    "truncated_rows": {"fullalpha_rows": 50, "ms_per_step": ms_t / 3, "value": 1_000_000 / (ms_t / 3 * 1e-3), "stages_ms": st_t,
+                                       "note": "scmerge_b200.ruv.FULLALPHA_ROWS = 'truncate': subspace iteration, same adjusted cells"},
                     "adjust_hbm_frac": by / (adj * 1e-3) * 1e-9 / hbm if adj > 0 else None, "adjust_algorithmic": "12*nnz read + 8*m*n written"}
         if world == 1:
             guarded("scmerge2", x_scm2)

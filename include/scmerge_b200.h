@@ -46,6 +46,8 @@ extern "C" {
 
 #define SCM_MAX_K 64     /* largest ruvK the fused adjust kernel is instantiated for */
 #define SCM_MAX_BLOCK 112 /* largest subspace block (s + oversampling) of the single-CTA Rayleigh-Ritz solver */
+#define SCM_MAX_TOPK_ROWS 88      /* fits returning more rows of fullalpha than this take the whole spectrum (block Jacobi) */
+#define SCM_MAX_FULL_EIG_N 4096   /* largest Gram the whole-spectrum solver is instantiated for */
 
 typedef struct scm_ctx scm_ctx;
 typedef struct scm_coef scm_coef;

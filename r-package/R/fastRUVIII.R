@@ -11,7 +11,20 @@
     list(key = as.integer(f) - 1L, G = nlevels(f))
   }
 }
-.rows_cap <- function(s, k, exact) { cap <- if (exact) 88L else 88L; if (s > cap) list(s = min(s, max(k, 50L), cap), exact = TRUE) else list(s = s, exact = exact) }
+## Rows of fullalpha the device returns.  Up to 88 (SCM_MAX_TOPK_ROWS) the subspace iteration serves.  More (the non-exact
+## branch asks for min(m - G, n_ctl) rows) come from the whole spectrum: of the n x n Gram when n <= 4096
+## (SCM_MAX_FULL_EIG_N), of the rows x rows side for a short matrix (pseudobulks; any n).  Otherwise, or with
+## options(scMergeB200.fullalpha_rows = "truncate"): max(k, 50) converged rows and a warning.
+.rows_cap <- function(s, k, exact, n = NA_integer_, rows = NA_integer_) {
+  cap <- 88L
+  if (s <= cap) return(list(s = s, exact = exact))
+  full <- !identical(getOption("scMergeB200.fullalpha_rows", "reference"), "truncate") && !is.na(n) &&
+    (n <= 4096L || (!is.na(rows) && rows < n && rows <= 4096L))
+  if (full) return(list(s = s, exact = TRUE))
+  want <- min(s, max(k, 50L), cap)
+  warning(sprintf("fullalpha truncated to %d rows (reference rule gives %d)", want, s))
+  list(s = want, exact = TRUE)
+}
 
 fastRUVIII <- function(Y, M, ctl, k = NULL, eta = NULL, svd_k = 50, include.intercept = TRUE, average = FALSE,
                        BPPARAM = SerialParam(), BSPARAM = ExactParam(), fullalpha = NULL, return.info = FALSE,
@@ -26,7 +39,7 @@ fastRUVIII <- function(Y, M, ctl, k = NULL, eta = NULL, svd_k = 50, include.inte
   } else {
     dY <- .Call("scm_upload", as.matrix(Y), 1L)                     # cells x genes column-major -> device transpose
     if (is.null(fullalpha)) {
-      cap <- .rows_cap(s, k, exact)
+      cap <- .rows_cap(s, k, exact, n)
       fit <- .Call("scm_fit", dY, g$key, g$G, NULL, 0L, cap$s, min(k, cap$s), if (cap$exact) 0L else 1L)
       fullalpha <- t(fit[[1]]); colnames(fullalpha) <- colnames(Y)
     }

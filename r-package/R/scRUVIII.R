@@ -22,7 +22,7 @@ scRUVIII <- function(Y = Y, M = M, ctl = ctl, fullalpha = NULL, k = k, cell_type
     if (return_all_RUV) { res$optimal_ruvK <- k[1]; return(res) }
     one <- res[[1]]; one$optimal_ruvK <- k[1]; return(one)
   }
-  cap <- .rows_cap(s, max(k), exact)
+  cap <- .rows_cap(s, max(k), exact, n)
   select <- length(k) > 1
   if (!select && is.null(fullalpha) && is.matrix(Y) && is.double(Y)) {
     ## a plain R matrix and one ruvK: the whole closure in ONE call on REAL(Y) itself (scm_ruv3_host / scm_multi_ruv3_host:
@@ -84,7 +84,7 @@ pseudoRUVIII <- function(Y, Y_pseudo, M, ctl, k = NULL, eta = NULL, include.inte
   if (g$G >= P | k == 0) return(Y_pseudo)                                                                 # :72-76
   if (is.null(fullalpha)) {
     dP <- .Call("scm_upload", as.matrix(Y_pseudo), 1L)
-    cap <- .rows_cap(s, k, exact)
+    cap <- .rows_cap(s, k, exact, n, rows = P)
     fit <- .Call("scm_fit", dP, g$key, g$G, NULL, 0L, cap$s, min(k, cap$s), if (cap$exact) 0L else 1L)
     fullalpha <- t(fit[[1]]); colnames(fullalpha) <- colnames(Y)
   }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libscmerge_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_SINGULAR, ERR_UNSUPPORTED, ERR_NOCONV, ERR_COMM = 0, -1, -2, -3, -4, -5, -6, -7
 MODE_EXACT, MODE_RANDOMIZED = 0, 1
 MAX_K, MAX_BLOCK = 64, 112
+MAX_TOPK_ROWS, MAX_FULL_EIG_N = 88, 4096  # include/scmerge_b200.h
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p)
 

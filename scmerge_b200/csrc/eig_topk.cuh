@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include "eig_full.cuh"
 
 namespace scm {
 
@@ -642,6 +643,8 @@ inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, in
                     const int64_t* d_nonfinite = nullptr) {
     if (n <= 0 || s <= 0 || s > n) return fail(SCM_ERR_INVALID, "eig_topk: bad n=%lld s=%d", (long long)n, s);
     if (n >= (int64_t)1 << 30) return fail(SCM_ERR_UNSUPPORTED, "eig_topk: n too large");
+    if (s > SCM_MAX_TOPK_ROWS)  // more rows than a subspace block carries: the whole spectrum (eig_full.cuh)
+        return eig_full(ctx, d_gram, n, s, d_vals, d_vecs, iters_out, resid_out, d_nonfinite);
     if (kconv <= 0 || kconv > s) kconv = s;
     int kmax = kconv;  // the largest rank that has to CONVERGE (scRUVIII with several ruvK lists more)
     for (int q = 0; q < ctx->n_conv_ranks; q++) { const int kq = ctx->conv_ranks[q] < s ? ctx->conv_ranks[q] : s; kmax = kmax > kq ? kmax : kq; }

@@ -6,6 +6,7 @@
 #include "csc_ingest.cuh"
 #include "eig_topk.cuh"
 #include "fit_core.cuh"
+#include "fit_dual.cuh"
 #include "gemm_f64.cuh"
 #include "gram_syrk.cuh"
 #include "gram_tma.cuh"
@@ -579,6 +580,8 @@ static int ruv3_fit_impl(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64
     if (!d_Y || !d_group || G <= 0 || n <= 0 || s <= 0 || !d_fullalpha)
         return fail(SCM_ERR_INVALID, "scm_ruv3_fit: bad arguments");
     if (d_batch && (Bt <= 0 || !d_mean || !d_sd)) return fail(SCM_ERR_INVALID, "scm_ruv3_fit: batch given without Bt / d_mean / d_sd");
+    if (fit_dual_applies(ctx, m_local, n, s, d_batch, d_gram_centred, d_colmean))  // short matrix, whole row space: the m x m side
+        return ruv3_fit_dual(ctx, d_Y, m_local, n, ld, d_group, G, s, d_fullalpha, d_sigma, iters_out, resid_out);
     cudaStream_t st = ctx->stream;
     Scratch ws(ctx);
     double *vals, *vecs, *inv_sd = nullptr;

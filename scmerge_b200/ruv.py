@@ -204,18 +204,24 @@ def _svd_k(m, G, n_ctl, exact, cap):
     return int(min(m - G, n_ctl, cap)) if exact else int(min(m - G, n_ctl))
 
 
-def _device_rows_cap(s: int, k: int, exact: bool):
-    """The device eigensolver's Rayleigh-Ritz block is limited to MAX_BLOCK columns.  In randomized mode the
-    reference's quirk asks for min(m - G, n_ctl) rows of fullalpha (often hundreds, i.e. rsvd at nearly full rank,
-    which is as accurate as the exact SVD).  The device path then returns max(k, 50) rows and, because three
-    products with a truncated block cannot reproduce that accuracy, runs the converged iteration instead.
-    Returns (rows, exact)."""
-    cap = L.MAX_BLOCK - (10 if not exact else 16)
-    cap = cap // 8 * 8 - 8
+FULLALPHA_ROWS = "reference"  # "truncate": keep the subspace iteration and hand back max(k, 50) rows when the reference rule gives more
+
+
+def _device_rows_cap(s: int, k: int, exact: bool, n: int | None = None, rows: int | None = None):
+    """How many rows of fullalpha the device fit returns, and with which solver.  Up to MAX_TOPK_ROWS rows the block subspace
+    iteration serves (its Rayleigh-Ritz block is limited to MAX_BLOCK columns).  In randomized mode the reference's rule asks for
+    min(m - G, n_ctl) rows (R/fastRUVIII.R:66-70, often hundreds: rsvd at nearly full rank, i.e. the exact SVD): with a Gram of
+    at most MAX_FULL_EIG_N genes the device computes the WHOLE spectrum (eig_full.cuh) and returns all of them, every row
+    exact.  A short matrix (`rows` < n, at most MAX_FULL_EIG_N rows, single rank: the pseudobulk fits of scMerge2) takes the
+    rows x rows side instead, whatever n (fit_dual.cuh).  Larger problems (or FULLALPHA_ROWS = "truncate") fall back to
+    max(k, 50) converged rows with a warning.  Returns (rows, exact)."""
+    cap = L.MAX_TOPK_ROWS
     if s > cap:
+        if FULLALPHA_ROWS == "reference" and n is not None and (n <= L.MAX_FULL_EIG_N or (rows is not None and rows < n and rows <= L.MAX_FULL_EIG_N)):
+            return s, True
         want = min(s, max(int(k), 50), cap)
-        warnings.warn(f"fullalpha truncated to {want} rows (reference rule gives {s}); the device eigensolver "
-                      f"block is limited to {L.MAX_BLOCK} columns", stacklevel=3)
+        warnings.warn(f"fullalpha truncated to {want} rows (reference rule gives {s}); the whole-spectrum solver serves Grams of "
+                      f"up to {L.MAX_FULL_EIG_N} genes", stacklevel=3)
         return want, True
     return s, exact
 
@@ -544,7 +550,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if _is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray)):
         # host matrix: one pipelined call (H2D / fit / adjust / D2H overlapped)
         if fullalpha is None:
-            s_dev, exact_dev = _device_rows_cap(s, k, exact)
+            s_dev, exact_dev = _device_rows_cap(s, k, exact, n)
             newY, fit = _host_pipeline(ctx, Y, ctl, int(k), keys=keys, G=G, s=s_dev, exact=exact_dev, out=out)
             fullalpha = fit.fullalpha
         else:
@@ -555,7 +561,7 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if fullalpha is None:
         # NA/Inf check (R/fastRUVIII.R:52-60) is fused into the first pass over Y; inputcheck=False only skips the raise
         del inputcheck
-        s_dev, exact_dev = _device_rows_cap(s, k, exact)
+        s_dev, exact_dev = _device_rows_cap(s, k, exact, n)
         fit = _fit(ctx, dY, keys, G, s_dev, int(k), exact_dev)
         fullalpha = fit.fullalpha
     fullalpha = np.asanyarray(fullalpha, dtype=np.float64)
@@ -599,7 +605,7 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
         ctlm = tological(ctl, n)
         exact = _is_exact(BSPARAM)
         s = _svd_k(m_total, G, int(ctlm.sum()), exact, svd_k)
-        s_dev, exact_dev = _device_rows_cap(s, ks[0], exact)
+        s_dev, exact_dev = _device_rows_cap(s, ks[0], exact, n)
         newY, fit = _host_pipeline(ctx, Yt, ctlm, ks[0], keys=keys, G=G, s=s_dev, exact=exact_dev, batch_keys=bkeys, Bt=Bt)
         res = {ks[0]: {"newY": newY, "M": M, "fullalpha": fit.fullalpha}, "optimal_ruvK": ks[0],
                "stand_mean": fit.stand_mean, "stand_sd": fit.stand_sd}
@@ -620,7 +626,7 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
     exact = _is_exact(BSPARAM)
     s = _svd_k(m_total, G, int(ctl.sum()), exact, svd_k)
     results = {}
-    s_dev, exact_dev = _device_rows_cap(s, max(ks), exact)
+    s_dev, exact_dev = _device_rows_cap(s, max(ks), exact, n)
     select = len(ks) > 1
     if fullalpha is None:
         # one fit serves every k (R/scRUVIII.R:64-75): the eigensolver must converge the top-k subspace for each of them
@@ -732,7 +738,7 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
         return Y_pseudo
     if fullalpha is None:
         dP, pcopied = _as_device(ctx, Y_pseudo)
-        s_dev, exact_dev = _device_rows_cap(s, k, exact)
+        s_dev, exact_dev = _device_rows_cap(s, k, exact, n, rows=P)
         try:
             fit = _fit(ctx, dP, keys, G, s_dev, int(k), exact_dev)
         except L.NonFiniteError as e:  # the reference only warns here (R/scMerge2_utilis.R:49-52) and then fails in svd

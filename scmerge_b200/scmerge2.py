@@ -204,7 +204,7 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
         s = _svd_k(P, G, int(ctl_mask.sum()), exact, ruvK)
         if G >= P or ruvK == 0:
             raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
-        s_dev, exact_dev = _device_rows_cap(s, ruvK, exact)
+        s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P)
         fit = _fit(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
         from .ruv import _Coef
         with _Coef(ctx, n, fit.fullalpha, ruvK, ctl_mask, center=means) as coef:
@@ -308,7 +308,7 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     s = _svd_k(P, G, int(ctl_mask.sum()), exact, ruvK)
     if G >= P or ruvK == 0:
         raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
-    s_dev, exact_dev = _device_rows_cap(s, ruvK, exact)
+    s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P)
     fit = _fit(ctx, dP, rkeys, G, s_dev, int(ruvK), exact_dev)
     dP.free()
     sub = None if return_subset_genes is None else np.nonzero(tological(return_subset_genes, n))[0]

@@ -92,8 +92,10 @@ def test_tological_chunks_and_svd_k_rule():
     assert _svd_k(400, 6, 400, True, 50) == 50 and _svd_k(400, 6, 400, False, 50) == 394
     assert _svd_k(40, 6, 400, True, 50) == 34
     assert _device_rows_cap(50, 20, True) == (50, True)
+    # more rows than a subspace block carries: the whole spectrum when the Gram is small enough, else truncation with a warning
+    assert _device_rows_cap(394, 20, False, 2000) == (394, True)
     with pytest.warns(UserWarning, match="truncated"):
-        assert _device_rows_cap(394, 20, False) == (50, True)  # truncated block -> converged iteration
+        assert _device_rows_cap(394, 20, False, 20000) == (50, True)
     assert _device_rows_cap(40, 20, False) == (40, False)
 
 

@@ -162,9 +162,10 @@ def test_fastruviii_label_vector_and_fortran_input(sm, sim):
 def test_fastruviii_randomized_close_to_exact(sm, sim):
     # tests/testthat/test-fastRUVIII.R:11-16, tol = 0.02 (mean relative difference)
     a = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20)
-    with pytest.warns(UserWarning):  # fullalpha rows capped on the device path (documented deviation)
-        b = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20, BSPARAM=sm.RandomParam(), svd_k=100)
-    assert mean_rel_diff(a, b) < 0.02
+    # the non-exact branch ignores svd_k and asks for min(m - G, n_ctl) rows (R/fastRUVIII.R:69): all of them are returned
+    b = sm.fastRUVIII(sim["Y"], sim["M"], sim["ctl"], k=20, BSPARAM=sm.RandomParam(), svd_k=100, return_info=True)
+    assert b["fullalpha"].shape[0] == min(sim["Y"].shape[0] - sim["M"].shape[1], int(np.sum(sim["ctl"])))
+    assert mean_rel_diff(a, b["newY"]) < 0.02
 
 
 def test_cell_permutation_equivariance(sm, sim):
@@ -471,10 +472,21 @@ def test_scmerge2_core_cosine_pseudobulk_ruv(sm):
     assert np.allclose(out["bulkExprs"], ref["bulkExprs"], rtol=1e-12, atol=1e-15)
     assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
     assert orc.principal_angles(out["fullalpha"][:6], ref["fullalpha"][:6]).max() < 1e-6
-    # scMerge2's default (RandomParam): reference rule asks for min(P - G, n) rows -> truncated + converged
-    with pytest.warns(UserWarning, match="truncated"):
-        rnd = scMerge2_core(Y, batch, clust, ruvK=6, k_pseudoBulk=10, which=which)
-    assert mean_rel_diff(ref["newY"], rnd["newY"]) < 0.02
+    # scMerge2's default (RandomParam): the reference rule asks for min(P - G, n) rows of fullalpha -- all of them come back
+    # (whole spectrum: the P x P side when there are fewer pseudobulks than genes), the adjusted matrix is the exact one
+    rnd = scMerge2_core(Y, batch, clust, ruvK=6, k_pseudoBulk=10, which=which)
+    Pn, Gn = len(ref["names"]), len(set(clust))
+    assert rnd["fullalpha"].shape == (min(Pn - Gn, 320), 320)
+    assert orc.rel_frobenius(rnd["newY"], ref["newY"]) < TOL_NEWY
+    # opt-out: max(k, 50) converged rows from the subspace iteration (what round 1 always did), with a warning
+    import scmerge_b200.ruv as ruv_mod
+    ruv_mod.FULLALPHA_ROWS = "truncate"
+    try:
+        with pytest.warns(UserWarning, match="truncated"):
+            trn = scMerge2_core(Y, batch, clust, ruvK=6, k_pseudoBulk=10, which=which)
+    finally:
+        ruv_mod.FULLALPHA_ROWS = "reference"
+    assert trn["fullalpha"].shape[0] == 50 and orc.rel_frobenius(trn["newY"], ref["newY"]) < TOL_NEWY
     # device-resident, in place
     dY2 = sm.DeviceMatrix.from_host(ctx, Y)
     res = scMerge2_core(dY2, batch, clust, ruvK=6, k_pseudoBulk=10, which=which, BSPARAM=sm.ExactParam())
@@ -917,3 +929,73 @@ def test_out_of_core_host_path_matches_in_core(sm, monkeypatch, pinned):
     assert orc.rel_frobenius(a1, ref1["newY"]) < TOL_NEWY
     a0 = sm.fastRUVIII(Y, P["types"], P["ctl"], k=5, fullalpha=fa, ctx=ctx)
     np.testing.assert_array_equal(np.asarray(a0), np.asarray(r_oc["newY"]))
+
+
+# ---- whole-spectrum solver (eig_full.cuh): fits that return more rows of fullalpha than a subspace block carries ----------
+@pytest.mark.parametrize("n,s", [(200, 150), (600, 300), (1100, 512), (2100, 120)])
+def test_eig_full_spectrum_vs_lapack(sm, ctx, n, s):
+    """One-sided block Jacobi on the Gram, every kernel geometry (n <= 512 / 1024 / 2048 / 4096): eigenvalues against LAPACK to
+    1e-10 relative (of the largest), eigenvectors through the residual ||G v - lambda v|| and orthonormality -- bulk eigenvalues
+    are nearly degenerate, so individual vectors are not comparable, invariant residuals are."""
+    lib = sm.lib()
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(3 * n, n)) * np.linspace(1, 4, n)[None, :]
+    A[:, :7] += rng.normal(size=(3 * n, 1)) * 6.0  # a few dominant directions
+    Gm = A.T @ A
+    d_G = ctx.to_device(Gm)
+    d_vals, d_vecs = ctx.empty((s,)), ctx.empty((s, n))
+    it, rs = C.c_int32(0), C.c_double(0.0)
+    L_ = sm._lib
+    L_.check(lib.scm_eig_topk(ctx.handle, d_G.ptr, n, s, s, 0, 1e-10, 500, 1, d_vals.ptr, d_vecs.ptr, C.byref(it), C.byref(rs)))
+    w = np.linalg.eigvalsh(Gm)[::-1]
+    vals, vecs = d_vals.to_host(), d_vecs.to_host()
+    assert np.all(np.diff(vals) <= 0)
+    assert np.abs(vals - w[:s]).max() <= 1e-10 * w[0], (n, s, it.value)
+    assert np.abs(vecs @ vecs.T - np.eye(s)).max() < 1e-10
+    assert np.abs(vecs @ Gm - vals[:, None] * vecs).max() <= 1e-9 * w[0]
+    assert ctx.fit_info()["conv_rank"] == s
+    for a in (d_G, d_vals, d_vecs):
+        a.free()
+
+
+def test_randomized_rule_returns_all_rows(sm):
+    """R/fastRUVIII.R:66-70: with a non-exact BSPARAM the reference asks for min(m - ncol(M), sum(ctl)) singular vectors and
+    `fullalpha` has that many rows.  The device returns all of them from the whole spectrum of the Gram; checked against the
+    oracle's exact SVD with the same row count through the rotation-invariant fullalpha' fullalpha (bulk singular values are
+    close, individual rows are not comparable), the singular values and the adjusted matrix.  A later call that re-uses the
+    array with another k must equal a direct fit."""
+    P = orc.planted_factors(3000, 400, 300, 10, n_types=6, n_batch=3, seed=77)
+    out = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=10, BSPARAM="random", return_info=True)
+    fa = np.asarray(out["fullalpha"])
+    assert fa.shape == (300, 400) and out["fullalpha"].conv_rank == 300
+    ref = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 10, svd_k=300, exact=True, return_info=True)
+    rfa = ref["fullalpha"]
+    assert orc.rel_frobenius(out["newY"], ref["newY"]) < TOL_NEWY
+    assert np.allclose(np.linalg.norm(fa, axis=1), np.linalg.norm(rfa, axis=1), rtol=1e-9)
+    assert orc.rel_frobenius(fa.T @ fa, rfa.T @ rfa) < 1e-9
+    again = sm.fastRUVIII(P["Y"], P["types"], P["ctl"], k=40, fullalpha=out["fullalpha"])
+    direct = orc.fastRUVIII(P["Y"], P["types"], P["ctl"], 40, svd_k=300, exact=True)
+    assert orc.rel_frobenius(again, direct) < TOL_NEWY
+
+
+@pytest.mark.parametrize("n", [320, 4500])
+def test_pseudobulk_fit_returns_the_full_row_space(sm, ctx, n):
+    """scMerge2's default (RandomParam, ctl = all genes): svd_k = P - ncol(M), the whole row space of the residual pseudobulk
+    matrix, whose Gram (n x n, n > P) is rank deficient -- the null space must be left alone and exactly P - G rows returned."""
+    rng = np.random.default_rng(3)
+    Pn, n, G = 150, 320, 6
+    types = np.repeat(np.arange(G), Pn // G)
+    B = rng.normal(size=(G, n)) * 2
+    Yp = B[types] + rng.normal(size=(Pn, 4)) @ rng.normal(size=(4, n)) + 0.3 * rng.normal(size=(Pn, n))
+    Y = Yp[rng.integers(0, Pn, size=2000)] + 0.1 * rng.normal(size=(2000, n))
+    ctl = np.ones(n, dtype=bool)
+    out = sm.pseudoRUVIII(Y, Yp, types, ctl, k=4, BSPARAM="random", return_info=True)
+    fa = np.asarray(out["fullalpha"])
+    assert fa.shape == (Pn - G, n)
+    # oracle: exact SVD of the residual pseudobulk matrix with every non-null singular vector
+    Y0 = orc.my_residop(Yp, orc.replicate_matrix(types))
+    U, S, Vt = np.linalg.svd(Y0, full_matrices=False)
+    rfa = U[:, :Pn - G].T @ Yp
+    assert np.allclose(np.linalg.norm(fa, axis=1), S[:Pn - G], rtol=1e-8)
+    assert orc.rel_frobenius(fa.T @ fa, (Vt[:Pn - G].T * S[:Pn - G] ** 2) @ Vt[:Pn - G]) < 1e-9
+    assert orc.principal_angles(fa[:4], rfa[:4]).max() < 1e-6

@@ -32,10 +32,17 @@ def test_config2_exact_vs_reduced_oracle(sm, c2):
     assert out["fullalpha"].shape == (50, 2000)
     assert orc.rel_frobenius(out["newY"], ref["newY"]) < 1e-8
     assert orc.principal_angles(out["fullalpha"][:20], ref["fullalpha"][:20]).max() < 1e-6
-    # randomized mode: the reference's rule asks for min(m - G, n_ctl) = 500 rows -> truncated + converged on the device
-    with pytest.warns(UserWarning, match="truncated"):
-        rnd = sm.fastRUVIII(c2["Y"], c2["types"], c2["ctl"], k=20, BSPARAM=sm.RandomParam())
-    assert np.abs(rnd - out["newY"]).sum() / np.abs(out["newY"]).sum() < 0.02  # tests/testthat/test-fastRUVIII.R:11-16
+    # randomized mode: the reference's rule asks for min(m - G, n_ctl) = 500 rows of fullalpha: all returned (whole spectrum of the
+    # 2000 x 2000 Gram), the leading 20 equal to the exact fit's converged ones, the adjusted matrix the exact one
+    rnd = sm.fastRUVIII(c2["Y"], c2["types"], c2["ctl"], k=20, BSPARAM=sm.RandomParam(), return_info=True)
+    assert rnd["fullalpha"].shape == (500, 2000) and rnd["fullalpha"].conv_rank == 500
+    assert np.abs(rnd["newY"] - out["newY"]).sum() / np.abs(out["newY"]).sum() < 0.02  # tests/testthat/test-fastRUVIII.R:11-16
+    assert orc.rel_frobenius(rnd["newY"], ref["newY"]) < 1e-8
+    assert np.allclose(np.linalg.norm(rnd["fullalpha"][:20], axis=1), np.linalg.norm(out["fullalpha"][:20], axis=1), rtol=1e-9)
+    ref500 = orc.fastRUVIII_reduced(c2["Y"], c2["types"], c2["ctl"], 20, svd_k=500)["fullalpha"]
+    fa = np.asarray(rnd["fullalpha"])
+    assert np.allclose(np.linalg.norm(fa, axis=1), np.linalg.norm(ref500, axis=1), rtol=1e-9)  # all 500 singular values
+    assert orc.rel_frobenius(fa.T @ fa, ref500.T @ ref500) < 1e-9  # rotation-invariant: the bulk is nearly degenerate
     # idempotence: the adjusted matrix is a fixed point of the adjustment with the same alpha
     again = sm.fastRUVIII(out["newY"], c2["types"], c2["ctl"], k=20, fullalpha=out["fullalpha"])
     assert orc.rel_frobenius(again, out["newY"]) < 1e-10
