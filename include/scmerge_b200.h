@@ -252,7 +252,13 @@ int scm_adjust(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld
  *   group : replicate id per local cell (from ruv::replicate.matrix(M), one-hot rows), G groups in total
  *   batch : NULL for fastRUVIII / pseudoRUVIII; batch id per cell (Bt batches) for scRUVIII, which adds
  *           standardize2 (R/scRUVIII.R:158-175): stand_mean / stand_sd are returned in d_mean / d_sd (n each)
- *   s     : rows of fullalpha to return (host applies the svd_k rule R/fastRUVIII.R:66-70), kconv = min(k, s)
+ *   s     : rows of fullalpha to return (host applies the svd_k rule R/fastRUVIII.R:66-70), kconv = min(k, s).
+ *           s <= SCM_MAX_TOPK_ROWS: block subspace iteration, the top kconv rows converged (scm_ctx_fit_info).
+ *           s  > SCM_MAX_TOPK_ROWS (the non-exact BSPARAM rule, R/fastRUVIII.R:69, R/scMerge2_utilis.R:64): the WHOLE
+ *           spectrum by one-sided block Jacobi -- of the n x n Gram (n <= SCM_MAX_FULL_EIG_N), or, for a short matrix
+ *           on one rank without batch (m_local < n, m_local <= SCM_MAX_FULL_EIG_N: pseudoRUVIII), of Y0 Y0' with
+ *           fullalpha = t(u) %*% Y as the reference writes it (R/scMerge2_utilis.R:84-86).  Every row exact;
+ *           SCM_ERR_UNSUPPORTED beyond those sizes.
  * Every local cell must carry a key in [0, G) (M assigns each cell to a replicate group; SCM_ERR_INVALID otherwise).
  * Cross-rank state is summed with TWO all-reduces per fit: [group sums | batch sums | counts | NA flag, rows] and
  * [n x n centred Gram | within-batch squared deviations] (built-in NCCL communicator or the hook).
