@@ -257,6 +257,7 @@ inline int csc_project_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr
 }
 
 // ---- K6 on sparse rows ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr int CSA_WARPS = 4, CSA_MT = 4, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256;  // 32 cells x 256 genes x 8 B = 64 KB tile
 
 template <int KT>
@@ -274,9 +275,12 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t ntiles = ceil_div(m, CSA_ROWS);
+    // the tile is all-zero at the start of every slab: zero-filled once here, and the DMMA phase clears what it reads
+    for (int e = tid; e < CSA_ROWS * (TLD / 2); e += CSA_WARPS * 32) *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(0.0, 0.0);
+    (void)Wsm;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * CSA_ROWS;
-        __syncthreads();  // previous tile fully consumed
+        __syncthreads();  // previous tile fully consumed (its cursors are rewritten below)
         if (tid < CSA_ROWS) {
             const int64_t cell = row0 + tid;
             const bool ok = cell < m;
@@ -284,27 +288,42 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
             endp[tid] = ok ? indptr[cell + 1] : 0;
             sc[tid] = ok ? inv[cell] : 0.0;
         }
-        __syncthreads();
-        // ---- W = (s x - center) B comes from csc_project_kernel (global memory, m x 8 KT): this tile's 32 rows into shared memory
-        for (int e = tid; e < CSA_ROWS * KT * 8; e += CSA_WARPS * 32) {
-            const int64_t cell = row0 + e / (KT * 8);
-            Wsm[e] = cell < m ? Wg[cell * (KT * 8) + e % (KT * 8)] : 0.0;
+        {   // the NEXT tile's non-zeros and rows of W into L2 while this one is processed: every later load of the tile is an L2
+            // hit (~300 cycles) instead of an HBM access -- the kernel is bound by load latency, not by bandwidth (ncu: 42 % of
+            // the warp samples on long_scoreboard at 12 warps per SM)
+            const int64_t tn = t + gridDim.x;
+            if (tn < ntiles) {
+                const int64_t r0n = tn * CSA_ROWS, r1n = min(m, r0n + (int64_t)CSA_ROWS);
+                const int64_t q0 = indptr[r0n], q1 = indptr[r1n];
+                for (int64_t q = (q0 & ~(int64_t)31) + tid * 32; q < q1; q += CSA_WARPS * 32 * 32) prefetch_l2(idx + q);
+                for (int64_t q = (q0 & ~(int64_t)15) + tid * 16; q < q1; q += CSA_WARPS * 32 * 16) prefetch_l2(val + q);
+                const int64_t w0 = r0n * (KT * 8), w1 = r1n * (KT * 8);
+                for (int64_t q = w0 + tid * 16; q < w1; q += CSA_WARPS * 32 * 16) prefetch_l2(Wg + q);
+            }
         }
-        __syncthreads();
+        // ---- W = (s x - center) B comes from csc_project_kernel (global memory, m x 8 KT): every lane reads its fragments directly
         double w[CSA_MT][KT][2];
 #pragma unroll
-        for (int mt = 0; mt < CSA_MT; mt++)
+        for (int mt = 0; mt < CSA_MT; mt++) {
+            const int64_t cell = row0 + mt * 8 + gid;
 #pragma unroll
             for (int nt = 0; nt < KT; nt++) {
-                const double2 v = *reinterpret_cast<const double2*>(Wsm + (mt * 8 + gid) * (KT * 8) + 8 * nt + 2 * tig);
+                const double2 v = cell < m ? __ldg(reinterpret_cast<const double2*>(Wg + cell * (KT * 8) + 8 * nt + 2 * tig)) : make_double2(0.0, 0.0);
                 w[mt][nt][0] = -v.x; w[mt][nt][1] = -v.y;  // pass B adds (-W) A
             }
+        }
+        // A fragments of this warp's first 16-gene block; inside the loop the next block's are always in flight (a warp's blocks
+        // are warp, warp + 4, ... across the slabs: a slab holds 16 of them)
+        double2 an[2 * KT];
+        {
+            const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)warp * KT * 128) + lane;
+#pragma unroll
+            for (int i = 0; i < 2 * KT; i++) an[i] = warp < nblk ? __ldg(af + i * 32) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
         // ---- pass B, slab by slab
         for (int64_t g0 = 0; g0 < n && !(dbg & 2); g0 += CSA_SLAB) {
             const int width = (int)min((int64_t)CSA_SLAB, n - g0);
-            __syncthreads();  // previous slab consumed
-            for (int e = tid; e < CSA_ROWS * (TLD / 2); e += CSA_WARPS * 32) *reinterpret_cast<double2*>(tile + 2 * e) = make_double2(0.0, 0.0);
-            __syncthreads();
             // scatter: warp w walks the cursors of its 8 cells (indices are sorted: the slab's non-zeros are a contiguous run).  The
             // first 32 candidates of ALL eight cells are loaded before any of them is used (eight independent loads in flight per
             // lane instead of a chain of eight); a cell with more than 32 non-zeros in the slab finishes in the loop below.
@@ -341,21 +360,27 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                 }
             }
             __syncthreads();
-            // DMMA over this slab's 16-gene blocks, warps round-robin
+            // DMMA over this slab's 16-gene blocks, warps round-robin; the fragments read from the tile are cleared behind the read
             const int nb_slab = (width + 15) / 16;
-            for (int b = warp; b < nb_slab && !(dbg & 4); b += CSA_WARPS) {
+            for (int b = warp; b < nb_slab; b += CSA_WARPS) {
                 const int gb = (int)(g0 / 16) + b;
+                double2 a[2 * KT];
+#pragma unroll
+                for (int i = 0; i < 2 * KT; i++) a[i] = an[i];
+                if (gb + CSA_WARPS < nblk) {
+                    const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)(gb + CSA_WARPS) * KT * 128) + lane;
+#pragma unroll
+                    for (int i = 0; i < 2 * KT; i++) an[i] = __ldg(af + i * 32);
+                }
                 double y[CSA_MT][4];
 #pragma unroll
                 for (int mt = 0; mt < CSA_MT; mt++) {
-                    const double* src = tile + (mt * 8 + gid) * TLD + b * 16 + 4 * tig;
-                    const double2 a = *reinterpret_cast<const double2*>(src), c2 = *reinterpret_cast<const double2*>(src + 2);
-                    y[mt][0] = a.x; y[mt][1] = a.y; y[mt][2] = c2.x; y[mt][3] = c2.y;
+                    double* src = tile + (mt * 8 + gid) * TLD + b * 16 + 4 * tig;
+                    const double2 a0 = *reinterpret_cast<const double2*>(src), c2 = *reinterpret_cast<const double2*>(src + 2);
+                    *reinterpret_cast<double2*>(src) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(src + 2) = make_double2(0.0, 0.0);
+                    y[mt][0] = a0.x; y[mt][1] = a0.y; y[mt][2] = c2.x; y[mt][3] = c2.y;
                 }
-                const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)gb * KT * 128) + lane;
-                double2 a[2 * KT];
-#pragma unroll
-                for (int i = 0; i < 2 * KT; i++) a[i] = __ldg(af + i * 32);
 #pragma unroll
                 for (int tau = 0; tau < 2; tau++)
 #pragma unroll
@@ -372,6 +397,7 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                     store4(out + (cell < m ? cell : 0) * ldo, gg, n, vec_out, cell < m, y[mt]);
                 }
             }
+            __syncthreads();  // slab consumed and cleared before the next scatter
         }
     }
 }
