@@ -325,13 +325,18 @@ def measured_peaks():
         return {}
 
 
+TRAFFIC_KERNEL_FILES = ("common.cuh", "seg_colsum.cuh", "fit_core.cuh", "gram_tma.cuh", "gram_syrk.cuh", "adjust.cuh", "adjust_tma.cuh")
+
+
 def kernel_source_hash():
-    """sha1 over the kernel sources: an ncu traffic figure is only attached to the roofline when it was captured for THIS code."""
+    """sha1 over the sources of the kernels the traffic figure is about (K1 seg_partial_kernel, K3 gram_tma_kernel, K6
+    adjust_tma_kernel, their launch code and common.cuh): an ncu traffic figure is only attached to the roofline when it was
+    captured for THIS code.  Host glue (scm_api.cu) and the other kernels do not enter."""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "scmerge_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in TRAFFIC_KERNEL_FILES:
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:12]
 
 

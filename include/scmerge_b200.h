@@ -185,7 +185,8 @@ int scm_seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_
 
 /* Same pass, followed by the division by the group sizes on the device: means[g, :] = sums[g, :] / counts[g]
  * (rows of empty groups are 0).  This is `res / cellTypes_n_mat` of create_pseudoBulk (R/scMerge2_utilis.R:474-477)
- * and colMeans (R/scMerge2_utilis.R:97, R/scMerge2.R:393). */
+ * and colMeans (R/scMerge2_utilis.R:97, R/scMerge2.R:393).  GLOBAL over the ranks of the context (sums and counts are
+ * all-reduced before the division: a pseudobulk's cells may live on any rank); so is scm_csc_seg_colmean. */
 int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld,
                     const int32_t* d_key, int32_t G, double* d_means, int64_t* d_counts, int32_t* d_nonfinite);
 

@@ -463,6 +463,8 @@ int scm_csc_seg_colmean(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_
     if (!d_counts) return fail(SCM_ERR_INVALID, "scm_csc_seg_colmean: d_counts is required");
     StageTimer t(ctx, ST_SEG);
     SCM_TRY(csc_seg_colsum(ctx, d_indptr, d_idx, d_val, d_inv_norm, m, n, d_key, G, d_means, ldn, d_counts));
+    SCM_TRY(allreduce(ctx, d_means, (int64_t)G * ldn, 0));  // global over the ranks, like scm_seg_colmean
+    SCM_TRY(allreduce(ctx, d_counts, G, 1));
     groupmean_kernel<<<(unsigned)ceil_div(ldn, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, ldn);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
@@ -502,6 +504,10 @@ int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64
     if (!d_counts) return fail(SCM_ERR_INVALID, "scm_seg_colmean: d_counts is required");
     StageTimer t(ctx, ST_SEG);
     SCM_TRY(seg_colsum(ctx, d_Y, m, n, ld, d_key, G, nullptr, d_means, d_counts, d_nonfinite));
+    // several ranks: a group's cells may live anywhere (pseudobulks of scMerge2, colMeans over ALL cells) -- sums and counts are
+    // summed over the ranks before the division, so every rank gets the same, global means
+    SCM_TRY(allreduce(ctx, d_means, (int64_t)G * n, 0));
+    SCM_TRY(allreduce(ctx, d_counts, G, 1));
     groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, n);
     SCM_LAUNCH_CHECK(ctx);
     return 0;

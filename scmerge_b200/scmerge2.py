@@ -122,21 +122,35 @@ def csc_to_device(ctx: Context, X, cosine: bool = True, min_norm: float = 1e-8, 
         d.free()
 
 
-def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
+def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None, ctx=None):
     """Composite pseudobulk key of every cell, mirroring create_pseudoBulk applied batch by batch
     (R/scMerge2_utilis.R:259-263,461-486): within batch b, cvTools::cvFolds assigns fold f = 1..K (K = min(n_b, k_fold))
     to a random order of the cells (`which = rep(1:K, length.out = n_b)`); the pseudobulk of (b, f, t) is the mean of the
     cells of cluster t in that fold.  Keys are ordered batch-major, then fold, then cluster level, which is the row
     order of the reference's `bulkExprs`.  `which` (fold id per cell, 1-based) may be passed to reproduce an R draw.
+    `ctx` with several ranks: batch / cluster levels and the set of populated (batch, fold, cluster) combinations are taken
+    over ALL ranks, so keys, P and names are the same everywhere; folds are drawn among the LOCAL cells of a batch (each rank
+    deals its cells of batch b round-robin over the K folds in a random order -- the union is again a partition of the batch
+    into K folds of equal size up to the number of ranks).
     Returns (keys int32, P, names 'i_t_f' (i = 1-based batch index), cluster level index per pseudobulk, batch index per pseudobulk)."""
-    blev, b = np.unique(np.asarray(batch), return_inverse=True)
-    tlev, t = np.unique(np.asarray(clust), return_inverse=True)
+    multi = ctx is not None and getattr(ctx, "world", 1) > 1
+    batch, clust = np.asarray(batch), np.asarray(clust)
+    if multi:
+        from .ruv import _global_levels
+        blev = _global_levels(ctx, np.unique(batch))
+        tlev = _global_levels(ctx, np.unique(clust))
+        b, t = np.searchsorted(blev, batch), np.searchsorted(tlev, clust)
+    else:
+        blev, b = np.unique(batch, return_inverse=True)
+        tlev, t = np.unique(clust, return_inverse=True)
     m, T = b.shape[0], tlev.shape[0]
     if which is None:
-        rng = np.random.default_rng(seed)
+        rng = np.random.default_rng(seed if not multi or seed is None else [int(seed), int(ctx.rank)])
         which = np.empty(m, dtype=np.int64)
         for bi in range(blev.shape[0]):
             idx = np.nonzero(b == bi)[0]
+            if idx.shape[0] == 0:
+                continue
             K = min(idx.shape[0], int(k_fold))
             order = rng.permutation(idx.shape[0])
             w = np.empty(idx.shape[0], dtype=np.int64)
@@ -145,7 +159,13 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
     which = np.asarray(which, dtype=np.int64)
     K = int(k_fold)
     raw = (b.astype(np.int64) * K + (which - 1)) * T + t  # dense id over (batch, fold, cluster)
-    present = np.bincount(raw, minlength=blev.shape[0] * K * T) > 0  # droplevels(): empty combinations give no row
+    count = np.bincount(raw, minlength=blev.shape[0] * K * T).astype(np.int64)
+    if multi:
+        d = ctx.to_device(count)
+        ctx.allreduce(d)
+        count = d.to_host()
+        d.free()
+    present = count > 0  # droplevels(): empty combinations give no row
     remap = np.cumsum(present) - 1
     keys = remap[raw].astype(np.int32)
     ids = np.nonzero(present)[0]
@@ -154,6 +174,25 @@ def pseudobulk_keys(batch, clust, k_fold: int = 30, which=None, seed=None):
     # (R/scMerge2_utilis.R:266, R/scMerge2.R:139): the batch INDEX, not its label
     names = [f"{bb + 1}_{tlev[tt]}_{ff + 1}" for bb, tt, ff in zip(pb_b, pb_t, pb_f)]
     return keys, int(ids.shape[0]), names, pb_t.astype(np.int32), pb_b.astype(np.int32)
+
+
+def _fit_pseudobulk(ctx: Context, dP: DeviceMatrix, rkeys, G: int, s: int, ruvK: int, exact: bool):
+    """RUV-III fit on the P x n pseudobulk matrix.  Several ranks: after the global means every rank holds the SAME matrix;
+    each fits its own contiguous block of rows through the ordinary multi-rank fit (group sums and Gram all-reduced), so the
+    work is shared and every rank gets the identical fullalpha."""
+    if getattr(ctx, "world", 1) <= 1:
+        return _fit(ctx, dP, rkeys, G, s, ruvK, exact)
+    P, w, r = dP.m, ctx.world, ctx.rank
+    base, rem = P // w, P % w
+    lo = r * base + min(r, rem)
+    hi = lo + base + (1 if r < rem else 0)
+
+    class _Rows:  # rows [lo, hi) of dP, in place
+        pass
+    v = _Rows()
+    v.ctx, v.m, v.n, v.ld = ctx, hi - lo, dP.n, dP.ld
+    v.ptr = C.c_void_p(dP.buf.address + lo * dP.ld * 8)
+    return _fit(ctx, v, np.asarray(rkeys)[lo:hi], G, s, ruvK, exact)
 
 
 def _adjust_to_host(ctx: Context, dY: DeviceMatrix, fullalpha, k: int, ctl_mask, center, host_out: np.ndarray) -> np.ndarray:
@@ -184,7 +223,7 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
     m, n = dcsc.m, dcsc.n
     ctl_mask = np.ones(n, dtype=bool) if ctl is None else tological(ctl, n)
     if pb is None:
-        pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed)
+        pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed, ctx=ctx)
     keys, P, names, pb_type, _pb_batch = pb
     d_inv = dcsc.row_scales(cosine=cosine, check_finite=check_finite)
     dP = DeviceMatrix(ctx, P, n)
@@ -204,8 +243,8 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
         s = _svd_k(P, G, int(ctl_mask.sum()), exact, ruvK)
         if G >= P or ruvK == 0:
             raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
-        s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P)
-        fit = _fit(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
+        s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P if getattr(ctx, "world", 1) <= 1 else None)
+        fit = _fit_pseudobulk(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
         from .ruv import _Coef
         with _Coef(ctx, n, fit.fullalpha, ruvK, ctl_mask, center=means) as coef:
             if host_out is not None:
@@ -283,7 +322,7 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     elif cosine:
         cosineNorm(dY)
     if pb is None:
-        pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed)
+        pb = pseudobulk_keys(batch, clust, k_pseudoBulk, which=which, seed=seed, ctx=ctx)
     keys, P, names, pb_type, _pb_batch = pb
     # K1 + device division straight into a device-resident P x genes matrix (the fit never leaves the GPU)
     dP = DeviceMatrix(ctx, P, n)
@@ -308,8 +347,8 @@ def scMerge2_core(exprs, batch, clust, ctl=None, ruvK: int = 20, k_pseudoBulk: i
     s = _svd_k(P, G, int(ctl_mask.sum()), exact, ruvK)
     if G >= P or ruvK == 0:
         raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
-    s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P)
-    fit = _fit(ctx, dP, rkeys, G, s_dev, int(ruvK), exact_dev)
+    s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P if getattr(ctx, "world", 1) <= 1 else None)
+    fit = _fit_pseudobulk(ctx, dP, rkeys, G, s_dev, int(ruvK), exact_dev)
     dP.free()
     sub = None if return_subset_genes is None else np.nonzero(tological(return_subset_genes, n))[0]
     if host_out is not None and sub is None:

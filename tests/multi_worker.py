@@ -77,15 +77,41 @@ def main():
     Y0 = Yall - Yall.mean(axis=0)
     U = np.linalg.svd(Y0[:, orc.tological(P["ctl"], 384)], full_matrices=False)[0][:, :8]
     e5 = orc.rel_frobenius(rg["newY"], (Yall - U @ (U.T @ Y0))[lo:hi])
+    # scMerge2 core across ranks (dense and sparse input): pseudobulks pool cells of ALL ranks (global level tables, sums and
+    # counts all-reduced before the division), the pseudobulk fit is shared row-wise, the adjust is rank-local.  The fold of
+    # every cell is drawn once for all cells and handed out with the shards, so the pseudobulks are those of the oracle.
+    from scmerge_b200.scmerge2 import scMerge2_core
+    import scipy.sparse as sp
+    Ypos = np.abs(Yall) + 0.1
+    rng = np.random.default_rng(5)
+    which_all = np.empty(9000, dtype=np.int64)
+    for bname in np.unique(batch_all):
+        idx = np.nonzero(batch_all == bname)[0]
+        w = np.empty(idx.shape[0], dtype=np.int64)
+        w[rng.permutation(idx.shape[0])] = (np.arange(idx.shape[0]) % 10) + 1
+        which_all[idx] = w
+    ref6 = orc.scmerge2_core(Ypos.T, batch_all, types_all, which_all, ruvK=6, k_fold=10, exact=True)
+    o6 = scMerge2_core(Ypos[lo:hi], batch_all[lo:hi], types_all[lo:hi], ruvK=6, k_pseudoBulk=10, which=which_all[lo:hi],
+                       BSPARAM=sm.ExactParam(), ctx=ctx)
+    e6 = orc.rel_frobenius(o6["newY"], ref6["newY"][lo:hi])
+    names_ok = o6["pseudobulk_names"] == ref6["names"]
+    e6b = float(np.abs(o6["bulkExprs"] - ref6["bulkExprs"]).max())
+    mask = np.random.default_rng(6).random(Ypos.shape) < 0.3
+    Ysp = np.where(mask, Ypos, 0.0)
+    ref7 = orc.scmerge2_core(Ysp.T, batch_all, types_all, which_all, ruvK=6, k_fold=10, exact=True)
+    o7 = scMerge2_core(sp.csr_matrix(Ysp[lo:hi]), batch_all[lo:hi], types_all[lo:hi], ruvK=6, k_pseudoBulk=10, which=which_all[lo:hi],
+                       BSPARAM=sm.ExactParam(), ctx=ctx)
+    e7 = orc.rel_frobenius(o7["newY"], ref7["newY"][lo:hi])
     # every rank must hold bit-identical fullalpha (no broadcast in the design)
     fa = torch.from_numpy(np.array(out["fullalpha"])).cuda()
     lst = [torch.empty_like(fa) for _ in range(world)]
     dist.all_gather(lst, fa)
     same = all(torch.equal(lst[0], t) for t in lst)
-    ok = (e1 < 1e-8 and e1d < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8)
+    ok = (e1 < 1e-8 and e1d < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8
+          and e6 < 1e-8 and names_ok and e6b < 1e-12 and e7 < 1e-8)
     print(f"rank {rank}/{world} [{transport}]: rows [{lo},{hi}) batches here {sorted(set(batch_all[lo:hi]))} fast err {e1:.2e} (device {e1d:.2e}) "
           f"angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same} selection sil err {e3:.2e} same_k {same_k} newY err {e4:.2e} "
-          f"scRUVg err {e5:.2e}", flush=True)
+          f"scRUVg err {e5:.2e} scMerge2 err {e6:.2e} (names {names_ok}, bulk {e6b:.1e}) sparse {e7:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -181,3 +181,52 @@ def test_label_tables_are_global_across_ranks_gloo():
             same, G, ref_G, _seen = out[name]
             assert same and G == ref_G, (rank, name, out[name])                   # global ids and global G on every rank
     assert res[0]["batch"][1] == 3 and res[0]["batch"][3] < 3                      # rank 0 saw fewer batches than exist
+
+
+def _pb_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    from scmerge_b200.dist import shard_rows
+    from scmerge_b200.scmerge2 import pseudobulk_keys
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = _GlooCtx(rank, world)
+        rng = np.random.default_rng(8)
+        m = 2003
+        batch = np.sort(rng.choice(["b1", "b2", "b3"], size=m))                   # ordered by batch: rank 0 never sees "b3"
+        clust = rng.choice(["ct_a", "ct_b", "ct_c", "ct_d"], size=m)
+        clust[:1200][clust[:1200] == "ct_d"] = "ct_a"                             # "ct_d" only occurs on the last rank
+        which = rng.integers(1, 8, size=m)                                        # a fixed fold draw (1..7) for all cells
+        lo, hi = shard_rows(m, world, rank)
+        keys, P, names, pb_t, pb_b = pseudobulk_keys(batch[lo:hi], clust[lo:hi], 7, which=which[lo:hi], ctx=ctx)
+        rk, rP, rnames, rt, rb = pseudobulk_keys(batch, clust, 7, which=which)   # single-process truth on ALL cells
+        drawn = pseudobulk_keys(batch[lo:hi], clust[lo:hi], 7, seed=3, ctx=ctx)   # folds drawn per rank: same table everywhere
+        q.put((rank, dict(same=bool(np.array_equal(keys, rk[lo:hi])), P=P, rP=rP, names=names == rnames,
+                          types=bool(np.array_equal(pb_t, rt)), batches=bool(np.array_equal(pb_b, rb)),
+                          drawn_P=drawn[1], drawn_names=drawn[2], drawn_max=int(drawn[0].max()))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_pseudobulk_keys_are_global_across_ranks_gloo():
+    """scMerge2 on several ranks: the (batch, fold, cluster) table, the keys and the row names of the pseudobulk matrix must be
+    those of the single-process construction even when a shard lacks a batch or a cluster."""
+    import torch.multiprocessing as mp
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = _free_port()
+    procs = [mpctx.Process(target=_pb_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        out = res[rank]
+        assert out["same"] and out["P"] == out["rP"] and out["names"] and out["types"] and out["batches"], (rank, out)
+    assert res[0]["drawn_P"] == res[1]["drawn_P"] and res[0]["drawn_names"] == res[1]["drawn_names"]
+    assert max(res[0]["drawn_max"], res[1]["drawn_max"]) == res[0]["drawn_P"] - 1

@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from bench import kernel_source_hash  # noqa: E402
+from bench import TRAFFIC_KERNEL_FILES, kernel_source_hash  # noqa: E402
 
 WANT = {"dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write", "gpu__time_duration.sum": "duration",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
@@ -43,7 +43,7 @@ def main(src, dst):
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
     except Exception:
         commit = None
-    out = {"cells": 1_000_000, "genes": 2000, "kernel_source_hash": kernel_source_hash(), "commit": commit or None,
+    out = {"cells": 1_000_000, "genes": 2000, "kernel_source_hash": kernel_source_hash(), "hash_files": list(TRAFFIC_KERNEL_FILES), "commit": commit or None,
            "source": f"{os.path.basename(src)}: ncu --set full --clock-control none, bench.py --steps 1 --warmup 1 (1M x 2000, one B200); "
                      "per kernel the longest launch; dram bytes = dram__bytes_read.sum + dram__bytes_write.sum",
            "dram_bytes_per_launch": {k: v.get("dram_read", 0.0) + v.get("dram_write", 0.0) for k, v in best.items()},
