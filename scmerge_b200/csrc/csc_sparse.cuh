@@ -327,7 +327,7 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
             // scatter: warp w walks the cursors of its 8 cells (indices are sorted: the slab's non-zeros are a contiguous run).  The
             // first 32 candidates of ALL eight cells are loaded before any of them is used (eight independent loads in flight per
             // lane instead of a chain of eight); a cell with more than 32 non-zeros in the slab finishes in the loop below.
-            {
+            if (!(dbg & 64)) {
                 int32_t gq[8];
                 double xq[8];
 #pragma unroll
@@ -368,7 +368,7 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
 #pragma unroll
                 for (int i = 0; i < 2 * KT; i++) a[i] = an[i];
                 if (gb + CSA_WARPS < nblk) {
-                    const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)(gb + CSA_WARPS) * KT * 128) + lane;
+                    const double2* af = reinterpret_cast<const double2*>(Afrag + (int64_t)((dbg & 8) ? 0 : gb + CSA_WARPS) * KT * 128) + lane;
 #pragma unroll
                     for (int i = 0; i < 2 * KT; i++) an[i] = __ldg(af + i * 32);
                 }
@@ -387,6 +387,7 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
                     for (int nt = 0; nt < KT; nt++)
 #pragma unroll
                         for (int mt = 0; mt < CSA_MT; mt++) {
+                            if (dbg & 32) { y[mt][2 * tau] += w[mt][nt][0] * a[tau * KT + nt].x; continue; }
                             dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
                             dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
                         }
@@ -394,7 +395,7 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
 #pragma unroll
                 for (int mt = 0; mt < CSA_MT; mt++) {
                     const int64_t cell = row0 + mt * 8 + gid;
-                    store4(out + (cell < m ? cell : 0) * ldo, gg, n, vec_out, cell < m, y[mt]);
+                    store4(out + (cell < m ? cell : 0) * ldo, gg, n, vec_out, cell < m && !(dbg & 16), y[mt]);
                 }
             }
             __syncthreads();  // slab consumed and cleared before the next scatter
@@ -414,7 +415,7 @@ inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_
     Scratch ws(ctx);
     double* W;
     SCM_TRY(ws.alloc(&W, m * KT * 8));
-    const int dbg = getenv("SCM_CSC_DEBUG") ? atoi(getenv("SCM_CSC_DEBUG")) : 0;  // diagnostics: 1 no projection, 2 no pass B, 4 no DMMA / store
+    const int dbg = getenv("SCM_CSC_DEBUG") ? atoi(getenv("SCM_CSC_DEBUG")) : 0;  // diagnostics (results are wrong with any bit set): 1 no projection, 2 no pass B, 8 A fragments from one block, 16 no stores, 32 no DMMA, 64 no scatter
     if (dbg & 1) SCM_TRY(zero_async(ctx, W, sizeof(double) * m * KT * 8));
     else SCM_TRY(csc_project_launch<KT>(ctx, ws, d_indptr, d_idx, d_val, d_inv, m, n, c, W));
     csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, W, c->Afrag, c->k, c->nblk,
