@@ -20,10 +20,11 @@
 //                           7.5 ms (6 sector look-ups per non-zero, L1TEX 73 % of peak); B staged per 32-cell tile in 256-gene
 //                           slabs 5.9 ms (eight staging round trips per tile); this form 2.85 ms, within 1.7x of the shared-memory
 //                           bandwidth bound (192 bytes of B per non-zero)
-//   csc_adjust_kernel       pass B, 32 cells per CTA: builds 32 x 256 tiles of the scaled sparse rows in shared memory (zero
-//                           fill + scatter through per-cell cursors, the first 32 candidates of all eight cells of a warp loaded
-//                           before any is used) and adds (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out
-//                           (6.6 ms: zero fill + scatter 1.8, DMMA + store 4.7)
+//   csc_adjust_kernel       pass B, 16 cells per CTA, 4 CTAs per SM: builds 16 x 256 tiles of the scaled sparse rows in shared
+//                           memory (scatter through per-cell cursors, the first 32 candidates of all cells of a warp loaded
+//                           before any is used; the tile is cleared behind the fragment reads, no zero-fill phase) and adds
+//                           (-W) A with DMMA.8x8x4 exactly like the dense kernel, streaming newY out; the next block's A
+//                           fragments are in flight, the next tile's non-zeros prefetched to L2 (5.9 ms; ablation in DESIGN.md)
 // All three require canonical cells (indices strictly increasing, what csc_check_kernel verifies); otherwise the caller
 // falls back to densify + the dense kernels.
 #pragma once
@@ -258,10 +259,18 @@ inline int csc_project_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr
 
 // ---- K6 on sparse rows ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-constexpr int CSA_WARPS = 4, CSA_MT = 4, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256;  // 32 cells x 256 genes x 8 B = 64 KB tile
+// Cells per CTA tile = 8 * SCM_CSA_MT, CTAs per SM.  A/B on one box (pass B alone): 32 cells x 3 CTAs (156 registers) 6.19 ms,
+// 16 cells x 4 CTAs (108 registers) 5.88, 16 x 5 (96 registers, 16 B spilled) 5.84, 16 x 6 (spills) 8.3, 8 x 8 9.5.
+#ifndef SCM_CSA_MT
+#define SCM_CSA_MT 2
+#endif
+#ifndef SCM_CSA_CTAS
+#define SCM_CSA_CTAS 4
+#endif
+constexpr int CSA_WARPS = 4, CSA_MT = SCM_CSA_MT, CSA_ROWS = 8 * CSA_MT, CSA_SLAB = 256, CSA_CPW = CSA_ROWS / CSA_WARPS, CSA_CTAS = SCM_CSA_CTAS;  // tile: 16 cells x 256 genes x 8 B = 33 KB
 
 template <int KT>
-__global__ void __launch_bounds__(CSA_WARPS * 32, 3)
+__global__ void __launch_bounds__(CSA_WARPS * 32, CSA_CTAS)
 csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                   const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Wg, const double* __restrict__ Afrag,
                   int k, int nblk, double* __restrict__ out, int64_t ldo, int vec_out, int dbg) {
@@ -328,19 +337,19 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
             // first 32 candidates of ALL eight cells are loaded before any of them is used (eight independent loads in flight per
             // lane instead of a chain of eight); a cell with more than 32 non-zeros in the slab finishes in the loop below.
             if (!(dbg & 64)) {
-                int32_t gq[8];
-                double xq[8];
+                int32_t gq[CSA_CPW];
+                double xq[CSA_CPW];
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int c = warp * 8 + r;
+                for (int r = 0; r < CSA_CPW; r++) {
+                    const int c = warp * CSA_CPW + r;
                     const int64_t q = cur[c] + lane;
                     const bool ok = q < endp[c];
                     gq[r] = ok ? idx[q] : INT32_MAX;
                     xq[r] = ok ? val[q] : 0.0;
                 }
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int c = warp * 8 + r;
+                for (int r = 0; r < CSA_CPW; r++) {
+                    const int c = warp * CSA_CPW + r;
                     const double s = sc[c];
                     const bool in = gq[r] < g0 + width;
                     if (in && gq[r] >= g0) tile[c * TLD + (gq[r] - (int32_t)g0)] = xq[r] * s;  // g < g0 only for un-sorted (unsupported) input
@@ -409,7 +418,7 @@ inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_
     const int smem = (CSA_ROWS * (CSA_SLAB + 2) + CSA_ROWS * KT * 8) * 8 + CSA_ROWS * (8 + 8 + 8);
     SCM_CUDA(cudaFuncSetAttribute(csc_adjust_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t ntiles = ceil_div(m, CSA_ROWS);
-    int64_t grid = (int64_t)ctx->num_sms * 3;
+    int64_t grid = (int64_t)ctx->num_sms * CSA_CTAS;
     if (grid > ntiles) grid = ntiles;
     const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
     Scratch ws(ctx);
