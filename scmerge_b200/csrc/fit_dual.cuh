@@ -39,6 +39,7 @@ __global__ void sqrt_vals_kernel(const double* __restrict__ vals, int s, double*
 
 inline bool fit_dual_applies(const scm_ctx* ctx, int64_t m_local, int64_t n, int32_t s, const int32_t* d_batch, const double* d_gram_centred,
                              const double* d_colmean) {
+    if (const char* e = getenv("SCM_FIT_DUAL")) if (atoi(e) == 0) return false;  // diagnostics: force the n x n route
     return s > SCM_MAX_TOPK_ROWS && !d_batch && ctx->world == 1 && m_local < n && m_local <= FULL_EIG_MAX_N && !d_gram_centred && !d_colmean;
 }
 

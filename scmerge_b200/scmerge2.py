@@ -183,6 +183,8 @@ def _fit_pseudobulk(ctx: Context, dP: DeviceMatrix, rkeys, G: int, s: int, ruvK:
     if getattr(ctx, "world", 1) <= 1:
         return _fit(ctx, dP, rkeys, G, s, ruvK, exact)
     P, w, r = dP.m, ctx.world, ctx.rank
+    if P < w:
+        raise ValueError(f"{P} pseudobulks cannot be shared by {w} ranks")
     base, rem = P // w, P % w
     lo = r * base + min(r, rem)
     hi = lo + base + (1 if r < rem else 0)

@@ -999,3 +999,23 @@ def test_pseudobulk_fit_returns_the_full_row_space(sm, ctx, n):
     assert np.allclose(np.linalg.norm(fa, axis=1), S[:Pn - G], rtol=1e-8)
     assert orc.rel_frobenius(fa.T @ fa, (Vt[:Pn - G].T * S[:Pn - G] ** 2) @ Vt[:Pn - G]) < 1e-9
     assert orc.principal_angles(fa[:4], rfa[:4]).max() < 1e-6
+
+
+def test_short_matrix_routes_agree(sm, monkeypatch):
+    """A pseudobulk matrix with fewer rows than genes and n <= 4096 can take either whole-spectrum route: the m x m side
+    (fit_dual.cuh, default) or the rank-deficient n x n Gram (eig_full.cuh, SCM_FIT_DUAL=0).  Same singular values, same
+    fullalpha' fullalpha, same adjusted cells."""
+    rng = np.random.default_rng(11)
+    Pn, n, G = 260, 700, 5
+    types = rng.integers(0, G, size=Pn)
+    Yp = rng.normal(size=(G, n))[types] * 2 + rng.normal(size=(Pn, 6)) @ rng.normal(size=(6, n)) + 0.4 * rng.normal(size=(Pn, n))
+    Y = Yp[rng.integers(0, Pn, size=1500)] + 0.1 * rng.normal(size=(1500, n))
+    ctl = np.ones(n, dtype=bool)
+    a = sm.pseudoRUVIII(Y, Yp, types, ctl, k=6, BSPARAM="random", return_info=True)
+    monkeypatch.setenv("SCM_FIT_DUAL", "0")
+    b = sm.pseudoRUVIII(Y, Yp, types, ctl, k=6, BSPARAM="random", return_info=True)
+    fa, fb = np.asarray(a["fullalpha"]), np.asarray(b["fullalpha"])
+    assert fa.shape == fb.shape == (Pn - G, n)
+    assert np.allclose(np.linalg.norm(fa, axis=1), np.linalg.norm(fb, axis=1), rtol=1e-7)
+    assert orc.rel_frobenius(fa.T @ fa, fb.T @ fb) < 1e-9
+    assert orc.rel_frobenius(a["newY"], b["newY"]) < 1e-9
