@@ -17,7 +17,6 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_f64.cuh"
-#include "eig_full.cuh"
 
 namespace scm {
 
@@ -636,6 +635,10 @@ inline int cholqr2(scm_ctx* ctx, const double* src, double* dst, int64_t n, int 
     SCM_TRY(trsm_rows_launch(ctx, dst, dst, n, l, Lfac, skip_b));
     return 0;
 }
+
+}  // namespace scm
+#include "eig_full.cuh"  // whole-spectrum solver (uses chol_factor_launch / trsm_rows_launch / gemm above)
+namespace scm {
 
 // d_nonfinite (optional, device int64): see eig_check_kernel.  Results: ctx->fit_iters / fit_resid / fit_conv_rank / fit_products.
 inline int eig_topk(scm_ctx* ctx, const double* d_gram, int64_t n, int32_t s, int32_t kconv, int mode, double tol,

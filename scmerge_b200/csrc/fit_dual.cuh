@@ -9,7 +9,7 @@
 // Single rank, no batch standardisation (pseudoRUVIII has none).
 #pragma once
 #include "common.cuh"
-#include "eig_full.cuh"
+#include "eig_topk.cuh"
 #include "gemm_f64.cuh"
 #include "seg_colsum.cuh"
 
