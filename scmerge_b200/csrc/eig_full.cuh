@@ -20,10 +20,12 @@
 // costs about one L2 read + write of it.  Steps whose small Gram is already diagonal to the tolerance write nothing.  The host
 // reads one word per sweep (largest |cos| seen between two rows) and stops at 1e-13 or when a sweep no longer improves it.
 //
-// Accuracy: the row Gram is G^2, so the relative gap information below ~1e-8 lambda_1 is lost -- the same limit the n x n Gram
-// formulation has everywhere in this library (sigma_i / sigma_1 < 1e-4 of Y0).  Rows whose norm is below 1e-12 of the largest
-// are treated as the null space (a P-row pseudobulk matrix has rank <= P - G) and left alone; the rows a fit returns
-// (s <= m - G) are never among them unless Y0 itself is rank deficient.
+// Start matrix: the Cholesky factor R of G (G = R'R, chol_start_rows below) when G is numerically positive definite -- its rows
+// end as sqrt(lambda_i) v_i' (the rows of fullalpha), need fewer sweeps and see the spectrum of G; otherwise G itself, whose row
+// Gram is G^2: there the relative gap information below ~1e-8 lambda_1 is lost (sigma_i / sigma_1 < 1e-4 of Y0), the limit the
+// n x n Gram formulation has everywhere in this library.  Rows whose norm is below 1e-12 of the largest are treated as the null
+// space (a P-row pseudobulk matrix has rank <= P - G) and left alone; the rows a fit returns (s <= m - G) are never among them
+// unless Y0 itself is rank deficient.
 #pragma once
 // included by eig_topk.cuh after its Cholesky / triangular-solve / GEMM helpers (do not include on its own)
 #include "common.cuh"
