@@ -64,6 +64,37 @@ def my_residop(A: np.ndarray, B: np.ndarray) -> np.ndarray:
     return A - BtBB_inv @ tBA
 
 
+def design_matrix(a, n: int, include_intercept: bool = True) -> np.ndarray:
+    """ruv::design.matrix as ruv::RUV1 uses it for gene-wise covariates (CRAN `ruv`, un-vendored; restated from the published
+    source): numeric input only.  1 -> a column of ones; a vector -> one column; a matrix with n columns and not n rows is
+    transposed.  include_intercept: cbind(1, A) unless sum(residop(1, A)^2) <= 1e-8.  Returns n x q."""
+    A = np.asarray(a, dtype=np.float64)
+    if A.ndim == 0:
+        A = np.ones((n, 1))
+    elif A.ndim == 1:
+        A = A.reshape(-1, 1)
+    if A.shape[0] != n:
+        A = A.T
+    assert A.shape[0] == n
+    if include_intercept:
+        one = np.ones((n, 1))
+        if (my_residop(one, A) ** 2).sum() > 1e-8:
+            A = np.concatenate([one, A], axis=1)
+    return A
+
+
+def RUV1(Y: np.ndarray, eta, ctl, include_intercept: bool = True) -> np.ndarray:
+    """ruv::RUV1 (call sites R/fastRUVIII.R:64, R/scRUVg.R:59, R/scMerge2_utilis.R:56), literal:
+    Y - Y[, ctl] etac' solve(etac etac') eta with eta = t(design.matrix(eta)) (q x n); eta = NULL returns Y."""
+    if eta is None:
+        return Y
+    Y = np.asarray(Y, dtype=np.float64)
+    ctl = tological(ctl, Y.shape[1])
+    E = design_matrix(eta, Y.shape[1], include_intercept).T
+    Ec = E[:, ctl]
+    return Y - Y[:, ctl] @ Ec.T @ np.linalg.inv(Ec @ Ec.T) @ E
+
+
 def rsvd(A: np.ndarray, k: int, p: int = 10, q: int = 2, rng=None):
     """rsvd::rsvd defaults as dispatched by BiocSingular::RandomParam (un-vendored; published algorithm:
     Erichson et al., 'Randomized matrix decompositions using R').  Returns (u, d, v) truncated to k."""
@@ -101,9 +132,9 @@ def svd_k_bound(m: int, n_groups: int, n_ctl: int, exact: bool, cap) -> int:
 
 
 def fastRUVIII(Y, M, ctl, k, svd_k=50, exact=True, fullalpha=None, return_info=False,
-               inputcheck=True, rng=None):
+               inputcheck=True, rng=None, eta=None, include_intercept=True):
     """R/fastRUVIII.R:41-111, literal.  Y is m x n (cells x genes).  `exact` <=> inherits(BSPARAM,
-    "ExactParam").  eta is always NULL at every call site, so ruv::RUV1 is the identity (:64)."""
+    "ExactParam").  eta is NULL at every scMerge call site, where ruv::RUV1 is the identity (:64)."""
     Y = np.asarray(Y, dtype=np.float64)
     m, n = Y.shape
     M = replicate_matrix(M)
@@ -113,6 +144,7 @@ def fastRUVIII(Y, M, ctl, k, svd_k=50, exact=True, fullalpha=None, return_info=F
             raise ValueError("Y contains missing values.  This is not supported.")
         if np.isinf(Y).sum() > 0:
             raise ValueError("Y contains infinities.  This is not supported.")
+    Y = RUV1(Y, eta, ctl, include_intercept)  # :63-64
     s = svd_k_bound(m, M.shape[1], int(ctl.sum()), exact, svd_k)
     if M.shape[1] >= m or k == 0:  # :78-80
         newY, fullalpha = Y, None
@@ -321,7 +353,7 @@ def create_pseudobulk(exprs, cell_info, which, k_fold=None):
 
 
 def pseudoRUVIII(Y, Y_pseudo, M, ctl, k, exact=True, fullalpha=None, subset=None, normalised=True,
-                 by_chunk=True, chunk_size=50000, rng=None):
+                 by_chunk=True, chunk_size=50000, rng=None, eta=None, include_intercept=True):
     """R/scMerge2_utilis.R:17-150.  Y: cells x genes, Y_pseudo: pseudobulks x genes, M over pseudobulks."""
     Y = np.asarray(Y, dtype=np.float64)
     Y_pseudo = np.asarray(Y_pseudo, dtype=np.float64)
@@ -329,6 +361,7 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k, exact=True, fullalpha=None, subset=None
     m_pseudo = Y_pseudo.shape[0]
     M = replicate_matrix(M)
     ctl = tological(ctl, n)
+    Y_pseudo = RUV1(Y_pseudo, eta, ctl, include_intercept)  # :56 (the pseudobulks only)
     s = svd_k_bound(m_pseudo, M.shape[1], int(ctl.sum()), exact, k)  # :60-65 (cap = k)
     if M.shape[1] >= m_pseudo or k == 0:  # :72-76 returns the pseudobulk matrix itself
         return Y_pseudo
@@ -385,9 +418,10 @@ def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, 
 # --------------------------------------------------------------------------------------------------
 
 
-def scRUVg(Y, ctl, k):
-    """R/scRUVg.R:30-85 with the default Z = 1, eta = NULL (literal: svd of Y0[, ctl] or of its m x m cross product when
-    the aspect ratio is >= 5, :66-73).  Returns dict(newY, W, alpha)."""
+def scRUVg(Y, ctl, k, eta=None, include_intercept=True, fullW=None):
+    """R/scRUVg.R:30-85 with the default Z = 1 (literal: svd of Y0[, ctl] or of its m x m cross product when the aspect ratio
+    is >= 5, :66-73).  `fullW` (m x >= k): the decomposition is skipped (:64) and W is its first k columns.  (`svdyc` alone
+    leaves fullW NULL in the reference and fails at :77; it is not restated.)  Returns dict(newY, W, alpha)."""
     Y = np.asarray(Y, dtype=np.float64)
     m, n = Y.shape
     ctl = tological(ctl, n)
@@ -395,13 +429,16 @@ def scRUVg(Y, ctl, k):
         raise ValueError("k must not be larger than the number of controls")
     Z = np.ones((m, 1))  # :37-41, design.matrix of an intercept
     q = 1
-    Y0 = my_residop(Y, Z)  # :61-63 (RUV1 is the identity for eta = NULL)
-    Y0ctl = Y0[:, ctl]
-    mat = Y0ctl
-    if max(mat.shape) / min(mat.shape) >= 5:  # :68-71
-        mat = Y0ctl @ Y0ctl.T
-    u = np.linalg.svd(mat, full_matrices=False)[0]  # :72
-    fullW = u[:, : min(m - q, int(ctl.sum()))]  # :73
+    Y0 = RUV1(Y, eta, ctl, include_intercept)  # :59
+    Y0 = my_residop(Y0, Z)  # :61-63
+    if fullW is None:  # :64-75
+        Y0ctl = Y0[:, ctl]
+        mat = Y0ctl
+        if max(mat.shape) / min(mat.shape) >= 5:  # :68-71
+            mat = Y0ctl @ Y0ctl.T
+        u = np.linalg.svd(mat, full_matrices=False)[0]  # :72
+        fullW = u[:, : min(m - q, int(ctl.sum()))]  # :73
+    fullW = np.asarray(fullW, dtype=np.float64)
     W = fullW[:, :k]  # :77
     alpha = np.linalg.solve(W.T @ W, W.T) @ Y0  # :78
     return {"newY": Y - W @ alpha, "W": W, "alpha": alpha}  # :80

@@ -241,8 +241,10 @@ inline int coef_from_factors(scm_ctx* ctx, const double* d_B, const double* d_A,
 // ---- K6 ---------------------------------------------------------------------------------------------
 // `nc`: the matrix is not written by this kernel, so it may be read through the non-coherent path (ld.global.nc, streaming).  An
 // IN-PLACE adjust (out == Y) must use ordinary loads: PTX leaves ld.global.nc undefined for locations the kernel also writes.
-__device__ __forceinline__ void load4(const double* rowp, int64_t g0, int64_t n, bool vec, bool rowok, bool nc, double (&v)[4]) {
+// `vec`: 0 scalar accesses, 1 two 16-byte accesses, 2 one 32-byte access (row base and leading dimension 32-byte aligned)
+__device__ __forceinline__ void load4(const double* rowp, int64_t g0, int64_t n, int vec, bool rowok, bool nc, double (&v)[4]) {
     if (rowok && vec && g0 + 3 < n) {
+        if (vec == 2 && nc) { ldg256_stream(rowp + g0, v[0], v[1], v[2], v[3]); return; }
         double2 a, b;
         if (nc) { a = ldg_stream2(rowp + g0); b = ldg_stream2(rowp + g0 + 2); }
         else { a = *reinterpret_cast<const double2*>(rowp + g0); b = *reinterpret_cast<const double2*>(rowp + g0 + 2); }
@@ -252,15 +254,23 @@ __device__ __forceinline__ void load4(const double* rowp, int64_t g0, int64_t n,
         for (int j = 0; j < 4; j++) v[j] = (rowok && g0 + j < n) ? (nc ? __ldg(rowp + g0 + j) : rowp[g0 + j]) : 0.0;
     }
 }
-__device__ __forceinline__ void store4(double* rowp, int64_t g0, int64_t n, bool vec, bool rowok, const double (&v)[4]) {
+__device__ __forceinline__ void store4(double* rowp, int64_t g0, int64_t n, int vec, bool rowok, const double (&v)[4]) {
     if (!rowok) return;
-    if (vec && g0 + 3 < n) {
+    if (vec == 2 && g0 + 3 < n) {
+        stg256_stream(rowp + g0, v[0], v[1], v[2], v[3]);
+    } else if (vec && g0 + 3 < n) {
         stg_stream2(rowp + g0, make_double2(v[0], v[1]));
         stg_stream2(rowp + g0 + 2, make_double2(v[2], v[3]));
     } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) if (g0 + j < n) rowp[g0 + j] = v[j];
     }
+}
+// 16-byte vector flag -> 2 when the 32-byte forms apply (SCM_NO_256=1 keeps the 16-byte pairs: A/B switch)
+inline int vec_flag(const void* base, int64_t ld) {
+    static const int no256 = getenv("SCM_NO_256") ? atoi(getenv("SCM_NO_256")) : 0;
+    if ((ld % 2 != 0) || (((uintptr_t)base) % 16 != 0)) return 0;
+    return (!no256 && ld % 4 == 0 && ((uintptr_t)base) % 32 == 0) ? 2 : 1;
 }
 
 constexpr int ADJ_WARPS = 4;
@@ -416,8 +426,8 @@ adjust_subset_kernel(const double* __restrict__ Y, int64_t m, int64_t n, int64_t
 template <int KT, int MT>
 inline int adjust_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* c, bool pass_b,
                          double* d_out, int64_t ldo, double* d_W) {
-    const int vec_in = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
-    const int vec_out = pass_b ? ((ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0)) : 0;
+    const int vec_in = vec_flag(d_Y, ld);
+    const int vec_out = pass_b ? vec_flag(d_out, ldo) : 0;
     const int64_t rows_per_cta = 8 * MT;
     const unsigned grid = (unsigned)ceil_div(m, rows_per_cta);
     const int nc = (d_out == nullptr || (const double*)d_out != d_Y) ? 1 : 0;  // in place: ordinary loads (see load4)

@@ -239,7 +239,7 @@ inline int adjust_tma_launch_t(scm_ctx* ctx, const CUtensorMap& tmap, int64_t m,
     const int64_t ntiles = ceil_div(m, TL::ROWS);
     int64_t grid = 2 * (int64_t)ctx->num_sms;
     if (grid > ntiles) grid = ntiles;
-    const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    const int vec_out = vec_flag(d_out, ldo);
     adjust_tma_kernel<KT, MT><<<(unsigned)grid, AT_THREADS, smem, ctx->stream>>>(tmap, m, n, c->Bfrag, c->Afrag, c->w0, c->ctl_blocks,
                                                                                  c->nblk_ctl, c->nblk, c->k, d_out, ldo, vec_out);
     SCM_LAUNCH_CHECK(ctx);

@@ -189,6 +189,18 @@ __device__ __forceinline__ void stg_stream2(double* p, double2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};\n" ::"l"(p), "d"(v.x), "d"(v.y));
 }
 
+// 32-byte global load / store (sm_100: LDG.E.256 / STG.E.256): one L1TEX request per lane where two 16-byte ones were needed;
+// the address must be 32-byte aligned
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void stg256_stream(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ldg256_stream(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 __device__ __forceinline__ bool nonfinite(double v) {
     return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000;
 }

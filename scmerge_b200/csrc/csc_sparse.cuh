@@ -413,6 +413,10 @@ csc_adjust_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
 }
 
 template <int KT>
+inline int csc_adjust_red_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val,
+                                 const double* d_inv, int64_t m, int64_t n, const scm_coef* c, const double* W, double* d_out, int64_t ldo);
+
+template <int KT>
 inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
                              int64_t m, int64_t n, const scm_coef* c, double* d_out, int64_t ldo) {
     const int smem = (CSA_ROWS * (CSA_SLAB + 2) + CSA_ROWS * KT * 8) * 8 + CSA_ROWS * (8 + 8 + 8);
@@ -420,16 +424,238 @@ inline int csc_adjust_launch(scm_ctx* ctx, const int64_t* d_indptr, const int32_
     const int64_t ntiles = ceil_div(m, CSA_ROWS);
     int64_t grid = (int64_t)ctx->num_sms * CSA_CTAS;
     if (grid > ntiles) grid = ntiles;
-    const int vec_out = (ldo % 2 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    const int vec_out = vec_flag(d_out, ldo);
     Scratch ws(ctx);
     double* W;
     SCM_TRY(ws.alloc(&W, m * KT * 8));
     const int dbg = getenv("SCM_CSC_DEBUG") ? atoi(getenv("SCM_CSC_DEBUG")) : 0;  // diagnostics (results are wrong with any bit set): 1 no projection, 2 no pass B, 8 A fragments from one block, 16 no stores, 32 no DMMA, 64 no scatter
     if (dbg & 1) SCM_TRY(zero_async(ctx, W, sizeof(double) * m * KT * 8));
     else SCM_TRY(csc_project_launch<KT>(ctx, ws, d_indptr, d_idx, d_val, d_inv, m, n, c, W));
+    static const int use_red = getenv("SCM_CSC_RED") ? atoi(getenv("SCM_CSC_RED")) : 1;  // 0: the tile kernel (kept for A/B runs)
+    if (use_red && !(dbg & ~1)) return csc_adjust_red_launch<KT>(ctx, ws, d_indptr, d_idx, d_val, d_inv, m, n, c, W, d_out, ldo);
     csc_adjust_kernel<KT><<<(unsigned)grid, CSA_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, W, c->Afrag, c->k, c->nblk,
                                                                                 d_out, ldo, vec_out, dbg);
     SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---- pass B without a tile: DMMA result stored, non-zeros added behind it with RED -------------------------------------------
+// csc_adjust_kernel above is bound by load LATENCY: its tile round trip (scatter -> barrier -> fragment
+// read -> clear -> barrier) serialises the candidate loads, the DMMAs and the stores of a CTA, and 12 warps per SM cannot fill the
+// gaps.  This form has no tile, no barrier and no shared-memory traffic for the cells: a WARP owns 8 MT cells; per slab of
+// genes it computes (-W) A with C = 0 and stores the result with ordinary (L2 write-back) stores, then walks the slab's
+// non-zeros of its cells -- 32 consecutive candidates of a cell per load, coalesced -- and adds s x to the element just written
+// with `red.global.add.f64` (fire and forget: no load latency anywhere on the scatter side; the line is still dirty in L2, so
+// the RED costs no DRAM traffic).  Canonical cells have unique indices: every element receives at most one RED, the result
+// is deterministic (fl(fl(-W A) + s x)).  The A fragments of a RANGE of gene blocks stay resident in shared memory for a
+// whole launch (one persistent 16-warp CTA per SM, conflict-free LDS.128 in fragment order; one launch per range, the
+// position where a cell's run ended is kept in `cursor` like in csc_project_kernel): through L1/L2 they would be 24 GB of
+// re-reads at 16 cells per warp.
+#ifndef SCM_CSR_MT
+#define SCM_CSR_MT 1
+#endif
+#ifndef SCM_CSR_ORDER
+#define SCM_CSR_ORDER 0
+#endif
+#ifndef SCM_CSR_PF
+#define SCM_CSR_PF 1
+#endif
+#ifndef SCM_CSR_WARPS
+#define SCM_CSR_WARPS 20
+#endif
+#ifndef SCM_CSR_SLAB
+#define SCM_CSR_SLAB 128
+#endif
+constexpr int CSR_WARPS = SCM_CSR_WARPS, CSR_MT = SCM_CSR_MT, CSR_ROWS = 8 * CSR_MT, CSR_SLAB = SCM_CSR_SLAB;
+
+template <int KT>
+__global__ void __launch_bounds__(CSR_WARPS * 32, 1)
+csc_adjust_red_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                      const double* __restrict__ inv, int64_t m, int64_t n, const double* __restrict__ Wg, const double* __restrict__ Afrag,
+                      int blk_lo, int blk_hi, int first, int last, int64_t* __restrict__ cursor, double* __restrict__ out, int64_t ldo,
+                      int vec_out) {
+    extern __shared__ __align__(16) double csr_A[];  // [(blk_hi - blk_lo)][2 KT][32] double2, the layout of Afrag
+    {
+        const double2* src = reinterpret_cast<const double2*>(Afrag + (int64_t)blk_lo * KT * 128);
+        double2* dst = reinterpret_cast<double2*>(csr_A);
+        const int cnt = (blk_hi - blk_lo) * KT * 64;
+        for (int e = threadIdx.x; e < cnt; e += CSR_WARPS * 32) cp_async16(dst + e, src + e, true);
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t nunits = ceil_div(m, CSR_ROWS);
+    const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x, nwarps = (int64_t)gridDim.x * CSR_WARPS;  // neighbouring units on different SMs
+    const int32_t g_lo = blk_lo * 16, g_hi = (int32_t)min((int64_t)blk_hi * 16, n);
+    for (int64_t unit = gwarp; unit < nunits; unit += nwarps) {
+        const int64_t row0 = unit * CSR_ROWS;
+        // lane r < CSR_ROWS keeps the cursor, the end and the scale of cell row0 + r
+        const int64_t cell_l = row0 + lane;
+        const bool okc = lane < CSR_ROWS && cell_l < m;
+        int64_t mycur = okc ? (first ? indptr[cell_l] : cursor[cell_l]) : 0;
+        const int64_t myend = okc ? indptr[cell_l + 1] : 0;
+        const double mysc = okc ? inv[cell_l] : 0.0;
+#if SCM_CSR_PF
+        {   // the next unit's rows of W, row pointers and scales into L2 while this one is processed (its start is two dependent
+            // DRAM latencies otherwise, against ~8 slabs of work)
+            const int64_t nr0 = (unit + nwarps) * CSR_ROWS;
+            if (nr0 < m) {
+                const int64_t wb = nr0 * (KT * 8), we = min(m, nr0 + CSR_ROWS) * (KT * 8);
+                if (wb + lane * 16 < we) prefetch_l2(Wg + wb + lane * 16);
+                if (lane == 31) { prefetch_l2(indptr + nr0); prefetch_l2(inv + nr0); if (!first) prefetch_l2(cursor + nr0); }
+                if (lane == 30) prefetch_l2(indptr + min(m, nr0 + CSR_ROWS));
+            }
+        }
+#endif
+        double w[CSR_MT][KT][2];
+#pragma unroll
+        for (int mt = 0; mt < CSR_MT; mt++) {
+            const int64_t cell = row0 + mt * 8 + gid;
+#pragma unroll
+            for (int nt = 0; nt < KT; nt++) {
+                const double2 v = cell < m ? __ldg(reinterpret_cast<const double2*>(Wg + cell * (KT * 8) + 8 * nt + 2 * tig)) : make_double2(0.0, 0.0);
+                w[mt][nt][0] = -v.x; w[mt][nt][1] = -v.y;
+            }
+        }
+        // 32 consecutive candidates of every cell of the unit, from the cells' cursors (coalesced)
+        auto load_cand = [&](int32_t (&gq)[CSR_ROWS], double (&xq)[CSR_ROWS]) {
+#pragma unroll
+            for (int r = 0; r < CSR_ROWS; r++) {
+                const int64_t q = __shfl_sync(0xffffffffu, mycur, r) + lane;
+                const bool ok = q < __shfl_sync(0xffffffffu, myend, r);
+                gq[r] = ok ? idx[q] : INT32_MAX;
+                xq[r] = ok ? val[q] : 0.0;
+            }
+        };
+        // candidates inside [g0, gend) stay (scaled), the others become -1; cursors advance; a cell with more than 32 non-zeros in
+        // the slab adds the rest at once
+        auto classify = [&](int32_t (&gq)[CSR_ROWS], double (&xq)[CSR_ROWS], int32_t g0, int32_t gend) {
+#pragma unroll
+            for (int r = 0; r < CSR_ROWS; r++) {
+                const double s = __shfl_sync(0xffffffffu, mysc, r);
+                const bool in = gq[r] < gend;
+                unsigned mask = __ballot_sync(0xffffffffu, in);
+                int adv = __popc(mask);
+                xq[r] *= s;
+                gq[r] = (in && gq[r] >= g0) ? gq[r] : -1;
+                if (mask == 0xffffffffu) {
+                    double* rowp = out + (row0 + r) * ldo;
+                    int64_t p = __shfl_sync(0xffffffffu, mycur, r) + 32;
+                    const int64_t p1 = __shfl_sync(0xffffffffu, myend, r);
+                    while (mask == 0xffffffffu) {
+                        const int64_t q = p + lane;
+                        const int32_t g = q < p1 ? idx[q] : INT32_MAX;
+                        const bool in2 = g < gend;
+                        if (in2 && g >= g0) atomicAdd(rowp + g, val[q] * s);
+                        mask = __ballot_sync(0xffffffffu, in2);
+                        const int c2 = __popc(mask);
+                        p += c2; adv += c2;
+                    }
+                }
+                if (lane == r) mycur += adv;
+            }
+        };
+        auto red_cand = [&](const int32_t (&gq)[CSR_ROWS], const double (&xq)[CSR_ROWS]) {
+#pragma unroll
+            for (int r = 0; r < CSR_ROWS; r++)
+                if (gq[r] >= 0) atomicAdd(out + (row0 + r) * ldo + gq[r], xq[r]);  // result unused: RED
+        };
+        // (-W) A for the slab's 16-gene blocks, stored with plain stores (the lines must stay in L2 for the REDs)
+        auto dmma_slab = [&](int32_t g0, int32_t gend) {
+            for (int gb = g0 >> 4; gb * 16 < gend; gb++) {
+                const double2* af = reinterpret_cast<const double2*>(csr_A) + (int64_t)(gb - blk_lo) * KT * 64 + lane;
+                double2 a[2 * KT];
+#pragma unroll
+                for (int i = 0; i < 2 * KT; i++) a[i] = af[i * 32];
+                double y[CSR_MT][4];
+#pragma unroll
+                for (int mt = 0; mt < CSR_MT; mt++) { y[mt][0] = y[mt][1] = y[mt][2] = y[mt][3] = 0.0; }
+#pragma unroll
+                for (int tau = 0; tau < 2; tau++)
+#pragma unroll
+                    for (int nt = 0; nt < KT; nt++)
+#pragma unroll
+                        for (int mt = 0; mt < CSR_MT; mt++) {
+                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][0], a[tau * KT + nt].x);
+                            dmma884(y[mt][2 * tau], y[mt][2 * tau + 1], w[mt][nt][1], a[tau * KT + nt].y);
+                        }
+                const int64_t gg = (int64_t)gb * 16 + 4 * tig;
+#pragma unroll
+                for (int mt = 0; mt < CSR_MT; mt++) {
+                    const int64_t cell = row0 + mt * 8 + gid;
+                    if (cell < m) {
+                        double* rowp = out + cell * ldo;
+                        if (vec_out == 2 && gg + 3 < n) {
+                            stg256(rowp + gg, y[mt][0], y[mt][1], y[mt][2], y[mt][3]);
+                        } else if (vec_out && gg + 3 < n) {
+                            *reinterpret_cast<double2*>(rowp + gg) = make_double2(y[mt][0], y[mt][1]);
+                            *reinterpret_cast<double2*>(rowp + gg + 2) = make_double2(y[mt][2], y[mt][3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) if (gg + j < n) rowp[gg + j] = y[mt][j];
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // orders this warp's stores before its REDs to the same elements
+        };
+#if SCM_CSR_ORDER == 2
+        // pipelined: the candidates of slab j are loaded one DMMA phase before they are classified, and added one DMMA phase after
+        // the slab was stored (a RED that follows the store of its line at once is slow: measured)
+        int32_t gc[CSR_ROWS], gs[CSR_ROWS];
+        double xc[CSR_ROWS], xs[CSR_ROWS];
+#pragma unroll
+        for (int r = 0; r < CSR_ROWS; r++) { gs[r] = -1; xs[r] = 0.0; }
+        load_cand(gc, xc);
+        for (int32_t g0 = g_lo; g0 < g_hi; g0 += CSR_SLAB) {
+            const int32_t gend = min(g_hi, g0 + CSR_SLAB);
+            dmma_slab(g0, gend);
+            classify(gc, xc, g0, gend);
+            red_cand(gs, xs);
+#pragma unroll
+            for (int r = 0; r < CSR_ROWS; r++) { gs[r] = gc[r]; xs[r] = xc[r]; }
+            if (g0 + CSR_SLAB < g_hi) load_cand(gc, xc);
+        }
+        red_cand(gs, xs);
+#else
+        for (int32_t g0 = g_lo; g0 < g_hi; g0 += CSR_SLAB) {
+            const int32_t gend = min(g_hi, g0 + CSR_SLAB);
+            int32_t gc[CSR_ROWS];
+            double xc[CSR_ROWS];
+            if (SCM_CSR_ORDER == 1) load_cand(gc, xc);
+            dmma_slab(g0, gend);
+            if (SCM_CSR_ORDER == 0) load_cand(gc, xc);
+            classify(gc, xc, g0, gend);
+            red_cand(gc, xc);
+        }
+#endif
+        if (!last && okc) cursor[cell_l] = mycur;
+    }
+}
+
+template <int KT>
+inline int csc_adjust_red_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val,
+                                 const double* d_inv, int64_t m, int64_t n, const scm_coef* c, const double* W, double* d_out, int64_t ldo) {
+    int per = (200 * 1024) / (KT * 1024);  // 16-gene blocks whose A fragments fit the shared memory of one CTA
+    per -= per % (CSR_SLAB / 16);          // ranges start on a slab boundary
+    if (per > c->nblk) per = c->nblk;
+    const int nr = (int)ceil_div((int64_t)c->nblk, (int64_t)per);
+    int64_t* cursor = nullptr;
+    if (nr > 1) SCM_TRY(ws.alloc(&cursor, m));
+    SCM_CUDA(cudaFuncSetAttribute(csc_adjust_red_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    const int vec_out = vec_flag(d_out, ldo);  // 2: one 32-byte store per lane and block
+    const int64_t nunits = ceil_div(m, CSR_ROWS);
+    int64_t grid = ctx->num_sms;
+    if (grid * CSR_WARPS > nunits) grid = ceil_div(nunits, CSR_WARPS);
+    for (int r = 0; r < nr; r++) {
+        const int lo = r * per, hi = lo + per < c->nblk ? lo + per : c->nblk;
+        const size_t smem = (size_t)(hi - lo) * KT * 1024;
+        csc_adjust_red_kernel<KT><<<(unsigned)grid, CSR_WARPS * 32, smem, ctx->stream>>>(d_indptr, d_idx, d_val, d_inv, m, n, W, c->Afrag, lo, hi,
+                                                                                         r == 0, r == nr - 1, cursor, d_out, ldo, vec_out);
+        SCM_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

@@ -204,6 +204,48 @@ def _svd_k(m, G, n_ctl, exact, cap):
     return int(min(m - G, n_ctl, cap)) if exact else int(min(m - G, n_ctl))
 
 
+def eta_design_rows(eta, n: int, include_intercept: bool = True) -> np.ndarray:
+    """Gene-wise covariates of ruv::RUV1 (CRAN `ruv`, un-vendored; call sites R/fastRUVIII.R:64, R/scRUVg.R:59,
+    R/scMerge2_utilis.R:56) -> the q x n matrix `t(design.matrix(eta))`.  Accepted like the `ruv` documentation states: the number
+    1 (an intercept), a vector of length n, a matrix with n rows (n x q) or with n columns (q x n).  `include_intercept`: a row
+    of ones is put first unless the constant vector already lies in the span of the covariates (design.matrix's test:
+    squared residual of 1 on eta > 1e-8).  Collinear covariates are rejected (design.matrix drops columns with a warning)."""
+    a = np.asarray(eta, dtype=np.float64)
+    if a.ndim == 0:
+        if a != 1:
+            raise ValueError("a scalar eta must be 1 (an intercept)")
+        a = np.ones((n, 1))
+    elif a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2 or n not in a.shape:
+        raise ValueError(f"eta must have one row (or one column) per gene (n = {n})")
+    if a.shape[0] != n:
+        a = a.T
+    if not np.all(np.isfinite(a)):
+        raise ValueError("eta contains missing values or infinities")
+    if include_intercept:
+        one = np.ones(n)
+        res = one - a @ np.linalg.lstsq(a, one, rcond=None)[0]
+        if float(res @ res) > 1e-8:
+            a = np.concatenate([one[:, None], a], axis=1)
+    sv = np.linalg.svd(a / np.maximum(np.linalg.norm(a, axis=0), 1e-300), compute_uv=False)
+    if a.shape[1] > n or sv[-1] < 1e-9 * sv[0]:
+        raise ValueError("eta is collinear (ruv::design.matrix would drop columns): remove the redundant covariates")
+    return np.ascontiguousarray(a.T)
+
+
+def _ruv1(ctx: Context, dY: DeviceMatrix, eta, ctl: np.ndarray, include_intercept: bool, in_place: bool) -> DeviceMatrix:
+    """ruv::RUV1 on the device: Y - Y[, ctl] etac' (etac etac')^-1 eta is the rank-q update of K5 + K6 with the rows of eta in
+    the place of alpha (no centre, no scaling).  `in_place`: overwrite dY (a private copy), else a new device matrix."""
+    rows = eta_design_rows(eta, dY.n, include_intercept)
+    if rows.shape[0] > L.MAX_K:
+        raise L.ScmError(L.ERR_UNSUPPORTED, f"eta with {rows.shape[0]} covariates > {L.MAX_K} is not supported by the fused adjust kernel")
+    if rows.shape[0] > int(ctl.sum()):
+        raise ValueError("eta has more covariates than there are control genes (etac etac' is singular)")
+    out, _ = _adjust(ctx, dY, rows, rows.shape[0], ctl, out=dY if in_place else None)
+    return out
+
+
 FULLALPHA_ROWS = "reference"  # "truncate": keep the subspace iteration and hand back max(k, 50) rows when the reference rule gives more
 
 
@@ -526,10 +568,10 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
                BSPARAM=None, fullalpha=None, return_info=False, inputcheck=True, ctx: Context | None = None, out=None):
     """R/fastRUVIII.R:41-111.  Y: m x n (cells x genes); M: replicate matrix or labels; ctl: mask / indices.
     Returns newY (m x n), or {'newY','M','fullalpha'} with return_info.  `BPPARAM`, `average`,
-    `include_intercept` are accepted and unused like in the reference (eta must be None: every caller passes NULL)."""
-    del BPPARAM, average, include_intercept
-    if eta is not None:
-        raise NotImplementedError("eta (gene-wise covariates, ruv::RUV1) is not supported; all scMerge callers pass NULL")
+    are accepted and unused like in the reference.  `eta` (gene-wise covariates, anything eta_design_rows() takes): Y is first
+    replaced by ruv::RUV1(Y, eta, ctl, include_intercept) (R/fastRUVIII.R:63-64) with the same rank-k update kernel, on the
+    device; the host-streaming pipeline is not used then (the matrix has to be resident for the extra pass)."""
+    del BPPARAM, average
     if k is None:
         raise TypeError("k must be given (the reference fails on k = NULL, R/fastRUVIII.R:78)")
     m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
@@ -541,13 +583,19 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     exact = _is_exact(BSPARAM)
     m_total = _total_cells(actx, m)  # several ranks: the reference's m is the number of cells over all of them
     s = _svd_k(m_total, G, int(ctl.sum()), exact, svd_k)
-    if G >= m_total or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input
+    if G >= m_total or k == 0:  # R/fastRUVIII.R:78-80: RUV-III not appropriate, return the input (after RUV1, :64)
         newY, fa = Y, None
+        if eta is not None:
+            ectx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
+            dY, copied = _as_device(ectx, Y)
+            newY = _finish(_ruv1(ectx, dY, eta, ctl, include_intercept, in_place=copied), copied)
         return {"newY": newY, "M": M, "fullalpha": fa} if return_info else newY
     if isinstance(ctx, MultiContext) and not (_is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray))):
         raise TypeError("a MultiContext drives HOST matrices (C-contiguous float64 cells x genes); device-resident shards use MultiContext.ctx(i)")
     ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
-    if _is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray)):
+    if eta is not None and isinstance(ctx, MultiContext):
+        raise L.ScmError(L.ERR_UNSUPPORTED, "eta is not supported on a MultiContext (host-streaming driver): use one context per device")
+    if eta is None and _is_host_matrix(Y) and (out is None or isinstance(out, np.ndarray)):
         # host matrix: one pipelined call (H2D / fit / adjust / D2H overlapped)
         if fullalpha is None:
             s_dev, exact_dev = _device_rows_cap(s, k, exact, n)
@@ -558,6 +606,9 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
             newY, _ = _host_pipeline(ctx, Y, ctl, int(k), fullalpha_in=fullalpha, center_mode=0, out=out)
         return {"newY": newY, "M": M, "fullalpha": fullalpha} if return_info else newY
     dY, copied = _as_device(ctx, Y)
+    if eta is not None:  # R/fastRUVIII.R:63-64: Y <- RUV1(Y, eta, ctl); everything below works on that matrix
+        d1 = _ruv1(ctx, dY, eta, ctl, include_intercept, in_place=copied)
+        dY, copied = d1, True
     if fullalpha is None:
         # NA/Inf check (R/fastRUVIII.R:52-60) is fused into the first pass over Y; inputcheck=False only skips the raise
         del inputcheck
@@ -565,8 +616,9 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
         fit = _fit(ctx, dY, keys, G, s_dev, int(k), exact_dev)
         fullalpha = fit.fullalpha
     fullalpha = np.asanyarray(fullalpha, dtype=np.float64)
+    host_result = not isinstance(Y, DeviceMatrix)
     dout, _ = _adjust(ctx, dY, fullalpha, int(k), ctl, out=out if isinstance(out, DeviceMatrix) else None)
-    newY = _finish(dout, copied, out if isinstance(out, np.ndarray) else None)
+    newY = _finish(dout, host_result, out if isinstance(out, np.ndarray) else None)
     if copied:
         dY.free()
     if not return_info:
@@ -724,9 +776,7 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
                  chunkSize=50000, ctx: Context | None = None, gene_names=None):
     """R/scMerge2_utilis.R:17-150.  Fit on the pseudobulk matrix (P x n), adjust every cell of Y (m x n).
     byChunk / chunkSize / BPPARAM are accepted for parity; the fused kernel streams all cells in one launch."""
-    del BPPARAM, include_intercept, verbose, byChunk, chunkSize, inputcheck
-    if eta is not None:
-        raise NotImplementedError("eta is not supported")
+    del BPPARAM, verbose, byChunk, chunkSize, inputcheck
     ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
     n = Y.n if isinstance(Y, DeviceMatrix) else np.shape(Y)[1]
     P = Y_pseudo.m if isinstance(Y_pseudo, DeviceMatrix) else np.shape(Y_pseudo)[0]
@@ -734,10 +784,15 @@ def pseudoRUVIII(Y, Y_pseudo, M, ctl, k=None, eta=None, include_intercept=True, 
     ctl = tological(ctl, n)
     exact = _is_exact(BSPARAM)
     s = _svd_k(P, G, int(ctl.sum()), exact, k)  # Exact branch caps at k here (R/scMerge2_utilis.R:60-61)
-    if G >= P or k == 0:  # R/scMerge2_utilis.R:72-76 returns the pseudobulk matrix itself
+    if G >= P or k == 0:  # R/scMerge2_utilis.R:72-76 returns the pseudobulk matrix itself (after RUV1, :56)
+        if eta is not None:
+            dP, pcopied = _as_device(ctx, Y_pseudo)
+            return _finish(_ruv1(ctx, dP, eta, ctl, include_intercept, in_place=pcopied), pcopied)
         return Y_pseudo
     if fullalpha is None:
         dP, pcopied = _as_device(ctx, Y_pseudo)
+        if eta is not None:  # R/scMerge2_utilis.R:56: Y_pseudo <- RUV1(Y_pseudo, eta, ctl) (the pseudobulks only, not the cells)
+            dP, pcopied = _ruv1(ctx, dP, eta, ctl, include_intercept, in_place=pcopied), True
         s_dev, exact_dev = _device_rows_cap(s, k, exact, n, rows=P)
         try:
             fit = _fit(ctx, dP, keys, G, s_dev, int(k), exact_dev)
