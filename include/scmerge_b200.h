@@ -323,7 +323,15 @@ int scm_ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, in
  *                         columns of D ordered by cluster (offsets on the host): compute_dist_res (R/scReplicate.R:507-513)
  *   scm_centred_gram      centred Gram sum (y - ybar)(y - ybar)' and column means of ALL cells (cross-rank like scm_ruv3_fit): with
  *                         scm_pca_scores(coef = NULL) this is BiocSingular::runPCA(x, rank = 10, scale = TRUE, center = TRUE)$x of
- *                         computePCA_byHVGMarker (R/scReplicate.R:793-819) and of the kmeans input (:392-395) */
+ *                         computePCA_byHVGMarker (R/scReplicate.R:793-819) and of the kmeans input (:392-395)
+ *   scm_kmeans            stats::kmeans(x, centers = K, nstart, algorithm = "Hartigan-Wong") of identifyCluster
+ *                         (R/scReplicate.R:394-395: kmeans(pca_current[, 1:10], centers = kmeansK[j], nstart = 1000)): every
+ *                         start draws K distinct rows (counter-based hash of (seed, start): R's RNG stream is not reproduced),
+ *                         runs Lloyd iterations to a fixed point (at most iter_max), the start with the smallest total
+ *                         within-cluster sum of squares wins and is finished with Hartigan-Wong single-point transfers until
+ *                         none lowers the objective (the reference's stopping rule).  d_X: m x d, d <= 16.  d_label: cluster
+ *                         ids in [0, K) (R: + 1); d_centers K x d; h_withinss / h_size K; h_info: [winning start, its Lloyd
+ *                         iterations, transfers, 1 if the transfer cap was hit].  Deterministic for a given seed */
 int scm_gather(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const int32_t* d_rows, int64_t msub,
                const int32_t* d_cols, int64_t nsub, double* d_out, int64_t ldo);
 int scm_group_median(scm_ctx* ctx, const double* d_X, int64_t m, int64_t n, int64_t ld, const int32_t* h_key, const int32_t* d_key,
@@ -336,6 +344,8 @@ int scm_block_median(scm_ctx* ctx, const double* d_D, int64_t ldd, const int64_t
                      int32_t K2, double* h_med);
 int scm_centred_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, double* d_gram, double* d_colmean,
                      int64_t* m_total_out);
+int scm_kmeans(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t ldx, int32_t K, int32_t nstart, int32_t iter_max, uint64_t seed,
+               int32_t* d_label, double* d_centers, double* h_withinss, int64_t* h_size, double* h_tot_withinss, int32_t* h_info);
 
 /* scm_ruv3_host: the whole closure on HOST matrices (what `.Call` hands over), with the PCIe copies overlapped with
  * the kernels: Y is uploaded in row chunks on a copy stream while the replicate sums and the Gram accumulate behind

@@ -602,3 +602,65 @@ def run_pca_scores(x, rank=10):
     U, S, _ = np.linalg.svd(Xs, full_matrices=False)
     r = min(rank, S.shape[0])
     return U[:, :r] * S[:r]
+
+
+def kmeans_hartigan_wong(x, centers, nstart=1, iter_max=10, rng=None, init=None):
+    """stats::kmeans(x, centers = K, nstart, algorithm = "Hartigan-Wong") as identifyCluster calls it (R/scReplicate.R:394-395),
+    restated from the published algorithm (Hartigan & Wong 1979, AS 136; base R's stats package is not part of the reference
+    tree): every start takes K distinct rows of unique(x) as centres, assigns every point to the nearest one, then sweeps the
+    points in order and moves point i from its cluster a (n_a > 1) to the cluster b minimising n_b |x - c_b|^2 / (n_b + 1)
+    whenever that is below n_a |x - c_a|^2 / (n_a - 1), updating both centres at once, until a whole sweep moves nothing (or
+    iter_max sweeps); the start with the smallest total within-cluster sum of squares is returned.  AS 136's live-set /
+    quick-transfer bookkeeping changes the order of the moves, not the set of partitions that stop it.  The random stream is
+    NumPy's, not R's.  `init`: list of index arrays (one per start) instead of random draws.  Pure Python loops: small cases.
+    Returns dict(cluster (1-based), centers, withinss, tot_withinss, size, iter)."""
+    x = np.asarray(x, dtype=np.float64)
+    m, d = x.shape
+    K = int(centers)
+    rng = rng or np.random.default_rng(0)
+    ux, first = np.unique(x, axis=0, return_index=True)
+    if ux.shape[0] < K:
+        raise ValueError("more cluster centers than distinct data points.")
+    best = None
+    for s in range(nstart):
+        idx = np.asarray(init[s]) if init is not None else np.sort(first)[rng.choice(first.shape[0], K, replace=False)]
+        cen = x[idx].copy()
+        lab = np.argmin(((x[:, None, :] - cen[None]) ** 2).sum(-1), axis=1)
+        cnt = np.bincount(lab, minlength=K).astype(np.float64)
+        if (cnt == 0).any():
+            continue
+        cen = np.stack([x[lab == c].mean(axis=0) for c in range(K)])
+        it = 0
+        for it in range(1, iter_max + 1):
+            moved = False
+            for i in range(m):
+                a = lab[i]
+                if cnt[a] <= 1:
+                    continue
+                d2 = ((x[i] - cen) ** 2).sum(axis=1)
+                r1 = cnt[a] * d2[a] / (cnt[a] - 1)
+                r2 = cnt * d2 / (cnt + 1)
+                r2[a] = np.inf
+                b = int(np.argmin(r2))
+                if r2[b] < r1:
+                    cen[a] = (cen[a] * cnt[a] - x[i]) / (cnt[a] - 1)
+                    cen[b] = (cen[b] * cnt[b] + x[i]) / (cnt[b] + 1)
+                    cnt[a] -= 1
+                    cnt[b] += 1
+                    lab[i] = b
+                    moved = True
+            if not moved:
+                break
+        cen = np.stack([x[lab == c].mean(axis=0) for c in range(K)])
+        wss = np.array([((x[lab == c] - cen[c]) ** 2).sum() for c in range(K)])
+        if best is None or wss.sum() < best["tot_withinss"]:
+            best = {"cluster": lab + 1, "centers": cen, "withinss": wss, "tot_withinss": float(wss.sum()),
+                    "size": np.bincount(lab, minlength=K), "iter": it}
+    return best
+
+
+def same_partition(a, b) -> bool:
+    """Two label vectors describe the same partition (cluster ids are arbitrary in kmeans)."""
+    a, b = np.asarray(a), np.asarray(b)
+    pairs = set(zip(a.tolist(), b.tolist()))
+    return len(pairs) == len(set(a.tolist())) == len(set(b.tolist()))

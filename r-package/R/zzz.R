@@ -3,7 +3,8 @@
 ## bindings there makes the unmodified drivers run the B200 path.  useB200(FALSE) restores the originals.
 .saved <- new.env(parent = emptyenv())
 .closures <- c("fastRUVIII", "scRUVIII", "pseudoRUVIII", "getAdjustedMat", "scRUVg",
-               "centroidDist", "compute_dist_mat", "compute_dist_res", "computePCA_byHVGMarker")   # scReplicate's arithmetic helpers
+               "centroidDist", "compute_dist_mat", "compute_dist_res", "computePCA_byHVGMarker",   # scReplicate's arithmetic helpers
+               "identifyCluster")                                                                   # ... and its kmeans(nstart = 1000)
 
 useB200 <- function(on = TRUE) {
   if (!requireNamespace("scMerge", quietly = TRUE)) stop("scMerge is not installed")

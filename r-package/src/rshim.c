@@ -427,7 +427,35 @@ SEXP scm_pca(SEXP X, SEXP rank_) {
     return out;
 }
 
+/* stats::kmeans(t(Xt), centers = K, nstart = nstart) of identifyCluster (R/scReplicate.R:394-395) on the device.  Xt: coordinates x
+ * points (the transposed score matrix: R's column-major memory is then points x coordinates by rows).  Returns
+ * list(cluster (1-based), centers (K x d), withinss, tot.withinss, size, iter, ifault). */
+SEXP scm_kmeans_(SEXP Xt, SEXP K_, SEXP nstart_, SEXP iter_max_, SEXP seed_) {
+    dmat d = up_gc(Xt);
+    int K = Rf_asInteger(K_), iter_max = Rf_asInteger(iter_max_);
+    int32_t* dl; double* dc;
+    CHECK(scm_dev_alloc(ctx(), d.m * 4, (void**)&dl)); CHECK(scm_dev_alloc(ctx(), (int64_t)K * d.n * 8, (void**)&dc));
+    double* wss = (double*)R_alloc(K, 8); int64_t* size = (int64_t*)R_alloc(K, 8);
+    double tot = 0.0; int32_t info[4];
+    CHECK(scm_kmeans(ctx(), d.p, d.m, (int32_t)d.n, d.ld, K, Rf_asInteger(nstart_), iter_max, (uint64_t)Rf_asReal(seed_), dl, dc, wss, size, &tot, info));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 7));
+    SEXP cl = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)d.m));
+    CHECK(scm_d2h(ctx(), INTEGER(cl), dl, d.m * 4));
+    for (int64_t i = 0; i < d.m; i++) INTEGER(cl)[i] += 1;
+    SEXP cen = PROTECT(Rf_allocMatrix(REALSXP, (int)d.n, K));          /* d x K image of the K x d row-major centres */
+    CHECK(scm_d2h(ctx(), REAL(cen), dc, (int64_t)K * d.n * 8));
+    SEXP w = PROTECT(Rf_allocVector(REALSXP, K)), sz = PROTECT(Rf_allocVector(INTSXP, K));
+    for (int c = 0; c < K; c++) { REAL(w)[c] = wss[c]; INTEGER(sz)[c] = (int)size[c]; }
+    SET_VECTOR_ELT(out, 0, cl); SET_VECTOR_ELT(out, 1, cen); SET_VECTOR_ELT(out, 2, w); SET_VECTOR_ELT(out, 3, Rf_ScalarReal(tot));
+    SET_VECTOR_ELT(out, 4, sz); SET_VECTOR_ELT(out, 5, Rf_ScalarInteger(info[1]));
+    SET_VECTOR_ELT(out, 6, Rf_ScalarInteger((info[1] >= iter_max || info[3]) ? 2 : 0));
+    scm_dev_free(ctx(), dl); scm_dev_free(ctx(), dc); scm_dev_free(ctx(), d.p);
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef calls[] = {
+    {"scm_kmeans_", (DL_FUNC)&scm_kmeans_, 5},
     {"scm_centroid_sqdist", (DL_FUNC)&scm_centroid_sqdist, 3}, {"scm_dist", (DL_FUNC)&scm_dist, 5}, {"scm_pca", (DL_FUNC)&scm_pca, 2},
     {"scm_use_gpus", (DL_FUNC)&scm_use_gpus, 1}, {"scm_host", (DL_FUNC)&scm_host, 12},
     {"scm_upload_csc", (DL_FUNC)&scm_upload_csc, 5}, {"scm_csc_pseudobulk", (DL_FUNC)&scm_csc_pseudobulk, 3},

@@ -149,6 +149,7 @@ inline int cosine_rows(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, in
 #include "select_k.cuh"
 #include "csc_sparse.cuh"
 #include "replicate.cuh"
+#include "kmeans.cuh"
 
 using namespace scm;
 
@@ -687,6 +688,11 @@ int scm_block_median(scm_ctx* ctx, const double* d_D, int64_t ldd, const int64_t
                      int32_t K2, double* h_med) {
     SCM_REQUIRE_CTX(ctx);
     return block_median(ctx, d_D, ldd, h_row_off, K1, h_col_off, K2, h_med);
+}
+int scm_kmeans(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t ldx, int32_t K, int32_t nstart, int32_t iter_max, uint64_t seed,
+               int32_t* d_label, double* d_centers, double* h_withinss, int64_t* h_size, double* h_tot_withinss, int32_t* h_info) {
+    SCM_REQUIRE_CTX(ctx);
+    return kmeans(ctx, d_X, m, d, ldx, K, nstart, iter_max, seed, d_label, d_centers, h_withinss, h_size, h_tot_withinss, h_info);
 }
 int scm_centred_gram(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, double* d_gram, double* d_colmean,
                      int64_t* m_total_out) {

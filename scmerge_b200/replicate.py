@@ -1,11 +1,13 @@
 """Replicate-finding numerics of scReplicate on the device: what is ARITHMETIC in
-R/scReplicate.R.  kmeans, the mutual-nearest-cluster graph and igraph stay in R (out of scope); their inputs and the quantities
-they consume come from here.
+R/scReplicate.R, including the kmeans with 1000 starts per batch.  The mutual-nearest-cluster graph and igraph stay in R (out
+of scope); their inputs and the quantities they consume come from here.
 
     centroidDist                R/scReplicate.R:458-464      per-gene medians of a cluster, squared distances, ranks
     cluster_centroid_dist       R/scReplicate.R:396-413      the same for every kmeans cluster of a batch in one pass
     compute_dist_mat / _res     R/scReplicate.R:470-520      cell-cell distances between two batches, medians per cluster pair
     computePCA_byHVGMarker      R/scReplicate.R:793-819      runPCA(rank 10, centred, scaled) of one batch on its genes
+    kmeans                      R/scReplicate.R:394-395      stats::kmeans(pca[, 1:10], centers = K, nstart = 1000)
+    identifyCluster             R/scReplicate.R:330-447      per batch: PCA -> kmeans -> centroidDist of every cluster
 
 Matrices follow the reference: `exprs_mat` is genes x cells (numpy; column-major R memory is the device's cells x genes rows).
 No arithmetic happens in Python: ranks (an ordering) and cluster offsets are index plumbing.
@@ -20,7 +22,8 @@ import numpy as np
 from . import _lib as L
 from .device import Context, DeviceMatrix, default_context
 
-__all__ = ["centroidDist", "cluster_centroid_dist", "compute_dist_mat", "compute_dist_res", "computePCA_byHVGMarker", "run_pca_scores"]
+__all__ = ["centroidDist", "cluster_centroid_dist", "compute_dist_mat", "compute_dist_res", "computePCA_byHVGMarker", "run_pca_scores",
+           "kmeans", "identifyCluster"]
 
 _METRIC = {"euclidean": 0, "cosine": 1, "cor": 2}
 
@@ -184,3 +187,67 @@ def computePCA_byHVGMarker(this_batch, batch, batch_oneType, marker, exprs_mat, 
         return run_pca_scores(dX, rank=10, ctx=ctx)
     finally:
         dX.free()
+
+
+def kmeans(x, centers: int, iter_max: int = 100, nstart: int = 1, seed: int = 1, ctx: Context | None = None):
+    """stats::kmeans(x, centers = K, nstart = nstart) the way identifyCluster calls it (R/scReplicate.R:394-395: the first 10 PCs
+    of a batch, K = kmeansK[j], nstart = 1000), on the device (scm_kmeans).  x: points x coordinates (numpy or DeviceMatrix, at
+    most 16 coordinates).  Every start draws K distinct rows, the start with the smallest total within-cluster sum of squares
+    wins and is finished with Hartigan-Wong transfers, so the partition is stable under the reference's own rule.  R's RNG
+    stream is not reproduced (the reference's clustering is seed-dependent itself): `seed` selects the starts, the result is
+    deterministic for a given seed.  `iter_max` bounds the Lloyd iterations of one start (R's iter.max = 10 counts
+    Hartigan-Wong passes, a different unit).  Returns R's fields: cluster (1-based), centers, withinss, tot_withinss, size,
+    iter, ifault (0; 2 = iteration / transfer cap hit, R's "did not converge")."""
+    ctx = ctx or (x.ctx if isinstance(x, DeviceMatrix) else default_context())
+    K = int(centers)
+    dX = x if isinstance(x, DeviceMatrix) else DeviceMatrix.from_host(ctx, np.asarray(x, dtype=np.float64))
+    m, d = dX.m, dX.n
+    if K > m:
+        raise ValueError("more cluster centers than data points")  # stats::kmeans, same condition on distinct points
+    d_label, d_cent = ctx.empty((m,), np.int32), ctx.empty((K, d))
+    wss, size = np.empty(K), np.empty(K, dtype=np.int64)
+    tot, info = C.c_double(0.0), np.zeros(4, dtype=np.int32)
+    try:
+        L.check(L.lib().scm_kmeans(ctx.handle, dX.ptr, m, d, dX.ld, K, int(nstart), int(iter_max), int(seed) & (2 ** 64 - 1), d_label.ptr,
+                                   d_cent.ptr, wss.ctypes.data_as(C.c_void_p), size.ctypes.data_as(C.c_void_p), C.byref(tot),
+                                   info.ctypes.data_as(C.c_void_p)))
+        label, cent = d_label.to_host(), d_cent.to_host()
+    finally:
+        d_label.free()
+        d_cent.free()
+        if dX is not x:
+            dX.free()
+    if (size == 0).any():
+        raise RuntimeError("empty cluster: try a better set of initial centers")  # stats::kmeans' message (ifault 1)
+    ifault = 2 if (info[1] >= iter_max or info[3]) else 0
+    if ifault:
+        warnings.warn(f"did not converge in {iter_max} iterations", stacklevel=2)
+    return {"cluster": label.astype(np.int64) + 1, "centers": cent, "withinss": wss, "tot_withinss": tot.value, "size": size,
+            "iter": int(info[1]), "ifault": ifault, "start": int(info[0]), "transfers": int(info[2])}
+
+
+def identifyCluster(exprs_mat, batch, marker, HVG_list, kmeansK, nstart: int = 1000, seed: int = 1, ctx: Context | None = None):
+    """identifyCluster (R/scReplicate.R:330-447).  exprs_mat: genes x cells; batch: label per cell; marker / HVG_list[b]: 0-based
+    gene indices; kmeansK: K per batch in the order of unique(batch) (first appearance).  Per batch: runPCA (rank 10) on its genes ->
+    kmeans(first 10 PCs, K, nstart) -> centroidDist of every cluster on the same genes; a batch with K == 1 is one cluster.
+    Returns (clustering_list, clustering_distProp): per batch the cluster id (1-based) and the rank fraction of every cell."""
+    ctx = ctx or default_context()
+    batch = np.asarray(batch)
+    _, first = np.unique(batch, return_index=True)
+    batch_list = batch[np.sort(first)]  # unique(batch): order of first appearance (R/scReplicate.R:361)
+    if len(kmeansK) != batch_list.shape[0]:
+        raise ValueError("length of kmeansK needs to be the same as the number of batch")
+    one_type = [b for b, K in zip(batch_list, kmeansK) if K == 1]
+    clustering, dist_prop = [], []
+    X = np.asarray(exprs_mat, dtype=np.float64)
+    for j, b in enumerate(batch_list):
+        cells = np.nonzero(batch == b)[0]
+        genes = np.asarray(marker if marker is not None else HVG_list[b], dtype=np.int64)
+        pca = computePCA_byHVGMarker(b, batch, one_type, marker, X, HVG_list, ctx=ctx)
+        if pca is None:
+            lab = np.ones(cells.shape[0], dtype=np.int64)
+        else:
+            lab = kmeans(pca[:, :10], int(kmeansK[j]), nstart=nstart, seed=seed + j, ctx=ctx)["cluster"]
+        clustering.append(lab)
+        dist_prop.append(cluster_centroid_dist(X[np.ix_(genes, cells)], lab, ctx=ctx)[0])
+    return clustering, dist_prop

@@ -580,6 +580,8 @@ def fastRUVIII(Y, M, ctl, k=None, eta=None, svd_k=50, include_intercept=True, av
     if keys.shape[0] != m:
         raise ValueError("M must have one row per row of Y")
     ctl = tological(ctl, n)
+    if eta is not None:
+        eta_design_rows(eta, n, include_intercept)  # argument errors before any device work
     exact = _is_exact(BSPARAM)
     m_total = _total_cells(actx, m)  # several ranks: the reference's m is the number of cells over all of them
     s = _svd_k(m_total, G, int(ctl.sum()), exact, svd_k)

@@ -19,6 +19,7 @@ double* REAL(SEXP x);
 SEXP Rf_getAttrib(SEXP x, SEXP name);
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP val);
 int Rf_asInteger(SEXP x);
+double Rf_asReal(SEXP x);
 int Rf_asLogical(SEXP x);
 Rboolean Rf_isNull(SEXP x);
 int Rf_length(SEXP x);
@@ -26,6 +27,8 @@ R_xlen_t Rf_xlength(SEXP x);
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
 SEXP Rf_allocMatrix(SEXPTYPE type, int nrow, int ncol);
 SEXP Rf_mkChar(const char* s);
+SEXP Rf_ScalarReal(double x);
+SEXP Rf_ScalarInteger(int x);
 SEXP Rf_protect(SEXP x);
 void Rf_unprotect(int n);
 #define PROTECT(x) Rf_protect(x)

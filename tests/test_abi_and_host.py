@@ -107,8 +107,8 @@ def test_early_out_needs_no_device():
     assert sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=0) is Y
     with pytest.raises(TypeError):
         sm.fastRUVIII(Y, np.arange(6) % 2, [0])
-    with pytest.raises(NotImplementedError):
-        sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=1, eta=np.ones((1, 2)))
+    with pytest.raises(ValueError):
+        sm.fastRUVIII(Y, np.arange(6) % 2, [0], k=1, eta=np.ones((3, 5)))  # eta must have one row / column per gene: device-free error
 
 
 def test_scruviii_early_out_needs_no_device():
@@ -302,3 +302,20 @@ def test_gene_selection_by_name():
     assert genes_by_name(np.array([True, False, True, False]), 4).tolist() == [True, False, True, False]
     with pytest.raises(ValueError, match="gene_names"):
         genes_by_name(["g1"], 4)
+
+
+def test_eta_design_rows_match_the_oracle_design_matrix():
+    """Host-side resolution of gene-wise covariates (ruv::RUV1's design.matrix) against the oracle's restatement."""
+    from scmerge_b200.ruv import eta_design_rows
+    from oracle import ruv_oracle as orc
+    n = 40
+    rng = np.random.default_rng(0)
+    eta = rng.normal(size=(n, 2))
+    for arg, inter in ((eta, True), (eta, False), (eta.T, True), (eta[:, 0], True), (1, True), (np.c_[np.ones(n), eta], True)):
+        assert np.array_equal(eta_design_rows(arg, n, inter), orc.design_matrix(arg, n, inter).T)
+    with pytest.raises(ValueError):
+        eta_design_rows(np.c_[eta, eta[:, :1] * 2], n, True)                # collinear
+    with pytest.raises(ValueError):
+        eta_design_rows(np.zeros((n + 1, 2)), n, True)                      # wrong shape
+    with pytest.raises(ValueError):
+        eta_design_rows(2, n, True)

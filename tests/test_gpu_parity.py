@@ -666,6 +666,37 @@ def test_sparse_native_kernels_vs_dense(sm, ctx, m, n, density, k, G):
     dcsc.free()
 
 
+# ---- eta: gene-wise covariates (ruv::RUV1, R/fastRUVIII.R:63-64, R/scMerge2_utilis.R:56) ---------------------------------
+@pytest.mark.parametrize("intercept", [True, False])
+def test_fastruviii_and_pseudoruviii_with_eta_vs_oracle(sm, ctx, intercept):
+    """Y <- RUV1(Y, eta, ctl) runs through the rank-k update kernels with the rows of eta in the place of alpha; host matrix,
+    device-resident matrix (the caller's matrix must stay untouched), the early-out and the pseudobulk fit."""
+    L = orc.ruv_simulate(m=300, n=600, nc=150, n_celltypes=4, rng=np.random.default_rng(77))
+    Y, M, ctl = L["Y"], L["M"], L["ctl"]
+    n = Y.shape[1]
+    eta = np.random.default_rng(5).normal(size=(n, 2))
+    ref = orc.fastRUVIII(Y, M, ctl, 6, eta=eta, include_intercept=intercept, return_info=True)
+    got = sm.fastRUVIII(Y, M, ctl, k=6, eta=eta, include_intercept=intercept, return_info=True)
+    assert orc.rel_frobenius(got["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(got["fullalpha"][:6], ref["fullalpha"][:6]).max() < 1e-6
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    dres = sm.fastRUVIII(dY, M, ctl, k=6, eta=eta.T, include_intercept=intercept)       # q x n orientation, resident input
+    assert isinstance(dres, sm.DeviceMatrix) and np.array_equal(dres.to_host(), got["newY"])
+    assert np.array_equal(dY.to_host(), Y)                                               # the caller's matrix is not overwritten
+    dres.free()
+    # early-out (k = 0): the reference returns RUV1(Y), not Y
+    r0 = sm.fastRUVIII(Y, M, ctl, k=0, eta=eta, include_intercept=intercept)
+    assert orc.rel_frobenius(r0, orc.RUV1(Y, eta, ctl, intercept)) < 1e-12
+    # pseudoRUVIII: RUV1 applies to the pseudobulk matrix only
+    grp = np.arange(Y.shape[0]) % 60
+    Yp = np.stack([Y[grp == g].mean(axis=0) for g in range(60)])
+    Mp = np.arange(60) % 12
+    pref = orc.pseudoRUVIII(Y, Yp, Mp, ctl, 5, eta=eta, include_intercept=intercept)
+    pgot = sm.pseudoRUVIII(Y, Yp, Mp, ctl, k=5, eta=eta, include_intercept=intercept, BSPARAM=sm.ExactParam(), return_info=True)
+    assert orc.rel_frobenius(pgot["newY"], pref["newY"]) < TOL_NEWY
+    dY.free()
+
+
 # ---- scRUVg (SURVEY.md 8f rank 3) ---------------------------------------------------------------------------
 @pytest.mark.parametrize("m,n,nc,k", [(80, 1000, 50, 20), (3000, 400, 120, 10)])
 def test_scruvg_vs_oracle(sm, m, n, nc, k):

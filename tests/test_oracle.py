@@ -251,3 +251,32 @@ def test_golden_select(golden_dir):
     r = orc.scRUVg(d["logcounts"].T, d["ctl"], 10)
     assert orc.rel_frobenius(r["newY"][:16], g["ruvg_newY_rows"]) < 1e-9
     assert np.allclose(np.abs(r["W"]).sum(axis=0), g["ruvg_absW_colsum"], rtol=1e-8)
+
+
+def test_ruv1_gene_covariates(sim):
+    """ruv::RUV1 restatement (call sites R/fastRUVIII.R:64, R/scRUVg.R:59, R/scMerge2_utilis.R:56): eta = NULL is the identity;
+    the removed part lies in the row space of eta, and anything already in that row space on ALL genes is removed entirely;
+    an intercept is added exactly when the constant is not in the span; fastRUVIII(eta) == fastRUVIII on RUV1(Y)."""
+    Y, M, ctl = sim["Y"], sim["M"], sim["ctl"]
+    n = Y.shape[1]
+    rng = np.random.default_rng(3)
+    assert orc.RUV1(Y, None, ctl) is Y
+    eta = rng.normal(size=(n, 2))
+    E = orc.design_matrix(eta, n, True)
+    assert E.shape == (n, 3) and np.all(E[:, 0] == 1)                      # intercept put first
+    assert orc.design_matrix(np.c_[np.ones(n), eta], n, True).shape == (n, 3)    # already there: not added twice
+    assert orc.design_matrix(eta.T, n, False).shape == (n, 2)                    # n columns -> transposed
+    assert orc.design_matrix(1, n).shape == (n, 1)
+    Y1 = orc.RUV1(Y, eta, ctl)
+    removed = Y - Y1
+    coef = np.linalg.lstsq(E, removed.T, rcond=None)[0]
+    assert np.allclose(E @ coef, removed.T, atol=1e-9)                      # removed part is in span(eta rows)
+    planted = rng.normal(size=(Y.shape[0], 3)) @ E.T                        # a signal living in the row space of eta
+    assert np.allclose(orc.RUV1(Y + planted, eta, ctl), Y1, atol=1e-8)       # ... is removed completely
+    a = orc.fastRUVIII(Y, M, ctl, 5, eta=eta)
+    b = orc.fastRUVIII(Y1, M, ctl, 5)
+    assert np.array_equal(a, b)
+    g = orc.scRUVg(Y, ctl, 4, eta=eta)
+    assert np.allclose(g["newY"], Y - g["W"] @ g["alpha"])                  # the subtraction is from the ORIGINAL Y (R/scRUVg.R:80)
+    g2 = orc.scRUVg(Y, ctl, 3, fullW=g["W"])                                # re-use of a decomposition (:64, :77)
+    assert np.allclose(g2["W"], g["W"][:, :3])

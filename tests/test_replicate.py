@@ -1,6 +1,6 @@
 """Replicate-finding numerics of scReplicate: oracle restatement (CPU) and device parity (GPU, through the C
 ABI).  Reference lines: centroidDist R/scReplicate.R:458-464, compute_dist_mat / compute_dist_res :470-520,
-computePCA_byHVGMarker :793-819."""
+computePCA_byHVGMarker :793-819, kmeans(nstart = 1000) of identifyCluster :394-395."""
 import numpy as np
 import pytest
 
@@ -136,3 +136,88 @@ def test_per_batch_pca_matches_oracle():
     ref = orc.run_pca_scores(exprs[:30, :500].T, rank=10)
     sg = np.sign((S * ref).sum(axis=0))
     assert np.allclose(S * sg, ref, rtol=0, atol=1e-7 * np.abs(ref).max())
+
+
+# ---- kmeans with many starts (R/scReplicate.R:394-395) ---------------------------------------------------------------------
+def _blobs(seed, K, d, per, spread=3.0, noise=1.0):
+    rng = np.random.default_rng(seed)
+    cent = rng.normal(size=(K, d)) * spread
+    x = np.concatenate([cent[c] + noise * rng.normal(size=(per, d)) for c in range(K)])
+    return x[rng.permutation(x.shape[0])]
+
+
+def test_oracle_kmeans_reaches_a_hartigan_wong_stable_optimum():
+    """The restated stats::kmeans: a stable partition under the transfer rule of AS 136, objective not above the best Lloyd
+    solution scikit-learn finds, and exactly the planted partition on separated blobs."""
+    from sklearn.cluster import KMeans
+    x = _blobs(1, 4, 10, 60)
+    r = orc.kmeans_hartigan_wong(x, 4, nstart=8, rng=np.random.default_rng(2))
+    km = KMeans(4, n_init=20, random_state=0).fit(x)
+    assert r["tot_withinss"] <= km.inertia_ * (1 + 1e-12) and orc.same_partition(r["cluster"], km.labels_)
+    lab, cen, cnt = r["cluster"] - 1, r["centers"], r["size"].astype(float)
+    assert np.allclose(cen, np.stack([x[lab == c].mean(axis=0) for c in range(4)]))
+    for i in range(x.shape[0]):                                  # no single transfer lowers the objective
+        a = lab[i]
+        d2 = ((x[i] - cen) ** 2).sum(axis=1)
+        r2 = cnt * d2 / (cnt + 1)
+        r2[a] = np.inf
+        assert r2.min() >= cnt[a] * d2[a] / (cnt[a] - 1)
+    assert np.isclose(r["withinss"].sum(), r["tot_withinss"]) and r["size"].sum() == x.shape[0]
+    with pytest.raises(ValueError):
+        orc.kmeans_hartigan_wong(np.zeros((5, 2)), 2)            # more centres than distinct points (stats::kmeans' error)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,d,per,spread", [(3, 10, 80, 3.0), (5, 10, 50, 1.2), (2, 3, 40, 0.8), (8, 16, 30, 2.0)])
+def test_kmeans_matches_oracle_optimum(K, d, per, spread):
+    """scm_kmeans against the restated stats::kmeans: the same optimum (total within-cluster sum of squares to 1e-10, the same
+    partition up to the arbitrary cluster ids), exact centres / sizes / withinss of that partition, Hartigan-Wong stability,
+    and bit-identical results for a given seed."""
+    import scmerge_b200 as sm
+    from scmerge_b200 import replicate as rp
+    x = _blobs(10 + K, K, d, per, spread=spread)
+    ref = orc.kmeans_hartigan_wong(x, K, nstart=30, rng=np.random.default_rng(K))
+    got = rp.kmeans(x, K, nstart=300, seed=1)
+    assert got["tot_withinss"] <= ref["tot_withinss"] * (1 + 1e-10)
+    if abs(got["tot_withinss"] - ref["tot_withinss"]) <= 1e-10 * ref["tot_withinss"]:
+        assert orc.same_partition(got["cluster"], ref["cluster"])
+    lab = got["cluster"] - 1
+    assert lab.min() == 0 and lab.max() == K - 1 and np.array_equal(np.bincount(lab, minlength=K), got["size"])
+    cen = np.stack([x[lab == c].mean(axis=0) for c in range(K)])
+    assert np.allclose(got["centers"], cen, rtol=1e-12, atol=1e-12)
+    wss = np.array([((x[lab == c] - cen[c]) ** 2).sum() for c in range(K)])
+    assert np.allclose(got["withinss"], wss, rtol=1e-11) and np.isclose(got["tot_withinss"], wss.sum(), rtol=1e-12)
+    cnt = got["size"].astype(float)
+    for i in range(x.shape[0]):                                  # stable under the reference's transfer rule
+        a = lab[i]
+        d2 = ((x[i] - cen) ** 2).sum(axis=1)
+        r2 = cnt * d2 / (cnt + 1)
+        r2[a] = np.inf
+        assert r2.min() >= cnt[a] * d2[a] / (cnt[a] - 1) * (1 - 1e-12)
+    again = rp.kmeans(sm.DeviceMatrix.from_host(sm.default_context(), x), K, nstart=300, seed=1)
+    assert np.array_equal(again["cluster"], got["cluster"]) and again["tot_withinss"] == got["tot_withinss"]
+    one = rp.kmeans(x, 1, nstart=3)
+    assert np.all(one["cluster"] == 1) and np.isclose(one["tot_withinss"], ((x - x.mean(axis=0)) ** 2).sum(), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_identify_cluster_pipeline_on_device():
+    """identifyCluster (R/scReplicate.R:358-447) end to end: per-batch PCA -> kmeans -> centroidDist, against the oracle pieces
+    chained the same way (planted clusters: the kmeans optimum is the planted partition)."""
+    from scmerge_b200 import replicate as rp
+    exprs, cells, labs = _toy(seed=11, n=80, m=(90, 70), K=(3, 2))
+    batch = np.concatenate([np.full(c.shape[0], b) for b, c in enumerate(cells)])
+    batch = np.where(batch == 0, "b2", "b1")                     # unique(batch) order is first appearance: b2, b1
+    genes = np.arange(exprs.shape[0])
+    cl, dp = rp.identifyCluster(exprs, batch, None, {"b2": genes, "b1": genes}, [3, 2], nstart=200)
+    for j, c in enumerate(cells):
+        X = exprs[:, c]
+        scores = orc.run_pca_scores(X.T, rank=10)
+        ref = orc.kmeans_hartigan_wong(scores[:, :10], (3, 2)[j], nstart=20, rng=np.random.default_rng(j))
+        assert orc.same_partition(cl[j], ref["cluster"])
+        want = np.empty(c.shape[0])
+        for g in np.unique(cl[j]):
+            want[cl[j] == g] = orc.centroid_dist(X[:, cl[j] == g])
+        assert np.allclose(dp[j], want)
+    cl1, dp1 = rp.identifyCluster(exprs, batch, genes, None, [1, 2], nstart=50)   # a batch with kmeansK == 1 is one cluster
+    assert np.all(cl1[0] == 1) and np.allclose(dp1[0], orc.centroid_dist(exprs[:, cells[0]]))
