@@ -307,6 +307,15 @@ int scm_silhouette(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_
 int scm_ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const uint8_t* d_ctl, int32_t k, int mode,
                  double tol, int32_t maxit, uint64_t seed, double* d_alpha, double* d_center, double* d_sigma, scm_coef** coef_out,
                  int32_t* iters_out, double* resid_out);
+/* scRUVg with a GIVEN factor matrix W (R/scRUVg.R:64,77-80: a re-used `fullW[, 1:k]`), and the last step of scRUVg with eta, where W
+ * comes from RUV1(Y) and is subtracted from Y itself:
+ *   scm_ls_coef         alpha = solve(W'W) W' (Y - 1 center')  (k x n; :78; center = colMeans of the matrix, Z = 1), sums over the
+ *                       cells all-reduced across ranks.  d_W: m_local x k row-major
+ *   scm_rankk_subtract  out = Y - W A for given W (m x k) and A (k x n): pass B of the fused rank-k update alone (:80) */
+int scm_ls_coef(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const double* d_W, int32_t k,
+                const double* d_center, double* d_alpha);
+int scm_rankk_subtract(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_W, int32_t k, const double* d_A,
+                       double* d_out, int64_t ldo);
 
 /* ---- replicate-finding numerics of scReplicate ----------------------------------------------------
  * What is arithmetic in R/scReplicate.R once kmeans / igraph (out of scope, they stay R) are taken away.

@@ -26,18 +26,40 @@
   list(s = want, exact = TRUE)
 }
 
+## Gene-wise covariates of ruv::RUV1 -> the q x n design rows t(design.matrix(eta)) (tested twin: scmerge_b200.ruv.eta_design_rows)
+.eta_rows <- function(eta, n, include.intercept) {
+  if (is.numeric(eta) && length(eta) == 1L) { stopifnot(eta == 1); eta <- matrix(1, n, 1) }
+  A <- as.matrix(eta)
+  if (nrow(A) != n) A <- t(A)
+  if (nrow(A) != n) stop("eta must have one row (or one column) per gene")
+  if (include.intercept && sum(stats::lm.fit(A, rep(1, n))$residuals^2) > 1e-8) A <- cbind(1, A)
+  d <- svd(scale(A, center = FALSE, scale = sqrt(colSums(A^2))))$d
+  if (ncol(A) > n || d[length(d)] < 1e-9 * d[1]) stop("eta is collinear: remove the redundant covariates")
+  t(A)
+}
+## Y <- ruv::RUV1(Y, eta, ctl) on a device handle (in place unless copy = TRUE): the rank-q update kernels with eta as alpha
+.ruv1 <- function(dY, eta, ctl2, include.intercept, copy = FALSE) {
+  E <- .eta_rows(eta, length(ctl2), include.intercept)
+  if (nrow(E) > sum(ctl2)) stop("eta has more covariates than there are control genes")
+  .Call("scm_ruv1_", dY, t(E), nrow(E), ctl2, as.integer(copy))
+}
+
 fastRUVIII <- function(Y, M, ctl, k = NULL, eta = NULL, svd_k = 50, include.intercept = TRUE, average = FALSE,
                        BPPARAM = SerialParam(), BSPARAM = ExactParam(), fullalpha = NULL, return.info = FALSE,
                        inputcheck = TRUE) {
-  if (!is.null(eta)) stop("eta is not supported on the device path")
   m <- nrow(Y); n <- ncol(Y)
   g <- .keys(M); ctl2 <- rep(FALSE, n); ctl2[ctl] <- TRUE
   exact <- inherits(BSPARAM, "ExactParam")
   s <- if (exact) min(m - g$G, sum(ctl2), svd_k, na.rm = TRUE) else min(m - g$G, sum(ctl2), na.rm = TRUE)
-  if (g$G >= m | k == 0) {
+  if ((g$G >= m | k == 0) && is.null(eta)) {
     newY <- Y; fullalpha <- NULL
+  } else if (g$G >= m | k == 0) {                                    # the early-out comes after RUV1 (R/fastRUVIII.R:64,78-80)
+    E <- .eta_rows(eta, n, include.intercept)
+    newY <- t(.Call("scm_adjust_", .Call("scm_upload", as.matrix(Y), 1L), t(E), nrow(E), ctl2, NULL, NULL, NULL, NULL))
+    dimnames(newY) <- dimnames(Y); fullalpha <- NULL
   } else {
     dY <- .Call("scm_upload", as.matrix(Y), 1L)                     # cells x genes column-major -> device transpose
+    if (!is.null(eta)) dY <- .ruv1(dY, eta, ctl2, include.intercept)  # R/fastRUVIII.R:63-64, in place on the private copy
     if (is.null(fullalpha)) {
       cap <- .rows_cap(s, k, exact, n)
       fit <- .Call("scm_fit", dY, g$key, g$G, NULL, 0L, cap$s, min(k, cap$s), if (cap$exact) 0L else 1L)
@@ -50,12 +72,21 @@ fastRUVIII <- function(Y, M, ctl, k = NULL, eta = NULL, svd_k = 50, include.inte
   if (!return.info) newY else list(newY = newY, M = M, fullalpha = fullalpha)
 }
 
-## scRUVg (R/scRUVg.R:30-85) with the default Z = 1, eta = NULL
+## scRUVg (R/scRUVg.R:30-85) with Z = 1.  eta: the decomposition and alpha use RUV1(Y), W alpha is subtracted from Y itself (:59,80);
+## fullW: W = fullW[, 1:k], alpha by least squares (:64,77-78).  svdyc without fullW fails in the reference too (:77).
 scRUVg <- function(Y, ctl, k, Z = 1, eta = NULL, include.intercept = TRUE, fullW = NULL, svdyc = NULL) {
-  stopifnot(is.null(eta), identical(Z, 1), is.null(fullW), is.null(svdyc))
+  stopifnot(identical(Z, 1))
+  if (!is.null(svdyc) && is.null(fullW)) stop("svdyc without fullW: pass fullW = svdyc$u (the reference never derives fullW from svdyc)")
   n <- ncol(Y); ctl2 <- rep(FALSE, n); ctl2[ctl] <- TRUE
   if (k > sum(ctl2)) stop("k must not be larger than the number of controls")
-  res <- .Call("scm_ruvg", .Call("scm_upload", as.matrix(Y), 1L), ctl2, as.integer(k))
+  dY <- .Call("scm_upload", as.matrix(Y), 1L)
+  if (is.null(eta) && is.null(fullW)) {
+    res <- .Call("scm_ruvg", dY, ctl2, as.integer(k))
+  } else {
+    dY0 <- if (is.null(eta)) dY else .ruv1(dY, eta, ctl2, include.intercept, copy = TRUE)
+    Wt <- if (is.null(fullW)) NULL else t(as.matrix(fullW)[, seq_len(k), drop = FALSE])
+    res <- .Call("scm_ruvg2", dY, dY0, ctl2, as.integer(k), Wt)
+  }
   list(newY = DelayedArray::DelayedArray(t(res[[1]])), W = t(res[[2]]), alpha = t(res[[3]]))
 }
 

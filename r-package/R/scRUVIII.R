@@ -76,14 +76,20 @@ pseudoRUVIII <- function(Y, Y_pseudo, M, ctl, k = NULL, eta = NULL, include.inte
                          fullalpha = NULL, return.info = FALSE, subset = NULL, BPPARAM = BiocParallel::SerialParam(),
                          BSPARAM = BiocSingular::ExactParam(), normalised = TRUE, verbose = TRUE, byChunk = TRUE,
                          chunkSize = 50000) {
-  if (!is.null(eta)) stop("eta is not supported on the device path")
   n <- ncol(Y); P <- nrow(Y_pseudo)
   g <- .keys(M); ctl2 <- .ctl_mask(ctl, n)
   exact <- inherits(BSPARAM, "ExactParam")
   s <- if (exact) min(P - g$G, sum(ctl2), k, na.rm = TRUE) else min(P - g$G, sum(ctl2), na.rm = TRUE)   # :60-65 (cap is k here)
-  if (g$G >= P | k == 0) return(Y_pseudo)                                                                 # :72-76
+  if (g$G >= P | k == 0) {                                                                                # :72-76 (after RUV1, :56)
+    if (is.null(eta)) return(Y_pseudo)
+    E <- .eta_rows(eta, n, include.intercept)
+    out <- t(.Call("scm_adjust_", .Call("scm_upload", as.matrix(Y_pseudo), 1L), t(E), nrow(E), ctl2, NULL, NULL, NULL, NULL))
+    dimnames(out) <- dimnames(Y_pseudo)
+    return(out)
+  }
   if (is.null(fullalpha)) {
     dP <- .Call("scm_upload", as.matrix(Y_pseudo), 1L)
+    if (!is.null(eta)) dP <- .ruv1(dP, eta, ctl2, include.intercept)                                      # :56: the pseudobulks only
     cap <- .rows_cap(s, k, exact, n, rows = P)
     fit <- .Call("scm_fit", dP, g$key, g$G, NULL, 0L, cap$s, min(k, cap$s), if (cap$exact) 0L else 1L)
     fullalpha <- t(fit[[1]]); colnames(fullalpha) <- colnames(Y)

@@ -219,6 +219,65 @@ SEXP scm_ruvg(SEXP Yp, SEXP ctl, SEXP k_) {
     return out;
 }
 
+/* ruv::RUV1 on a device matrix, in place: Y <- Y - Y[, ctl] etac' (etac etac')^-1 eta (R/fastRUVIII.R:63-64, R/scMerge2_utilis.R:56).
+ * eta_t: n x q image of the q x n design rows.  `copy` != 0: the result goes to a NEW device matrix (the handle given stays as it is). */
+SEXP scm_ruv1_(SEXP Yp, SEXP eta_t, SEXP q_, SEXP ctl, SEXP copy) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp);
+    int q = Rf_asInteger(q_);
+    double* de = (double*)to_dev(REAL(eta_t), (int64_t)q * d->n * 8);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    scm_coef* coef; CHECK(scm_coef_create(ctx(), de, d->n, q, dc, NULL, NULL, NULL, &coef));
+    SEXP out = Yp;
+    if (Rf_asInteger(copy)) {
+        dmat* o = R_Calloc(1, dmat); *o = *d;
+        CHECK(scm_dev_alloc(ctx(), d->m * d->ld * 8, (void**)&o->p));
+        CHECK(scm_adjust(ctx(), d->p, d->m, d->n, d->ld, coef, NULL, 0, o->p, o->ld, NULL));
+        out = PROTECT(R_MakeExternalPtr(o, R_NilValue, R_NilValue));
+        R_RegisterCFinalizerEx(out, dmat_fin, TRUE);
+        UNPROTECT(1);
+    } else {
+        CHECK(scm_adjust(ctx(), d->p, d->m, d->n, d->ld, coef, NULL, 0, d->p, d->ld, NULL));
+    }
+    scm_coef_destroy(ctx(), coef); scm_dev_free(ctx(), de); scm_dev_free(ctx(), dc);
+    return out;
+}
+
+/* scRUVg with eta and / or a re-used fullW (R/scRUVg.R:59,64,77-80).  Yp: the original matrix, Y0p: RUV1(Y) (the same handle when
+ * eta is NULL), Wt: k x m image of W = fullW[, 1:k] or NULL (then W comes from the decomposition of Y0). */
+SEXP scm_ruvg2(SEXP Yp, SEXP Y0p, SEXP ctl, SEXP k_, SEXP Wt) {
+    dmat* d = (dmat*)R_ExternalPtrAddr(Yp); dmat* d0 = (dmat*)R_ExternalPtrAddr(Y0p);
+    int k = Rf_asInteger(k_);
+    uint8_t* hc = (uint8_t*)R_alloc(d->n, 1); for (int64_t j = 0; j < d->n; j++) hc[j] = LOGICAL(ctl)[j] != 0;
+    uint8_t* dc = (uint8_t*)to_dev(hc, d->n);
+    double *dal, *dce, *dout, *dW; scm_coef* coef = NULL; int32_t iters; double resid;
+    CHECK(scm_dev_alloc(ctx(), (int64_t)k * d->n * 8, (void**)&dal)); CHECK(scm_dev_alloc(ctx(), d->n * 8, (void**)&dce));
+    CHECK(scm_dev_alloc(ctx(), d->m * d->ld * 8, (void**)&dout)); CHECK(scm_dev_alloc(ctx(), d->m * k * 8, (void**)&dW));
+    if (Rf_isNull(Wt)) {
+        CHECK(scm_ruvg_fit(ctx(), d0->p, d0->m, d0->n, d0->ld, dc, k, SCM_MODE_EXACT, 1e-10, 500, 1, dal, dce, NULL, &coef, &iters, &resid));
+        CHECK(scm_adjust(ctx(), d0->p, d0->m, d0->n, d0->ld, coef, NULL, 0, NULL, 0, dW));     /* projection only: W = (Y0 - mean) B */
+    } else {
+        CHECK(scm_h2d(ctx(), dW, REAL(Wt), d->m * k * 8));
+        int32_t* dk; int64_t* dcnt;
+        CHECK(scm_dev_alloc(ctx(), d->m * 4, (void**)&dk)); CHECK(scm_dev_alloc(ctx(), 8, (void**)&dcnt));
+        int32_t* hk = (int32_t*)R_alloc(d->m, 4); for (int64_t i = 0; i < d->m; i++) hk[i] = 0;
+        CHECK(scm_h2d(ctx(), dk, hk, d->m * 4));
+        CHECK(scm_seg_colmean(ctx(), d0->p, d0->m, d0->n, d0->ld, dk, 1, dce, dcnt, NULL));   /* colMeans(Y0): Z = 1 */
+        CHECK(scm_ls_coef(ctx(), d0->p, d0->m, d0->n, d0->ld, dW, k, dce, dal));
+        scm_dev_free(ctx(), dk); scm_dev_free(ctx(), dcnt);
+    }
+    CHECK(scm_rankk_subtract(ctx(), d->p, d->m, d->n, d->ld, dW, k, dal, dout, d->ld));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP ny = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, (int)d->m));
+    CHECK(scm_copy2d(ctx(), REAL(ny), d->n * 8, dout, d->ld * 8, d->n * 8, d->m, 1)); SET_VECTOR_ELT(out, 0, ny);
+    SEXP W = PROTECT(Rf_allocMatrix(REALSXP, k, (int)d->m)); CHECK(scm_d2h(ctx(), REAL(W), dW, d->m * k * 8)); SET_VECTOR_ELT(out, 1, W);
+    SEXP al = PROTECT(Rf_allocMatrix(REALSXP, (int)d->n, k)); CHECK(scm_d2h(ctx(), REAL(al), dal, (int64_t)k * d->n * 8)); SET_VECTOR_ELT(out, 2, al);
+    if (coef) scm_coef_destroy(ctx(), coef);
+    scm_dev_free(ctx(), dc); scm_dev_free(ctx(), dal); scm_dev_free(ctx(), dce); scm_dev_free(ctx(), dout); scm_dev_free(ctx(), dW);
+    UNPROTECT(4);
+    return out;
+}
+
 /* choice of ruvK (R/scRUVIII.R:83-105): for the candidate described by (alpha, k, ctl, center, pre, post) returns
  * c(silhouette(cell_type), silhouette(batch)) in the first `rank` PCs of the adjusted matrix.  gram / colmean are the external
  * pointers returned by scm_fit_gram (scm_ruv3_fit_gram); labels are 0-based ints. */
@@ -455,7 +514,7 @@ SEXP scm_kmeans_(SEXP Xt, SEXP K_, SEXP nstart_, SEXP iter_max_, SEXP seed_) {
 }
 
 static const R_CallMethodDef calls[] = {
-    {"scm_kmeans_", (DL_FUNC)&scm_kmeans_, 5},
+    {"scm_kmeans_", (DL_FUNC)&scm_kmeans_, 5}, {"scm_ruv1_", (DL_FUNC)&scm_ruv1_, 5}, {"scm_ruvg2", (DL_FUNC)&scm_ruvg2, 5},
     {"scm_centroid_sqdist", (DL_FUNC)&scm_centroid_sqdist, 3}, {"scm_dist", (DL_FUNC)&scm_dist, 5}, {"scm_pca", (DL_FUNC)&scm_pca, 2},
     {"scm_use_gpus", (DL_FUNC)&scm_use_gpus, 1}, {"scm_host", (DL_FUNC)&scm_host, 12},
     {"scm_upload_csc", (DL_FUNC)&scm_upload_csc, 5}, {"scm_csc_pseudobulk", (DL_FUNC)&scm_csc_pseudobulk, 3},

@@ -87,6 +87,8 @@ SIGNATURES = {
     "scm_pair_dist": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _i64],
     "scm_block_median": [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp],
     "scm_centred_gram": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, C.POINTER(_i64)],
+    "scm_ls_coef": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp],
+    "scm_rankk_subtract": [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _i64],
     "scm_kmeans": [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, C.POINTER(_dbl), _vp],
     "scm_timers": [_vp, C.POINTER(_dbl), _int],
 }

@@ -279,12 +279,12 @@ constexpr int ADJ_WARPS = 4;
 // four warps touch adjacent 128-byte lines of the same rows, the part of the rows pass A has read is at most
 // 8*MT rows x c genes per CTA (it is still in L2 when pass B re-reads it), and every warp keeps one block of
 // loads in flight while it computes on the previous one (explicit double buffering: ya / yb).
-template <int KT, int MT, bool PASS_B>
+template <int KT, int MT, bool PASS_B, bool GIVEN_W = false>  // GIVEN_W: no pass A, the rows of W (m x k) are read from `Wout`
 __global__ void __launch_bounds__(ADJ_WARPS * 32, (KT <= 3) ? 3 : 2)
 adjust_kernel(const double* Y /* may alias out */, int64_t m, int64_t n, int64_t ld, const double* __restrict__ Bfrag,
               const double* __restrict__ Afrag, const double* __restrict__ w0, const int32_t* __restrict__ ctl_blocks,
               int nblk_ctl, int nblk, int k, double* out, int64_t ldo, double* __restrict__ Wout, int vec_in, int vec_out, int nc) {
-    __shared__ double s_part[ADJ_WARPS][MT * KT * 2][32];
+    __shared__ double s_part[GIVEN_W ? 1 : ADJ_WARPS][MT * KT * 2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t row0 = (int64_t)blockIdx.x * (8 * MT);
@@ -307,61 +307,75 @@ adjust_kernel(const double* Y /* may alias out */, int64_t m, int64_t n, int64_t
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) w[mt][nt][0] = w[mt][nt][1] = 0.0;
-    auto pass_a_block = [&](const double (&y)[MT][4], int gb) {
-        const double2* bf = reinterpret_cast<const double2*>(Bfrag + (int64_t)gb * KT * 128) + lane;
+    if constexpr (GIVEN_W) {
+        (void)s_part;
 #pragma unroll
         for (int nt = 0; nt < KT; nt++) {
-            const double2 b01 = __ldg(bf + (nt * 2) * 32), b23 = __ldg(bf + (nt * 2 + 1) * 32);
-            const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+            const int kk = 8 * nt + 2 * tig;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) dmma884(w[mt][nt][0], w[mt][nt][1], y[mt][j], b[j]);
-        }
-    };
-    {
-        double ya[MT][4], yb[MT][4];
-        int bi = warp;
-        if (bi < nblk_ctl) load_block(ya, ctl_blocks[bi]);
-        while (bi < nblk_ctl) {
-            int nb = bi + ADJ_WARPS;
-            if (nb < nblk_ctl) load_block(yb, ctl_blocks[nb]);
-            pass_a_block(ya, ctl_blocks[bi]);
-            bi = nb;
-            if (bi >= nblk_ctl) break;
-            nb = bi + ADJ_WARPS;
-            if (nb < nblk_ctl) load_block(ya, ctl_blocks[nb]);
-            pass_a_block(yb, ctl_blocks[bi]);
-            bi = nb;
-        }
-    }
-    // ---- combine the four partial W tiles (fixed order => deterministic), subtract center' B
-#pragma unroll
-    for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-        for (int nt = 0; nt < KT; nt++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) s_part[warp][(mt * KT + nt) * 2 + e][lane] = w[mt][nt][e];
-    __syncthreads();
-#pragma unroll
-    for (int nt = 0; nt < KT; nt++) {
-        const int kk = 8 * nt + 2 * tig;
-        const double c0 = kk < k ? w0[kk] : 0.0, c1 = kk + 1 < k ? w0[kk + 1] : 0.0;
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-            for (int ww = 0; ww < ADJ_WARPS; ww++) {
-                t0 += s_part[ww][(mt * KT + nt) * 2 + 0][lane];
-                t1 += s_part[ww][(mt * KT + nt) * 2 + 1][lane];
+            for (int mt = 0; mt < MT; mt++) {
+                const double* wr = Wout + (row0 + mt * 8 + gid) * k;
+                w[mt][nt][0] = (rowok[mt] && kk < k) ? -wr[kk] : 0.0;
+                w[mt][nt][1] = (rowok[mt] && kk + 1 < k) ? -wr[kk + 1] : 0.0;
             }
-            t0 -= c0; t1 -= c1;
-            if (Wout && warp == 0 && rowok[mt]) {
-                double* wr = Wout + (row0 + mt * 8 + gid) * k;
-                if (kk < k) wr[kk] = t0;
-                if (kk + 1 < k) wr[kk + 1] = t1;
+        }
+    } else {
+        auto pass_a_block = [&](const double (&y)[MT][4], int gb) {
+            const double2* bf = reinterpret_cast<const double2*>(Bfrag + (int64_t)gb * KT * 128) + lane;
+    #pragma unroll
+            for (int nt = 0; nt < KT; nt++) {
+                const double2 b01 = __ldg(bf + (nt * 2) * 32), b23 = __ldg(bf + (nt * 2 + 1) * 32);
+                const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+    #pragma unroll
+                for (int j = 0; j < 4; j++)
+    #pragma unroll
+                    for (int mt = 0; mt < MT; mt++) dmma884(w[mt][nt][0], w[mt][nt][1], y[mt][j], b[j]);
             }
-            w[mt][nt][0] = -t0; w[mt][nt][1] = -t1;  // pass B adds (-W) A
+        };
+        {
+            double ya[MT][4], yb[MT][4];
+            int bi = warp;
+            if (bi < nblk_ctl) load_block(ya, ctl_blocks[bi]);
+            while (bi < nblk_ctl) {
+                int nb = bi + ADJ_WARPS;
+                if (nb < nblk_ctl) load_block(yb, ctl_blocks[nb]);
+                pass_a_block(ya, ctl_blocks[bi]);
+                bi = nb;
+                if (bi >= nblk_ctl) break;
+                nb = bi + ADJ_WARPS;
+                if (nb < nblk_ctl) load_block(ya, ctl_blocks[nb]);
+                pass_a_block(yb, ctl_blocks[bi]);
+                bi = nb;
+            }
+        }
+        // ---- combine the four partial W tiles (fixed order => deterministic), subtract center' B
+    #pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+    #pragma unroll
+            for (int nt = 0; nt < KT; nt++)
+    #pragma unroll
+                for (int e = 0; e < 2; e++) s_part[warp][(mt * KT + nt) * 2 + e][lane] = w[mt][nt][e];
+        __syncthreads();
+    #pragma unroll
+        for (int nt = 0; nt < KT; nt++) {
+            const int kk = 8 * nt + 2 * tig;
+            const double c0 = kk < k ? w0[kk] : 0.0, c1 = kk + 1 < k ? w0[kk + 1] : 0.0;
+    #pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                double t0 = 0.0, t1 = 0.0;
+    #pragma unroll
+                for (int ww = 0; ww < ADJ_WARPS; ww++) {
+                    t0 += s_part[ww][(mt * KT + nt) * 2 + 0][lane];
+                    t1 += s_part[ww][(mt * KT + nt) * 2 + 1][lane];
+                }
+                t0 -= c0; t1 -= c1;
+                if (Wout && warp == 0 && rowok[mt]) {
+                    double* wr = Wout + (row0 + mt * 8 + gid) * k;
+                    if (kk < k) wr[kk] = t0;
+                    if (kk + 1 < k) wr[kk + 1] = t1;
+                }
+                w[mt][nt][0] = -t0; w[mt][nt][1] = -t1;  // pass B adds (-W) A
+            }
         }
     }
     if constexpr (PASS_B) {
@@ -439,6 +453,48 @@ inline int adjust_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, 
                                                                               c->nblk_ctl, c->nblk, c->k, d_out, ldo, d_W, vec_in, vec_out, nc);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// out = Y - W A for GIVEN factors W (m x k, row-major) and A (k x n): pass B of K6 alone.  scRUVg with a re-used `fullW`, and
+// scRUVg with eta, where W comes from RUV1(Y) but is subtracted from Y itself (R/scRUVg.R:59,77-80).
+template <int KT, int MT>
+inline int rankk_subtract_launch(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const scm_coef* c, const double* d_W,
+                                 double* d_out, int64_t ldo) {
+    const int nc = ((const double*)d_out != d_Y) ? 1 : 0;
+    adjust_kernel<KT, MT, true, true><<<(unsigned)ceil_div(m, (int64_t)8 * MT), ADJ_WARPS * 32, 0, ctx->stream>>>(
+        d_Y, m, n, ld, c->Bfrag, c->Afrag, c->w0, c->ctl_blocks, 0, c->nblk, c->k, d_out, ldo, const_cast<double*>(d_W), vec_flag(d_Y, ld),
+        vec_flag(d_out, ldo), nc);
+    SCM_LAUNCH_CHECK(ctx);
+    return 0;
+}
+inline int rankk_subtract(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_W, int32_t k, const double* d_A,
+                          double* d_out, int64_t ldo) {
+    if (!d_Y || !d_W || !d_A || !d_out || n <= 0 || m < 0 || ld < n || ldo < n || k <= 0) return fail(SCM_ERR_INVALID, "rankk_subtract: bad arguments");
+    if (k > SCM_MAX_K) return fail(SCM_ERR_UNSUPPORTED, "rankk_subtract: k=%d > %d", k, SCM_MAX_K);
+    if (m == 0) return 0;
+    scm_coef* c = nullptr;
+    SCM_TRY(coef_alloc(ctx, n, k, &c));
+    struct Guard { scm_ctx* ctx; scm_coef* c; ~Guard() { coef_destroy(ctx, c); } } guard{ctx, c};
+    Scratch ws(ctx);
+    uint8_t* rows;
+    SCM_TRY(ws.alloc(&rows, n + 4));
+    SCM_TRY(zero_async(ctx, rows, (n + 3) & ~(int64_t)3));
+    SCM_TRY(zero_async(ctx, c->Bmat, sizeof(double) * n * k));
+    SCM_CUDA(cudaMemcpyAsync(c->Amat, d_A, sizeof(double) * n * k, cudaMemcpyDeviceToDevice, ctx->stream));
+    SCM_TRY(coef_finalize(ctx, c, rows, nullptr));
+    int rc;
+    switch (c->KT) {
+        case 1: rc = rankk_subtract_launch<1, 4>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 2: rc = rankk_subtract_launch<2, 4>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 3: rc = rankk_subtract_launch<3, 4>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 4: rc = rankk_subtract_launch<4, 4>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 5: rc = rankk_subtract_launch<5, 2>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 6: rc = rankk_subtract_launch<6, 2>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 7: rc = rankk_subtract_launch<7, 2>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        case 8: rc = rankk_subtract_launch<8, 2>(ctx, d_Y, m, n, ld, c, d_W, d_out, ldo); break;
+        default: return fail(SCM_ERR_UNSUPPORTED, "rankk_subtract: k=%d not supported", k);
+    }
+    return rc;  // the coefficient object is released in stream order
 }
 
 // TMA-staged variant (adjust_tma.cuh): returns 1 when not applicable

@@ -124,4 +124,59 @@ inline int ruvg_fit(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n,
     return rc;
 }
 
+// alpha = solve(W'W) W' (Y - 1 center')   (R/scRUVg.R:78 with a GIVEN W, e.g. a re-used `fullW[, 1:k]`; center = colMeans of the
+// matrix the residual operator of Z = 1 is applied to, :61-63).  W: m_local x k row-major.  Sums over cells are all-reduced.
+// One skinny DMMA GEMM over the cells (k x n, reduction length m, split over the SMs and reduced in order) + k x k work.
+__global__ void ls_rank1_kernel(double* __restrict__ P, const double* __restrict__ s, const double* __restrict__ center, int k, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)k * n) return;
+    const int a = (int)(e / n);
+    const int64_t g = e - (int64_t)a * n;
+    P[e] -= s[a] * center[g];
+}
+__global__ void ls_colsum_kernel(const double* __restrict__ W, int64_t m, int k, double* __restrict__ s) {  // s[a] = sum_i W[i, a]; one CTA per column
+    __shared__ double wb[32];
+    const int a = blockIdx.x;
+    double t = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) t += W[i * k + a];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) wb[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) { double r = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += wb[w]; s[a] = r; }
+}
+inline int ls_coef(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const double* d_W, int32_t k,
+                   const double* d_center, double* d_alpha) {
+    if (!d_Y || !d_W || !d_alpha || n <= 0 || m_local < 0 || ld < n || k <= 0) return fail(SCM_ERR_INVALID, "ls_coef: bad arguments");
+    if (k > SCM_MAX_K) return fail(SCM_ERR_UNSUPPORTED, "ls_coef: k=%d > %d", k, SCM_MAX_K);
+    if (m_local >= ((int64_t)1 << 31)) return fail(SCM_ERR_UNSUPPORTED, "ls_coef: m >= 2^31");
+    cudaStream_t st = ctx->stream;
+    Scratch ws(ctx);
+    const int64_t len = (int64_t)k * k + (int64_t)k * n + k;
+    double *buf, *Linv, *Ninv;
+    int* flag;
+    SCM_TRY(ws.alloc(&buf, len)); SCM_TRY(ws.alloc(&Linv, (int64_t)k * k)); SCM_TRY(ws.alloc(&Ninv, (int64_t)k * k)); SCM_TRY(ws.alloc(&flag, 2));
+    double *N = buf, *P = buf + (int64_t)k * k, *s = P + (int64_t)k * n;
+    SCM_TRY(zero_async(ctx, buf, sizeof(double) * len));
+    SCM_TRY(zero_async(ctx, flag, sizeof(int) * 2));
+    if (m_local > 0) {
+        SCM_TRY(gemm(ctx, k, k, (int)m_local, 1.0, transposed(d_W, k), rowmajor(d_W, k), 0.0, N, k));
+        SCM_TRY(gemm(ctx, k, (int)n, (int)m_local, 1.0, transposed(d_W, k), rowmajor(d_Y, ld), 0.0, P, n));
+        ls_colsum_kernel<<<k, 256, 0, st>>>(d_W, m_local, k, s);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    SCM_TRY(allreduce(ctx, buf, len, 0));
+    if (d_center) {
+        ls_rank1_kernel<<<(unsigned)ceil_div((int64_t)k * n, 256), 256, 0, st>>>(P, s, d_center, k, n);
+        SCM_LAUNCH_CHECK(ctx);
+    }
+    SCM_TRY(chol_inv_launch(ctx, N, k, 0.0, Linv, flag));
+    SCM_TRY(gemm(ctx, k, k, k, 1.0, transposed(Linv, k), rowmajor(Linv, k), 0.0, Ninv, k));
+    SCM_TRY(gemm(ctx, k, (int)n, k, 1.0, rowmajor(Ninv, k), rowmajor(P, n), 0.0, d_alpha, n));
+    int h = 0;
+    SCM_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCM_CUDA(cudaStreamSynchronize(st));
+    if (h) return fail(SCM_ERR_SINGULAR, "ls_coef: W'W is not positive definite (k=%d)", k);
+    return 0;
+}
+
 }  // namespace scm

@@ -689,6 +689,16 @@ int scm_block_median(scm_ctx* ctx, const double* d_D, int64_t ldd, const int64_t
     SCM_REQUIRE_CTX(ctx);
     return block_median(ctx, d_D, ldd, h_row_off, K1, h_col_off, K2, h_med);
 }
+int scm_ls_coef(scm_ctx* ctx, const double* d_Y, int64_t m_local, int64_t n, int64_t ld, const double* d_W, int32_t k,
+                const double* d_center, double* d_alpha) {
+    SCM_REQUIRE_CTX(ctx);
+    return ls_coef(ctx, d_Y, m_local, n, ld, d_W, k, d_center, d_alpha);
+}
+int scm_rankk_subtract(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64_t ld, const double* d_W, int32_t k, const double* d_A,
+                       double* d_out, int64_t ldo) {
+    SCM_REQUIRE_CTX(ctx);
+    return rankk_subtract(ctx, d_Y, m, n, ld, d_W, k, d_A, d_out, ldo);
+}
 int scm_kmeans(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t ldx, int32_t K, int32_t nstart, int32_t iter_max, uint64_t seed,
                int32_t* d_label, double* d_centers, double* h_withinss, int64_t* h_size, double* h_tot_withinss, int32_t* h_info) {
     SCM_REQUIRE_CTX(ctx);

@@ -727,14 +727,17 @@ def scRUVIII(Y, M, ctl, fullalpha=None, k=None, cell_type=None, batch=None, retu
 
 def scRUVg(Y, ctl, k, Z=1, eta=None, include_intercept=True, fullW=None, svdyc=None, BSPARAM=None, ctx: Context | None = None):
     """R/scRUVg.R:30-85.  Y: m x n (cells x genes, numpy or DeviceMatrix).  Returns {'newY', 'W' (m x k), 'alpha' (k x n)}.
-    Only the default covariate structure is implemented on the device (Z = 1: an intercept, eta = NULL), which is what
-    every documented call uses; `fullW` / `svdyc` (re-use of a previous decomposition) are not supported.  Columns of W
-    (and the matching rows of alpha) are defined up to sign, exactly like the reference's `svd`."""
-    del include_intercept
-    if eta is not None or not (np.isscalar(Z) and Z == 1):
-        raise NotImplementedError("scRUVg on the device supports Z = 1 (intercept only) and eta = NULL")
-    if fullW is not None or svdyc is not None:
-        raise NotImplementedError("fullW / svdyc re-use is not supported on the device path")
+    Z = 1 (an intercept: what every documented call uses) is the covariate structure implemented on the device.
+    `eta` (gene-wise covariates): the decomposition and alpha use Y0 = RUV1(Y, eta, ctl) (:59) while W alpha is subtracted
+    from Y itself (:80).  `fullW` (m x >= k, a previous decomposition): W = fullW[, 1:k], alpha = solve(W'W) W' Y0 (:64,77-78;
+    scm_ls_coef + scm_rankk_subtract).  `svdyc` without `fullW` leaves fullW NULL in the reference, which then fails at :77 --
+    it is rejected here with that explanation.  Columns of W (and the matching rows of alpha) are defined up to sign, exactly
+    like the reference's `svd`."""
+    if not (np.isscalar(Z) and Z == 1):
+        raise NotImplementedError("scRUVg on the device supports Z = 1 (intercept only)")
+    if svdyc is not None and fullW is None:
+        raise ValueError("svdyc without fullW: the reference never derives fullW from a given svdyc (R/scRUVg.R:64-75) and fails at "
+                         "fullW[, seq_len(k)]; pass fullW = svdyc$u instead")
     ctx = ctx or (Y.ctx if isinstance(Y, DeviceMatrix) else default_context())
     m, n = (Y.m, Y.n) if isinstance(Y, DeviceMatrix) else np.shape(Y)
     ctlm = tological(ctl, n)
@@ -743,30 +746,55 @@ def scRUVg(Y, ctl, k, Z=1, eta=None, include_intercept=True, fullW=None, svdyc=N
         raise ValueError("k must not be larger than the number of controls")  # R/scRUVg.R:56-58
     if k > min(L.MAX_K, m - 1):
         raise L.ScmError(L.ERR_UNSUPPORTED, f"k = {k} outside 1..min({L.MAX_K}, m - 1)")
+    if eta is not None:
+        eta_design_rows(eta, n, include_intercept)  # argument errors before any device work
+    if fullW is not None:
+        fullW = np.asarray(fullW, dtype=np.float64)
+        if fullW.ndim != 2 or fullW.shape[0] != m or fullW.shape[1] < k:
+            raise ValueError("fullW must be m x (at least k)")
     lib = L.lib()
     dY, copied = _as_device(ctx, Y)
+    dY0 = _ruv1(ctx, dY, eta, ctlm, include_intercept, in_place=False) if eta is not None else dY  # Y itself is needed for :80
     d_ctl = ctx.to_device(np.ascontiguousarray(ctlm, dtype=np.uint8))
     d_alpha, d_center, d_sigma = ctx.empty((k, n)), ctx.empty((n,)), ctx.empty((k,))
+    d_W = ctx.empty((m, k))
+    dout = DeviceMatrix(ctx, m, n)
     coef = C.c_void_p()
     iters, resid = C.c_int32(0), C.c_double(0.0)
     try:
-        rc = lib.scm_ruvg_fit(ctx.handle, dY.ptr, m, n, dY.ld, d_ctl.ptr, k, L.MODE_EXACT if _is_exact(BSPARAM) else L.MODE_RANDOMIZED,
-                              1e-10, 500, 1, d_alpha.ptr, d_center.ptr, d_sigma.ptr, C.byref(coef), C.byref(iters), C.byref(resid))
-        if rc == L.ERR_NOCONV:
-            warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=2)
+        if fullW is None:
+            rc = lib.scm_ruvg_fit(ctx.handle, dY0.ptr, m, n, dY0.ld, d_ctl.ptr, k, L.MODE_EXACT if _is_exact(BSPARAM) else L.MODE_RANDOMIZED,
+                                  1e-10, 500, 1, d_alpha.ptr, d_center.ptr, d_sigma.ptr, C.byref(coef), C.byref(iters), C.byref(resid))
+            if rc == L.ERR_NOCONV:
+                warnings.warn(lib.scm_last_error().decode(), L.NotConvergedWarning, stacklevel=2)
+            else:
+                L.check(rc)
+            if eta is None:
+                L.check(lib.scm_adjust(ctx.handle, dY.ptr, m, n, dY.ld, coef, None, 0, dout.ptr, dout.ld, d_W.ptr))
+            else:  # W = (Y0 - mean) B from the projection pass alone, then Y - W alpha on the ORIGINAL matrix
+                L.check(lib.scm_adjust(ctx.handle, dY0.ptr, m, n, dY0.ld, coef, None, 0, None, 0, d_W.ptr))
+                L.check(lib.scm_rankk_subtract(ctx.handle, dY.ptr, m, n, dY.ld, d_W.ptr, k, d_alpha.ptr, dout.ptr, dout.ld))
         else:
-            L.check(rc)
-        dout = DeviceMatrix(ctx, m, n)
-        d_W = ctx.empty((m, k))
-        L.check(lib.scm_adjust(ctx.handle, dY.ptr, m, n, dY.ld, coef, None, 0, dout.ptr, dout.ld, d_W.ptr))
+            W = np.ascontiguousarray(fullW[:, :k])
+            L.check(lib.scm_h2d(ctx.handle, d_W.ptr, W.ctypes.data_as(C.c_void_p), W.nbytes))
+            d_mean = ctx.to_device(column_means(dY0))
+            try:
+                L.check(lib.scm_ls_coef(ctx.handle, dY0.ptr, m, n, dY0.ld, d_W.ptr, k, d_mean.ptr, d_alpha.ptr))
+            finally:
+                d_mean.free()
+            L.check(lib.scm_rankk_subtract(ctx.handle, dY.ptr, m, n, dY.ld, d_W.ptr, k, d_alpha.ptr, dout.ptr, dout.ld))
         ctx.sync()
         W, alpha = d_W.to_host(), d_alpha.to_host()
-        d_W.free()
+    except Exception:
+        dout.free()
+        raise
     finally:
         if coef:
             lib.scm_coef_destroy(ctx.handle, coef)
-        for a in (d_ctl, d_alpha, d_center, d_sigma):
+        for a in (d_ctl, d_alpha, d_center, d_sigma, d_W):
             a.free()
+        if dY0 is not dY:
+            dY0.free()
     newY = _finish(dout, copied)
     if copied:
         dY.free()

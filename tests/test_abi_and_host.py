@@ -176,7 +176,7 @@ def test_r_shim_typechecks_and_matches_the_r_closures():
                             "-I" + os.path.join(ROOT, "tests", "r_stub"), "-I" + os.path.join(ROOT, "include"), shim],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
-    table = dict((nm, int(na)) for nm, na in re.findall(r'\{"([a-z_]+)",\s*\(DL_FUNC\)&[a-z_]+,\s*(\d+)\}', open(shim).read()))
+    table = dict((nm, int(na)) for nm, na in re.findall(r'\{"([a-z0-9_]+)",\s*\(DL_FUNC\)&[a-z0-9_]+,\s*(\d+)\}', open(shim).read()))
     assert table, "no R_CallMethodDef entries found"
     sites = []
     for path in glob.glob(os.path.join(ROOT, "r-package", "R", "*.R")):

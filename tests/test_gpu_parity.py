@@ -666,6 +666,29 @@ def test_sparse_native_kernels_vs_dense(sm, ctx, m, n, density, k, G):
     dcsc.free()
 
 
+def test_scruvg_eta_and_fullw_reuse_vs_oracle(sm):
+    """scRUVg's remaining arguments (R/scRUVg.R:59,64,77-80): eta (the decomposition sees RUV1(Y), the subtraction the original
+    Y) and a re-used fullW (alpha by least squares on the given W: scm_ls_coef + scm_rankk_subtract)."""
+    L = orc.ruv_simulate(m=400, n=700, nc=90, n_celltypes=4, rng=np.random.default_rng(321))
+    Y, ctl, k = L["Y"], L["ctl"], 7
+    eta = np.random.default_rng(2).normal(size=(Y.shape[1], 2))
+    ref = orc.scRUVg(Y, ctl, k, eta=eta)
+    got = sm.scRUVg(Y, ctl, k, eta=eta)
+    assert orc.rel_frobenius(got["newY"], ref["newY"]) < TOL_NEWY
+    assert orc.principal_angles(got["W"].T, ref["W"].T).max() < 1e-6
+    assert orc.principal_angles(got["alpha"], ref["alpha"]).max() < 1e-6
+    base = orc.scRUVg(Y, ctl, 12)                                      # a previous decomposition with more columns
+    for e in (None, eta):
+        ref2 = orc.scRUVg(Y, ctl, k, eta=e, fullW=base["W"])
+        got2 = sm.scRUVg(Y, ctl, k, eta=e, fullW=base["W"])
+        assert orc.rel_frobenius(got2["newY"], ref2["newY"]) < TOL_NEWY
+        assert np.allclose(got2["W"], base["W"][:, :k]) and np.allclose(got2["alpha"], ref2["alpha"], rtol=1e-8, atol=1e-10)
+    with pytest.raises(ValueError):
+        sm.scRUVg(Y, ctl, k, svdyc=object())                           # svdyc alone fails in the reference too (:77)
+    with pytest.raises(ValueError):
+        sm.scRUVg(Y, ctl, k, fullW=base["W"][:, :3])
+
+
 # ---- eta: gene-wise covariates (ruv::RUV1, R/fastRUVIII.R:63-64, R/scMerge2_utilis.R:56) ---------------------------------
 @pytest.mark.parametrize("intercept", [True, False])
 def test_fastruviii_and_pseudoruviii_with_eta_vs_oracle(sm, ctx, intercept):
