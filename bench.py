@@ -69,7 +69,7 @@ def parse():
                    help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] as the headline of this run")
     p.add_argument("--density", type=float, default=0.1, help="scmerge2: fraction of non-zero entries of the sparse expression matrix")
     p.add_argument("--dense-input", action="store_true", help="scmerge2 workload: dense device matrix instead of the sparse one")
-    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k,out_of_core | all | none")
+    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k,out_of_core,kmeans | all | none")
     p.add_argument("--ooc-cells", type=int, default=2_000_000, help="out_of_core extra: cells of the host matrix (x 3000 genes; 4000000 = BASELINE configs[3] on ONE GPU, needs ~100 GB of host RAM)")
     p.add_argument("--transport", default="nccl", choices=["nccl", "hook"], help="cross-rank sums: the library's NCCL communicator or the torch hook")
     p.add_argument("--no-e2e", action="store_true")
@@ -77,7 +77,7 @@ def parse():
     p.add_argument("--no-parity", action="store_true")
     a = p.parse_args()
     ex = a.extras.lower()
-    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k", "out_of_core"} if ex == "all" else set(ex.split(",")))
+    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k", "out_of_core", "kmeans"} if ex == "all" else set(ex.split(",")))
     return a
 
 
@@ -737,6 +737,27 @@ def run_ours(a):
         if world == 1:
             guarded("out_of_core", x_ooc)
 
+        def x_kmeans():
+            """identifyCluster's kmeans (R/scReplicate.R:394-395): 1000 starts on the first 10 PCs of one batch, on the device."""
+            from scmerge_b200 import replicate as rp
+            rng = np.random.default_rng(0)
+            res = {}
+            for mb, K in ((50_000, 3), (200_000, 8)):
+                cent = rng.normal(size=(K, 10)) * 2.0
+                x = cent[rng.integers(0, K, mb)] + rng.normal(size=(mb, 10))
+                dX = sm.DeviceMatrix.from_host(ctx, x)
+                rp.kmeans(dX, K, nstart=10, ctx=ctx)
+                ctx.sync()
+                t0 = time.perf_counter()
+                r = rp.kmeans(dX, K, nstart=1000, ctx=ctx)
+                ctx.sync()
+                res[f"{mb}x10_K{K}_nstart1000"] = {"ms": 1e3 * (time.perf_counter() - t0), "tot_withinss": r["tot_withinss"], "lloyd_iterations_of_winner": r["iter"],
+                                                   "hartigan_wong_transfers": r["transfers"]}
+                dX.free()
+            return res
+        if world == 1:
+            guarded("kmeans", x_kmeans)
+
     if rank == 0:
         m = m_local
         syrk_ms = stages.get("gram_syrk_kernel", 0.0)
@@ -759,9 +780,9 @@ def run_ours(a):
                 by = 12.0 * Xh.nnz + 8.0 * m * n
                 adj = dict(adj, achieved=by / (adj["ms"] * 1e-3) * 1e-9, frac=by / (adj["ms"] * 1e-3) * 1e-9 / hbm)
                 sec["adjust_rank_k"] = adj
-            roof = {"kernel": "csc_adjust_kernel (rank-k update on sparse rows)" if sparse else "adjust_tma_kernel (fused rank-k update)",
+            roof = {"kernel": "csc_project_kernel + csc_adjust_red_kernel (rank-k update on sparse rows)" if sparse else "adjust_tma_kernel (fused rank-k update)",
                     "bound": "hbm", "achieved": adj.get("achieved"), "peak": hbm,
-                    "unit": "GB/s", "frac": adj.get("frac"), "traffic": traffic.get("csc_adjust_kernel" if sparse else "adjust_tma_kernel"),
+                    "unit": "GB/s", "frac": adj.get("frac"), "traffic": traffic.get("csc_adjust_red_kernel" if sparse else "adjust_tma_kernel"),
                     "traffic_source": traffic_src,
                     "algorithmic": "12*nnz read + 8*m*n written per launch" if sparse else "8*m*n read + 8*m*n written per launch",
                     "ms_per_launch": adj.get("ms"), "peak_source": hbm_src}

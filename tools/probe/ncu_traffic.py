@@ -30,7 +30,7 @@ def main(src, dst):
         if len(r) <= kn:
             continue
         name = r[kn]
-        for short in ("gram_tma_kernel", "adjust_tma_kernel", "seg_partial_kernel", "csc_adjust_kernel", "shift_copy_kernel"):
+        for short in ("gram_tma_kernel", "adjust_tma_kernel", "seg_partial_kernel", "csc_adjust_red_kernel", "csc_adjust_kernel", "shift_copy_kernel"):
             if short in name:
                 vals = {}
                 for full, key in WANT.items():
