@@ -124,6 +124,29 @@ def test_oracle_scruvg_matches_r(ex):
     assert np.allclose(np.abs(r["W"]), mat("scRUVg_k5_absW"), rtol=1e-7, atol=1e-10)   # the reference's own sign-invariant idiom
 
 
+@needs_r
+def test_oracle_eta_fullw_and_kmeans_match_r(ex):
+    """ruv::RUV1 / design.matrix, scRUVg's eta and fullW arguments, and the optimum of stats::kmeans(nstart = 1000)."""
+    if not os.path.exists(os.path.join(RDIR, "eta_genes_x_2.csv")):
+        pytest.skip("golden vectors predate the eta / fullW / kmeans cases: re-run tools/r/make_reference_golden.R")
+    Y = ex["exprs"].T
+    eta = mat("eta_genes_x_2")
+    check_rows(orc.RUV1(Y, eta, ex["ctl"])[ROWS], "RUV1_eta_rows")
+    check_rows(orc.fastRUVIII(Y, ex["types"], ex["ctl"], 10, eta=eta)[ROWS], "fastRUVIII_eta_k10_newY_rows")
+    check_rows(orc.scRUVg(Y, ex["ctl"], 5, eta=eta)["newY"][ROWS], "scRUVg_eta_k5_newY_rows")
+    base = orc.scRUVg(Y, ex["ctl"], 5)
+    r = orc.scRUVg(Y, ex["ctl"], 3, fullW=base["W"])
+    check_rows(r["newY"][ROWS], "scRUVg_fullW_k3_newY_rows")
+    for i in (1, 2):
+        if not os.path.exists(os.path.join(RDIR, f"kmeans_batch{i}_pca_scores.csv")):
+            continue
+        x = mat(f"kmeans_batch{i}_pca_scores")
+        want = vec(f"kmeans_batch{i}_totwithinss_and_sizes")
+        got = orc.kmeans_hartigan_wong(x, 3, nstart=50, rng=np.random.default_rng(i))
+        assert np.isclose(got["tot_withinss"], want[0], rtol=1e-10)
+        assert orc.same_partition(got["cluster"], vec(f"kmeans_batch{i}_cluster").astype(int))
+
+
 # ---- the CUDA path against R (through the C ABI) -----------------------------------------------------------------------
 @needs_r
 @pytest.mark.gpu
@@ -154,6 +177,18 @@ def test_cuda_path_matches_r(ex):
     g = sm.scRUVg(Y, ex["ctl"], 5)
     check_rows(g["newY"][ROWS], "scRUVg_k5_newY_rows")
     assert np.allclose(np.abs(g["W"]), mat("scRUVg_k5_absW"), rtol=1e-7, atol=1e-10)
+    if os.path.exists(os.path.join(RDIR, "eta_genes_x_2.csv")):
+        from scmerge_b200 import replicate as rp
+        eta = mat("eta_genes_x_2")
+        check_rows(sm.fastRUVIII(Y, ex["types"], ex["ctl"], k=10, eta=eta)[ROWS], "fastRUVIII_eta_k10_newY_rows")
+        check_rows(sm.scRUVg(Y, ex["ctl"], 5, eta=eta)["newY"][ROWS], "scRUVg_eta_k5_newY_rows")
+        check_rows(sm.scRUVg(Y, ex["ctl"], 3, fullW=g["W"])["newY"][ROWS], "scRUVg_fullW_k3_newY_rows")
+        for i in (1, 2):
+            x = mat(f"kmeans_batch{i}_pca_scores")
+            want = vec(f"kmeans_batch{i}_totwithinss_and_sizes")
+            km = rp.kmeans(x, 3, nstart=1000, seed=i)
+            assert np.isclose(km["tot_withinss"], want[0], rtol=1e-10)
+            assert orc.same_partition(km["cluster"], vec(f"kmeans_batch{i}_cluster").astype(int))
 
 
 def test_generator_script_is_committed_and_names_every_file_the_tests_read():
@@ -163,6 +198,9 @@ def test_generator_script_is_committed_and_names_every_file_the_tests_read():
                "fastRUVIII_k20_newY_frobenius", "ruv_RUVIII_k20_newY_rows", "stand_mean", "stand_sd", "scRUVIII_k20_newY_rows",
                "scRUVIII_k5_10_20_optimal_ruvK", 'paste0("scRUVIII_multi_k", kk, "_newY_rows")', "pseudobulk_fold_of_cell",
                "pseudobulk_names", "pseudobulk_means", "pseudoRUVIII_k20_newY_rows", "pseudoRUVIII_fullalpha",
-               "getAdjustedMat_k10_newY_rows", "scRUVg_k5_newY_rows", "scRUVg_k5_absW"]
+               "getAdjustedMat_k10_newY_rows", "scRUVg_k5_newY_rows", "scRUVg_k5_absW", "eta_genes_x_2", "RUV1_eta_rows",
+               "fastRUVIII_eta_k10_newY_rows", "scRUVg_eta_k5_newY_rows", "scRUVg_fullW_k3_newY_rows",
+               'paste0("kmeans_batch", i, "_pca_scores")', 'paste0("kmeans_batch", i, "_cluster")',
+               'paste0("kmeans_batch", i, "_totwithinss_and_sizes")']
     for name in written:
         assert name in script, f"{name} is read by the tests but never written by tools/r/make_reference_golden.R"

@@ -86,6 +86,28 @@ write_mat(t(as.matrix(r5))[rows, ], "getAdjustedMat_k10_newY_rows")
 r6 <- scMerge:::scRUVg(Y = Y, ctl = ctl, k = 5)
 write_mat(as.matrix(r6$newY)[rows, ], "scRUVg_k5_newY_rows"); write_mat(abs(r6$W), "scRUVg_k5_absW")
 
+## 5. gene-wise covariates eta (ruv::RUV1 at R/fastRUVIII.R:63-64 and R/scRUVg.R:59) and a re-used fullW (R/scRUVg.R:64,77-80).
+##    eta: two deterministic covariates per gene (its mean expression and the fraction of zero cells), intercept added by RUV1.
+eta <- cbind(rowMeans(exprs), rowMeans(exprs == 0))
+write_mat(eta, "eta_genes_x_2")
+r7 <- scMerge::fastRUVIII(Y = Y, M = M, ctl = ctl, k = 10, eta = eta, BSPARAM = BiocSingular::ExactParam(), return.info = TRUE)
+write_mat(as.matrix(r7$newY)[rows, ], "fastRUVIII_eta_k10_newY_rows")
+write_mat(ruv::RUV1(Y, eta, seq_len(ncol(Y)) %in% ctl)[rows, ], "RUV1_eta_rows")
+r8 <- scMerge:::scRUVg(Y = Y, ctl = ctl, k = 5, eta = eta)
+write_mat(as.matrix(r8$newY)[rows, ], "scRUVg_eta_k5_newY_rows")
+r9 <- scMerge:::scRUVg(Y = Y, ctl = ctl, k = 3, fullW = r6$W)
+write_mat(as.matrix(r9$newY)[rows, ], "scRUVg_fullW_k3_newY_rows"); write_mat(r9$alpha, "scRUVg_fullW_k3_alpha")
+
+## 6. kmeans as identifyCluster calls it (R/scReplicate.R:394-395) on the first 10 PCs of every batch.  The labels depend on R's
+##    RNG stream; what is compared is the optimum: tot.withinss and the partition (as a co-membership checksum).
+for (i in seq_along(batch_list)) {
+  sel <- which(batch == batch_list[i])
+  pca <- BiocSingular::runPCA(t(exprs[, sel]), rank = 10, scale = TRUE, center = TRUE, BSPARAM = BiocSingular::ExactParam())$x
+  set.seed(1); km <- stats::kmeans(pca[, seq_len(10)], centers = 3, nstart = 1000)
+  write_mat(pca, paste0("kmeans_batch", i, "_pca_scores")); write_vec(km$cluster, paste0("kmeans_batch", i, "_cluster"))
+  write_vec(c(km$tot.withinss, sort(km$size)), paste0("kmeans_batch", i, "_totwithinss_and_sizes"))
+}
+
 writeLines(c(paste("scMerge", as.character(utils::packageVersion("scMerge"))), paste("ruv", as.character(utils::packageVersion("ruv"))),
              paste("BiocSingular", as.character(utils::packageVersion("BiocSingular"))), R.version.string,
              paste("generated", format(Sys.time(), tz = "UTC", usetz = TRUE))), file.path(out_dir, "MANIFEST.txt"))
