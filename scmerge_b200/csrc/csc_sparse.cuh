@@ -14,8 +14,8 @@
 //                           row (no atomics: indices inside a cell are unique), the warp rows are added in warp order and
 //                           the chunk partial goes through the same ordered final reduction: deterministic
 //   csc_project_kernel      pass A of K6 on sparse rows, W_i = s_i sum_nz x_ij B[j, :] - c'B, as its own kernel: the rows of B for
-//                           a range of genes stay resident in shared memory for the whole launch (1066 genes at k <= 24, one
-//                           launch per range), a quad of lanes per cell, eight non-zeros per trip.  History of this gather: lanes
+//                           a range of genes stay resident in shared memory for the whole launch (682 genes at k <= 24 in 128 KB,
+//                           one launch per range), a quad of lanes per cell, eight non-zeros per trip.  History of this gather: lanes
 //                           over the k factors with shuffles 26 ms; one lane per non-zero 14 ms; a quad per non-zero through L1TEX
 //                           7.5 ms (6 sector look-ups per non-zero, L1TEX 73 % of peak); B staged per 32-cell tile in 256-gene
 //                           slabs 5.9 ms (eight staging round trips per tile); this form 2.85 ms, within 1.7x of the shared-memory
@@ -241,7 +241,9 @@ template <int KT>
 inline int csc_project_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val, const double* d_inv,
                               int64_t m, int64_t n, const scm_coef* c, double* W) {
     constexpr int KP = KT * 8;
-    int64_t per = (200 * 1024) / (KP * 8);  // genes whose rows of B fit the shared memory of one CTA
+    static const int smem_kb = getenv("SCM_CSP_SMEM_KB") ? atoi(getenv("SCM_CSP_SMEM_KB")) : 128;  // shared-memory budget in KB.  Measured at 1M x 2000, k = 20 (projection + pass B): 200 KB (228 KB carve-out, 2 gene ranges) 6.90 ms,
+                                                                                              // 192 KB 6.62, 160 KB 6.59, 128 KB (4 ranges) 6.55, 96 KB 6.61, 64 KB 6.77: the L1 that is left matters more than the launches
+    int64_t per = ((int64_t)smem_kb * 1024) / (KP * 8);  // genes whose rows of B fit the shared memory of one CTA
     if (per > n) per = n;
     const int nr = (int)ceil_div(n, per);
     int64_t* cursor = nullptr;
@@ -638,7 +640,8 @@ csc_adjust_red_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
 template <int KT>
 inline int csc_adjust_red_launch(scm_ctx* ctx, Scratch& ws, const int64_t* d_indptr, const int32_t* d_idx, const double* d_val,
                                  const double* d_inv, int64_t m, int64_t n, const scm_coef* c, const double* W, double* d_out, int64_t ldo) {
-    int per = (200 * 1024) / (KT * 1024);  // 16-gene blocks whose A fragments fit the shared memory of one CTA
+    int per = (192 * 1024) / (KT * 1024);  // 16-gene blocks whose A fragments fit 192 KB: one byte more and the driver takes the 228 KB
+                                           // carve-out, and with the L1 that is left the kernel runs 26 % slower per gene (measured)
     per -= per % (CSR_SLAB / 16);          // ranges start on a slab boundary
     if (per > c->nblk) per = c->nblk;
     const int nr = (int)ceil_div((int64_t)c->nblk, (int64_t)per);
