@@ -81,26 +81,34 @@ csc_seg_partial_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
         __syncthreads();
         if (warp < nwarp) {
             double* acc = csg_acc + (int64_t)warp * n;
-            // warp w takes cells w, w + nwarp, ... of the chunk, one after the other: a fixed summation order per gene
-            for (int r = warp; r < len; r += nwarp) {
-                const int64_t cell = perm[start + r];
-                const int64_t p0 = indptr[cell], p1 = indptr[cell + 1];
-                const double s = inv[cell];
-                for (int64_t pb = p0 + lane; pb < p1; pb += 128) {  // 4 independent loads in flight per lane
-                    int32_t gi[4];
-                    double gv[4];
+            // warp w takes cells w, w + nwarp, ... of the chunk, one after the other: a fixed summation order per gene.  A cell costs
+            // a chain of dependent loads (perm -> indptr -> idx / val): the chain of the NEXT cell is started before the current
+            // cell's non-zeros are used, and a lane keeps eight index / value loads in flight (a cell of 200 non-zeros is one trip)
+            int r = warp;
+            int64_t cell = r < len ? perm[start + r] : 0;
+            int64_t p0 = r < len ? indptr[cell] : 0, p1 = r < len ? indptr[cell + 1] : 0;
+            double sc = r < len ? inv[cell] : 0.0;
+            for (; r < len; r += nwarp) {
+                const int rn = r + nwarp;
+                int64_t celln = 0, p0n = 0, p1n = 0;
+                double scn = 0.0;
+                if (rn < len) { celln = perm[start + rn]; p0n = indptr[celln]; p1n = indptr[celln + 1]; scn = inv[celln]; }
+                for (int64_t pb = p0 + lane; pb < p1; pb += 256) {
+                    int32_t gi[8];
+                    double gv[8];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < 8; u++) {
                         const int64_t p = pb + 32 * u;
                         gi[u] = p < p1 ? idx[p] : -1;
                         gv[u] = p < p1 ? val[p] : 0.0;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if ((unsigned)gi[u] < (unsigned)n) acc[gi[u]] += gv[u] * s;  // unique indices inside a cell: no conflicts (a corrupt
-                                                                                      // index can never leave the accumulator row)
+                    for (int u = 0; u < 8; u++)
+                        if ((unsigned)gi[u] < (unsigned)n) acc[gi[u]] += gv[u] * sc;  // unique indices inside a cell: no conflicts (a corrupt
+                                                                                       // index can never leave the accumulator row)
                 }
                 __syncwarp();
+                cell = celln; p0 = p0n; p1 = p1n; sc = scn;
             }
         }
         __syncthreads();

@@ -54,15 +54,30 @@ __global__ void group_total_kernel(const double* __restrict__ sums, int32_t G, i
     tot[j] = s;
 }
 
-// out[j] = sum_g counts[g] * means[g, j] / sum_g counts[g]: the column means of all cells from the group means
-__global__ void weighted_colmean_kernel(const double* __restrict__ means, const int64_t* __restrict__ counts, int32_t G, int64_t n,
-                                        int64_t ldm, double* __restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double s = 0.0;
-    int64_t tot = 0;
-    for (int g = 0; g < G; g++) { const int64_t c = counts[g]; tot += c; s += (double)c * means[(int64_t)g * ldm + j]; }
-    out[j] = tot > 0 ? s / (double)tot : 0.0;
+// out[j] = sum_g counts[g] * means[g, j] / sum_g counts[g]: the column means of all cells from the group means.  A CTA takes 32
+// genes; its 32 thread rows split the groups (g = ty, ty + 32, ...: with the 4800 pseudobulks of scMerge2 one thread per gene was a
+// 4800-long dependent chain, ~1 ms) and are added in row order: deterministic, independent of the grid.
+__global__ void __launch_bounds__(1024)
+weighted_colmean_kernel(const double* __restrict__ means, const int64_t* __restrict__ counts, int32_t G, int64_t n, int64_t ldm,
+                        double* __restrict__ out) {
+    __shared__ double ps[32][33];
+    __shared__ double pc[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    double s = 0.0, tot = 0.0;  // counts < 2^53 are exact in float64
+    for (int g = ty; g < G; g += 32) {
+        const double c = (double)counts[g];
+        tot += c;
+        if (j < n) s += c * means[(int64_t)g * ldm + j];
+    }
+    ps[ty][tx] = s;
+    if (tx == 0) pc[ty] = tot;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+        double a = 0.0, t = 0.0;
+        for (int r = 0; r < 32; r++) { a += ps[r][tx]; t += pc[r]; }
+        out[j] = t > 0.0 ? a / t : 0.0;
+    }
 }
 
 // pooled within-batch sd (R/scRUVIII.R:170): sd[j] = sqrt( sum_b ssq[b, j] / (m - #non-empty batches) )
@@ -466,7 +481,7 @@ int scm_csc_seg_colmean(scm_ctx* ctx, const int64_t* d_indptr, const int32_t* d_
     SCM_TRY(csc_seg_colsum(ctx, d_indptr, d_idx, d_val, d_inv_norm, m, n, d_key, G, d_means, ldn, d_counts));
     SCM_TRY(allreduce(ctx, d_means, (int64_t)G * ldn, 0));  // global over the ranks, like scm_seg_colmean
     SCM_TRY(allreduce(ctx, d_counts, G, 1));
-    groupmean_kernel<<<(unsigned)ceil_div(ldn, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, ldn);
+    groupmean_kernel<<<dim3((unsigned)ceil_div(ldn, 256), (unsigned)(G < 2048 ? G : 2048)), 256, 0, ctx->stream>>>(d_means, d_counts, G, ldn);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -509,14 +524,14 @@ int scm_seg_colmean(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int64
     // summed over the ranks before the division, so every rank gets the same, global means
     SCM_TRY(allreduce(ctx, d_means, (int64_t)G * n, 0));
     SCM_TRY(allreduce(ctx, d_counts, G, 1));
-    groupmean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_means, d_counts, G, n);
+    groupmean_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)(G < 2048 ? G : 2048)), 256, 0, ctx->stream>>>(d_means, d_counts, G, n);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 int scm_group_colmean(scm_ctx* ctx, const double* d_means, const int64_t* d_counts, int32_t G, int64_t n, int64_t ldm, double* d_out) {
     SCM_REQUIRE_CTX(ctx);
-    weighted_colmean_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, ctx->stream>>>(d_means, d_counts, G, n, ldm, d_out);
+    weighted_colmean_kernel<<<(unsigned)ceil_div(n, 32), 1024, 0, ctx->stream>>>(d_means, d_counts, G, n, ldm, d_out);
     SCM_LAUNCH_CHECK(ctx);
     return 0;
 }
