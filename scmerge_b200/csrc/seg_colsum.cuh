@@ -86,8 +86,10 @@ __global__ void seg_scan_kernel(const int* __restrict__ cnt, int32_t G, int64_t*
 
 // COPY: every visited element is also written, shifted, to copy_out[row, col] = Y[row, col] - copy_shift[col] (the pre-shifted
 // copy of the cells the fit's Gram reads): the stream that is being summed anyway pays for the copy's read.
+// VEC columns per thread: 4 = one 32-byte access per row (LDG / STG.E.256 on sm_100: half the L1TEX requests of VEC = 2), 2 = 16 bytes,
+// 1 = scalar (odd leading dimension).  A column is summed by ONE thread in row order whatever VEC is: the sums do not depend on it.
 template <int VEC, bool SQUARE, bool COPY = false>
-__global__ void __launch_bounds__(SEG_THREADS)
+__global__ void __launch_bounds__(SEG_THREADS, VEC == 4 ? 2 : 1)
 seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const int32_t* __restrict__ perm,
                    const int64_t* __restrict__ seg_start, const int* __restrict__ chunk_off,
                    const int* __restrict__ pslot_off, int32_t G, const double* __restrict__ center,
@@ -95,13 +97,11 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
                    const double* __restrict__ copy_shift = nullptr, double* __restrict__ copy_out = nullptr, int64_t ldc = 0) {
     const int nchunks = chunk_off[G];
     const int64_t col = ((int64_t)blockIdx.x * SEG_THREADS + threadIdx.x) * VEC;
-    const bool v0 = col < n, v1 = (VEC == 2) && (col + 1 < n);
+    const bool v0 = col < n, full = col + VEC <= n;  // `full`: all VEC columns exist (vector access); else column by column
     bool bad = false;
-    double h0 = 0.0, h1 = 0.0;
-    if (COPY) {
-        if (v0) h0 = copy_shift[col];
-        if (v1) h1 = copy_shift[col + 1];
-    }
+    double h[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; e++) h[e] = (COPY && col + e < n) ? copy_shift[col + e] : 0.0;
     for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
         int lo = 0, hi = G;  // largest g with chunk_off[g] <= chunk (empty groups share offsets: take the last)
         while (hi - lo > 1) {
@@ -112,15 +112,12 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
         const int j = chunk - chunk_off[g];
         const int64_t start = seg_start[g] + (int64_t)j * SEG_R;
         const int len = (int)min((int64_t)SEG_R, seg_start[g + 1] - start);
-        double c0 = 0.0, c1 = 0.0;
-        if (SQUARE) {
-            if (v0) c0 = center[(int64_t)g * n + col];
-            if (v1) c1 = center[(int64_t)g * n + col + 1];
-        }
-        double a0 = 0.0, a1 = 0.0;
+        double c[VEC], acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e++) { c[e] = (SQUARE && col + e < n) ? center[(int64_t)g * n + col + e] : 0.0; acc[e] = 0.0; }
         if (v0) {
             for (int r = 0; r < len; r += 8) {
-                double x0[8], x1[8];
+                double x[8][VEC];
                 int rows[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
@@ -128,30 +125,42 @@ seg_partial_kernel(const double* __restrict__ Y, int64_t n, int64_t ld, const in
                     const int64_t row = ok ? (int64_t)perm[start + r + u] : 0;
                     rows[u] = (int)row;
                     const double* p = Y + row * ld + col;
-                    x0[u] = 0.0; x1[u] = 0.0;
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) x[u][e] = 0.0;
                     if (ok) {
-                        if (VEC == 2 && v1) { double2 t = ldg_stream2(p); x0[u] = t.x; x1[u] = t.y; }
-                        else x0[u] = __ldg(p);
+                        if (VEC == 4 && full) ldg256_stream(p, x[u][0], x[u][1], x[u][2], x[u][3]);
+                        else if (VEC == 2 && full) { const double2 t = ldg_stream2(p); x[u][0] = t.x; x[u][1] = t.y; }
+                        else {
+#pragma unroll
+                            for (int e = 0; e < VEC; e++) if (col + e < n) x[u][e] = __ldg(p + e);
+                        }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     if (r + u < len) {
-                        bad |= nonfinite(x0[u]) | nonfinite(x1[u]);
-                        if (SQUARE) { double d0 = x0[u] - c0, d1 = x1[u] - c1; a0 += d0 * d0; a1 += d1 * d1; }
-                        else { a0 += x0[u]; a1 += x1[u]; }
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) {
+                            bad |= nonfinite(x[u][e]);
+                            if (SQUARE) { const double d = x[u][e] - c[e]; acc[e] += d * d; }
+                            else acc[e] += x[u][e];
+                        }
                         if (COPY) {
                             double* q = copy_out + (int64_t)rows[u] * ldc + col;
-                            if (VEC == 2 && v1) __stcs(reinterpret_cast<double2*>(q), make_double2(x0[u] - h0, x1[u] - h1));
-                            else __stcs(q, x0[u] - h0);
+                            if (VEC == 4 && full) stg256_stream(q, x[u][0] - h[0], x[u][1] - h[1], x[u][2] - h[2], x[u][3] - h[3]);
+                            else if (VEC == 2 && full) __stcs(reinterpret_cast<double2*>(q), make_double2(x[u][0] - h[0], x[u][1] - h[1]));
+                            else {
+#pragma unroll
+                                for (int e = 0; e < VEC; e++) if (col + e < n) __stcs(q + e, x[u][e] - h[e]);
+                            }
                         }
                     }
                 }
             }
             const int nch = chunk_off[g + 1] - chunk_off[g];
             double* dst = (nch == 1) ? (sums + (int64_t)g * n) : (partial + (int64_t)(pslot_off[g] + j) * n);
-            dst[col] = a0;
-            if (v1) dst[col + 1] = a1;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) if (col + e < n) dst[col + e] = acc[e];
         }
     }
     if (bad && flag) *flag = 1;
@@ -245,8 +254,12 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     double* partial;
     SCM_TRY(ws.alloc(&partial, max_slots * n));
     SCM_TRY(zero_async(ctx, d_sums, sizeof(double) * G * n));  // empty groups stay 0
+    static const int no256 = getenv("SCM_NO_256") ? atoi(getenv("SCM_NO_256")) : 0;  // A/B switch: 16-byte accesses only
     const bool vec2 = (ld % 2 == 0) && (((uintptr_t)d_Y) % 16 == 0);
-    const int vec = vec2 ? 2 : 1;
+    bool vec4 = !no256 && (ld % 4 == 0) && (((uintptr_t)d_Y) % 32 == 0);
+    if (d_copy_out) vec4 = vec4 && (ldc % 4 == 0) && (((uintptr_t)d_copy_out) % 32 == 0);
+    const bool vec2c = vec2 && (!d_copy_out || ((ldc % 2 == 0) && (((uintptr_t)d_copy_out) % 16 == 0)));
+    const int vec = vec4 ? 4 : (vec2c ? 2 : 1);
     dim3 grid((unsigned)ceil_div(n, (int64_t)SEG_THREADS * vec), 1);
     const int64_t max_chunks = ceil_div(m, SEG_R) + G;
     int64_t gy = ((int64_t)ctx->num_sms * 8) / grid.x;
@@ -255,20 +268,16 @@ inline int seg_colsum(scm_ctx* ctx, const double* d_Y, int64_t m, int64_t n, int
     if (gy > 65535) gy = 65535;
     grid.y = (unsigned)gy;
     const bool sq = d_center != nullptr;
-#define SEG_LAUNCH(V, S) seg_partial_kernel<V, S><<<grid, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, d_center, partial, d_sums, d_nonfinite)
+#define SEG_LAUNCH(V, S, C) seg_partial_kernel<V, S, C><<<grid, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, d_center, partial, d_sums, d_nonfinite, d_copy_shift, d_copy_out, ldc)
     if (d_copy_out) {
         if (sq || !d_copy_shift || ldc < n) return fail(SCM_ERR_INVALID, "seg_colsum: the shifted copy needs a shift vector, ldc >= n and the plain-sum mode");
-        const bool vec2c = vec2 && (ldc % 2 == 0) && (((uintptr_t)d_copy_out) % 16 == 0);
-        if (vec2c) seg_partial_kernel<2, false, true><<<grid, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, nullptr, partial, d_sums, d_nonfinite, d_copy_shift, d_copy_out, ldc);
-        else {
-            dim3 grid1((unsigned)ceil_div(n, (int64_t)SEG_THREADS), grid.y);
-            seg_partial_kernel<1, false, true><<<grid1, SEG_THREADS, 0, st>>>(d_Y, n, ld, perm, seg_start, chunk_off, pslot_off, G, nullptr, partial, d_sums, d_nonfinite, d_copy_shift, d_copy_out, ldc);
-        }
+        if (vec == 4) SEG_LAUNCH(4, false, true); else if (vec == 2) SEG_LAUNCH(2, false, true); else SEG_LAUNCH(1, false, true);
         SCM_LAUNCH_CHECK(ctx);
         seg_copy_skipped_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(d_Y, m, n, ld, perm, seg_start, G, d_copy_shift, d_copy_out, ldc);
     }
-    else if (vec2) { if (sq) SEG_LAUNCH(2, true); else SEG_LAUNCH(2, false); }
-    else      { if (sq) SEG_LAUNCH(1, true); else SEG_LAUNCH(1, false); }
+    else if (vec == 4) { if (sq) SEG_LAUNCH(4, true, false); else SEG_LAUNCH(4, false, false); }
+    else if (vec == 2) { if (sq) SEG_LAUNCH(2, true, false); else SEG_LAUNCH(2, false, false); }
+    else               { if (sq) SEG_LAUNCH(1, true, false); else SEG_LAUNCH(1, false, false); }
 #undef SEG_LAUNCH
     SCM_LAUNCH_CHECK(ctx);
     dim3 fgrid((unsigned)G, (unsigned)ceil_div(n, 256));
