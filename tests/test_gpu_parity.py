@@ -689,6 +689,36 @@ def test_scruvg_eta_and_fullw_reuse_vs_oracle(sm):
         sm.scRUVg(Y, ctl, k, fullW=base["W"][:, :3])
 
 
+def test_group_means_with_thousands_of_groups(sm, ctx):
+    """scm_seg_colmean / scm_group_colmean with more groups than any launch dimension they use (2-D grid clamped at 2048 group
+    rows, 32 thread rows per gene): the 4800 pseudobulks of scMerge2 and beyond; empty groups stay 0; colMeans of ALL cells
+    recovered from the group means and counts."""
+    rng = np.random.default_rng(11)
+    m, n, G = 30000, 130, 5000
+    Y = rng.normal(size=(m, n)) + 3.0
+    keys = rng.integers(0, G, m).astype(np.int32)
+    keys[keys == 7] = 8                                                  # group 7 is empty
+    dY = sm.DeviceMatrix.from_host(ctx, Y)
+    d_keys, d_cnt = ctx.to_device(keys), ctx.empty((G,), np.int64)
+    dP = sm.DeviceMatrix(ctx, G, n)
+    lib = sm.lib()
+    assert lib.scm_seg_colmean(ctx.handle, dY.ptr, m, n, dY.ld, d_keys.ptr, G, dP.ptr, d_cnt.ptr, None) == 0, lib.scm_last_error()
+    cnt = np.bincount(keys, minlength=G)
+    assert np.array_equal(d_cnt.to_host(), cnt)
+    want = np.zeros((G, n))
+    np.add.at(want, keys, Y)
+    want[cnt > 0] /= cnt[cnt > 0, None]
+    got = dP.to_host()
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-14) and np.all(got[7] == 0)
+    d_mean = ctx.empty((n,))
+    assert lib.scm_group_colmean(ctx.handle, dP.ptr, d_cnt.ptr, G, n, dP.ld, d_mean.ptr) == 0
+    assert np.allclose(d_mean.to_host(), Y.mean(axis=0), rtol=1e-12)
+    for a in (d_keys, d_cnt, d_mean):
+        a.free()
+    dP.free()
+    dY.free()
+
+
 # ---- eta: gene-wise covariates (ruv::RUV1, R/fastRUVIII.R:63-64, R/scMerge2_utilis.R:56) ---------------------------------
 @pytest.mark.parametrize("intercept", [True, False])
 def test_fastruviii_and_pseudoruviii_with_eta_vs_oracle(sm, ctx, intercept):
