@@ -69,7 +69,7 @@ def parse():
                    help="fastruviii = the BASELINE.json metric workload (default); scmerge2 = configs[2] as the headline of this run")
     p.add_argument("--density", type=float, default=0.1, help="scmerge2: fraction of non-zero entries of the sparse expression matrix")
     p.add_argument("--dense-input", action="store_true", help="scmerge2 workload: dense device matrix instead of the sparse one")
-    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k,out_of_core,kmeans | all | none")
+    p.add_argument("--extras", default="all", help="comma list of weak,c4,k_sweep,scmerge2,pageable,cpu200k,out_of_core,kmeans,adjust_only | all | none")
     p.add_argument("--ooc-cells", type=int, default=2_000_000, help="out_of_core extra: cells of the host matrix (x 3000 genes; 4000000 = BASELINE configs[3] on ONE GPU, needs ~100 GB of host RAM)")
     p.add_argument("--transport", default="nccl", choices=["nccl", "hook"], help="cross-rank sums: the library's NCCL communicator or the torch hook")
     p.add_argument("--no-e2e", action="store_true")
@@ -77,7 +77,7 @@ def parse():
     p.add_argument("--no-parity", action="store_true")
     a = p.parse_args()
     ex = a.extras.lower()
-    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k", "out_of_core", "kmeans"} if ex == "all" else set(ex.split(",")))
+    a.extra_set = set() if ex == "none" else ({"weak", "c4", "k_sweep", "scmerge2", "pageable", "cpu200k", "out_of_core", "kmeans", "adjust_only"} if ex == "all" else set(ex.split(",")))
     return a
 
 
@@ -736,6 +736,31 @@ def run_ours(a):
                     "conv_rank": int(res["fullalpha"].conv_rank), "device_bytes_for_cells": 3 * 512 * 2**20}
         if world == 1:
             guarded("out_of_core", x_ooc)
+
+        def x_adjust_only():
+            """The second half of the reference's fit / adjust checkpoint through the public call with HOST buffers (pinned):
+            fastRUVIII(Y, fullalpha = stored) -- nothing has to be known about the cells first, so the host driver streams every
+            chunk up, adjusts it and sends it home in one full-duplex pass."""
+            mo = 1_000_000
+            dYx, kx, cx, _ = make_data(a, ctx, rank, torch, mo, n=n, c=a.ctl)
+            fit = sm.fastRUVIII(dYx, kx, cx, k=a.k, return_info=True, ctx=ctx)
+            fit["newY"].free()
+            Yh, Oh = sm.pinned_empty((mo, n)), sm.pinned_empty((mo, n))
+            dYx.to_host(Yh)
+            dYx.free()
+            ctx.release_scratch()
+            sm.fastRUVIII(Yh, kx, cx, k=a.k, fullalpha=fit["fullalpha"], ctx=ctx, out=Oh)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                sm.fastRUVIII(Yh, kx, cx, k=a.k, fullalpha=fit["fullalpha"], ctx=ctx, out=Oh)
+                ts.append(time.perf_counter() - t0)
+            t = min(ts)
+            return {"workload": f"fastRUVIII(Y, fullalpha = stored) {mo} cells x {n} genes, pinned host in / out, one pass, uploads and downloads concurrent",
+                    "ms": 1e3 * t, "cells_per_s": mo / t, "h2d_bytes": mo * n * 8, "d2h_bytes": mo * n * 8,
+                    "pcie_gb_s_each_way": mo * n * 8 / t * 1e-9}
+        if world == 1:
+            guarded("adjust_only", x_adjust_only)
 
         def x_kmeans():
             """identifyCluster's kmeans (R/scReplicate.R:394-395): 1000 starts on the first 10 PCs of one batch, on the device."""

@@ -425,8 +425,11 @@ inline int ruv3_host(scm_ctx* ctx, const HostArgs& a) {
     const int nchunks = pl.nchunks;
     const bool need_sums = do_fit || a.center_mode == 1;
     constexpr int RING = 3;
+    // an adjust-only call that needs no pass over the cells first (fullalpha given, centre none or given: getAdjustedMat with the
+    // stored adjusted_means, fastRUVIII(fullalpha = )) ALWAYS streams: one pass, every chunk goes up, is adjusted and comes home
+    // while the next ones are in flight in both directions -- half the PCIe wall time of upload-then-download
     const bool stream_mode = nchunks > RING && (getenv("SCM_HOST_STREAM") ? atoi(getenv("SCM_HOST_STREAM")) != 0
-                                                                           : m * ld * 8 + n * n * 32 > host_device_budget());
+                                                                           : (!need_sums || m * ld * 8 + n * n * 32 > host_device_budget()));
     const bool staged_in = host_is_pageable(a.h_Y), staged_out = host_is_pageable(a.h_out);
     if (staged_in || staged_out) SCM_TRY(stage_reserve(ctx, (size_t)rows_per_chunk * n * 8));
 

@@ -895,11 +895,7 @@ def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, 
     device layout, which *is* genes x cells column-major) when given one.  `ctl` / `return_subset_genes` may be masks,
     0-based indices or gene names (matched against `gene_names` = rownames(exprsMat), as the reference does)."""
     ctx = ctx or (exprsMat.ctx if isinstance(exprsMat, DeviceMatrix) else default_context())
-    if isinstance(exprsMat, DeviceMatrix):
-        dY, copied = exprsMat, False
-    else:
-        dY, copied = DeviceMatrix.from_host(ctx, np.asarray(exprsMat, dtype=np.float64).T), True
-    n = dY.n
+    n = exprsMat.n if isinstance(exprsMat, DeviceMatrix) else np.shape(exprsMat)[0]
     ctl_mask = np.ones(n, dtype=bool) if ctl is None else genes_by_name(ctl, n, gene_names)
     if ctl_mask.sum() == 0:
         raise ValueError("No provided ctl genes in the data")
@@ -908,6 +904,22 @@ def getAdjustedMat(exprsMat, fullalpha, ctl=None, adjusted_means=None, ruvK=20, 
         sub = np.nonzero(genes_by_name(return_subset_genes, n, gene_names))[0]
         if sub.shape[0] == 0:
             raise ValueError("No provided return_subset_genes genes in the data")
+    if sub is None and isinstance(exprsMat, np.ndarray) and _is_host_matrix(exprsMat.T):
+        # genes x cells in column-major order (R's layout) is cells x genes by rows: the host-streaming driver.  With the stored
+        # `adjusted_means` nothing has to be known about the cells beforehand, so every chunk goes up, is adjusted and comes
+        # home in ONE pass with uploads and downloads running concurrently; without them the column means accumulate during the
+        # upload first (the in-core form)
+        fa = np.asanyarray(fullalpha, dtype=np.float64)
+        if adjusted_means is None:
+            newY, _ = _host_pipeline(ctx, exprsMat.T, ctl_mask, int(ruvK), fullalpha_in=fa, center_mode=1)
+        else:
+            newY, _ = _host_pipeline(ctx, exprsMat.T, ctl_mask, int(ruvK), fullalpha_in=fa, center_mode=2,
+                                     center=np.asarray(adjusted_means, dtype=np.float64))
+        return newY.T
+    if isinstance(exprsMat, DeviceMatrix):
+        dY, copied = exprsMat, False
+    else:
+        dY, copied = DeviceMatrix.from_host(ctx, np.asarray(exprsMat, dtype=np.float64).T), True
     means = column_means(dY) if adjusted_means is None else np.asarray(adjusted_means, dtype=np.float64)
     dout, _ = _adjust(ctx, dY, np.asanyarray(fullalpha, dtype=np.float64), int(ruvK), ctl_mask, center=means, subset=sub)
     if copied:

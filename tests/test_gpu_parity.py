@@ -386,6 +386,16 @@ def test_host_pipeline_multichunk(sm, monkeypatch):
     ref_adj = orc.pseudoRUVIII(P["Y"], P["Y"][:300], P["types"][:300], P["ctl"], 5, fullalpha=ref["fullalpha"])
     assert orc.rel_frobenius(adj["newY"], ref_adj["newY"]) < TOL_NEWY
     assert np.allclose(adj["adjusted_means"], P["Y"].mean(axis=0), rtol=1e-12)
+    # getAdjustedMat on R's layout: with the stored adjusted_means the call streams in ONE pass (upload / adjust / download of
+    # different chunks at the same time), without them the means accumulate during the upload first; both equal the oracle,
+    # the resident path, and each other's bits
+    ctlm = orc.tological(P["ctl"], P["Y"].shape[1])
+    ref_g = orc.getAdjustedMat(P["Y"].T, ref["fullalpha"], ctl=ctlm, ruvK=5)
+    g1 = sm.getAdjustedMat(Yg, res["fullalpha"], ctl=ctlm, ruvK=5)
+    g2 = sm.getAdjustedMat(Yg, res["fullalpha"], ctl=ctlm, ruvK=5, adjusted_means=adj["adjusted_means"])
+    g3 = sm.getAdjustedMat(np.ascontiguousarray(Yg), res["fullalpha"], ctl=ctlm, ruvK=5)      # C-ordered: resident path
+    assert g1.shape == ref_g.shape and orc.rel_frobenius(g1, ref_g) < TOL_NEWY and orc.rel_frobenius(g3, ref_g) < TOL_NEWY
+    assert np.array_equal(g1, g2)
     bad = P["Y"].copy()
     bad[4321, 17] = np.inf  # NA/Inf in a late chunk is still caught (R/fastRUVIII.R:52-60)
     with pytest.raises(ValueError, match="missing values or infinities"):
