@@ -7,11 +7,11 @@ from ._lib import LIB_PATH, NonFiniteError, NotConvergedWarning, ScmError, Singu
 from .device import Context, DeviceArray, DeviceMatrix, MultiContext, bind_host_to_gpu, default_context, pinned_empty  # noqa: F401
 from .ruv import (ExactParam, FullAlpha, IrlbaParam, RandomParam, RUVFit, aggregate_matrix, createChunk,  # noqa: F401
                   create_pseudoBulk, fastRUVIII, genes_by_name, getAdjustedMat, multi_fastRUVIII, pseudoRUVIII, replicate_keys, replicate_matrix,
-                  scRUVg, scRUVIII, tological)
+                  scRUVg, scRUVIII, tological, eta_design_rows)
 
 from .scmerge2 import DeviceCSC, cosineNorm, csc_to_device, pseudobulk_keys, scMerge2_core  # noqa: F401,E402
 
 from .replicate import (centroidDist, cluster_centroid_dist, compute_dist_mat, compute_dist_res,  # noqa: F401,E402
-                        computePCA_byHVGMarker, run_pca_scores)
+                        computePCA_byHVGMarker, identifyCluster, kmeans, run_pca_scores)
 
-__version__ = "0.2.0"
+__version__ = "0.3.0"

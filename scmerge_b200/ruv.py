@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib as L
 from .device import Context, DeviceArray, DeviceMatrix, MultiContext, default_context
 
-__all__ = ["FullAlpha", "fastRUVIII", "scRUVIII", "scRUVg", "genes_by_name", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
+__all__ = ["eta_design_rows", "FullAlpha", "fastRUVIII", "scRUVIII", "scRUVg", "genes_by_name", "pseudoRUVIII", "getAdjustedMat", "create_pseudoBulk", "aggregate_matrix",
            "replicate_matrix", "replicate_keys", "tological", "createChunk", "RUVFit", "ExactParam", "RandomParam",
            "IrlbaParam"]
 
