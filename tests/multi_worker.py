@@ -77,6 +77,14 @@ def main():
     Y0 = Yall - Yall.mean(axis=0)
     U = np.linalg.svd(Y0[:, orc.tological(P["ctl"], 384)], full_matrices=False)[0][:, :8]
     e5 = orc.rel_frobenius(rg["newY"], (Yall - U @ (U.T @ Y0))[lo:hi])
+    # scRUVg with a GIVEN W sharded by rows (W'W, W'Y0 and W'1 are all-reduced in scm_ls_coef), and eta (ruv::RUV1: rank-local given
+    # the covariates) in front of the cross-rank fit
+    rgw = sm.scRUVg(Yall[lo:hi], P["ctl"], 5, fullW=U[lo:hi], ctx=ctx)
+    W5 = U[:, :5]
+    e5w = orc.rel_frobenius(rgw["newY"], (Yall - W5 @ np.linalg.solve(W5.T @ W5, W5.T @ Y0))[lo:hi])
+    eta = np.random.default_rng(8).normal(size=(384, 2))
+    oeta = sm.fastRUVIII(Yall[lo:hi], types_all[lo:hi], P["ctl"], k=6, eta=eta, ctx=ctx)
+    e5e = orc.rel_frobenius(oeta, orc.fastRUVIII(Yall, types_all, P["ctl"], 6, eta=eta)[lo:hi])
     # scMerge2 core across ranks (dense and sparse input): pseudobulks pool cells of ALL ranks (global level tables, sums and
     # counts all-reduced before the division), the pseudobulk fit is shared row-wise, the adjust is rank-local.  The fold of
     # every cell is drawn once for all cells and handed out with the shards, so the pseudobulks are those of the oracle.
@@ -107,11 +115,11 @@ def main():
     lst = [torch.empty_like(fa) for _ in range(world)]
     dist.all_gather(lst, fa)
     same = all(torch.equal(lst[0], t) for t in lst)
-    ok = (e1 < 1e-8 and e1d < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8
+    ok = (e1 < 1e-8 and e1d < 1e-8 and a1 < 1e-6 and e2 < 1e-8 and same and e3 < 1e-7 and same_k and e4 < 1e-8 and e5 < 1e-8 and e5w < 1e-8 and e5e < 1e-8
           and e6 < 1e-8 and names_ok and e6b < 1e-12 and e7 < 1e-8)
     print(f"rank {rank}/{world} [{transport}]: rows [{lo},{hi}) batches here {sorted(set(batch_all[lo:hi]))} fast err {e1:.2e} (device {e1d:.2e}) "
           f"angle {a1:.2e} scRUVIII err {e2:.2e} identical_alpha {same} selection sil err {e3:.2e} same_k {same_k} newY err {e4:.2e} "
-          f"scRUVg err {e5:.2e} scMerge2 err {e6:.2e} (names {names_ok}, bulk {e6b:.1e}) sparse {e7:.2e}", flush=True)
+          f"scRUVg err {e5:.2e} (fullW {e5w:.2e}) eta err {e5e:.2e} scMerge2 err {e6:.2e} (names {names_ok}, bulk {e6b:.1e}) sparse {e7:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
