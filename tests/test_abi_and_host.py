@@ -319,3 +319,18 @@ def test_eta_design_rows_match_the_oracle_design_matrix():
         eta_design_rows(np.zeros((n + 1, 2)), n, True)                      # wrong shape
     with pytest.raises(ValueError):
         eta_design_rows(2, n, True)
+
+
+def test_committed_ncu_traffic_stamp_matches_the_kernel_sources():
+    """bench.py attaches `roofline.traffic` (DRAM bytes per launch from an ncu capture) only when profiles/ncu_traffic.json was
+    captured for the kernel sources in the tree.  A kernel edit without a new capture (tools/probe/ncu_traffic.sh on a B200)
+    would silently turn the figure into null: fail here instead."""
+    import json
+    import bench
+    stamp = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert stamp["kernel_source_hash"] == bench.kernel_source_hash(), \
+        "kernel sources changed since profiles/ncu_traffic.json was captured: re-run tools/probe/ncu_traffic.sh under gpurun"
+    algo = stamp["algorithmic_bytes"]
+    for kern, got in stamp["dram_bytes_per_launch"].items():
+        assert got >= 0.99 * algo[kern], kern                       # never below the algorithmic bytes
+    assert stamp["dram_bytes_per_launch"]["gram_tma_kernel"] <= 4.0 * algo["gram_tma_kernel"]   # VERDICT r01 item 5: <= 4x
