@@ -3,6 +3,7 @@
 ## libscmerge_b200 behind src/rshim.c.  scMerge()/scMerge2() call these exactly as they call the originals.
 
 .keys <- function(M) {            # ruv::replicate.matrix semantics -> 0-based int keys (one-hot rows required)
+  if (methods::is(M, "DelayedArray") || methods::is(M, "Matrix")) M <- as.matrix(M)   # the reference's tests pass DelayedArray(M)
   if (is.matrix(M) && is.numeric(M)) {
     stopifnot(all(M == 0 | M == 1), all(rowSums(M) == 1))
     list(key = as.integer(max.col(M, ties.method = "first") - 1L), G = ncol(M))
