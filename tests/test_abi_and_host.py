@@ -334,3 +334,49 @@ def test_committed_ncu_traffic_stamp_matches_the_kernel_sources():
     for kern, got in stamp["dram_bytes_per_launch"].items():
         assert got >= 0.99 * algo[kern], kern                       # never below the algorithmic bytes
     assert stamp["dram_bytes_per_launch"]["gram_tma_kernel"] <= 4.0 * algo["gram_tma_kernel"]   # <= 4x
+
+
+def test_host_argument_resolution_properties():
+    """Property checks (hypothesis) of the host-side index plumbing against the oracle's restatements: replicate keys are a
+    relabelling of the input partition with levels in sorted order, createChunk covers 1..n without gaps like the reference's,
+    the svd_k rule, and `subset` resolution keeps the given order."""
+    from hypothesis import given, settings, strategies as st
+    from scmerge_b200.ruv import _resolve_subset, _svd_k, createChunk, replicate_keys, replicate_matrix
+    from oracle import ruv_oracle as orc
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=-5, max_value=40), min_size=1, max_size=200))
+    def keys_ok(labels):
+        a = np.array(labels)
+        k, G = replicate_keys(a)
+        lv = np.unique(a)
+        assert G == lv.shape[0] and np.array_equal(lv[k], a)                    # sorted level order, a pure relabelling
+        assert np.array_equal(replicate_matrix(a), orc.replicate_matrix(a))
+        ks, Gs = replicate_keys(np.array([f"t{v}" for v in labels]))            # strings sort like R's factor levels (C locale)
+        assert Gs == G and len(set(zip(ks.tolist(), k.tolist()))) == G
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(min_value=1, max_value=5000), st.integers(min_value=1, max_value=700))
+    def chunks_ok(n, size):
+        ch = createChunk(n, size)
+        assert ch == orc.create_chunk(n, size)
+        assert ch[0][0] == 1 and ch[-1][1] == n and all(b[0] == a[1] + 1 for a, b in zip(ch, ch[1:]))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 10**6), st.integers(1, 500), st.integers(1, 5000), st.booleans(), st.integers(1, 200))
+    def svdk_ok(m, G, nctl, exact, cap):
+        assert _svd_k(m, G, nctl, exact, cap) == orc.svd_k_bound(m, G, nctl, exact, cap)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(0, 29), min_size=1, max_size=40))
+    def subset_ok(idx):
+        names = np.array([f"g{i}" for i in range(30)])
+        assert np.array_equal(_resolve_subset(np.array(idx), 30), idx)                              # order and repeats kept
+        assert np.array_equal(_resolve_subset(names[idx], 30, gene_names=names), idx)               # match(subset, colnames(Y))
+        mask = np.zeros(30, bool)
+        mask[idx] = True
+        assert np.array_equal(_resolve_subset(mask, 30), np.nonzero(mask)[0])                       # which()
+
+    keys_ok(); chunks_ok(); svdk_ok(); subset_ok()
+    with pytest.raises(IndexError):
+        _resolve_subset(np.array(["nope"]), 30, gene_names=np.array([f"g{i}" for i in range(30)]))
