@@ -64,7 +64,7 @@ int scm_version(void);
 /* PCI bus id ("0000:3b:00.0") of a device: lets the host bind its threads / page-locked buffers to the NUMA node the GPU hangs
  * on (sysfs local_cpulist) before scm_host_alloc_pinned -- cross-socket staging halves the end-to-end rate on 2-socket hosts. */
 int scm_device_pci_bus_id(int device, char* buf, int len);
-int scm_ctx_create(int device, void* cuda_stream /* NULL = own stream */, scm_ctx** out);
+int scm_ctx_create(int device, void* cuda_stream /* NULL = own stream; (void*)1 = the legacy default stream; (void*)2 = own stream of the LEAST priority (background context) */, scm_ctx** out);
 int scm_ctx_destroy(scm_ctx* ctx);
 int scm_ctx_set_allreduce(scm_ctx* ctx, scm_allreduce_fn fn, void* user, int world_size);
 /* Built-in communicator: NCCL, resolved with dlopen("libnccl.so.2") at first use (no link-time dependency; SCM_ERR_COMM when it

@@ -208,8 +208,15 @@ int scm_ctx_create(int device, void* cuda_stream, scm_ctx** out) {
     if (const char* e = getenv("SCM_GRAM_ORDER")) c->gram_class_order = (e[0] != '0');
     if (const char* e = getenv("SCM_GRAM_PRESHIFT")) c->gram_preshift = (e[0] != '0');
     if (const char* e = getenv("SCM_K1_FUSED_COPY")) c->k1_fused_copy = (e[0] != '0');
-    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
-    else { SCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    if (cuda_stream && cuda_stream != (void*)2) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else {
+        // own stream: the greatest priority, or -- handle 2, a BACKGROUND context -- the least one: the block scheduler then gives
+        // free SMs to the foreground context's kernels first (scMerge2: the whole-spectrum solve beside the adjust + download)
+        int least = 0, greatest = 0;
+        SCM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SCM_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, cuda_stream ? least : greatest));
+        c->own_stream = true;
+    }
     for (int i = 0; i < ST_COUNT; i++) {
         SCM_CUDA(cudaEventCreate(&c->ev0[i]));
         SCM_CUDA(cudaEventCreate(&c->ev1[i]));

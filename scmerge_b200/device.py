@@ -18,7 +18,7 @@ class Context:
     """Owns a `scm_ctx` (one GPU, one stream).  `stream` may be a raw cudaStream_t (int), e.g.
     `torch.cuda.current_stream().cuda_stream`, so that torch events and NCCL order with our kernels."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, _borrowed=None):
+    def __init__(self, device: int = 0, stream: int | None = None, _borrowed=None, background: bool = False):
         self._h = C.c_void_p()
         self.device = int(device)
         self.stream = stream
@@ -33,7 +33,8 @@ class Context:
             return
         # stream=None: the library creates its own non-blocking stream.  stream=0 is torch's default stream, i.e. the
         # legacy NULL stream, which must be passed as the cudaStreamLegacy handle (1) because NULL means "own stream".
-        handle = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
+        # background=True: an own stream of the least priority (handle 2): work that should yield the SMs to another context
+        handle = (2 if background else 0) if stream is None else (1 if int(stream) == 0 else int(stream))
         L.check(L.lib().scm_ctx_create(int(device), C.c_void_p(handle), C.byref(self._h)))
         self._fin = weakref.finalize(self, L.lib().scm_ctx_destroy, self._h)
 

@@ -10,6 +10,7 @@ supervised case where clusters with the same label are replicates of each other 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -231,6 +232,7 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
     dP = DeviceMatrix(ctx, P, n)
     d_keys, d_cnt = ctx.to_device(np.ascontiguousarray(keys, dtype=np.int32)), ctx.empty((P,), np.int64)
     coef = None
+    side = None  # the whole-spectrum fit running beside the download (see below)
     try:
         L.check(lib.scm_csc_seg_colmean(ctx.handle, dcsc.indptr.ptr, dcsc.indices.ptr, dcsc.data.ptr, d_inv.ptr, m, n, d_keys.ptr, P,
                                         dP.ptr, dP.ld, d_cnt.ptr))
@@ -246,8 +248,37 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
         if G >= P or ruvK == 0:
             raise ValueError("replicate structure leaves no residual degrees of freedom (ncol(M) >= number of pseudobulks)")
         s_dev, exact_dev = _device_rows_cap(s, ruvK, exact, n, rows=P if getattr(ctx, "world", 1) <= 1 else None)
-        fit = _fit_pseudobulk(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
         from .ruv import _Coef
+        if (host_out is not None and s_dev > L.MAX_TOPK_ROWS and getattr(ctx, "world", 1) <= 1
+                and os.environ.get("SCM_SCM2_OVERLAP", "1") != "0"):
+            # The cells only need the first ruvK rows of fullalpha; the hundreds of further rows the reference's rule returns come
+            # from the whole-spectrum solve (~110 ms at 2000 genes).  With a host result the adjust is a ~300 ms PCIe download, so
+            # the top rows are fitted first (subspace iteration, ~2 ms), the cells start leaving at once, and the whole-spectrum
+            # solve runs meanwhile on a second context (own stream, own host thread) of the same device.
+            import threading
+            fit_top = _fit(ctx, dP, rkeys, G, min(s, max(int(ruvK), 50), L.MAX_TOPK_ROWS), ruvK, True)
+            ctx.sync()
+            aux = getattr(ctx, "_aux_ctx", None)
+            if aux is None:
+                aux = ctx._aux_ctx = Context(ctx.device, background=True)  # least-priority stream: yields the SMs to the adjust
+
+            class _View:  # dP as seen from the second context (same device memory)
+                pass
+            v = _View()
+            v.ctx, v.m, v.n, v.ld, v.ptr = aux, dP.m, dP.n, dP.ld, dP.ptr
+            side = {}
+
+            def _whole_spectrum():
+                try:
+                    side["fit"] = _fit(aux, v, rkeys, G, s_dev, ruvK, exact_dev)
+                    aux.sync()
+                except BaseException as exc:  # noqa: BLE001 -- re-raised in the calling thread
+                    side["error"] = exc
+            side["thread"] = threading.Thread(target=_whole_spectrum, name="scm-whole-spectrum")
+            side["thread"].start()
+            fit = fit_top
+        else:
+            fit = _fit_pseudobulk(ctx, dP, rkeys, G, s_dev, ruvK, exact_dev)
         with _Coef(ctx, n, fit.fullalpha, ruvK, ctl_mask, center=means) as coef:
             if host_out is not None:
                 assert host_out.shape == (m, n) and host_out.dtype == np.float64 and host_out.flags.c_contiguous
@@ -263,7 +294,15 @@ def _scmerge2_sparse(ctx: Context, dcsc: "DeviceCSC", batch, clust, ctl, ruvK: i
                 if to_host:  # host input without a caller-supplied buffer: hand back numpy like every other host path
                     newY = dout.to_host()
                     dout.free()
+        if side is not None:  # every row of fullalpha from the whole-spectrum solve that ran beside the download
+            side["thread"].join()
+            side.pop("thread")
+            if "error" in side:
+                raise side["error"]
+            fit = side["fit"]
     finally:
+        if side is not None and "thread" in side:  # an error on the main path: the side fit still reads dP
+            side["thread"].join()
         for a in (d_inv, d_keys, d_cnt):
             a.free()
         dP.free()

@@ -600,6 +600,22 @@ def test_scmerge2_core_sparse_input_matches_dense(sm):
     assert orc.rel_frobenius(host_out, ref["newY"]) < TOL_NEWY
     dense = scMerge2_core(D, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam())
     assert orc.rel_frobenius(dense["newY"], host_out) < 1e-10
+    # scMerge2's default BSPARAM (RandomParam): every row of fullalpha the reference's rule asks for (here P - G = 92 > 88: the
+    # whole-spectrum solve).  With a host result that solve runs on a second context beside the download, the cells being
+    # adjusted with the top rows of a subspace iteration: same cells, same rows as the sequential order (SCM_SCM2_OVERLAP=0)
+    import os
+    r_over = scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, out=host_out)
+    y_over = np.array(host_out)
+    os.environ["SCM_SCM2_OVERLAP"] = "0"
+    try:
+        r_seq = scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, out=host_out)
+    finally:
+        del os.environ["SCM_SCM2_OVERLAP"]
+    assert r_over["fullalpha"].shape == r_seq["fullalpha"].shape and r_over["fullalpha"].shape[0] > 88
+    assert orc.rel_frobenius(y_over, host_out) < 1e-9 and orc.rel_frobenius(y_over, ref["newY"]) < TOL_NEWY
+    assert np.array_equal(np.asarray(r_over["fullalpha"]), np.asarray(r_seq["fullalpha"]))     # the same solver on the same matrix
+    assert orc.principal_angles(r_over["fullalpha"][:8], ref["fullalpha"][:8]).max() < 1e-6
+    scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam(), out=host_out)   # back to the exact run
     # the densify-first path (what un-canonical input takes) agrees with the sparse-native kernels
     dens = scMerge2_core(Xs, batch, clust, ruvK=8, k_pseudoBulk=8, which=which, BSPARAM=sm.ExactParam(), sparse_native=False)
     assert orc.rel_frobenius(dens["newY"], host_out) < 1e-10
