@@ -370,7 +370,7 @@ inline int kmeans(scm_ctx* ctx, const double* d_X, int64_t m, int32_t d, int64_t
     SCM_TRY(ws.alloc(&d_info, 4));
     km_transpose_kernel<<<(unsigned)std::min<int64_t>(ceil_div(m * d, 256), 4096), 256, 0, ctx->stream>>>(d_X, m, d, ldx, Xt);
     SCM_LAUNCH_CHECK(ctx);
-    const int max_transfers = 100000;
+    const int max_transfers = 5000;  // every transfer is one pass of a single CTA over the points; after a converged Lloyd run a handful are needed (the cap is reported: h_info[3])
     int rc;
 #define SCM_KM_GO(T_, DD_) rc = kmeans_launch<T_, DD_>(ctx, Xt, m, d, K, nstart, iter_max, seed, max_transfers, d_label, d_centers, d_stats, d_info, ws)
     if (nslots * 128 * 8 <= 96 * 1024) { if (d == 10) SCM_KM_GO(128, 10); else SCM_KM_GO(128, 0); }  // d = 10: scReplicate's first 10 PCs
